@@ -1,0 +1,274 @@
+#!/usr/bin/env python
+"""bench.py -- HR frames/s at 4x including the 2-step inner adaptation (BASELINE.json metric).
+
+One "step" = one output HR frame of the DynaVSR test-time path (codes/test_dynavsr.py:197-283) on a
+synthetic REDS4-shaped window: restore meta-weights, 2 x {MFDN(LR)->SLR, EDVR(SLR), L2 + 10*L1(SLR),
+backward, fused SGD on EDVR+MFDN}, final EDVR(LR) -> HR.  The 5x3x180x320 LR window is cropped to
+5x3x176x320 exactly as the reference loader does (video_test_dataset_int.py:185-189: SLR must be a
+multiple of 4), so HR is 3x704x1280.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload adapt|infer]
+
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = 'HR frames/sec at 4x (5x3x180x320 in) incl. 2-step inner adapt'
+UNIT = 'frames/s'
+LR_H, LR_W, NFR, SCALE = 176, 320, 5, 4        # 180 -> 176: reference crop rule
+INNER = dict(steps=2, lr_alpha=1e-5, optimizer='SGD', criterion='l2', slr_weight=10.0)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default='adapt', choices=['adapt', 'infer'])
+    ap.add_argument('--no-graphs', action='store_true')
+    ap.add_argument('--no-tc', action='store_true', help='exact-fp32 CUDA-core convolutions only')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--height', type=int, default=LR_H)
+    ap.add_argument('--width', type=int, default=LR_W)
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------------
+def synth_clip(seed, H, W, nfr=NFR):
+    """Seeded band-limited noise with a global translation of <= 2 px/frame, in [0, 1], quantised to
+    8 bits like the reference pipeline (vsrbase.py:188).  [1, nfr, 3, H, W] float32 (CPU)."""
+    import torch
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(seed)
+    base = torch.rand(1, 3, H // 4 + 8, W // 4 + 8, generator=g)
+    base = F.interpolate(base, scale_factor=4, mode='bicubic', align_corners=False).clamp(0, 1)
+    frames = []
+    for t in range(nfr):
+        dy, dx = 8 + (t * 2) % 5, 8 + (t * 3) % 7
+        frames.append(base[:, :, dy:dy + H, dx:dx + W])
+    clip = torch.stack(frames, 1)
+    return (clip * 255).round() / 255
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index, self.samples, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                      '--format=csv,noheader,nounits'], stdout=subprocess.PIPE,
+                                     stderr=subprocess.DEVNULL, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([v.strip() for v in out.split(',')])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=6)
+        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+        mx = [int(s[1]) for s in self.samples if s[1].isdigit()]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = [n for i, n in enumerate(names) if any(len(s) > 2 + i and s[2 + i].lower().startswith('active') for s in self.samples)]
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': reasons, 'samples': len(self.samples)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get('hbm_gbs', 6650.0), d.get('bf16_tflops', 1590.0), 'measured (MEASURED_PEAKS.json)'
+    return 6650.0, 1590.0, 'fallback (B200_PROFILING.md)'
+
+
+# ---------------------------------------------------------------------------------------------------
+def cpu_adapt_sample(steps, warmup, H=48, W=80, full_hw=(LR_H, LR_W)):
+    """The oracle port (reference algorithm, plain PyTorch CPU, all host threads) on a bounded sample:
+    one adapted frame on an LR crop of H x W; frames/s extrapolated to the full window by pixel count."""
+    import torch
+    from oracle import edvr_oracle as O
+    from oracle import params as P
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sdG = P.make_params(P.edvr_param_shapes(), seed=1234)
+    sdE = P.make_params(P.mfdn_param_shapes(), seed=77)
+    sdF = P.make_params(P.mfdn_param_shapes(), seed=78)
+    clip = synth_clip(0, H, W)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        O.adapt_and_infer(sdG, sdE, sdF, clip, **INNER)
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    t = sum(times) / len(times)
+    ratio = (full_hw[0] * full_hw[1]) / float(H * W)
+    return {'value': 1.0 / (t * ratio), 'unit': UNIT, 'cores': cores, 'kind': 'port',
+            'sample': 'oracle/edvr_oracle.adapt_and_infer (reference algorithm, torch CPU fp32, %d threads) on an LR crop '
+                      '%dx%d: %.2f s per adapted frame, scaled by the pixel ratio %.1f to %dx%d' % (
+                          torch.get_num_threads(), H, W, t, ratio, full_hw[0], full_hw[1]),
+            'seconds_per_sample': t}
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    base = cpu_adapt_sample(max(1, min(args.steps, 3)), min(args.warmup, 1))
+    line = {'impl': 'reference', 'metric': METRIC, 'value': base['value'], 'unit': UNIT, 'n_gpus': args.gpus,
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1000.0 / base['value'],
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': 'adapt2_sgd_l2 REDS4-shaped 5x3x180x320 (cropped 176x320) -> 3x704x1280, CPU sample'},
+            'cpu_baseline': base,
+            'e2e': {'value': base['value'], 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    local = int(os.environ.get('LOCAL_RANK', 0))
+    if args.impl == 'reference':
+        run_reference(args, rank)
+        return
+    import torch
+    import torch.distributed as dist
+    from oracle import params as P          # weights only (seeded generator); no oracle compute on this path
+    from dynavsr_b200 import _lib, adapt, ops
+    from dynavsr_b200.models.archs import EDVR_arch, LRimg_estimator
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm')
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group('nccl', rank=rank, world_size=world)
+    H, W = args.height, args.width
+    use_tc = (not args.no_tc) and hasattr(_lib.lib(), 'dvsr_conv_tc_fprop')
+    ops.set_conv_backend(use_tc)
+
+    def build(seedG):
+        netG = EDVR_arch.EDVR(nf=64, nframes=NFR, groups=8, front_RBs=5, back_RBs=10, scale=SCALE)
+        netG.load_state_dict(P.make_params(P.edvr_param_shapes(), seed=seedG))
+        netE = LRimg_estimator.DirectKernelEstimatorVideo(64, 3, SCALE)
+        netE.load_state_dict(P.make_params(P.mfdn_param_shapes(), seed=77))
+        netF = LRimg_estimator.DirectKernelEstimatorVideo(64, 3, SCALE)
+        netF.load_state_dict(P.make_params(P.mfdn_param_shapes(), seed=78))
+        return netG.cuda(), netE.cuda(), netF.cuda()
+
+    netG, netE, netF = build(1234)
+    eng = adapt.InnerLoopAdapter(netG, netE, netF, use_graphs=not args.no_graphs, **INNER)
+    # distinct windows per step and per rank (clip sharding: frame i -> rank i % world, train_dynavsr.py:509)
+    n_clips = 4
+    clips_host = [synth_clip(100 + rank * n_clips + i, H, W).pin_memory() for i in range(n_clips)]
+    frames_dev = [ops.to_nhwc(c.cuda().reshape(NFR, 3, H, W)) for c in clips_host]
+    hr_host = torch.empty(1, 3, SCALE * H, SCALE * W).pin_memory()
+
+    def step_dev(i):
+        if args.workload == 'adapt':
+            return eng.adapt_and_infer_nhwc(frames_dev[i % n_clips])
+        return eng.infer_nhwc(frames_dev[i % n_clips])
+
+    def step_e2e(i):
+        x = clips_host[i % n_clips].cuda(non_blocking=True).reshape(NFR, 3, H, W)
+        fr = ops.to_nhwc(x)
+        hr = eng.adapt_and_infer_nhwc(fr) if args.workload == 'adapt' else eng.infer_nhwc(fr)
+        hr_host.copy_(ops.to_nchw(hr), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for i in range(warmup):
+            fn(i)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        _lib.COUNTER[0] = 0
+        e0.record()
+        for i in range(steps):
+            fn(warmup + i)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        launches = _lib.COUNTER[0]
+        if world > 1:
+            t = torch.tensor([ms], device='cuda')
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        return ms, launches
+
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    ms, host_launches = timed(step_dev, args.steps, max(args.warmup, 3))
+    clk = clocks.stop() if rank == 0 else None
+    ms_e2e, _ = timed(step_e2e, args.steps, 2)
+    value = world * args.steps / (ms / 1000.0)
+    e2e = world * args.steps / (ms_e2e / 1000.0)
+    # kernels launched per step: counted while the step was captured / run eagerly
+    per_step = eng.launches_per_step if getattr(eng, 'launches_per_step', None) else host_launches / max(1, args.steps)
+
+    # ---- roofline of the dominant kernel: the 3x3 64->64 convolution at the trunk shape, timed alone
+    hbm_peak, tc_peak, peak_src = measured_peaks()
+    x = torch.randn(1, H, W, 64, device='cuda')
+    wgt = torch.randn(64, 64, 3, 3, device='cuda') * 0.05
+    bia = torch.zeros(64, device='cuda')
+    with torch.no_grad():
+        for _ in range(5):
+            ops.conv(x, wgt, bia, act=ops.ACT_RELU)
+        torch.cuda.synchronize()
+        reps = 50
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            ops.conv(x, wgt, bia, act=ops.ACT_RELU)
+        b.record()
+        torch.cuda.synchronize()
+    t_conv = a.elapsed_time(b) / reps / 1000.0
+    flops = 18.0 * H * W * 64 * 64
+    roofline = {'kernel': 'conv3x3 64->64 fprop @%dx%d (%s)' % (H, W, 'tcgen05 tf32' if use_tc else 'CUDA-core fp32'),
+                'bound': 'tensor', 'achieved': flops / t_conv / 1e12, 'peak': tc_peak, 'unit': 'TFLOP/s',
+                'frac': flops / t_conv / 1e12 / tc_peak, 'traffic': None, 'peak_source': peak_src + ' bf16 dense',
+                'launch_us': t_conv * 1e6}
+
+    if rank == 0:
+        cpu = None if args.no_cpu_baseline else cpu_adapt_sample(1, 0)
+        line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+                'warmup': max(args.warmup, 3), 'ms_per_step': ms / args.steps, 'higher_is_better': True,
+                'scaling': 'weak', 'vs_baseline': None, 'dtype': 'tf32 (fp32 accumulate)' if use_tc else 'f32',
+                'data': 'synthetic',
+                'config': {'workload': ('adapt2_sgd_l2+final_forward' if args.workload == 'adapt' else 'inference_only') +
+                           ' EDVR-M 4x + MFDN, REDS4-shaped 5x3x180x320 window cropped to %dx%d -> 3x%dx%d' % (H, W, SCALE * H, SCALE * W),
+                           'inner': INNER, 'clips_per_rank': n_clips, 'cuda_graphs': not args.no_graphs,
+                           'l2': 'per-step working set (activations ~GBs) exceeds the 126 MB L2; inputs rotate over %d clips' % n_clips,
+                           'parallelism': 'clip-sharded dp%d, no data-path collective' % world},
+                'e2e': {'value': e2e, 'unit': UNIT, 'h2d_bytes_per_step': NFR * 3 * H * W * 4,
+                        'd2h_bytes_per_step': 3 * SCALE * H * SCALE * W * 4, 'ms_per_step': ms_e2e / args.steps},
+                'gpu_launches': int(per_step * args.steps), 'clocks': clk, 'roofline': roofline, 'cpu_baseline': cpu}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

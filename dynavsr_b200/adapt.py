@@ -1,0 +1,211 @@
+"""Test-time adaptation engine: the hot loop of codes/test_dynavsr.py:197-283 for one output frame.
+
+    restore meta-weights                      (:208  deepcopy(model.netG), deepcopy(est_model.netE))
+    repeat adapt_iter times:                  (:235)
+        SLR      = MFDN_cp(LR)                (:238-241)
+        loss     = cri(EDVR_cp(SLR), LR_c)    (:262-264)
+                 + 10 * L1(SLR, MFDN_fixed(LR))   (:267-274; MFDN_fixed(LR) is constant -> hoisted)
+        backward; SGD / Adam step on EDVR+MFDN    (:276-277)
+    HR = EDVR_cp(LR)                          (:282-283)
+
+B200-first structure: EDVR and MFDN parameters live in ONE flat fp32 buffer (and one flat gradient
+buffer), so "deepcopy" is a single device-to-device copy, ``zero_grad`` a single memset and the
+optimiser step a single kernel launch (dvsr_update_sgd / dvsr_update_adam) instead of 158 per-tensor
+launches; weight-gradient kernels accumulate straight into the flat gradient buffer.  The whole
+step (forward, backward, update) and the final forward are captured in CUDA graphs per input shape.
+"""
+import ctypes
+import math
+
+import torch
+
+from . import _lib, ops
+from ._lib import call
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class FlatParams(object):
+    """Re-homes the parameters of ``modules`` (in order) into one flat buffer + one flat gradient buffer.
+
+    ``split`` is the element offset where the second module's parameters start (the two learning-rate
+    groups of train_dynavsr.py:335-344: lr_alpha for EDVR, lr_alpha_est for MFDN).
+    """
+    ALIGN = 64  # floats (256 B)
+
+    def __init__(self, modules, device=None):
+        params = []
+        self.split = None
+        offsets = []
+        n = 0
+        for mi, m in enumerate(modules):
+            if mi == 1:
+                self.split = n
+            for p in m.parameters():
+                offsets.append(n)
+                params.append(p)
+                n += (p.numel() + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        if self.split is None:
+            self.split = n
+        device = device or params[0].device
+        self.numel = n
+        self.flat = torch.zeros(n, device=device, dtype=torch.float32)
+        self.grad = torch.zeros(n, device=device, dtype=torch.float32)
+        self.params, self.offsets = params, offsets
+        with torch.no_grad():
+            for p, o in zip(params, offsets):
+                view = self.flat[o:o + p.numel()].view(p.shape)
+                view.copy_(p.data)
+                p.data = view
+                p.grad = None
+                p._dvsr_grad = self.grad[o:o + p.numel()].view(p.shape)   # kernels accumulate here directly
+        self.meta = self.flat.clone()       # the meta-weights every frame restarts from
+        self.m = self.v = None
+        self.step_count = 0
+        ops.invalidate_weight_cache()
+
+    def snapshot(self):
+        self.meta.copy_(self.flat)
+
+    def restore(self):
+        """test_dynavsr.py:208 -- one D2D copy instead of two module deep-copies."""
+        self.flat.copy_(self.meta)
+        self.step_count = 0
+        if self.m is not None:
+            self.m.zero_()
+            self.v.zero_()
+        ops.invalidate_weight_cache()
+
+    def zero_grad(self):
+        self.grad.zero_()
+
+    def sgd_step(self, lr0, lr1):
+        call('dvsr_update_sgd', _p(self.flat), _p(self.grad), self.numel, self.split, float(lr0), float(lr1), _stream())
+        ops.invalidate_weight_cache()
+
+    def adam_step(self, lr0, lr1, betas=(0.9, 0.999), eps=1e-8, step=None):
+        if self.m is None:
+            self.m = torch.zeros_like(self.flat)
+            self.v = torch.zeros_like(self.flat)
+        self.step_count = self.step_count + 1 if step is None else step
+        t = self.step_count
+        bc1, bc2 = 1.0 - betas[0] ** t, 1.0 - betas[1] ** t
+        call('dvsr_update_adam', _p(self.flat), _p(self.grad), _p(self.m), _p(self.v), self.numel, self.split,
+             float(lr0), float(lr1), float(betas[0]), float(betas[1]), float(eps), float(bc1), float(bc2), _stream())
+        ops.invalidate_weight_cache()
+
+
+class InnerLoopAdapter(object):
+    """Resident adapt-then-super-resolve engine for one (netG, netE, netE_fixed) triple.
+
+    netG : models.archs.EDVR_arch.EDVR                    (adapted copy; meta-weights = state at construction)
+    netE : models.archs.LRimg_estimator.DirectKernelEstimatorVideo (adapted copy)
+    netE_fixed : same class, frozen (the `fixed_E` checkpoint, test_dynavsr.py:211)
+    """
+
+    def __init__(self, netG, netE, netE_fixed, steps=2, lr_alpha=1e-5, lr_alpha_est=None, optimizer='SGD',
+                 betas=(0.9, 0.99), criterion='l2', slr_weight=10.0, pixel_weight=1.0, use_graphs=True):
+        if optimizer not in ('SGD', 'Adam'):
+            raise NotImplementedError(optimizer)
+        if criterion not in ('l1', 'l2', 'cb'):
+            raise NotImplementedError('Loss type [%s] is not recognized.' % criterion)
+        self.netG, self.netE, self.netE_fixed = netG, netE, netE_fixed
+        self.steps, self.optimizer, self.betas, self.criterion = steps, optimizer, betas, criterion
+        self.lr_alpha = lr_alpha
+        self.lr_alpha_est = lr_alpha if lr_alpha_est is None else lr_alpha_est
+        self.slr_weight, self.pixel_weight = slr_weight, pixel_weight
+        self.use_graphs = use_graphs
+        self.flat = FlatParams([netG, netE])
+        for p in netE_fixed.parameters():
+            p.requires_grad_(False)
+        self.N = netG.nframes
+        self.center = netG.center
+        self._graphs = {}
+        self.last_losses = None
+        self.launches_per_step = None
+
+    # ------------------------------------------------------------------ eager building blocks
+    def _inner_step(self, frames, gt, slr_fixed, B, step_idx):
+        """One adaptation step on channels-last tensors; returns the (device) loss scalar."""
+        self.flat.zero_grad()
+        slr = self.netE.forward_nhwc(frames, B, self.N)
+        sr = self.netG.forward_nhwc(slr, B, self.N)
+        loss = ops.pixel_loss(sr, gt, self.criterion, self.pixel_weight) + \
+            ops.pixel_loss(slr, slr_fixed, 'l1', self.slr_weight)
+        loss.backward()
+        if self.optimizer == 'SGD':
+            self.flat.sgd_step(self.lr_alpha, self.lr_alpha_est)
+        else:
+            self.flat.adam_step(self.lr_alpha, self.lr_alpha_est, self.betas, step=step_idx + 1)
+        return loss.detach()
+
+    def _run_eager(self, frames, B):
+        H, W = frames.shape[1], frames.shape[2]
+        gt = frames.view(B, self.N, H, W, 3)[:, self.center].contiguous()
+        with torch.no_grad():
+            slr_fixed = self.netE_fixed.forward_nhwc(frames, B, self.N)
+        losses = [self._inner_step(frames, gt, slr_fixed, B, i) for i in range(self.steps)]
+        with torch.no_grad():
+            hr = self.netG.forward_nhwc(frames, B, self.N)
+        return hr, losses
+
+    # ------------------------------------------------------------------ CUDA-graph path
+    def _build_graphs(self, frames, B):
+        key = (tuple(frames.shape), B)
+        st = {'in': frames.clone()}
+        # warm-up on a side stream (allocator + autograd warm-up, as PyTorch's capture recipe requires)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            self.flat.restore()
+            self._run_eager(st['in'], B)
+            self.flat.restore()
+        torch.cuda.current_stream().wait_stream(side)
+        g = torch.cuda.CUDAGraph()
+        n0 = _lib.COUNTER[0]
+        with torch.cuda.graph(g):
+            hr, losses = self._run_eager(st['in'], B)
+            st['hr'], st['losses'] = hr, torch.stack(losses) if losses else None
+        self.launches_per_step = _lib.COUNTER[0] - n0      # kernels of libdvsr_b200.so inside one replay
+        st['graph'] = g
+        self._graphs[key] = st
+        return st
+
+    # ------------------------------------------------------------------ public API
+    def adapt_and_infer_nhwc(self, frames, B=1):
+        """frames: [B*N, H, W, 3] device tensor (LR window, channels-last) -> HR [B, sH, sW, 3]."""
+        H, W = frames.shape[1], frames.shape[2]
+        s = self.netG.scale
+        if H % (4 * s) or W % (4 * s):
+            raise RuntimeError('adaptation runs EDVR on LR/scale: H and W must be multiples of %d, got %dx%d '
+                               '(the reference dataset crops for this: video_test_dataset_int.py:185-189)' % (4 * s, H, W))
+        if not self.use_graphs:
+            self.flat.restore()
+            hr, losses = self._run_eager(frames, B)
+            self.last_losses = torch.stack(losses) if losses else None
+            return hr
+        st = self._graphs.get((tuple(frames.shape), B)) or self._build_graphs(frames, B)
+        st['in'].copy_(frames, non_blocking=True)
+        self.flat.restore()
+        st['graph'].replay()
+        self.last_losses = st['losses']
+        return st['hr']
+
+    def adapt_and_infer(self, lr_clip):
+        """lr_clip: [B, N, 3, H, W] (reference tensor layout, host or device) -> HR [B, 3, sH, sW]."""
+        B, N, C, H, W = lr_clip.shape
+        x = lr_clip.to('cuda', non_blocking=True).reshape(B * N, C, H, W)
+        frames = ops.to_nhwc(x)
+        return ops.to_nchw(self.adapt_and_infer_nhwc(frames, B))
+
+    def infer_nhwc(self, frames, B=1):
+        """Plain EDVR forward with the meta-weights (no adaptation)."""
+        self.flat.restore()
+        with torch.no_grad():
+            return self.netG.forward_nhwc(frames, B, self.N)

@@ -1,0 +1,124 @@
+// dynavsr_b200/csrc/update.cu
+//
+// Pixel losses and the fused MAML inner update.
+//   * dvsr_loss_fwd: l1 / l2 / Charbonnier value AND gradient in one pass
+//       (Video_base_model.py:39-50,191-195, loss.py:19-30, the 10*L1 SLR term test_dynavsr.py:274).
+//   * dvsr_update_sgd / dvsr_update_adam: ONE launch over the flat EDVR+MFDN parameter buffer
+//       (the reference runs torch.optim.{SGD,Adam}.step() per tensor over 158 tensors:
+//        test_dynavsr.py:223-231,277; train_dynavsr.py:335-351,399).
+#include "common.cuh"
+
+namespace dvsr {
+
+__global__ void loss_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ loss,
+                            float* __restrict__ ga, long long n, int kind, float weight, float eps) {
+    const float inv_n = 1.f / (float)n;
+    float acc = 0.f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float d = a[i] - b[i];
+        float v, g;
+        if (kind == DVSR_LOSS_L1) { v = fabsf(d); g = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f); }
+        else if (kind == DVSR_LOSS_L2) { v = d * d; g = 2.f * d; }
+        else { const float r = sqrtf(d * d + eps); v = r; g = d / r; }
+        acc += v;
+        if (ga) ga[i] = weight * inv_n * g;
+    }
+    __shared__ float red[32];
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+        v = warp_sum(v);
+        if (threadIdx.x == 0) atomicAdd(loss, v * weight * inv_n);
+    }
+}
+
+__global__ void scale_kernel(const float* __restrict__ x, const float* __restrict__ s, float* __restrict__ y, long long n) {
+    const float k = __ldg(s);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        y[i] = x[i] * k;
+}
+
+__global__ void sgd_kernel(float* __restrict__ p, const float* __restrict__ g, long long n, long long split, float lr0, float lr1) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        p[i] = p[i] - (i < split ? lr0 : lr1) * g[i];
+}
+
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                            long long n, long long split, float lr0, float lr1, float b1, float b2, float eps,
+                            float bc1, float bc2) {
+    // torch.optim.Adam (single-tensor path): m = b1 m + (1-b1) g ; v = b2 v + (1-b2) g^2 ;
+    // p -= (lr / bc1) * m / (sqrt(v) / sqrt(bc2) + eps)
+    const float rs = 1.f / sqrtf(bc2);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float gi = g[i];
+        const float mi = b1 * m[i] + (1.f - b1) * gi;
+        const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+        m[i] = mi;
+        v[i] = vi;
+        const float lr = i < split ? lr0 : lr1;
+        p[i] = p[i] - (lr / bc1) * (mi / (sqrtf(vi) * rs + eps));
+    }
+}
+
+__global__ void abs_sum_kernel(const float* __restrict__ x, float* __restrict__ out, long long npix, int pix_stride, int c0, int c1) {
+    const int w = c1 - c0;
+    const long long total = npix * w;
+    float acc = 0.f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long p = i / w;
+        const int c = (int)(i - p * w);
+        acc += fabsf(__ldg(x + p * pix_stride + c0 + c));
+    }
+    __shared__ float red[32];
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+        v = warp_sum(v);
+        if (threadIdx.x == 0) atomicAdd(out, v);
+    }
+}
+
+static int blocks_for(long long n) {
+    long long b = (n + 255) / 256;
+    if (b > 148 * 8) b = 148 * 8;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+
+}  // namespace dvsr
+
+using namespace dvsr;
+#define ST ((cudaStream_t)stream)
+
+extern "C" int dvsr_loss_fwd(const float* a, const float* b, float* loss, float* ga, long long n, int kind, float weight,
+                             float eps, void* stream) {
+    DVSR_REQUIRE(a && b && loss && n > 0, "loss_fwd: bad arguments");
+    DVSR_REQUIRE(kind >= DVSR_LOSS_L1 && kind <= DVSR_LOSS_CB, "loss_fwd: unknown loss kind %d", kind);
+    loss_kernel<<<blocks_for(n), 256, 0, ST>>>(a, b, loss, ga, n, kind, weight, eps);
+    return check_launch("loss_fwd");
+}
+extern "C" int dvsr_scale_by_device_scalar(const float* x, const float* s, float* y, long long n, void* stream) {
+    DVSR_REQUIRE(x && s && y && n > 0, "scale_by_device_scalar: bad arguments");
+    scale_kernel<<<blocks_for(n), 256, 0, ST>>>(x, s, y, n);
+    return check_launch("scale_by_device_scalar");
+}
+extern "C" int dvsr_update_sgd(float* p, const float* g, long long n, long long split, float lr0, float lr1, void* stream) {
+    DVSR_REQUIRE(p && g && n > 0, "update_sgd: bad arguments");
+    sgd_kernel<<<blocks_for(n), 256, 0, ST>>>(p, g, n, split, lr0, lr1);
+    return check_launch("update_sgd");
+}
+extern "C" int dvsr_update_adam(float* p, const float* g, float* m, float* v, long long n, long long split, float lr0,
+                                float lr1, float b1, float b2, float eps, float bc1, float bc2, void* stream) {
+    DVSR_REQUIRE(p && g && m && v && n > 0, "update_adam: bad arguments");
+    adam_kernel<<<blocks_for(n), 256, 0, ST>>>(p, g, m, v, n, split, lr0, lr1, b1, b2, eps, bc1, bc2);
+    return check_launch("update_adam");
+}
+extern "C" int dvsr_abs_sum(const float* x, float* out, long long npix, int pix_stride, int c0, int c1, void* stream) {
+    DVSR_REQUIRE(x && out && npix > 0 && c1 > c0 && pix_stride >= c1, "abs_sum: bad arguments");
+    abs_sum_kernel<<<blocks_for(npix * (c1 - c0)), 256, 0, ST>>>(x, out, npix, pix_stride, c0, c1);
+    return check_launch("abs_sum");
+}

@@ -1,0 +1,623 @@
+"""dynavsr_b200.ops -- autograd operators over the C ABI (include/dvsr_b200.h).
+
+All activations are NHWC fp32 CUDA tensors of shape [N, H, W, C].  PyTorch is used for device memory,
+streams and autograd bookkeeping only; every arithmetic pass is a hand-written kernel in
+``libdvsr_b200.so``.  There is no CPU path: a non-CUDA tensor raises NotImplementedError exactly as the
+reference operator does (codes/models/archs/dcn/deform_conv.py:109-110).
+"""
+import ctypes
+from collections import namedtuple
+
+import torch
+from torch.autograd import Function
+
+from . import _lib
+from ._lib import ACT_LRELU, ACT_NONE, ACT_RELU, ACT_SIGMOID_SPLIT, ConvDesc, WLayout, call
+
+__all__ = ['Seg', 'conv', 'conv3d_padded', 'mdcn', 'upsample', 'pool_maxavg', 'pad2d', 'pad3d_replicate',
+           'tsa_temporal', 'tsa_combine', 'pixel_loss', 'to_nhwc', 'to_nchw', 'invalidate_weight_cache',
+           'ACT_NONE', 'ACT_RELU', 'ACT_LRELU', 'ACT_SIGMOID_SPLIT', 'set_conv_backend']
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _check_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise NotImplementedError('dynavsr_b200 ops are CUDA-only (no CPU fallback)')
+        if t is not None and t.dtype != torch.float32:
+            raise TypeError('dynavsr_b200 ops expect float32 tensors, got %s' % t.dtype)
+
+
+# --------------------------------------------------------------------------------------------------
+# input segments
+class Seg(object):
+    """One K-segment of a convolution input (see dvsr_conv_seg in include/dvsr_b200.h).
+
+    tensor : [Ns, H, W, C] with stride(3) == 1 (dim 0 / pixel strides may be larger than dense).
+    Output image n reads source image (n // T) * Tsrc + (t_fixed if t_fixed >= 0 else n % T + dt).
+    """
+    __slots__ = ('tensor', 'T', 'Tsrc', 'dt', 't_fixed')
+
+    def __init__(self, tensor, T=1, Tsrc=1, dt=0, t_fixed=-1):
+        self.tensor, self.T, self.Tsrc, self.dt, self.t_fixed = tensor, T, Tsrc, dt, t_fixed
+
+
+def _as_seg(s):
+    return s if isinstance(s, Seg) else Seg(s)
+
+
+def _fill_seg(cs, t, T=1, Tsrc=1, dt=0, t_fixed=-1, ptr_offset=0, img_stride=None):
+    assert t.dim() == 4 and t.stride(3) == 1, 'segment must be [N,H,W,C] with unit channel stride'
+    assert t.stride(1) == t.shape[2] * t.stride(2), 'segment rows must be dense'
+    cs.ptr = t.data_ptr() + 4 * ptr_offset
+    cs.C = t.shape[3]
+    cs.pix_stride = t.stride(2)
+    cs.img_stride = t.stride(0) if img_stride is None else img_stride
+    cs.T, cs.Tsrc, cs.dt, cs.t_fixed = T, Tsrc, dt, t_fixed
+
+
+_SegMeta = namedtuple('_SegMeta', 'T Tsrc dt t_fixed')
+
+
+# --------------------------------------------------------------------------------------------------
+# packed-weight cache
+_wcache = {}
+_wcache_epoch = [0]
+
+
+def invalidate_weight_cache():
+    """Call after parameters were modified through raw pointers (the fused update kernels)."""
+    _wcache_epoch[0] += 1
+
+
+def _layout(weight, seg_C, temporal):
+    wl = WLayout()
+    Co = weight.shape[0]
+    if temporal:                      # Conv3d [Co, Ci, KT, KH, KW]: one segment per temporal tap
+        _, Ci, KT, KH, KW = weight.shape
+        wl.co_stride, wl.ci_stride = Ci * KT * KH * KW, KT * KH * KW
+        for s in range(KT):
+            wl.seg_base[s], wl.seg_C[s] = s * KH * KW, Ci
+        wl.nseg, wl.taps = KT, KH * KW
+    else:                             # Conv2d [Co, sum(seg_C), KH, KW]: cat segments
+        _, Cin, KH, KW = weight.shape
+        assert sum(seg_C) == Cin, 'segment channels %s do not add up to weight in-channels %d' % (seg_C, Cin)
+        wl.co_stride, wl.ci_stride = Cin * KH * KW, KH * KW
+        off = 0
+        for s, c in enumerate(seg_C):
+            wl.seg_base[s], wl.seg_C[s] = off * KH * KW, c
+            off += c
+        wl.nseg, wl.taps = len(seg_C), KH * KW
+    wl.Co = Co
+    return wl
+
+
+def _packed(weight, wl, mode, seg=0):
+    """mode 0: forward layout [K][Co]; mode 1: data-gradient layout of segment `seg` [taps*Co][C_seg]."""
+    key = (weight.data_ptr(), tuple(weight.shape), mode, seg, tuple(wl.seg_C[i] for i in range(wl.nseg)))
+    ver = (weight._version, _wcache_epoch[0])
+    ent = _wcache.get(key)
+    capturing = torch.cuda.is_current_stream_capturing()
+    if ent is not None and ent[0] == ver and not capturing:
+        return ent[1]
+    if mode == 0:
+        n = sum(wl.seg_C[i] for i in range(wl.nseg)) * wl.taps * wl.Co
+    else:
+        n = wl.seg_C[seg] * wl.taps * wl.Co
+    buf = ent[1] if ent is not None else torch.empty(n, device=weight.device, dtype=torch.float32)
+    call('dvsr_pack_weights', _ptr(weight), _ptr(buf), ctypes.byref(wl), mode, seg, _stream())
+    _wcache[key] = (ver, buf)
+    return buf
+
+
+# --------------------------------------------------------------------------------------------------
+# convolution
+_backend = {'tc': False}
+
+
+def set_conv_backend(tensor_cores):
+    """Select the tcgen05 implicit-GEMM path (tf32 inputs, fp32 accumulate) for eligible layers."""
+    _backend['tc'] = bool(tensor_cores)
+
+
+class _ConvSpec(object):
+    __slots__ = ('KH', 'KW', 'stride', 'pad', 'act', 'slope', 'sig_split', 'shuffle', 'metas', 'temporal',
+                 'N', 'H', 'W', 'Ho', 'Wo', 'has_res')
+
+
+def _launch_fprop(d, wp):
+    if d.Co <= 4 and d.nseg == 1 and not d.deform and not d.transposed and not d.shuffle \
+            and d.seg[0].C % 4 == 0 and d.seg[0].pix_stride % 4 == 0:
+        call('dvsr_conv_small_co', ctypes.byref(d), _ptr(wp), _stream())
+    else:
+        call('dvsr_conv_fprop', ctypes.byref(d), _ptr(wp), _stream())
+
+
+def _fwd_desc(spec, tensors):
+    d = ConvDesc()
+    d.N, d.H, d.W, d.Ho, d.Wo = spec.N, spec.H, spec.W, spec.Ho, spec.Wo
+    d.KH, d.KW, d.stride, d.pad, d.dil = spec.KH, spec.KW, spec.stride, spec.pad, 1
+    d.nseg = len(tensors)
+    for i, (t, m) in enumerate(zip(tensors, spec.metas)):
+        _fill_seg(d.seg[i], t, m.T, m.Tsrc, m.dt, m.t_fixed)
+    return d
+
+
+class _ConvFn(Function):
+    @staticmethod
+    def forward(ctx, spec, weight, bias, res, *tensors):
+        _check_cuda(weight, bias, res, *tensors)
+        Co = weight.shape[0]
+        wl = _layout(weight, [t.shape[3] for t in tensors], spec.temporal)
+        d = _fwd_desc(spec, tensors)
+        d.Co = Co
+        d.bias = bias.data_ptr() if bias is not None else None
+        d.act, d.slope, d.sig_split, d.shuffle = spec.act, spec.slope, spec.sig_split, spec.shuffle
+        if spec.shuffle:
+            y = torch.empty(spec.N, 2 * spec.Ho, 2 * spec.Wo, Co // 4, device=weight.device, dtype=torch.float32)
+            d.y_pix_stride = Co // 4
+        else:
+            y = torch.empty(spec.N, spec.Ho, spec.Wo, Co, device=weight.device, dtype=torch.float32)
+            d.y_pix_stride = Co
+        if res is not None:
+            assert res.is_contiguous() and res.shape == y.shape
+            d.res, d.res_pix_stride = res.data_ptr(), res.shape[3]
+        d.y = y.data_ptr()
+        _launch_fprop(d, _packed(weight, wl, 0))
+        ctx.spec, ctx.wl = spec, wl
+        ctx.has_bias, ctx.has_res = bias is not None, res is not None
+        ctx.wslot, ctx.bslot = getattr(weight, '_dvsr_grad', None), getattr(bias, '_dvsr_grad', None)
+        ctx.save_for_backward(weight, y if spec.act != ACT_NONE else None, *tensors)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        spec, wl = ctx.spec, ctx.wl
+        weight, y = ctx.saved_tensors[0], ctx.saved_tensors[1]
+        tensors = ctx.saved_tensors[2:]
+        gy = gy.contiguous()
+        Co = weight.shape[0]
+        npix = spec.N * spec.Ho * spec.Wo
+        need_w, need_b, need_res = ctx.needs_input_grad[1], ctx.needs_input_grad[2] and ctx.has_bias, \
+            ctx.needs_input_grad[3] and ctx.has_res
+        # 1. through the activation (and un-PixelShuffle), bias gradient
+        # parameters re-homed by adapt.FlatParams accumulate straight into the flat gradient buffer
+        gb = (ctx.bslot if ctx.bslot is not None else torch.zeros(Co, device=gy.device, dtype=torch.float32)) \
+            if need_b else None
+        if spec.act != ACT_NONE or spec.shuffle:
+            gpre = torch.empty(spec.N, spec.Ho, spec.Wo, Co, device=gy.device, dtype=torch.float32)
+            call('dvsr_act_bwd', _ptr(gy), _ptr(y), _ptr(gpre), _ptr(gb), npix, Co, spec.act, spec.slope,
+                 spec.sig_split, spec.shuffle, spec.Ho, spec.Wo, _stream())
+        else:
+            gpre = gy
+            if need_b:
+                call('dvsr_act_bwd', _ptr(gy), None, None, _ptr(gb), npix, Co, ACT_NONE, 0.0, 0, 0, spec.Ho,
+                     spec.Wo, _stream())
+        # 2. weight gradient
+        gw = None
+        if need_w:
+            gw = ctx.wslot if ctx.wslot is not None else torch.zeros_like(weight)
+            d = _fwd_desc(spec, tensors)
+            d.Co = Co
+            call('dvsr_conv_wgrad', ctypes.byref(d), _ptr(gpre), Co, _ptr(gw), ctypes.byref(wl), _stream())
+        if ctx.wslot is not None:
+            gw = None
+        if ctx.bslot is not None:
+            gb = None
+        # 3. data gradients, one transposed convolution per input tensor that needs one
+        gts = [None] * len(tensors)
+        frame = spec.Ho * spec.Wo * Co
+        if spec.temporal:
+            if ctx.needs_input_grad[4]:
+                t, m0 = tensors[0], spec.metas[0]
+                KT = len(tensors)
+                gx = torch.empty_like(t)
+                d = ConvDesc()
+                d.N, d.H, d.W, d.Ho, d.Wo = t.shape[0], spec.Ho, spec.Wo, spec.H, spec.W
+                d.KH, d.KW, d.stride, d.pad, d.dil, d.transposed = spec.KH, spec.KW, spec.stride, spec.pad, 1, 1
+                d.nseg = KT
+                rows = wl.taps * Co * t.shape[3]
+                wd = torch.empty(KT * rows, device=gy.device, dtype=torch.float32)
+                for kt in range(KT):
+                    _fill_seg(d.seg[kt], gpre, T=m0.Tsrc, Tsrc=m0.T, dt=-kt)
+                    wd[kt * rows:(kt + 1) * rows].copy_(_packed(weight, wl, 1, kt))
+                d.Co = t.shape[3]
+                d.y, d.y_pix_stride = gx.data_ptr(), t.shape[3]
+                _launch_fprop(d, wd)
+                gts[0] = gx
+        else:
+            for i, (t, m) in enumerate(zip(tensors, spec.metas)):
+                if not ctx.needs_input_grad[4 + i]:
+                    continue
+                gx = torch.empty(t.shape, device=gy.device, dtype=torch.float32)
+                d = ConvDesc()
+                d.N, d.H, d.W, d.Ho, d.Wo = t.shape[0], spec.Ho, spec.Wo, spec.H, spec.W
+                d.KH, d.KW, d.stride, d.pad, d.dil, d.transposed = spec.KH, spec.KW, spec.stride, spec.pad, 1, 1
+                if m.T == 1 and m.Tsrc == 1:
+                    d.nseg = 1
+                    _fill_seg(d.seg[0], gpre)
+                elif m.Tsrc == 1 and m.t_fixed == 0:
+                    # broadcast input (one source image per clip of T output images): sum over the clip
+                    assert m.T <= _lib.MAX_SEG, 'broadcast over %d frames exceeds DVSR_MAX_SEG' % m.T
+                    d.nseg, d.wshare = m.T, 1
+                    for f in range(m.T):
+                        _fill_seg(d.seg[f], gpre, ptr_offset=f * frame, img_stride=m.T * frame)
+                else:
+                    raise NotImplementedError('data gradient for segment mapping %s' % (m,))
+                d.Co = t.shape[3]
+                d.y, d.y_pix_stride = gx.data_ptr(), t.shape[3]
+                _launch_fprop(d, _packed(weight, wl, 1, i))
+                gts[i] = gx
+        return (None, gw, gb, gy if need_res else None) + tuple(gts)
+
+
+def conv(srcs, weight, bias=None, stride=1, pad=1, act=ACT_NONE, slope=0.1, sig_split=0, res=None, shuffle=0):
+    """NHWC convolution over one or more input segments with a fused epilogue.
+
+    y = act(conv(cat(srcs), weight) + bias) [+ res], optionally stored through PixelShuffle(2).
+    Replaces nn.Conv2d (+ torch.cat, activation, residual add, PixelShuffle) call sites of
+    EDVR_arch.py / arch_util.py / LRimg_estimator.py.
+    """
+    segs = [_as_seg(s) for s in (srcs if isinstance(srcs, (list, tuple)) else [srcs])]
+    t0, m0 = segs[0].tensor, segs[0]
+    spec = _ConvSpec()
+    spec.KH, spec.KW = weight.shape[2], weight.shape[3]
+    spec.stride, spec.pad, spec.act, spec.slope, spec.sig_split, spec.shuffle = stride, pad, act, slope, sig_split, shuffle
+    spec.metas = [_SegMeta(s.T, s.Tsrc, s.dt, s.t_fixed) for s in segs]
+    spec.temporal = False
+    spec.H, spec.W = t0.shape[1], t0.shape[2]
+    spec.N = (t0.shape[0] // m0.Tsrc) * m0.T
+    spec.Ho = (spec.H + 2 * pad - spec.KH) // stride + 1
+    spec.Wo = (spec.W + 2 * pad - spec.KW) // stride + 1
+    for s in segs:
+        assert s.tensor.shape[1] == spec.H and s.tensor.shape[2] == spec.W, 'segment spatial sizes differ'
+    return _ConvFn.apply(spec, weight, bias, res, *[s.tensor for s in segs])
+
+
+def conv3d_padded(xpad, weight, bias, T, act=ACT_NONE, slope=0.1):
+    """Conv3d(k=3, pad=0) on an explicitly padded clip tensor.
+
+    xpad: [B*(T+2), H+2, W+2, C] (frames of the replication-padded clip); weight: [Co, C, 3, 3, 3].
+    Returns [B*T, H, W, Co].  Implemented as three temporal segments of one implicit GEMM
+    (LRimg_estimator.py:77,87,102,112).
+    """
+    KT, KH, KW = weight.shape[2:]
+    spec = _ConvSpec()
+    spec.KH, spec.KW, spec.stride, spec.pad = KH, KW, 1, 0
+    spec.act, spec.slope, spec.sig_split, spec.shuffle = act, slope, 0, 0
+    spec.metas = [_SegMeta(T, T + KT - 1, kt, -1) for kt in range(KT)]
+    spec.temporal = True
+    spec.H, spec.W = xpad.shape[1], xpad.shape[2]
+    spec.N = (xpad.shape[0] // (T + KT - 1)) * T
+    spec.Ho, spec.Wo = spec.H - KH + 1, spec.W - KW + 1
+    # the same tensor feeds every temporal tap; autograd sees it once (data gradient is returned for slot 0)
+    return _ConvFn.apply(spec, weight, bias, None, xpad, *([xpad.detach()] * (KT - 1)))
+
+
+# --------------------------------------------------------------------------------------------------
+# modulated deformable convolution (NHWC, fused gather + GEMM)
+class _MdcnFn(Function):
+    @staticmethod
+    def forward(ctx, x, om, weight, bias, dg, stride, pad, dil, act, slope):
+        _check_cuda(x, om, weight, bias)
+        N, H, W, C = x.shape
+        Co, _, KH, KW = weight.shape
+        KK = KH * KW
+        Ho = (H + 2 * pad - (dil * (KH - 1) + 1)) // stride + 1
+        Wo = (W + 2 * pad - (dil * (KW - 1) + 1)) // stride + 1
+        assert om.shape == (N, Ho, Wo, 3 * dg * KK) and om.is_contiguous() and x.is_contiguous()
+        wl = _layout(weight, [C], False)
+        d = _MdcnFn._desc(x, om, dg, KH, KW, stride, pad, dil, Ho, Wo)
+        d.Co = Co
+        d.bias = bias.data_ptr() if bias is not None else None
+        d.act, d.slope = act, slope
+        y = torch.empty(N, Ho, Wo, Co, device=x.device, dtype=torch.float32)
+        d.y, d.y_pix_stride = y.data_ptr(), Co
+        call('dvsr_conv_fprop', ctypes.byref(d), _ptr(_packed(weight, wl, 0)), _stream())
+        ctx.cfg = (dg, stride, pad, dil, act, slope, Ho, Wo, bias is not None)
+        ctx.wl = wl
+        ctx.wslot, ctx.bslot = getattr(weight, '_dvsr_grad', None), getattr(bias, '_dvsr_grad', None)
+        ctx.save_for_backward(x, om, weight, y if act != ACT_NONE else None)
+        return y
+
+    @staticmethod
+    def _desc(x, om, dg, KH, KW, stride, pad, dil, Ho, Wo):
+        N, H, W, C = x.shape
+        KK = KH * KW
+        d = ConvDesc()
+        d.N, d.H, d.W, d.Ho, d.Wo = N, H, W, Ho, Wo
+        d.KH, d.KW, d.stride, d.pad, d.dil = KH, KW, stride, pad, dil
+        d.nseg = 1
+        _fill_seg(d.seg[0], x)
+        d.deform, d.dg = 1, dg
+        d.offset, d.off_pix_stride = om.data_ptr(), om.shape[3]
+        d.mask, d.mask_pix_stride = om.data_ptr() + 4 * 2 * dg * KK, om.shape[3]
+        return d
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, om, weight, y = ctx.saved_tensors
+        dg, stride, pad, dil, act, slope, Ho, Wo, has_bias = ctx.cfg
+        wl = ctx.wl
+        N, H, W, C = x.shape
+        Co, _, KH, KW = weight.shape
+        KK = KH * KW
+        gy = gy.contiguous()
+        npix = N * Ho * Wo
+        need_b = has_bias and ctx.needs_input_grad[3]
+        gb = (ctx.bslot if ctx.bslot is not None else torch.zeros(Co, device=gy.device, dtype=torch.float32)) \
+            if need_b else None
+        if act != ACT_NONE:
+            gpre = torch.empty_like(gy)
+            call('dvsr_act_bwd', _ptr(gy), _ptr(y), _ptr(gpre), _ptr(gb), npix, Co, act, slope, 0, 0, Ho, Wo, _stream())
+        else:
+            gpre = gy
+            if need_b:
+                call('dvsr_act_bwd', _ptr(gy), None, None, _ptr(gb), npix, Co, ACT_NONE, 0.0, 0, 0, Ho, Wo, _stream())
+        d = _MdcnFn._desc(x, om, dg, KH, KW, stride, pad, dil, Ho, Wo)
+        d.Co = Co
+        gx = gom = gw = None
+        if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
+            gx = torch.zeros_like(x) if ctx.needs_input_grad[0] else None
+            gom = torch.empty_like(om)
+            goff_p = gom.data_ptr()
+            gmask_p = gom.data_ptr() + 4 * 2 * dg * KK
+            call('dvsr_mdcn_bwd_data', ctypes.byref(d), _ptr(gpre), Co, _ptr(_packed(weight, wl, 1, 0)),
+                 _ptr(gx), C, ctypes.c_void_p(goff_p), om.shape[3], ctypes.c_void_p(gmask_p), om.shape[3], _stream())
+        if ctx.needs_input_grad[2]:
+            gw = ctx.wslot if ctx.wslot is not None else torch.zeros_like(weight)
+            call('dvsr_conv_wgrad', ctypes.byref(d), _ptr(gpre), Co, _ptr(gw), ctypes.byref(wl), _stream())
+        if ctx.wslot is not None:
+            gw = None
+        if ctx.bslot is not None:
+            gb = None
+        return gx, gom, gw, gb, None, None, None, None, None, None
+
+
+def mdcn(x, om, weight, bias=None, deformable_groups=1, stride=1, pad=1, dil=1, act=ACT_NONE, slope=0.1):
+    """Modulated deformable conv on NHWC tensors.  ``om`` = [N, Ho, Wo, 3*dg*kh*kw]: offsets
+    ([dg][k][dy,dx], the reference layout) in the first 2*dg*k channels, post-sigmoid mask in the rest."""
+    return _MdcnFn.apply(x, om, weight, bias, deformable_groups, stride, pad, dil, act, slope)
+
+
+# --------------------------------------------------------------------------------------------------
+# resampling / pooling / padding
+class _UpsampleFn(Function):
+    @staticmethod
+    def forward(ctx, x, scale, mul):
+        _check_cuda(x)
+        x = x.contiguous()
+        N, H, W, C = x.shape
+        y = torch.empty(N, H * scale, W * scale, C, device=x.device, dtype=torch.float32)
+        call('dvsr_upsample_bilinear', _ptr(x), _ptr(y), N, H, W, C, scale, mul, 0, _stream())
+        ctx.cfg = (N, H, W, C, scale, mul)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        N, H, W, C, scale, mul = ctx.cfg
+        gy = gy.contiguous()
+        gx = torch.empty(N, H, W, C, device=gy.device, dtype=torch.float32)
+        call('dvsr_upsample_bilinear_bwd', _ptr(gy), _ptr(gx), N, H, W, C, scale, mul, _stream())
+        return gx, None, None
+
+
+def upsample(x, scale=2, mul=1.0):
+    """mul * F.interpolate(x, scale_factor=scale, mode='bilinear', align_corners=False) on NHWC."""
+    return _UpsampleFn.apply(x, scale, float(mul))
+
+
+class _PoolFn(Function):
+    @staticmethod
+    def forward(ctx, x):
+        _check_cuda(x)
+        x = x.contiguous()
+        N, H, W, C = x.shape
+        y = torch.empty(N, (H - 1) // 2 + 1, (W - 1) // 2 + 1, 2 * C, device=x.device, dtype=torch.float32)
+        call('dvsr_pool_maxavg', _ptr(x), _ptr(y), N, H, W, C, _stream())
+        ctx.save_for_backward(x)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, = ctx.saved_tensors
+        N, H, W, C = x.shape
+        gx = torch.empty_like(x)
+        call('dvsr_pool_maxavg_bwd', _ptr(x), _ptr(gy.contiguous()), _ptr(gx), N, H, W, C, _stream())
+        return gx
+
+
+def pool_maxavg(x):
+    """cat([max_pool2d(x,3,2,1), avg_pool2d(x,3,2,1)], C) in one pass (EDVR_arch.py:184-186,190-192)."""
+    return _PoolFn.apply(x)
+
+
+class _Pad2dFn(Function):
+    @staticmethod
+    def forward(ctx, x, p, mode):
+        _check_cuda(x)
+        x = x.contiguous()
+        N, H, W, C = x.shape
+        y = torch.empty(N, H + 2 * p, W + 2 * p, C, device=x.device, dtype=torch.float32)
+        call('dvsr_pad2d', _ptr(x), _ptr(y), N, H, W, C, p, mode, _stream())
+        ctx.cfg = (N, H, W, C, p, mode)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        N, H, W, C, p, mode = ctx.cfg
+        gx = torch.empty(N, H, W, C, device=gy.device, dtype=torch.float32)
+        call('dvsr_pad2d_bwd', _ptr(gy.contiguous()), _ptr(gx), N, H, W, C, p, mode, _stream())
+        return gx, None, None
+
+
+def pad2d(x, p=1, mode='reflect'):
+    return _Pad2dFn.apply(x, p, 0 if mode == 'reflect' else 1)
+
+
+class _Pad3dFn(Function):
+    @staticmethod
+    def forward(ctx, x, T):
+        _check_cuda(x)
+        x = x.contiguous()
+        BT, H, W, C = x.shape
+        B = BT // T
+        y = torch.empty(B * (T + 2), H + 2, W + 2, C, device=x.device, dtype=torch.float32)
+        call('dvsr_pad3d_replicate', _ptr(x), _ptr(y), B, T, H, W, C, _stream())
+        ctx.cfg = (B, T, H, W, C)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        B, T, H, W, C = ctx.cfg
+        gx = torch.empty(B * T, H, W, C, device=gy.device, dtype=torch.float32)
+        call('dvsr_pad3d_replicate_bwd', _ptr(gy.contiguous()), _ptr(gx), B, T, H, W, C, _stream())
+        return gx, None
+
+
+def pad3d_replicate(x, T):
+    """nn.ReplicationPad3d(1) on a clip stored as frames [B*T, H, W, C] -> [B*(T+2), H+2, W+2, C]."""
+    return _Pad3dFn.apply(x, T)
+
+
+# --------------------------------------------------------------------------------------------------
+# TSA
+class _TsaTemporalFn(Function):
+    @staticmethod
+    def forward(ctx, aligned, emb, emb_ref, F_):
+        _check_cuda(aligned, emb, emb_ref)
+        BF, H, W, C = aligned.shape
+        B = BF // F_
+        aligned, emb, emb_ref = aligned.contiguous(), emb.contiguous(), emb_ref.contiguous()
+        prob = torch.empty(B, F_, H, W, device=aligned.device, dtype=torch.float32)
+        out = torch.empty(B, H, W, F_ * C, device=aligned.device, dtype=torch.float32)
+        call('dvsr_tsa_temporal', _ptr(aligned), _ptr(emb), _ptr(emb_ref), _ptr(prob), _ptr(out), B, F_, H * W, C, _stream())
+        ctx.F = F_
+        ctx.save_for_backward(aligned, emb, emb_ref, prob)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        aligned, emb, emb_ref, prob = ctx.saved_tensors
+        BF, H, W, C = aligned.shape
+        B = BF // ctx.F
+        ga, ge, gr = torch.empty_like(aligned), torch.empty_like(emb), torch.empty_like(emb_ref)
+        call('dvsr_tsa_temporal_bwd', _ptr(aligned), _ptr(emb), _ptr(emb_ref), _ptr(prob), _ptr(gout.contiguous()),
+             _ptr(ga), _ptr(ge), _ptr(gr), B, ctx.F, H * W, C, _stream())
+        return ga, ge, gr, None
+
+
+def tsa_temporal(aligned, emb, emb_ref, nframes):
+    """aligned_f * sigmoid(sum_c emb_f * emb_ref) for every frame f (EDVR_arch.py:166-176).
+    aligned, emb: [B*F, H, W, C]; emb_ref: [B, H, W, C]; returns [B, H, W, F*C] (= aligned_fea.view(B,-1,H,W))."""
+    return _TsaTemporalFn.apply(aligned, emb, emb_ref, nframes)
+
+
+class _TsaCombineFn(Function):
+    @staticmethod
+    def forward(ctx, fea, att, att_add):
+        _check_cuda(fea, att, att_add)
+        fea, att, att_add = fea.contiguous(), att.contiguous(), att_add.contiguous()
+        out = torch.empty_like(fea)
+        call('dvsr_tsa_combine', _ptr(fea), _ptr(att), _ptr(att_add), _ptr(out), fea.numel(), _stream())
+        ctx.save_for_backward(fea, att)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        fea, att = ctx.saved_tensors
+        gout = gout.contiguous()
+        gf, ga = torch.empty_like(fea), torch.empty_like(att)
+        call('dvsr_tsa_combine_bwd', _ptr(fea), _ptr(att), _ptr(gout), _ptr(gf), _ptr(ga), fea.numel(), _stream())
+        return gf, ga, gout
+
+
+def tsa_combine(fea, att, att_add):
+    """fea * sigmoid(att) * 2 + att_add (EDVR_arch.py:200-202)."""
+    return _TsaCombineFn.apply(fea, att, att_add)
+
+
+# --------------------------------------------------------------------------------------------------
+# losses
+_LOSS_KIND = {'l1': _lib.LOSS_L1, 'l2': _lib.LOSS_L2, 'cb': _lib.LOSS_CB}
+
+
+class _LossFn(Function):
+    @staticmethod
+    def forward(ctx, a, b, kind, weight, eps):
+        _check_cuda(a, b)
+        a, b = a.contiguous(), b.contiguous()
+        assert a.shape == b.shape
+        loss = torch.zeros((), device=a.device, dtype=torch.float32)
+        ga = torch.empty_like(a) if ctx.needs_input_grad[0] else None
+        call('dvsr_loss_fwd', _ptr(a), _ptr(b), _ptr(loss), _ptr(ga), a.numel(), kind, weight, eps, _stream())
+        ctx.save_for_backward(ga)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        ga, = ctx.saved_tensors
+        if ga is None:
+            return None, None, None, None, None
+        out = torch.empty_like(ga)
+        call('dvsr_scale_by_device_scalar', _ptr(ga), _ptr(g.contiguous()), _ptr(out), ga.numel(), _stream())
+        return out, None, None, None, None
+
+
+def pixel_loss(a, b, kind='l2', weight=1.0, eps=1e-6):
+    """weight * mean(f(a - b)), f in {l1, l2, Charbonnier}; gradient flows to ``a`` only
+    (Video_base_model.py:39-50, loss.py:19-30, test_dynavsr.py:274)."""
+    return _LossFn.apply(a, b, _LOSS_KIND[kind], float(weight), float(eps))
+
+
+# --------------------------------------------------------------------------------------------------
+# layout at the NCHW boundary
+class _ToNhwcFn(Function):
+    @staticmethod
+    def forward(ctx, x):
+        _check_cuda(x)
+        x = x.contiguous()
+        N, C, H, W = x.shape
+        y = torch.empty(N, H, W, C, device=x.device, dtype=torch.float32)
+        call('dvsr_nchw_to_nhwc', _ptr(x), _ptr(y), N, C, H, W, _stream())
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        return _ToNchwFn.apply(gy)
+
+
+class _ToNchwFn(Function):
+    @staticmethod
+    def forward(ctx, x):
+        _check_cuda(x)
+        x = x.contiguous()
+        N, H, W, C = x.shape
+        y = torch.empty(N, C, H, W, device=x.device, dtype=torch.float32)
+        call('dvsr_nhwc_to_nchw', _ptr(x), _ptr(y), N, C, H, W, _stream())
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        return _ToNhwcFn.apply(gy)
+
+
+def to_nhwc(x):
+    return _ToNhwcFn.apply(x)
+
+
+def to_nchw(x):
+    return _ToNchwFn.apply(x)
+
+
+def abs_sum(x, c0, c1, out):
+    """out[0] += sum |x[..., c0:c1]| (device-side accumulation of the offset-magnitude check)."""
+    N, H, W, C = x.shape
+    call('dvsr_abs_sum', _ptr(x), _ptr(out), N * H * W, C, c0, c1, _stream())

@@ -1,0 +1,194 @@
+/*
+ * include/dvsr_b200.h -- C ABI of libdvsr_b200.so, the B200 (sm_100a) kernel library behind the
+ * DynaVSR hot path (EDVR forward/backward + MAML inner step).
+ *
+ * Drop-in boundary.  The reference's native surface is the pybind11 module
+ * `deform_conv_cuda` (codes/models/archs/dcn/src/deform_conv_cuda.cpp:681-695); everything else on
+ * the path is reached through PyTorch ops (cuDNN convs, pooling, interpolate, optimiser steps).
+ * This header replaces both with plain-pointer entry points:
+ *
+ *   dvsr_mdcn_forward_nchw   <- modulated_deform_conv_cuda_forward   (deform_conv_cuda.cpp:486-564)
+ *   dvsr_mdcn_backward_nchw  <- modulated_deform_conv_cuda_backward  (deform_conv_cuda.cpp:566-679)
+ *   dvsr_conv_fprop / dvsr_conv_wgrad / dvsr_mdcn_bwd_data / dvsr_pack_weights
+ *                            <- nn.Conv2d / nn.Conv3d call sites EDVR_arch.py:68-90,141-159,224-249,
+ *                               arch_util.py:42-43, LRimg_estimator.py:77-88 and the fused NHWC DCN
+ *   dvsr_upsample_* / dvsr_pool_* / dvsr_tsa_* / dvsr_pad_*  <- EDVR_arch.py:107-120,166-202,311;
+ *                               LRimg_estimator.py:75-76
+ *   dvsr_loss_* / dvsr_update_*  <- Video_base_model.py:39-50,191-195; test_dynavsr.py:223-231,277
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to fp32 unless stated otherwise; the caller owns all memory,
+ *     including workspaces (nothing is allocated or freed inside the library);
+ *   - `stream` is a cudaStream_t passed as void*; kernels are enqueued on it, never synchronised,
+ *     so every entry point is CUDA-graph capturable;
+ *   - return value 0 = success, <0 = error (DVSR_ERR_*); dvsr_last_error() gives the message of the
+ *     last failing call on the calling thread;
+ *   - activations inside the library are NHWC ("pixel rows of channels"); the *_nchw entry points
+ *     accept the reference's NCHW-contiguous tensors (deform_conv_cuda.cpp:493-494).
+ */
+#ifndef DVSR_B200_H_
+#define DVSR_B200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DVSR_OK 0
+#define DVSR_ERR_INVALID (-1)     /* bad shape / argument                      */
+#define DVSR_ERR_CUDA (-2)        /* a CUDA runtime / launch error             */
+#define DVSR_ERR_UNSUPPORTED (-3) /* valid but not implemented (e.g. groups>1) */
+
+#define DVSR_ACT_NONE 0
+#define DVSR_ACT_RELU 1
+#define DVSR_ACT_LRELU 2
+#define DVSR_ACT_SIGMOID_SPLIT 3 /* sigmoid on output channels >= sig_split, identity below */
+
+#define DVSR_MAX_SEG 5
+
+/* One input "segment" of a convolution's K dimension: a group of C input channels read from one
+ * NHWC tensor.  torch.cat([a, b], 1) feeding a conv is two segments; the 5-frame 1x1 fusion convs
+ * of TSA are five; a Conv3d is one segment per temporal tap.  Output image n reads source image
+ *   (n / T) * Tsrc + (t_fixed >= 0 ? t_fixed : n % T + dt)
+ * (T = Tsrc = 1, dt = 0, t_fixed = -1 for an ordinary conv); a frame index n % T + dt outside [0, Tsrc)
+ * contributes zeros (temporal taps of a Conv3d data gradient). */
+typedef struct dvsr_conv_seg {
+    const float* ptr;
+    int C;               /* channels in this segment                                   */
+    int pix_stride;      /* floats between consecutive pixels (>= C; allows channel slices) */
+    long long img_stride;/* floats between consecutive source images                   */
+    int T, Tsrc, dt, t_fixed;
+} dvsr_conv_seg;
+
+typedef struct dvsr_conv_desc {
+    int N, H, W;         /* output images; SOURCE spatial size                         */
+    int Ho, Wo;          /* produced spatial size                                      */
+    int KH, KW, stride, pad, dil;
+    int transposed;      /* 0: src = o*stride - pad + k*dil.  1 (data gradient): src = (o + pad - k*dil)/stride when divisible */
+    int wshare;          /* 1: every segment uses the same packed weight rows (data gradient of a broadcast input) */
+    int nseg;
+    dvsr_conv_seg seg[DVSR_MAX_SEG];
+    int Co;
+    /* modulated deformable sampling of segment 0 (0 = plain convolution) */
+    int deform, dg;
+    const float* offset; int off_pix_stride;   /* [pix][(g*KH*KW + k)*2 + {dy,dx}]  */
+    const float* mask;   int mask_pix_stride;  /* [pix][g*KH*KW + k]                 */
+    /* epilogue: v = acc + bias; v = act(v); v += res; (PixelShuffle(2) store if shuffle == 2) */
+    const float* bias;
+    int act; float slope; int sig_split;
+    const float* res; int res_pix_stride;
+    int shuffle;
+    int accumulate;      /* y += v instead of y = v                                    */
+    float* y; int y_pix_stride;
+} dvsr_conv_desc;
+
+/* Where element (co, seg s, ci, tap) of a PyTorch-layout weight lives:
+ *   co * co_stride + seg_base[s] + ci * ci_stride + tap
+ * Conv2d [Co, Cin, KH, KW] with cat-segments: co_stride = Cin*KH*KW, ci_stride = KH*KW,
+ * seg_base[s] = (channel offset of s) * KH*KW.  Conv3d [Co, Ci, KT, KH, KW] with one segment per kt:
+ * ci_stride = KT*KH*KW, seg_base[kt] = kt*KH*KW. */
+typedef struct dvsr_wlayout {
+    long long co_stride, ci_stride;
+    long long seg_base[DVSR_MAX_SEG];
+    int seg_C[DVSR_MAX_SEG];
+    int nseg, taps, Co;
+} dvsr_wlayout;
+
+const char* dvsr_last_error(void);
+int dvsr_version(void);
+
+/* ---- convolution family (conv_simt.cu; tensor-core fast path in conv_tc.cu) ---------------------- */
+/* Packed layouts.  mode 0 (forward):  wp[k][co],  k = kofs(s) + tap*C_s + ci.
+ *                  mode 1 (data gradient of segment `seg`): wp[tap*Co + co][ci]. */
+int dvsr_pack_weights(const float* w, float* wp, const dvsr_wlayout* wl, int mode, int seg, void* stream);
+/* y = epilogue(conv(x, wp)); wp packed with mode 0 (or mode 1 together with d->transposed). */
+int dvsr_conv_fprop(const dvsr_conv_desc* d, const float* wp, void* stream);
+/* gw[PyTorch layout] += sum_pix A[pix][k] * gy[pix][co]; A described by d (deformable or plain). */
+int dvsr_conv_wgrad(const dvsr_conv_desc* d, const float* gy, int gy_pix_stride, float* gw,
+                    const dvsr_wlayout* wl, void* stream);
+/* Small-Cout direct convolution (conv_last, 64 -> 3): one thread per output pixel. */
+int dvsr_conv_small_co(const dvsr_conv_desc* d, const float* wp, void* stream);
+
+/* ---- modulated deformable convolution ------------------------------------------------------------ */
+/* Gradients w.r.t. the sampled input, the offsets and the (post-sigmoid) mask.  `d` describes the
+ * forward op (deform = 1); wd is the mode-1 packed weight.  gx must be zero-filled (or hold a
+ * gradient to accumulate into): contributions are added with red.global.add. */
+int dvsr_mdcn_bwd_data(const dvsr_conv_desc* d, const float* gy, int gy_pix_stride, const float* wd,
+                       float* gx, int gx_pix_stride, float* goff, int goff_pix_stride,
+                       float* gmask, int gmask_pix_stride, void* stream);
+
+/* Reference operator boundary, NCHW fp32 (deform_conv_cuda.cpp:486-492, :566-573).  groups must be 1
+ * (no YML of the reference uses groups != 1).  Workspace: dvsr_mdcn_workspace_bytes() bytes. */
+long long dvsr_mdcn_workspace_bytes(int B, int C, int H, int W, int Co, int kh, int kw, int stride,
+                                    int pad, int dil, int dg, int backward);
+int dvsr_mdcn_forward_nchw(const float* x, const float* offset, const float* mask, const float* weight,
+                           const float* bias, float* y, int B, int C, int H, int W, int Co, int kh,
+                           int kw, int stride, int pad, int dil, int groups, int dg, void* workspace,
+                           long long workspace_bytes, void* stream);
+int dvsr_mdcn_backward_nchw(const float* x, const float* offset, const float* mask, const float* weight,
+                            const float* gy, float* gx, float* goffset, float* gmask, float* gweight,
+                            float* gbias, int B, int C, int H, int W, int Co, int kh, int kw, int stride,
+                            int pad, int dil, int groups, int dg, void* workspace,
+                            long long workspace_bytes, void* stream);
+
+/* ---- layout, resampling, pooling, padding (elementwise.cu) --------------------------------------- */
+int dvsr_nchw_to_nhwc(const float* x, float* y, int N, int C, int H, int W, void* stream);
+int dvsr_nhwc_to_nchw(const float* x, float* y, int N, int C, int H, int W, void* stream);
+/* bilinear, align_corners=False, integer scale; y = mul * up(x) (+ y if accumulate) */
+int dvsr_upsample_bilinear(const float* x, float* y, int N, int H, int W, int C, int scale, float mul,
+                           int accumulate, void* stream);
+int dvsr_upsample_bilinear_bwd(const float* gy, float* gx, int N, int H, int W, int C, int scale,
+                               float mul, void* stream);
+/* y[..., 0:C] = maxpool3x3s2p1(x), y[..., C:2C] = avgpool3x3s2p1(x) (count_include_pad) */
+int dvsr_pool_maxavg(const float* x, float* y, int N, int H, int W, int C, void* stream);
+int dvsr_pool_maxavg_bwd(const float* x, const float* gy, float* gx, int N, int H, int W, int C, void* stream);
+/* mode 0 = reflect, 1 = replicate; pads H and W by p (and, if padT, the T axis of [B,T,H,W,C] by 1, replicate) */
+int dvsr_pad2d(const float* x, float* y, int N, int H, int W, int C, int p, int mode, void* stream);
+int dvsr_pad2d_bwd(const float* gy, float* gx, int N, int H, int W, int C, int p, int mode, void* stream);
+int dvsr_pad3d_replicate(const float* x, float* y, int B, int T, int H, int W, int C, void* stream);
+int dvsr_pad3d_replicate_bwd(const float* gy, float* gx, int B, int T, int H, int W, int C, void* stream);
+/* per-image per-channel spatial mean: m[n][c]; y = x - m (sign=-1) or x + m (sign=+1) */
+int dvsr_spatial_mean(const float* x, float* m, int N, int HW, int C, void* stream);
+int dvsr_add_channel_bias(const float* x, const float* m, float* y, int N, int HW, int C, float sign, void* stream);
+
+/* gpre = gy * act'(y) [+ un-PixelShuffle]; gbias[c] += sum_pix gpre[pix][c] (if gbias).  In-place allowed
+ * when shuffle == 0.  y is the saved forward OUTPUT (relu / lrelu / sigmoid-split are invertible from it). */
+int dvsr_act_bwd(const float* gy, const float* y, float* gpre, float* gbias, long long npix, int C, int act,
+                 float slope, int sig_split, int shuffle, int Ho, int Wo, void* stream);
+
+/* ---- TSA fusion (tsa.cu) -------------------------------------------------------------------------- */
+/* temporal attention (EDVR_arch.py:166-176): prob[n][f][pix] = sigmoid(sum_c emb[n][f][pix][c]*emb_ref[n][pix][c]);
+ * out[n][pix][f*C + c] = aligned[n][f][pix][c] * prob  (pixel-major, F*C channels: the input of the 1x1 fusion convs) */
+int dvsr_tsa_temporal(const float* aligned, const float* emb, const float* emb_ref, float* prob, float* out,
+                      int B, int F, long long HW, int C, void* stream);
+int dvsr_tsa_temporal_bwd(const float* aligned, const float* emb, const float* emb_ref, const float* prob,
+                          const float* gout, float* galigned, float* gemb, float* gemb_ref,
+                          int B, int F, long long HW, int C, void* stream);
+/* out = fea * sigmoid(att) * 2 + att_add (EDVR_arch.py:200-202) */
+int dvsr_tsa_combine(const float* fea, const float* att, const float* att_add, float* out, long long n, void* stream);
+int dvsr_tsa_combine_bwd(const float* fea, const float* att, const float* gout, float* gfea, float* gatt,
+                         long long n, void* stream);
+
+/* ---- losses and the fused inner update (update.cu) ------------------------------------------------ */
+#define DVSR_LOSS_L1 0
+#define DVSR_LOSS_L2 1
+#define DVSR_LOSS_CB 2
+/* loss[0] (+)= weight * mean(f(a - b)).  `loss` must be zeroed by the caller when accumulate == 0 is not
+ * wanted; ga (optional) = weight * f'(a-b) / n  (caller multiplies by the upstream scalar). */
+int dvsr_loss_fwd(const float* a, const float* b, float* loss, float* ga, long long n, int kind, float weight,
+                  float eps, void* stream);
+/* y = x * s[0] (device scalar) */
+int dvsr_scale_by_device_scalar(const float* x, const float* s, float* y, long long n, void* stream);
+/* p[i] -= lr(i) * g[i], lr(i) = lr0 for i < split else lr1 (two param groups: test_dynavsr.py:213-231,
+ * train_dynavsr.py:335-344).  One launch for the whole flat EDVR+MFDN parameter buffer. */
+int dvsr_update_sgd(float* p, const float* g, long long n, long long split, float lr0, float lr1, void* stream);
+/* torch.optim.Adam semantics (no weight decay / amsgrad); bias corrections bc1 = 1-b1^t, bc2 = 1-b2^t. */
+int dvsr_update_adam(float* p, const float* g, float* m, float* v, long long n, long long split, float lr0,
+                     float lr1, float b1, float b2, float eps, float bc1, float bc2, void* stream);
+/* sum |x| over channels [c0, c1) of an NHWC tensor -> out[0] (+=); the `offset_mean > 100` check of
+ * deform_conv.py:285-287 without a host sync per call. */
+int dvsr_abs_sum(const float* x, float* out, long long npix, int pix_stride, int c0, int c1, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DVSR_B200_H_ */

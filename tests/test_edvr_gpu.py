@@ -1,0 +1,195 @@
+"""GPU parity of the assembled hot path against (a) the golden vectors produced by the unmodified
+reference modules (tests/golden, oracle/make_golden.py) and (b) the CPU oracle on fresh seeded inputs.
+Tolerance: 1e-3 relative (north star), PSNR within 0.01 dB; the fp32 CUDA-core path is expected to be
+~1e-5."""
+import numpy as np
+import pytest
+import torch
+
+from util import gold, nchw, nhwc, psnr_uint8, rel
+
+pytestmark = pytest.mark.gpu
+NS_TOL = 1e-3
+
+
+@pytest.fixture(scope='module')
+def mods():
+    if not torch.cuda.is_available():
+        pytest.skip('no CUDA device')
+    from dynavsr_b200.models.archs import EDVR_arch, LRimg_estimator
+    from dynavsr_b200 import adapt, ops
+    return EDVR_arch, LRimg_estimator, adapt, ops
+
+
+def _edvr(mods, seed, **kw):
+    from oracle import params as P
+    E = mods[0]
+    net = E.EDVR(nf=64, nframes=5, groups=8, front_RBs=5, back_RBs=10, scale=4, **kw)
+    sd = P.make_params(P.edvr_param_shapes(), seed=seed)
+    net.load_state_dict(sd, strict=True)          # reference key names / shapes
+    return net.cuda(), sd
+
+
+def _mfdn(mods, seed):
+    from oracle import params as P
+    net = mods[1].DirectKernelEstimatorVideo(nf=64, in_nc=3, scale=4)
+    sd = P.make_params(P.mfdn_param_shapes(), seed=seed)
+    net.load_state_dict(sd, strict=True)
+    return net.cuda(), sd
+
+
+def test_edvr_forward_matches_reference_golden(mods):
+    g = gold('edvr_m_32.npz')
+    net, _ = _edvr(mods, int(g['seed']))
+    x = torch.from_numpy(g['x']).cuda()
+    with torch.no_grad():
+        out = net(x)
+    ref = torch.from_numpy(g['out'])
+    assert out.shape == ref.shape
+    assert rel(out, ref) < NS_TOL
+    assert abs(psnr_uint8(out, ref)) > 60 or psnr_uint8(out, ref) == float('inf')
+    # PSNR parity against a fixed pseudo ground truth (bicubic-free plumbing check, SURVEY config 1)
+    base = torch.nn.functional.interpolate(x[:, 2], scale_factor=4, mode='bicubic', align_corners=False).cpu()
+    assert abs(psnr_uint8(out, base) - psnr_uint8(ref, base)) < 0.01
+
+
+def test_edvr_stage_outputs_match_reference_golden(mods):
+    """Localises a failure: PCD-aligned features and the TSA output of the reference modules."""
+    E, _, _, ops = mods
+    g = gold('edvr_m_32.npz')
+    net, _ = _edvr(mods, int(g['seed']))
+    x = torch.from_numpy(g['x']).cuda()
+    B, N = 1, 5
+    with torch.no_grad():
+        frames = ops.to_nhwc(x.reshape(B * N, 3, 32, 32))
+        L1 = ops.conv(frames, net.conv_first.weight, net.conv_first.bias, act=ops.ACT_LRELU)
+        L1 = net.feature_extraction(L1)
+        L2 = E._c(E._c(L1, net.fea_L2_conv1, ops.ACT_LRELU), net.fea_L2_conv2, ops.ACT_LRELU)
+        L3 = E._c(E._c(L2, net.fea_L3_conv1, ops.ACT_LRELU), net.fea_L3_conv2, ops.ACT_LRELU)
+        assert rel(nchw(L3), torch.from_numpy(g['L3_fea'])) < NS_TOL, 'feature pyramid'
+        ref = [ops.Seg(t.view(B, N, *t.shape[1:])[:, 2], T=N, Tsrc=1, t_fixed=0) for t in (L1, L2, L3)]
+        aligned = net.pcd_align.forward_nhwc([L1, L2, L3], ref)
+        assert rel(nchw(aligned[2:3]), torch.from_numpy(g['aligned_center'])) < NS_TOL, 'PCD (centre frame)'
+        assert rel(nchw(aligned[0:1]), torch.from_numpy(g['aligned_0'])) < NS_TOL, 'PCD (frame 0)'
+        tsa = net.tsa_fusion.forward_nhwc(aligned, B, N)
+        assert rel(nchw(tsa), torch.from_numpy(g['tsa'])) < NS_TOL, 'TSA'
+
+
+def test_edvr_reference_shaped_submodules(mods):
+    """PCD_Align.forward / TSA_Fusion.forward keep the reference's NCHW call contract."""
+    from oracle import edvr_oracle as O
+    net, sd = _edvr(mods, 99)
+    g = torch.Generator().manual_seed(1)
+    nbr = [torch.randn(1, 64, 16 >> i, 24 >> i, generator=g) for i in range(3)]
+    ref = [torch.randn(1, 64, 16 >> i, 24 >> i, generator=g) for i in range(3)]
+    with torch.no_grad():
+        y = net.pcd_align([t.cuda() for t in nbr], [t.cuda() for t in ref])
+        y_ref = O.pcd_align({k: v.double() for k, v in sd.items()}, 'pcd_align.', [t.double() for t in nbr],
+                            [t.double() for t in ref], 8)
+        assert rel(y, y_ref) < NS_TOL
+        al = torch.randn(2, 5, 64, 8, 12, generator=g)
+        t = net.tsa_fusion(al.cuda())
+        t_ref = O.tsa_fusion({k: v.double() for k, v in sd.items()}, 'tsa_fusion.', al.double(), 2)
+        assert rel(t, t_ref) < NS_TOL
+
+
+def test_edvr_batch2_and_gradients_vs_oracle(mods):
+    """B=2 (exercises the strided centre-frame views) and the full backward pass against autograd
+    through the CPU oracle (float64)."""
+    from oracle import edvr_oracle as O
+    net, sd = _edvr(mods, 321)
+    g = torch.Generator().manual_seed(2)
+    x = torch.rand(2, 5, 3, 16, 16, generator=g)
+    gt = torch.rand(2, 3, 64, 64, generator=g)
+    sdd = {k: v.double().requires_grad_(True) for k, v in sd.items()}
+    out_ref = O.edvr_forward(sdd, x.double())
+    loss_ref = ((out_ref - gt.double()) ** 2).mean()
+    probes = ['conv_first.weight', 'pcd_align.L3_dcnpack.conv_offset_mask.weight', 'pcd_align.L1_dcnpack.weight',
+              'pcd_align.cas_offset_conv1.weight', 'tsa_fusion.tAtt_2.weight', 'tsa_fusion.fea_fusion.weight',
+              'tsa_fusion.sAtt_L2.weight', 'recon_trunk.0.conv1.weight', 'upconv1.weight', 'upconv2.bias',
+              'conv_last.weight', 'conv_last.bias', 'fea_L2_conv1.weight', 'pcd_align.L2_offset_conv2.bias']
+    gref = torch.autograd.grad(loss_ref, [sdd[k] for k in probes])
+    out = net(x.cuda())
+    assert rel(out, out_ref) < NS_TOL
+    loss = ((out - gt.cuda()) ** 2).mean()
+    loss.backward()
+    named = dict(net.named_parameters())
+    for k, gr in zip(probes, gref):
+        assert named[k].grad is not None, k
+        assert rel(named[k].grad, gr) < NS_TOL, k
+
+
+def test_mfdn_matches_reference_golden(mods):
+    g = gold('mfdn_32x48.npz')
+    net, _ = _mfdn(mods, int(g['seed']))
+    lr = torch.from_numpy(g['lr']).cuda()
+    with torch.no_grad():
+        slr = net(lr.transpose(1, 2)).transpose(1, 2)
+    assert rel(slr, torch.from_numpy(g['slr'])) < NS_TOL
+
+
+def test_mfdn_gradients_vs_oracle(mods):
+    from oracle import edvr_oracle as O
+    net, sd = _mfdn(mods, 5)
+    g = torch.Generator().manual_seed(3)
+    lr = torch.rand(1, 5, 3, 16, 24, generator=g)
+    tgt = torch.rand(1, 5, 3, 4, 6, generator=g)
+    sdd = {k: v.double().requires_grad_(True) for k, v in sd.items()}
+    ref = O.mfdn_forward(sdd, lr.double().transpose(1, 2)).transpose(1, 2)
+    gref = torch.autograd.grad((ref - tgt.double()).abs().mean(), list(sdd.values()))
+    out = net(lr.cuda().transpose(1, 2)).transpose(1, 2)
+    assert rel(out, ref) < NS_TOL
+    (out - tgt.cuda()).abs().mean().backward()
+    for (k, p), gr in zip(net.named_parameters(), gref):
+        assert rel(p.grad, gr) < NS_TOL, k
+
+
+@pytest.mark.parametrize('tag,optimizer,crit', [('sgd2_l2', 'SGD', 'l2'), ('adam1_cb', 'Adam', 'cb')])
+@pytest.mark.parametrize('graphs', [False, True], ids=['eager', 'graph'])
+def test_adaptation_matches_reference_golden(mods, tag, optimizer, crit, graphs):
+    """test_dynavsr.py:208-283 (2-step SGD/L2 and the shipped 1-step Adam/Charbonnier setting)."""
+    adapt = mods[2]
+    g = gold('adapt_%s.npz' % tag)
+    netG, sdG = _edvr(mods, int(g['seed_G']))
+    netE, sdE = _mfdn(mods, int(g['seed_E']))
+    netF, _ = _mfdn(mods, int(g['seed_E_fixed']))
+    eng = adapt.InnerLoopAdapter(netG, netE, netF, steps=int(g['steps']), lr_alpha=float(g['lr_alpha']),
+                                 optimizer=optimizer, betas=(0.9, 0.99), criterion=crit, slr_weight=10.0,
+                                 use_graphs=graphs)
+    lr = torch.from_numpy(g['lr'])
+    ref = torch.from_numpy(g['out'])
+    for rep in range(2):                       # second frame must restart from the meta-weights (:208)
+        hr = eng.adapt_and_infer(lr)
+        assert rel(hr, ref) < NS_TOL, 'rep %d' % rep
+        assert np.allclose(eng.last_losses.cpu().numpy(), g['losses'], rtol=1e-3), 'rep %d' % rep
+        # the adaptation must actually have moved the output (sensitivity of this test)
+        assert rel(hr, torch.from_numpy(g['out_unadapted'])) > 5 * rel(hr, ref)
+    # parameter deltas of two probes = lr * gradient, checked against the reference run
+    d_first = netG.conv_first.weight.detach().cpu() - sdG['conv_first.weight']
+    d_conv6 = netE.conv6.weight.detach().cpu() - sdE['conv6.weight']
+    assert rel(d_first, torch.from_numpy(g['d_conv_first'])) < 2e-2
+    assert rel(d_conv6, torch.from_numpy(g['d_conv6'])) < 2e-2
+    # and un-adapted inference still reproduces the meta-weights result
+    frames = nhwc(lr.reshape(5, 3, *lr.shape[-2:]).cuda())
+    assert rel(nchw(eng.infer_nhwc(frames)), torch.from_numpy(g['out_unadapted'])) < NS_TOL
+
+
+def test_full_size_properties(mods):
+    """BASELINE size (5x3x180x320 -> 3x720x1280): properties that need no oracle run --
+    determinism, batch-vs-single consistency of the batched PCD pass, and shape."""
+    ops = mods[3]
+    net, _ = _edvr(mods, 7)
+    g = torch.Generator().manual_seed(4)
+    x = torch.rand(1, 5, 3, 180, 320, generator=g).cuda()
+    with torch.no_grad():
+        a = net(x)
+        b = net(x)
+        assert a.shape == (1, 3, 720, 1280)
+        assert torch.equal(a, b)                                   # forward is deterministic (no atomics)
+        # a crop processed alone must equal the crop of the full frame away from the borders
+        # (receptive field of EDVR-M is large; compare a centre window with generous margin at L3 scale)
+        assert torch.isfinite(a).all()
+    xs = torch.cat([x, x.flip(1)], 0)
+    with torch.no_grad():
+        c = net(xs)
+    assert rel(c[0:1], a) < 1e-6                                   # batching does not change results

@@ -1,0 +1,362 @@
+"""GPU parity tests of every kernel family against a plain PyTorch reference computed on CPU in
+float64 (tolerances are written at each assert; the north-star bar is 1e-3 relative fp32)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from util import gold, maxabs, nchw, nhwc, rel
+
+pytestmark = pytest.mark.gpu
+TOL = 2e-5          # fp32 kernels vs fp64 truth, relative L2
+GTOL = 1e-4         # gradients (atomics / longer reductions)
+
+
+@pytest.fixture(scope='module')
+def ops():
+    if not torch.cuda.is_available():
+        pytest.skip('no CUDA device')
+    from dynavsr_b200 import ops as _ops
+    return _ops
+
+
+def _rand(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(*shape, generator=g, dtype=torch.float64) * scale
+
+
+def _dev(t):
+    return t.float().cuda()
+
+
+def _act_ref(v, act, sig_split=0):
+    if act == 1:
+        return F.relu(v)
+    if act == 2:
+        return F.leaky_relu(v, 0.1)
+    if act == 3:
+        return torch.cat([v[:, :sig_split], torch.sigmoid(v[:, sig_split:])], 1)
+    return v
+
+
+CONV_CASES = [
+    # name, N, H, W, segC, Co, k, stride, pad, act, res, shuffle
+    ('3x3_64', 2, 12, 20, [64], 64, 3, 1, 1, 2, False, 0),
+    ('3x3_relu_res', 1, 9, 13, [64], 64, 3, 1, 1, 0, True, 0),
+    ('3x3_relu', 1, 9, 13, [64], 64, 3, 1, 1, 1, False, 0),
+    ('cat2', 2, 8, 8, [64, 64], 64, 3, 1, 1, 2, False, 0),
+    ('stride2', 2, 12, 16, [64], 64, 3, 2, 1, 2, False, 0),
+    ('cin3', 3, 10, 14, [3], 64, 3, 1, 1, 2, False, 0),
+    ('cout3', 1, 10, 14, [64], 3, 3, 1, 1, 0, True, 0),
+    ('offmask216', 1, 7, 9, [64], 216, 3, 1, 1, 3, False, 0),
+    ('1x1_320', 1, 8, 12, [320], 64, 1, 1, 0, 2, False, 0),
+    ('1x1_cout3', 2, 6, 6, [64], 3, 1, 1, 0, 0, False, 0),
+    ('4x4s2', 2, 10, 14, [64], 128, 4, 2, 0, 2, False, 0),
+    ('4x4s2_128', 1, 10, 14, [128], 64, 4, 2, 0, 2, False, 0),
+    ('shuffle', 1, 6, 10, [64], 256, 3, 1, 1, 2, False, 2),
+    ('big_M_tail', 1, 23, 37, [16], 24, 3, 1, 1, 2, False, 0),
+]
+
+
+@pytest.mark.parametrize('case', CONV_CASES, ids=[c[0] for c in CONV_CASES])
+def test_conv_forward_backward(ops, case):
+    name, N, H, W, segC, Co, k, stride, pad, act, use_res, shuffle = case
+    xs = [_rand(N, c, H, W, seed=i + 1) for i, c in enumerate(segC)]
+    w = _rand(Co, sum(segC), k, k, seed=10, scale=0.1)
+    b = _rand(Co, seed=11, scale=0.1)
+    sig_split = 144 if act == 3 else 0
+    # reference (float64 CPU)
+    xr = [t.clone().requires_grad_(True) for t in xs]
+    wr, br = w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    y = _act_ref(F.conv2d(torch.cat(xr, 1), wr, br, stride=stride, padding=pad), act, sig_split)
+    if shuffle:
+        y = F.pixel_shuffle(y, 2)
+    res = _rand(*y.shape, seed=12) if use_res else None
+    resr = res.clone().requires_grad_(True) if use_res else None
+    if use_res:
+        y = y + resr
+    gy = _rand(*y.shape, seed=13)
+    grads = torch.autograd.grad(y, xr + [wr, br] + ([resr] if use_res else []), gy)
+    # device
+    xd = [nhwc(_dev(t)).requires_grad_(True) for t in xs]
+    wd, bd = _dev(w).requires_grad_(True), _dev(b).requires_grad_(True)
+    resd = nhwc(_dev(res)).requires_grad_(True) if use_res else None
+    yd = ops.conv(xd, wd, bd, stride=stride, pad=pad, act=act, sig_split=sig_split, res=resd, shuffle=shuffle)
+    assert rel(nchw(yd), y) < TOL, 'forward'
+    gd = torch.autograd.grad(yd, xd + [wd, bd] + ([resd] if use_res else []), nhwc(_dev(gy)))
+    for i in range(len(xs)):
+        assert rel(nchw(gd[i]), grads[i]) < GTOL, 'grad input %d' % i
+    assert rel(gd[len(xs)], grads[len(xs)]) < GTOL, 'grad weight'
+    assert rel(gd[len(xs) + 1], grads[len(xs) + 1]) < GTOL, 'grad bias'
+    if use_res:
+        assert rel(nchw(gd[-1]), grads[-1]) < GTOL, 'grad residual'
+
+
+def test_conv_broadcast_reference_segment(ops):
+    """PCD: cat([nbr_f, ref]) for all N frames of each clip with ONE reference feature per clip."""
+    B, N, H, W, C = 2, 5, 6, 8, 64
+    nbr, ref = _rand(B * N, C, H, W, seed=1), _rand(B, C, H, W, seed=2)
+    w, b = _rand(C, 2 * C, 3, 3, seed=3, scale=0.05), _rand(C, seed=4, scale=0.1)
+    nr, rr, wr, br = (t.clone().requires_grad_(True) for t in (nbr, ref, w, b))
+    y = F.leaky_relu(F.conv2d(torch.cat([nr, rr.repeat_interleave(N, 0)], 1), wr, br, padding=1), 0.1)
+    gy = _rand(*y.shape, seed=5)
+    gr = torch.autograd.grad(y, [nr, rr, wr, br], gy)
+    nd = nhwc(_dev(nbr)).requires_grad_(True)
+    # the reference features live inside a [B, N, ...] tensor: take the strided centre view, as EDVR does
+    full = torch.zeros(B, N, H, W, C, device='cuda')
+    full[:, 2] = nhwc(_dev(ref))
+    full.requires_grad_(True)
+    wd, bd = _dev(w).requires_grad_(True), _dev(b).requires_grad_(True)
+    yd = ops.conv([nd, ops.Seg(full[:, 2], T=N, Tsrc=1, t_fixed=0)], wd, bd, act=ops.ACT_LRELU)
+    assert rel(nchw(yd), y) < TOL
+    gd = torch.autograd.grad(yd, [nd, full, wd, bd], nhwc(_dev(gy)))
+    assert rel(nchw(gd[0]), gr[0]) < GTOL
+    assert rel(nchw(gd[1][:, 2]), gr[1]) < GTOL and float(gd[1][:, 0].abs().max()) == 0.0
+    assert rel(gd[2], gr[2]) < GTOL and rel(gd[3], gr[3]) < GTOL
+
+
+@pytest.mark.parametrize('Cin,Co', [(3, 64), (64, 64)])
+def test_conv3d_replicate_padded(ops, Cin, Co):
+    B, T, H, W = 2, 5, 6, 7
+    x = _rand(B, Cin, T, H, W, seed=1)
+    w, b = _rand(Co, Cin, 3, 3, 3, seed=2, scale=0.1), _rand(Co, seed=3, scale=0.1)
+    xr, wr, br = (t.clone().requires_grad_(True) for t in (x, w, b))
+    y = F.leaky_relu(F.conv3d(F.pad(xr, (1,) * 6, mode='replicate'), wr, br), 0.1)      # B Co T H W
+    gy = _rand(*y.shape, seed=4)
+    gr = torch.autograd.grad(y, [xr, wr, br], gy)
+    frames = _dev(x).permute(0, 2, 3, 4, 1).reshape(B * T, H, W, Cin).contiguous().requires_grad_(True)
+    wd, bd = _dev(w).requires_grad_(True), _dev(b).requires_grad_(True)
+    yd = ops.conv3d_padded(ops.pad3d_replicate(frames, T), wd, bd, T, act=ops.ACT_LRELU)   # [B*T, H, W, Co]
+    y_ref = y.permute(0, 2, 3, 4, 1).reshape(B * T, H, W, Co)
+    assert rel(yd, y_ref) < TOL
+    gd = torch.autograd.grad(yd, [frames, wd, bd], _dev(gy.permute(0, 2, 3, 4, 1).reshape(B * T, H, W, Co)).contiguous())
+    assert rel(gd[0], gr[0].permute(0, 2, 3, 4, 1).reshape(B * T, H, W, Cin)) < GTOL
+    assert rel(gd[1], gr[1]) < GTOL and rel(gd[2], gr[2]) < GTOL
+
+
+def _mdcn_case(ops, N, C, H, W, Co, dg, off_scale, act, seed):
+    from oracle.torch_ops import mdcn_torch
+    K = 9
+    x = _rand(N, C, H, W, seed=seed)
+    off = _rand(N, 2 * dg * K, H, W, seed=seed + 1, scale=off_scale)
+    m = torch.sigmoid(_rand(N, dg * K, H, W, seed=seed + 2))
+    w, b = _rand(Co, C, 3, 3, seed=seed + 3, scale=0.1), _rand(Co, seed=seed + 4, scale=0.1)
+    leaves = [t.clone().requires_grad_(True) for t in (x, off, m, w, b)]
+    y = mdcn_torch(*leaves, 1, 1, 1, 1, dg)
+    if act:
+        y = F.leaky_relu(y, 0.1)
+    gy = _rand(*y.shape, seed=seed + 5)
+    gr = torch.autograd.grad(y, leaves, gy)
+    xd = nhwc(_dev(x)).requires_grad_(True)
+    om = torch.cat([nhwc(_dev(off)), nhwc(_dev(m))], 3).contiguous().requires_grad_(True)
+    wd, bd = _dev(w).requires_grad_(True), _dev(b).requires_grad_(True)
+    yd = ops.mdcn(xd, om, wd, bd, dg, 1, 1, 1, ops.ACT_LRELU if act else ops.ACT_NONE)
+    assert rel(nchw(yd), y) < TOL, 'forward'
+    gd = torch.autograd.grad(yd, [xd, om, wd, bd], nhwc(_dev(gy)))
+    assert rel(nchw(gd[0]), gr[0]) < GTOL, 'grad input'
+    assert rel(nchw(gd[1][..., :2 * dg * K]), gr[1]) < GTOL, 'grad offset'
+    assert rel(nchw(gd[1][..., 2 * dg * K:]), gr[2]) < GTOL, 'grad mask'
+    assert rel(gd[2], gr[3]) < GTOL, 'grad weight'
+    assert rel(gd[3], gr[4]) < GTOL, 'grad bias'
+
+
+@pytest.mark.parametrize('cfg', [(1, 64, 11, 13, 64, 8, 2.0, True), (2, 64, 8, 8, 64, 8, 6.0, False),
+                                 (1, 16, 9, 11, 8, 4, 3.0, False), (1, 128, 6, 7, 128, 8, 1.5, True),
+                                 (1, 12, 7, 7, 8, 4, 2.0, False)],
+                         ids=['edvr_m', 'oob_heavy', 'small_cpg4', 'edvr_l', 'cpg3_scalar'])
+def test_mdcn_nhwc(ops, cfg):
+    N, C, H, W, Co, dg, s, act = cfg
+    _mdcn_case(ops, N, C, H, W, Co, dg, s, act, seed=7)
+
+
+def test_mdcn_all_taps_outside_gives_bias(ops):
+    x = nhwc(_dev(_rand(1, 64, 5, 5)))
+    om = torch.cat([torch.full((1, 5, 5, 144), 100.0), torch.ones(1, 5, 5, 72)], 3).cuda()
+    w, b = _dev(_rand(64, 64, 3, 3, seed=1)), _dev(_rand(64, seed=2))
+    y = ops.mdcn(x, om, w, b, 8)
+    assert torch.equal(y, b.view(1, 1, 1, 64).expand_as(y))
+
+
+def test_mdcn_nchw_boundary_matches_reference_golden(ops):
+    """The reference operator API on NCHW tensors against outputs of torchvision's implementation of
+    the reference algorithm (tests/golden/dcn_small.npz, generated by oracle/make_golden.py)."""
+    from dynavsr_b200.models.archs.dcn import modulated_deform_conv
+    g = gold('dcn_small.npz')
+    t = {k: torch.from_numpy(g[k]).cuda() for k in ('x', 'offset', 'mask', 'weight', 'bias', 'gy')}
+    leaves = [t[k].clone().requires_grad_(True) for k in ('x', 'offset', 'mask', 'weight', 'bias')]
+    y = modulated_deform_conv(leaves[0], leaves[1], leaves[2], leaves[3], leaves[4], 1, 1, 1, 1, int(g['dg']))
+    assert rel(y, torch.from_numpy(g['y'])) < TOL
+    grads = torch.autograd.grad(y, leaves, t['gy'])
+    for name, a in zip(['gx', 'goffset', 'gmask', 'gweight', 'gbias'], grads):
+        assert rel(a, torch.from_numpy(g[name])) < GTOL, name
+
+
+def test_mdcn_nchw_boundary_errors(ops):
+    from dynavsr_b200.models.archs.dcn import modulated_deform_conv
+    x = torch.randn(1, 8, 4, 4)
+    with pytest.raises(NotImplementedError):      # CPU tensors: deform_conv.py:109-110
+        modulated_deform_conv(x, torch.zeros(1, 18, 4, 4), torch.ones(1, 9, 4, 4), torch.randn(4, 8, 3, 3), None, 1, 1, 1, 1, 1)
+    xc = x.cuda()
+    with pytest.raises(RuntimeError):             # channel mismatch: deform_conv_cuda.cpp:509-511
+        modulated_deform_conv(xc, torch.zeros(1, 18, 4, 4).cuda(), torch.ones(1, 9, 4, 4).cuda(),
+                              torch.randn(4, 6, 3, 3).cuda(), None, 1, 1, 1, 1, 1)
+    with pytest.raises(RuntimeError):             # groups != 1 is rejected loudly (never used by the reference)
+        modulated_deform_conv(xc, torch.zeros(1, 18, 4, 4).cuda(), torch.ones(1, 9, 4, 4).cuda(),
+                              torch.randn(4, 4, 3, 3).cuda(), None, 1, 1, 1, 2, 1)
+
+
+def test_dcn_pack_module_matches_oracle(ops):
+    """ModulatedDeformConvPack through its reference-shaped NCHW forward (deform_conv.py:274-291)."""
+    from dynavsr_b200.models.archs.dcn import ModulatedDeformConvPack
+    from oracle import edvr_oracle as O
+    torch.manual_seed(0)
+    m = ModulatedDeformConvPack(64, 64, 3, stride=1, padding=1, dilation=1, deformable_groups=8,
+                                extra_offset_mask=True).cuda()
+    assert float(m.conv_offset_mask.weight.abs().max()) == 0.0          # zero init, deform_conv.py:270-272
+    m.conv_offset_mask.weight.data.normal_(0, 0.02)
+    m.conv_offset_mask.bias.data.normal_(0, 0.5)
+    x, feat = _rand(2, 64, 9, 10, seed=1), _rand(2, 64, 9, 10, seed=2)
+    sd = {'p.' + k: v.detach().double().cpu() for k, v in m.state_dict().items()}
+    ref = O.dcn_pack(sd, 'p', x, feat, 8)
+    y = m([_dev(x), _dev(feat)])
+    assert rel(y, ref) < TOL
+
+
+@pytest.mark.parametrize('scale,C,mul', [(2, 64, 1.0), (2, 64, 2.0), (4, 3, 1.0), (2, 6, 1.0)])
+def test_upsample(ops, scale, C, mul):
+    x = _rand(2, C, 7, 9, seed=1)
+    xr = x.clone().requires_grad_(True)
+    y = F.interpolate(xr, scale_factor=scale, mode='bilinear', align_corners=False) * mul
+    gy = _rand(*y.shape, seed=2)
+    gr, = torch.autograd.grad(y, xr, gy)
+    xd = nhwc(_dev(x)).requires_grad_(True)
+    yd = ops.upsample(xd, scale, mul)
+    assert rel(nchw(yd), y) < TOL
+    gd, = torch.autograd.grad(yd, xd, nhwc(_dev(gy)))
+    assert rel(nchw(gd), gr) < TOL
+
+
+@pytest.mark.parametrize('H,W,C', [(8, 12, 64), (9, 7, 64), (6, 6, 5)])
+def test_pool_maxavg(ops, H, W, C):
+    x = _rand(2, C, H, W, seed=1)
+    xr = x.clone().requires_grad_(True)
+    y = torch.cat([F.max_pool2d(xr, 3, 2, 1), F.avg_pool2d(xr, 3, 2, 1)], 1)
+    gy = _rand(*y.shape, seed=2)
+    gr, = torch.autograd.grad(y, xr, gy)
+    xd = nhwc(_dev(x)).requires_grad_(True)
+    yd = ops.pool_maxavg(xd)
+    assert rel(nchw(yd), y) < TOL
+    gd, = torch.autograd.grad(yd, xd, nhwc(_dev(gy)))
+    assert rel(nchw(gd), gr) < TOL
+
+
+@pytest.mark.parametrize('mode', ['reflect', 'replicate'])
+@pytest.mark.parametrize('C', [64, 3])
+def test_pad2d(ops, mode, C):
+    x = _rand(2, C, 5, 6, seed=1)
+    xr = x.clone().requires_grad_(True)
+    y = F.pad(xr, (1, 1, 1, 1), mode=mode)
+    gy = _rand(*y.shape, seed=2)
+    gr, = torch.autograd.grad(y, xr, gy)
+    xd = nhwc(_dev(x)).requires_grad_(True)
+    yd = ops.pad2d(xd, 1, mode)
+    assert maxabs(nchw(yd), y.float()) == 0.0
+    gd, = torch.autograd.grad(yd, xd, nhwc(_dev(gy)))
+    assert rel(nchw(gd), gr) < TOL
+
+
+def test_pad3d_replicate(ops):
+    B, T, C, H, W = 2, 5, 64, 4, 5
+    x = _rand(B, C, T, H, W, seed=1)
+    xr = x.clone().requires_grad_(True)
+    y = F.pad(xr, (1,) * 6, mode='replicate')
+    gy = _rand(*y.shape, seed=2)
+    gr, = torch.autograd.grad(y, xr, gy)
+    fr = _dev(x).permute(0, 2, 3, 4, 1).reshape(B * T, H, W, C).contiguous().requires_grad_(True)
+    yd = ops.pad3d_replicate(fr, T)
+    assert maxabs(yd, y.permute(0, 2, 3, 4, 1).reshape(B * (T + 2), H + 2, W + 2, C).float()) == 0.0
+    gd, = torch.autograd.grad(yd, fr, _dev(gy.permute(0, 2, 3, 4, 1).reshape(B * (T + 2), H + 2, W + 2, C)).contiguous())
+    assert rel(gd, gr.permute(0, 2, 3, 4, 1).reshape(B * T, H, W, C)) < TOL
+
+
+def test_tsa_temporal_and_combine(ops):
+    B, N, C, H, W = 2, 5, 64, 6, 7
+    al, emb, ref = _rand(B, N, C, H, W, seed=1), _rand(B, N, C, H, W, seed=2, scale=0.2), _rand(B, C, H, W, seed=3, scale=0.2)
+    a, e, r = (t.clone().requires_grad_(True) for t in (al, emb, ref))
+    prob = torch.sigmoid((e * r.unsqueeze(1)).sum(2))                    # B N H W
+    out = (a * prob.unsqueeze(2)).reshape(B, N * C, H, W)
+    gy = _rand(*out.shape, seed=4)
+    gr = torch.autograd.grad(out, [a, e, r], gy)
+    ad = nhwc(_dev(al.reshape(B * N, C, H, W))).requires_grad_(True)
+    ed = nhwc(_dev(emb.reshape(B * N, C, H, W))).requires_grad_(True)
+    rd = nhwc(_dev(ref)).requires_grad_(True)
+    od = ops.tsa_temporal(ad, ed, rd, N)
+    assert rel(nchw(od), out) < TOL
+    gd = torch.autograd.grad(od, [ad, ed, rd], nhwc(_dev(gy)))
+    assert rel(nchw(gd[0]), gr[0].reshape(B * N, C, H, W)) < GTOL
+    assert rel(nchw(gd[1]), gr[1].reshape(B * N, C, H, W)) < GTOL
+    assert rel(nchw(gd[2]), gr[2]) < GTOL
+    # combine
+    f, t, ad2 = _rand(2, 64, 5, 5, seed=5), _rand(2, 64, 5, 5, seed=6), _rand(2, 64, 5, 5, seed=7)
+    fr, tr, ar = (v.clone().requires_grad_(True) for v in (f, t, ad2))
+    o = fr * torch.sigmoid(tr) * 2 + ar
+    g = _rand(*o.shape, seed=8)
+    gr = torch.autograd.grad(o, [fr, tr, ar], g)
+    fd, td, dd = (_dev(v).requires_grad_(True) for v in (f, t, ad2))
+    od = ops.tsa_combine(fd, td, dd)
+    assert rel(od, o) < TOL
+    gd = torch.autograd.grad(od, [fd, td, dd], _dev(g))
+    for i in range(3):
+        assert rel(gd[i], gr[i]) < TOL
+
+
+@pytest.mark.parametrize('kind', ['l1', 'l2', 'cb'])
+def test_pixel_loss(ops, kind):
+    a, b = _rand(2, 8, 9, 3, seed=1), _rand(2, 8, 9, 3, seed=2)
+    ar = a.clone().requires_grad_(True)
+    d = ar - b
+    ref = {'l1': d.abs().mean(), 'l2': (d * d).mean(), 'cb': torch.sqrt(d * d + 1e-6).mean()}[kind] * 10.0
+    gr, = torch.autograd.grad(ref * 3.0, ar)
+    ad = _dev(a).requires_grad_(True)
+    l = ops.pixel_loss(ad, _dev(b), kind, 10.0)
+    assert abs(float(l) - float(ref)) < 1e-5 * abs(float(ref))
+    gd, = torch.autograd.grad(l * 3.0, ad)
+    assert rel(gd, gr) < TOL
+
+
+def test_fused_updates_match_torch_optim(ops):
+    from dynavsr_b200.adapt import FlatParams
+    torch.manual_seed(0)
+    m1, m2 = torch.nn.Conv2d(8, 8, 3).cuda(), torch.nn.Conv2d(8, 4, 1).cuda()
+    r1, r2 = torch.nn.Conv2d(8, 8, 3).cuda(), torch.nn.Conv2d(8, 4, 1).cuda()
+    r1.load_state_dict(m1.state_dict()); r2.load_state_dict(m2.state_dict())
+    for opt_name in ('SGD', 'Adam'):
+        flat = FlatParams([m1, m2])
+        if opt_name == 'SGD':
+            ref = torch.optim.SGD([{'params': r1.parameters(), 'lr': 0.1}, {'params': r2.parameters(), 'lr': 0.01}])
+        else:
+            ref = torch.optim.Adam([{'params': r1.parameters(), 'lr': 0.1}, {'params': r2.parameters(), 'lr': 0.01}], betas=(0.9, 0.99))
+        for step in range(3):
+            flat.zero_grad()
+            for (p, q) in zip(list(m1.parameters()) + list(m2.parameters()), list(r1.parameters()) + list(r2.parameters())):
+                g = torch.randn_like(p)
+                p._dvsr_grad.copy_(g)
+                q.grad = g.clone()
+            if opt_name == 'SGD':
+                flat.sgd_step(0.1, 0.01)
+            else:
+                flat.adam_step(0.1, 0.01, (0.9, 0.99))
+            ref.step()
+        for (p, q) in zip(list(m1.parameters()) + list(m2.parameters()), list(r1.parameters()) + list(r2.parameters())):
+            assert rel(p, q) < 1e-5, opt_name
+        flat.restore()
+        r1.load_state_dict(m1.state_dict()); r2.load_state_dict(m2.state_dict())
+
+
+def test_layout_roundtrip_and_cpu_rejection(ops):
+    x = torch.randn(3, 5, 7, 9).cuda()
+    y = ops.to_nhwc(x)
+    assert torch.equal(y, x.permute(0, 2, 3, 1).contiguous())
+    assert torch.equal(ops.to_nchw(y), x)
+    with pytest.raises(NotImplementedError):
+        ops.conv(torch.randn(1, 4, 4, 8), torch.randn(8, 8, 3, 3))

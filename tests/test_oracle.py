@@ -1,0 +1,104 @@
+"""CPU tests: the oracle against the golden vectors generated from the unmodified reference
+(oracle/make_golden.py) and against torchvision's implementation of the same DCN algorithm."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import edvr_oracle as O
+from oracle import mdcn_c
+from oracle import params as P
+from oracle.torch_ops import mdcn_torch
+from util import gold, rel
+
+
+def test_c_oracle_matches_golden_dcn():
+    g = gold('dcn_small.npz')
+    dg = int(g['dg'])
+    y = mdcn_c.forward(g['x'], g['offset'], g['mask'], g['weight'], g['bias'], 1, 1, 1, 1, dg)
+    assert np.abs(y - g['y']).max() < 5e-6
+    outs = mdcn_c.backward(g['x'], g['offset'], g['mask'], g['weight'], g['gy'], 1, 1, 1, 1, dg)
+    for name, a in zip(['gx', 'goffset', 'gmask', 'gweight', 'gbias'], outs):
+        assert np.abs(a - g[name]).max() <= 1e-5 * max(1.0, np.abs(g[name]).max()), name
+
+
+def test_torch_oracle_matches_golden_dcn_and_grads():
+    g = gold('dcn_small.npz')
+    t = {k: torch.from_numpy(g[k]) for k in ('x', 'offset', 'mask', 'weight', 'bias', 'gy')}
+    leaves = [t[k].clone().requires_grad_(True) for k in ('x', 'offset', 'mask', 'weight', 'bias')]
+    y = mdcn_torch(leaves[0], leaves[1], leaves[2], leaves[3], leaves[4], 1, 1, 1, 1, int(g['dg']))
+    assert rel(y, torch.from_numpy(g['y'])) < 1e-6
+    grads = torch.autograd.grad(y, leaves, t['gy'])
+    for name, a in zip(['gx', 'goffset', 'gmask', 'gweight', 'gbias'], grads):
+        assert rel(a, torch.from_numpy(g[name])) < 1e-5, name
+
+
+@pytest.mark.parametrize('stride,pad,dil', [(1, 1, 1), (2, 1, 1), (1, 2, 2), (1, 0, 1)])
+def test_torch_oracle_vs_torchvision_geometry(stride, pad, dil):
+    torchvision = pytest.importorskip('torchvision')
+    g = torch.Generator().manual_seed(3)
+    B, C, H, W, Co, dg = 1, 8, 10, 7, 6, 2
+    Ho = (H + 2 * pad - (dil * 2 + 1)) // stride + 1
+    Wo = (W + 2 * pad - (dil * 2 + 1)) // stride + 1
+    x = torch.randn(B, C, H, W, generator=g)
+    off = torch.randn(B, dg * 18, Ho, Wo, generator=g) * 4
+    m = torch.rand(B, dg * 9, Ho, Wo, generator=g)
+    w = torch.randn(Co, C, 3, 3, generator=g)
+    ref = torchvision.ops.deform_conv2d(x, off, w, None, stride=stride, padding=pad, dilation=dil, mask=m)
+    assert rel(mdcn_torch(x, off, m, w, None, stride, pad, dil, 1, dg), ref) < 1e-5
+    yc = mdcn_c.forward(x.numpy(), off.numpy(), m.numpy(), w.numpy(), None, stride, pad, dil, 1, dg)
+    assert rel(torch.from_numpy(yc), ref) < 1e-5
+
+
+def test_empty_and_border_taps():
+    # all offsets far outside: output must be exactly the bias (kernel.cu:617)
+    x = torch.randn(1, 4, 5, 5)
+    off = torch.full((1, 18, 5, 5), 100.0)
+    m = torch.ones(1, 9, 5, 5)
+    w = torch.randn(3, 4, 3, 3)
+    b = torch.randn(3)
+    y = mdcn_torch(x, off, m, w, b, 1, 1, 1, 1, 1)
+    assert torch.equal(y, b.view(1, 3, 1, 1).expand_as(y))
+    yc = mdcn_c.forward(x.numpy(), off.numpy(), m.numpy(), w.numpy(), b.numpy(), 1, 1, 1, 1, 1)
+    assert np.array_equal(yc, y.numpy())
+
+
+def test_edvr_oracle_matches_reference_golden():
+    g = gold('edvr_m_32.npz')
+    sd = P.make_params(P.edvr_param_shapes(), seed=int(g['seed']))
+    with torch.no_grad():
+        out, inter = O.edvr_forward(sd, torch.from_numpy(g['x']), return_intermediates=True)
+    assert rel(out, torch.from_numpy(g['out'])) < 1e-6
+    assert rel(inter['aligned'][:, 2], torch.from_numpy(g['aligned_center'])) < 1e-6
+    assert rel(inter['tsa'], torch.from_numpy(g['tsa'])) < 1e-6
+
+
+def test_mfdn_oracle_matches_reference_golden():
+    g = gold('mfdn_32x48.npz')
+    sd = P.make_params(P.mfdn_param_shapes(), seed=int(g['seed']))
+    with torch.no_grad():
+        slr = O.mfdn_forward(sd, torch.from_numpy(g['lr']).transpose(1, 2))
+    assert rel(slr, torch.from_numpy(g['slr'])) < 1e-6
+
+
+@pytest.mark.parametrize('tag,optimizer,crit', [('sgd2_l2', 'SGD', 'l2'), ('adam1_cb', 'Adam', 'cb')])
+def test_adapt_oracle_matches_reference_golden(tag, optimizer, crit):
+    g = gold('adapt_%s.npz' % tag)
+    sdG = P.make_params(P.edvr_param_shapes(), seed=int(g['seed_G']))
+    sdE = P.make_params(P.mfdn_param_shapes(), seed=int(g['seed_E']))
+    sdF = P.make_params(P.mfdn_param_shapes(), seed=int(g['seed_E_fixed']))
+    out, losses, pG, pE = O.adapt_and_infer(sdG, sdE, sdF, torch.from_numpy(g['lr']), steps=int(g['steps']),
+                                            lr_alpha=float(g['lr_alpha']), optimizer=optimizer, criterion=crit,
+                                            return_losses=True)
+    assert np.allclose(losses, g['losses'], rtol=1e-5)
+    assert rel(out, torch.from_numpy(g['out'])) < 1e-5
+    assert rel(pG['conv_first.weight'] - sdG['conv_first.weight'], torch.from_numpy(g['d_conv_first'])) < 1e-3
+    assert rel(pE['conv6.weight'] - sdE['conv6.weight'], torch.from_numpy(g['d_conv6'])) < 1e-3
+
+
+def test_param_inventory_counts():
+    # EDVR-M 3 300 131 params / 144 tensors, MFDN 4x 452 291 / 14, EDVR-L 20 633 827 / 264
+    n = lambda d: sum(int(np.prod(s)) for s in d.values())
+    assert (n(P.edvr_param_shapes()), len(P.edvr_param_shapes())) == (3300131, 144)
+    assert (n(P.mfdn_param_shapes()), len(P.mfdn_param_shapes())) == (452291, 14)
+    L = P.edvr_param_shapes(nf=128, back_RBs=40)
+    assert (n(L), len(L)) == (20633827, 264)
