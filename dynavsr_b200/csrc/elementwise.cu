@@ -363,9 +363,9 @@ __global__ void add_channel_bias_kernel(const float* __restrict__ x, const float
 // gpre[pix][c] = gy[..] * act'(y[..]);  gbias[c] += sum_pix gpre[pix][c]
 // shuffle == 2: gy / y are in the PixelShuffled layout [n][2Ho][2Wo][C/4]; gpre is [n][Ho][Wo][C].
 template <int VEC>
-__global__ void act_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ y, float* __restrict__ gpre,
-                               float* __restrict__ gbias, long long npix, int C, int act, float slope, int sig_split,
-                               int shuffle, int Ho, int Wo, long long pix_per_block) {
+__global__ void act_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ y, const float* __restrict__ res,
+                               float* __restrict__ gpre, float* __restrict__ gbias, long long npix, int C, int act,
+                               float slope, int sig_split, int shuffle, int Ho, int Wo, long long pix_per_block) {
     const int cw = C / VEC;                 // channel vectors per pixel
     const int rows = blockDim.x / cw;       // pixels handled per block iteration
     const int t = threadIdx.x;
@@ -396,10 +396,13 @@ __global__ void act_bwd_kernel(const float* __restrict__ gy, const float* __rest
                 if (VEC == 4) {
                     const float4 a = ldg4(gy + e);
                     g[0] = a.x; g[1 % VEC] = a.y; g[2 % VEC] = a.z; g[3 % VEC] = a.w;
-                    if (y) { const float4 b = ldg4(y + e); yv[0] = b.x; yv[1 % VEC] = b.y; yv[2 % VEC] = b.z; yv[3 % VEC] = b.w; }
+                if (y) { const float4 b = ldg4(y + e); yv[0] = b.x; yv[1 % VEC] = b.y; yv[2 % VEC] = b.z; yv[3 % VEC] = b.w; }
+                    // epilogue order is act(v) + res: recover act(v) when a residual was fused after the activation
+                    if (y && res) { const float4 r4 = ldg4(res + e); yv[0] -= r4.x; yv[1 % VEC] -= r4.y; yv[2 % VEC] -= r4.z; yv[3 % VEC] -= r4.w; }
                 } else {
                     g[0] = __ldg(gy + e);
                     if (y) yv[0] = __ldg(y + e);
+                    if (y && res) yv[0] -= __ldg(res + e);
                 }
             }
 #pragma unroll
@@ -558,12 +561,12 @@ extern "C" int dvsr_add_channel_bias(const float* x, const float* m, float* y, i
     return check_launch("add_channel_bias");
 }
 
-extern "C" int dvsr_act_bwd(const float* gy, const float* y, float* gpre, float* gbias, long long npix, int C, int act,
-                            float slope, int sig_split, int shuffle, int Ho, int Wo, void* stream) {
+extern "C" int dvsr_act_bwd(const float* gy, const float* y, const float* res, float* gpre, float* gbias, long long npix,
+                            int C, int act, float slope, int sig_split, int shuffle, int Ho, int Wo, void* stream) {
     DVSR_REQUIRE(gy && npix > 0 && C > 0, "act_bwd: bad arguments");
     DVSR_REQUIRE(act == DVSR_ACT_NONE || y, "act_bwd: activation derivative needs the saved output");
-    DVSR_REQUIRE(shuffle == 0 || (shuffle == 2 && C % 4 == 0 && gpre && gpre != gy), "act_bwd: bad shuffle arguments");
-    const bool v4 = (C % 4 == 0) && (C / 4 <= 256) && A16(gy) && (!y || A16(y)) && (!gpre || A16(gpre)) && shuffle == 0;
+    DVSR_REQUIRE(shuffle == 0 || (shuffle == 2 && C % 4 == 0 && gpre && gpre != gy && !res), "act_bwd: bad shuffle arguments");
+    const bool v4 = (C % 4 == 0) && (C / 4 <= 256) && A16(gy) && (!y || A16(y)) && (!res || A16(res)) && (!gpre || A16(gpre)) && shuffle == 0;
     DVSR_REQUIRE(v4 || C <= 256, "act_bwd: C=%d too wide for the scalar path", C);
     const int vec = v4 ? 4 : 1;
     const int rows = 256 / (C / vec);
@@ -574,9 +577,9 @@ extern "C" int dvsr_act_bwd(const float* gy, const float* y, float* gpre, float*
     per = (per + rows - 1) / rows * rows;
     blocks = (npix + per - 1) / per;
     const size_t smem = gbias ? sizeof(float) * 256 * vec : 0;
-    if (v4) act_bwd_kernel<4><<<(int)blocks, 256, smem, ST>>>(gy, y, gpre, gbias, npix, C, act, slope, sig_split, shuffle, Ho, Wo, per);
+    if (v4) act_bwd_kernel<4><<<(int)blocks, 256, smem, ST>>>(gy, y, res, gpre, gbias, npix, C, act, slope, sig_split, shuffle, Ho, Wo, per);
     else {
-        act_bwd_kernel<1><<<(int)blocks, 256, smem, ST>>>(gy, y, gpre, gbias, npix, C, act, slope, sig_split, shuffle, Ho, Wo, per);
+        act_bwd_kernel<1><<<(int)blocks, 256, smem, ST>>>(gy, y, res, gpre, gbias, npix, C, act, slope, sig_split, shuffle, Ho, Wo, per);
     }
     return check_launch("act_bwd");
 }

@@ -339,7 +339,7 @@ extern "C" int dvsr_mdcn_backward_nchw(const float* x, const float* offset, cons
     if ((rc = dvsr_conv_wgrad(&d, ws + w.gy, Co, gweight, &wl, stream))) return rc;
     if (gbias) {
         if (cudaMemsetAsync(gbias, 0, sizeof(float) * (size_t)Co, st) != cudaSuccess) return check_launch("memset gb");
-        if ((rc = dvsr_act_bwd(ws + w.gy, nullptr, nullptr, gbias, (long long)B * Ho * Wo, Co, DVSR_ACT_NONE, 0.f, 0, 0, Ho, Wo, stream))) return rc;
+        if ((rc = dvsr_act_bwd(ws + w.gy, nullptr, nullptr, nullptr, gbias, (long long)B * Ho * Wo, Co, DVSR_ACT_NONE, 0.f, 0, 0, Ho, Wo, stream))) return rc;
     }
     if ((rc = dvsr_nhwc_to_nchw(ws + w.gx, gx, B, C, H, W, stream))) return rc;
     if ((rc = dvsr_nhwc_to_nchw(ws + w.goff, goffset, B, 2 * dg * KK, Ho, Wo, stream))) return rc;

@@ -174,14 +174,15 @@ class _ConvFn(Function):
         ctx.spec, ctx.wl = spec, wl
         ctx.has_bias, ctx.has_res = bias is not None, res is not None
         ctx.wslot, ctx.bslot = getattr(weight, '_dvsr_grad', None), getattr(bias, '_dvsr_grad', None)
-        ctx.save_for_backward(weight, y if spec.act != ACT_NONE else None, *tensors)
+        with_act = spec.act != ACT_NONE
+        ctx.save_for_backward(weight, y if with_act else None, res if (with_act and res is not None) else None, *tensors)
         return y
 
     @staticmethod
     def backward(ctx, gy):
         spec, wl = ctx.spec, ctx.wl
-        weight, y = ctx.saved_tensors[0], ctx.saved_tensors[1]
-        tensors = ctx.saved_tensors[2:]
+        weight, y, res = ctx.saved_tensors[0], ctx.saved_tensors[1], ctx.saved_tensors[2]
+        tensors = ctx.saved_tensors[3:]
         gy = gy.contiguous()
         Co = weight.shape[0]
         npix = spec.N * spec.Ho * spec.Wo
@@ -193,12 +194,12 @@ class _ConvFn(Function):
             if need_b else None
         if spec.act != ACT_NONE or spec.shuffle:
             gpre = torch.empty(spec.N, spec.Ho, spec.Wo, Co, device=gy.device, dtype=torch.float32)
-            call('dvsr_act_bwd', _ptr(gy), _ptr(y), _ptr(gpre), _ptr(gb), npix, Co, spec.act, spec.slope,
+            call('dvsr_act_bwd', _ptr(gy), _ptr(y), _ptr(res), _ptr(gpre), _ptr(gb), npix, Co, spec.act, spec.slope,
                  spec.sig_split, spec.shuffle, spec.Ho, spec.Wo, _stream())
         else:
             gpre = gy
             if need_b:
-                call('dvsr_act_bwd', _ptr(gy), None, None, _ptr(gb), npix, Co, ACT_NONE, 0.0, 0, 0, spec.Ho,
+                call('dvsr_act_bwd', _ptr(gy), None, None, None, _ptr(gb), npix, Co, ACT_NONE, 0.0, 0, 0, spec.Ho,
                      spec.Wo, _stream())
         # 2. weight gradient
         gw = None
@@ -356,11 +357,11 @@ class _MdcnFn(Function):
             if need_b else None
         if act != ACT_NONE:
             gpre = torch.empty_like(gy)
-            call('dvsr_act_bwd', _ptr(gy), _ptr(y), _ptr(gpre), _ptr(gb), npix, Co, act, slope, 0, 0, Ho, Wo, _stream())
+            call('dvsr_act_bwd', _ptr(gy), _ptr(y), None, _ptr(gpre), _ptr(gb), npix, Co, act, slope, 0, 0, Ho, Wo, _stream())
         else:
             gpre = gy
             if need_b:
-                call('dvsr_act_bwd', _ptr(gy), None, None, _ptr(gb), npix, Co, ACT_NONE, 0.0, 0, 0, Ho, Wo, _stream())
+                call('dvsr_act_bwd', _ptr(gy), None, None, None, _ptr(gb), npix, Co, ACT_NONE, 0.0, 0, 0, Ho, Wo, _stream())
         d = _MdcnFn._desc(x, om, dg, KH, KW, stride, pad, dil, Ho, Wo)
         d.Co = Co
         gx = gom = gw = None

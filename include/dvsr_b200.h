@@ -150,10 +150,11 @@ int dvsr_pad3d_replicate_bwd(const float* gy, float* gx, int B, int T, int H, in
 int dvsr_spatial_mean(const float* x, float* m, int N, int HW, int C, void* stream);
 int dvsr_add_channel_bias(const float* x, const float* m, float* y, int N, int HW, int C, float sign, void* stream);
 
-/* gpre = gy * act'(y) [+ un-PixelShuffle]; gbias[c] += sum_pix gpre[pix][c] (if gbias).  In-place allowed
- * when shuffle == 0.  y is the saved forward OUTPUT (relu / lrelu / sigmoid-split are invertible from it). */
-int dvsr_act_bwd(const float* gy, const float* y, float* gpre, float* gbias, long long npix, int C, int act,
-                 float slope, int sig_split, int shuffle, int Ho, int Wo, void* stream);
+/* gpre = gy * act'(y - res) [+ un-PixelShuffle]; gbias[c] += sum_pix gpre[pix][c] (if gbias).  In-place allowed
+ * when shuffle == 0.  y is the saved forward OUTPUT (relu / lrelu / sigmoid-split derivatives are functions of
+ * it); res (optional) is the residual that the forward epilogue added AFTER the activation. */
+int dvsr_act_bwd(const float* gy, const float* y, const float* res, float* gpre, float* gbias, long long npix,
+                 int C, int act, float slope, int sig_split, int shuffle, int Ho, int Wo, void* stream);
 
 /* ---- TSA fusion (tsa.cu) -------------------------------------------------------------------------- */
 /* temporal attention (EDVR_arch.py:166-176): prob[n][f][pix] = sigmoid(sum_c emb[n][f][pix][c]*emb_ref[n][pix][c]);

@@ -114,9 +114,9 @@ def test_edvr_batch2_and_gradients_vs_oracle(mods):
     loss = ((out - gt.cuda()) ** 2).mean()
     loss.backward()
     named = dict(net.named_parameters())
-    for k, gr in zip(probes, gref):
-        assert named[k].grad is not None, k
-        assert rel(named[k].grad, gr) < NS_TOL, k
+    errs = {k: rel(named[k].grad, gr) for k, gr in zip(probes, gref)}
+    bad = {k: v for k, v in errs.items() if not v < NS_TOL}
+    assert not bad, 'gradient mismatches: %s' % bad
 
 
 def test_mfdn_matches_reference_golden(mods):
@@ -124,7 +124,7 @@ def test_mfdn_matches_reference_golden(mods):
     net, _ = _mfdn(mods, int(g['seed']))
     lr = torch.from_numpy(g['lr']).cuda()
     with torch.no_grad():
-        slr = net(lr.transpose(1, 2)).transpose(1, 2)
+        slr = net(lr.transpose(1, 2))                 # [B, C, T, h, w], the reference module's own contract
     assert rel(slr, torch.from_numpy(g['slr'])) < NS_TOL
 
 

@@ -44,6 +44,7 @@ CONV_CASES = [
     ('3x3_64', 2, 12, 20, [64], 64, 3, 1, 1, 2, False, 0),
     ('3x3_relu_res', 1, 9, 13, [64], 64, 3, 1, 1, 0, True, 0),
     ('3x3_relu', 1, 9, 13, [64], 64, 3, 1, 1, 1, False, 0),
+    ('3x3_lrelu_then_res', 2, 9, 13, [64], 64, 3, 1, 1, 2, True, 0),
     ('cat2', 2, 8, 8, [64, 64], 64, 3, 1, 1, 2, False, 0),
     ('stride2', 2, 12, 16, [64], 64, 3, 2, 1, 2, False, 0),
     ('cin3', 3, 10, 14, [3], 64, 3, 1, 1, 2, False, 0),
