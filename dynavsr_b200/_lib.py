@@ -55,6 +55,10 @@ SIGNATURES = {
     'dvsr_conv_fprop': [_DP, _P, _P],
     'dvsr_conv_wgrad': [_DP, _P, _I, _P, _WP, _P],
     'dvsr_conv_small_co': [_DP, _P, _P],
+    'dvsr_conv_tc_supported': [_DP],
+    'dvsr_conv_tc_packed_floats': [_WP, _I, _I],
+    'dvsr_pack_weights_tc': [_P, _P, _WP, _I, _I, _P],
+    'dvsr_conv_tc_fprop': [_DP, _P, _P],
     'dvsr_mdcn_bwd_data': [_DP, _P, _I, _P, _P, _I, _P, _I, _P, _I, _P],
     'dvsr_mdcn_workspace_bytes': [_I] * 12,
     'dvsr_mdcn_forward_nchw': [_P] * 6 + [_I] * 12 + [_P, _LL, _P],
@@ -84,7 +88,8 @@ SIGNATURES = {
     'dvsr_last_error': [],
     'dvsr_version': [],
 }
-_RESTYPE = {'dvsr_last_error': ctypes.c_char_p, 'dvsr_mdcn_workspace_bytes': ctypes.c_longlong}
+_RESTYPE = {'dvsr_last_error': ctypes.c_char_p, 'dvsr_mdcn_workspace_bytes': ctypes.c_longlong,
+            'dvsr_conv_tc_packed_floats': ctypes.c_longlong}
 
 _lib = None
 

@@ -1,0 +1,453 @@
+// dynavsr_b200/csrc/conv_tc.cu
+//
+// Implicit-GEMM convolution on the 5th-generation tensor cores (tcgen05 / TMEM / TMA), sm_100a only.
+//
+//   y[pix][co] = epilogue( sum_{seg, tap, ci} x_seg[pix + tap][ci] * W[(seg, tap, ci)][co] )
+//
+// * NHWC fp32 activations are read as TF32 (kind::tf32, fp32 accumulation in TMEM) -- no conversion pass,
+//   no im2col: for every (segment, tap, 32-channel chunk) the TMA engine drops the tap-shifted
+//   8 x 16-pixel x 32-channel box straight into shared memory in the 128-byte-swizzled K-major layout the
+//   MMA descriptor expects; out-of-image pixels (the conv padding and tile overhang) are zero-filled by
+//   the TMA unit itself.
+// * CTA tile: M = 128 output pixels (8 rows x 16 columns of one image) x N = all output channels
+//   (<= 256, padded to a multiple of 16), so activations are fetched once per tile regardless of Co.
+// * Warp-specialised: warp 0 = TMA producer (one elected lane), warp 1 = TMEM owner + MMA issuer (one
+//   elected lane issues tcgen05.mma, tcgen05.commit releases smem stages / publishes the accumulator),
+//   warps 2-5 = operand rounding during the main loop, then the epilogue (tcgen05.ld -> bias / ReLU /
+//   LeakyReLU / sigmoid-split / residual / PixelShuffle(2) store).  4-stage mbarrier ring.
+// * Numerics: the tensor core TRUNCATES fp32 operands to TF32 (a systematic shrink of ~2^-11 per operand
+//   that compounds layer after layer).  Weights are therefore rounded to nearest TF32 when packed and the
+//   activation tile is rounded to nearest (cvt.rna.tf32.f32) in shared memory by warps 2-5 between the TMA
+//   arrival and the MMA, which makes the per-layer error unbiased (~2e-4 relative).
+// * The same kernel computes data gradients of stride-1 convs (taps mirrored: src = o + pad - k) and
+//   sums over broadcast segments (`wshare`).
+//
+// Replaces cuDNN for the heavy layers of EDVR_arch.py:68-90,141-159,224-249 / arch_util.py:42-43.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace dvsr {
+
+constexpr int TC_TH = 8, TC_TW = 16;          // pixel tile
+constexpr int TC_KC = 32;                     // channels per K chunk (128 bytes of fp32)
+constexpr int TC_STAGES = 4;
+constexpr int TC_A_BYTES = TC_TH * TC_TW * TC_KC * 4;   // 16 KiB
+constexpr int TC_THREADS = 192;
+
+struct TcSeg { int C, T, Tsrc, dt, t_fixed; };
+struct TcParams {
+    int N, Ho, Wo;                 // output images / size
+    int KH, KW, tap_sign, tap_base;  // src = o + tap_base + tap_sign * k
+    int nseg, wshare;
+    TcSeg seg[DVSR_MAX_SEG];
+    int Co, Co_pad;
+    const float* bias;
+    int act; float slope; int sig_split;
+    const float* res; int res_pix_stride;
+    int shuffle;
+    float* y; int y_pix_stride;
+};
+struct __align__(64) TcMaps { CUtensorMap x[DVSR_MAX_SEG]; CUtensorMap w; };
+
+// ------------------------------------------------------------------------------------------------ PTX
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ float round_tf32(float x) {
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+    return __uint_as_float(u);
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done = 0;
+    const uint32_t a = smem_u32(bar);
+    while (!done) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(a), "r"(parity) : "memory");
+    }
+}
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+// K-major, 128-byte swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
+//   [0,14) start>>4 | [16,30) LBO>>4 (unused for swizzled K-major, 1) | [32,46) SBO>>4 (1024 B between
+//   8-row groups) | [46,48) version = 1 | [61,64) layout = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_desc_k128(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// kind::tf32 instruction descriptor (cute::UMMA::InstrDescriptor): c_format F32 (1) at [4,6),
+// a/b_format TF32 (2) at [7,10)/[10,13), a/b major K (0) at 15/16, N>>3 at [17,23), M>>4 at [24,29)
+__device__ __forceinline__ uint32_t make_idesc_tf32(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+    uint32_t r[32];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                 "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                   "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ int tc_seg_image(const TcSeg& sg, int n) {
+    const int T = sg.T > 0 ? sg.T : 1;
+    const int q = n / T, r = n - q * T;
+    const int t = sg.t_fixed >= 0 ? sg.t_fixed : r + sg.dt;
+    if (t < 0 || t >= sg.Tsrc) return -1;
+    return q * sg.Tsrc + t;
+}
+
+// ------------------------------------------------------------------------------------------------ kernel
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    // 1024-byte alignment is required by the 128B swizzle atoms
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int b_bytes = p.Co_pad * TC_KC * 4;
+    uint8_t* smem_a = smem;                               // [stages][16 KiB]
+    uint8_t* smem_b = smem + TC_STAGES * TC_A_BYTES;      // [stages][Co_pad * 128 B]
+    uint64_t* bars = (uint64_t*)(smem_b + TC_STAGES * b_bytes);
+    uint64_t* full_bar = bars;                            // [stages]
+    uint64_t* empty_bar = bars + TC_STAGES;               // [stages]
+    uint64_t* ready_bar = bars + 2 * TC_STAGES;           // [stages] activation tile rounded to TF32
+    uint64_t* accum_bar = bars + 3 * TC_STAGES;           // [1]
+    uint32_t* tmem_slot = (uint32_t*)(bars + 3 * TC_STAGES + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tiles_w = (p.Wo + TC_TW - 1) / TC_TW, tiles_h = (p.Ho + TC_TH - 1) / TC_TH;
+    int tile = blockIdx.x;
+    const int n_img = tile / (tiles_w * tiles_h);
+    tile -= n_img * tiles_w * tiles_h;
+    const int oy0 = (tile / tiles_w) * TC_TH, ox0 = (tile % tiles_w) * TC_TW;
+
+    // TMEM columns: power of two >= max(32, Co_pad)
+    uint32_t tmem_cols = 32;
+    while ((int)tmem_cols < p.Co_pad) tmem_cols <<= 1;
+
+    if (warp == 0 && elect_one()) {
+        for (int s = 0; s < p.nseg; ++s) prefetch_tmap(&maps.x[s]);
+        prefetch_tmap(&maps.w);
+    }
+    if (warp == 1) {
+        if (elect_one()) {
+            for (int i = 0; i < TC_STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); mbar_init(&ready_bar[i], 128); }
+            mbar_init(accum_bar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int KK = p.KH * p.KW;
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (elect_one()) {
+            int stage = 0, phase = 0, wrow = 0;
+            for (int s = 0; s < p.nseg; ++s) {
+                const int img = tc_seg_image(p.seg[s], n_img);
+                if (p.wshare) wrow = 0;
+                const int chunks = (p.seg[s].C + TC_KC - 1) / TC_KC;
+                for (int tap = 0; tap < KK; ++tap) {
+                    const int kh = tap / p.KW, kw = tap - kh * p.KW;
+                    const int dy = p.tap_base + p.tap_sign * kh, dx = p.tap_base + p.tap_sign * kw;
+                    for (int c = 0; c < chunks; ++c, ++wrow) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        mbar_expect_tx(&full_bar[stage], TC_A_BYTES + b_bytes);
+                        // a temporal tap outside the clip reads image index N (fully out of bounds -> zeros)
+                        tma_load_4d(&maps.x[s], &full_bar[stage], smem_a + stage * TC_A_BYTES, c * TC_KC, ox0 + dx, oy0 + dy,
+                                    img < 0 ? 0x3fffffff : img);
+                        tma_load_2d(&maps.w, &full_bar[stage], smem_b + stage * b_bytes, 0, wrow * p.Co_pad);
+                        if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        const uint32_t idesc = make_idesc_tf32(128, p.Co_pad);
+        int stage = 0, phase = 0;
+        int total = 0;
+        for (int s = 0; s < p.nseg; ++s) total += KK * ((p.seg[s].C + TC_KC - 1) / TC_KC);
+        for (int it = 0; it < total; ++it) {
+            mbar_wait(&ready_bar[stage], phase);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (elect_one()) {
+                const uint64_t adesc = make_desc_k128(smem_u32(smem_a + stage * TC_A_BYTES));
+                const uint64_t bdesc = make_desc_k128(smem_u32(smem_b + stage * b_bytes));
+#pragma unroll
+                for (int k = 0; k < TC_KC / 8; ++k) {
+                    // advance 8 tf32 = 32 bytes along K inside the 128-byte swizzle span: +2 in the (addr >> 4) field
+                    mma_tf32(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (it > 0 || k > 0) ? 1u : 0u);
+                }
+                mma_commit(&empty_bar[stage]);                 // frees this smem stage when the MMAs retire
+                if (it == total - 1) mma_commit(accum_bar);    // accumulator complete
+            }
+            __syncwarp();
+            if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+        }
+    } else {
+        // ===================== main loop: round the activation tile to nearest TF32 in place =====================
+        {
+            const int t = threadIdx.x - 64;      // 0..127
+            int stage = 0, phase = 0, total = 0;
+            for (int s = 0; s < p.nseg; ++s) total += KK * ((p.seg[s].C + TC_KC - 1) / TC_KC);
+            for (int it = 0; it < total; ++it) {
+                mbar_wait(&full_bar[stage], phase);
+                float4* a4 = reinterpret_cast<float4*>(smem_a + stage * TC_A_BYTES);
+#pragma unroll
+                for (int i = 0; i < TC_A_BYTES / 16 / 128; ++i) {
+                    float4 v = a4[t + i * 128];
+                    v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w);
+                    a4[t + i * 128] = v;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> async proxy (MMA)
+                mbar_arrive(&ready_bar[stage]);
+                if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+        // ===================== epilogue: 4 warps, one TMEM lane (= output pixel) per thread =====================
+        mbar_wait(accum_bar, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int q = warp & 3;                    // TMEM lane quarter this warp may access
+        const int row = q * 32 + lane;             // pixel index inside the tile: row = ty * 16 + tx
+        const int oy = oy0 + row / TC_TW, ox = ox0 + row % TC_TW;
+        const bool valid = (oy < p.Ho) && (ox < p.Wo);
+        const long long pix = ((long long)n_img * p.Ho + oy) * p.Wo + ox;
+        for (int c0 = 0; c0 < p.Co_pad; c0 += 32) {
+            float v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);   // warp-collective: no divergence before it
+            if (!valid) continue;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const int co = c0 + j;
+                float t = v[j] + ((p.bias && co < p.Co) ? __ldg(p.bias + co) : 0.f);
+                if (p.act == DVSR_ACT_SIGMOID_SPLIT) t = (co >= p.sig_split) ? sigmoidf_(t) : t;
+                else t = act_apply(t, p.act, p.slope);
+                v[j] = t;
+            }
+            if (p.res) {
+                const float* r = p.res + pix * p.res_pix_stride + c0;
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    if (c0 + j < p.Co) {
+                        const float4 t = ldg4(r + j);
+                        v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
+                    }
+                }
+            }
+            if (p.shuffle == 2) {
+                // out[n][2*oy + i][2*ox + jj][c] = v[4c + 2i + jj]: 8 output channels per 32-column chunk
+                const int cq = c0 >> 2;
+#pragma unroll
+                for (int sub = 0; sub < 4; ++sub) {
+                    const long long op = ((long long)n_img * (2 * p.Ho) + 2 * oy + (sub >> 1)) * (2 * p.Wo) + 2 * ox + (sub & 1);
+                    float* yo = p.y + op * p.y_pix_stride + cq;
+                    if (c0 < p.Co) {
+                        *reinterpret_cast<float4*>(yo) = make_float4(v[sub], v[4 + sub], v[8 + sub], v[12 + sub]);
+                        *reinterpret_cast<float4*>(yo + 4) = make_float4(v[16 + sub], v[20 + sub], v[24 + sub], v[28 + sub]);
+                    }
+                }
+            } else {
+                float* yo = p.y + pix * p.y_pix_stride + c0;
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                    if (c0 + j < p.Co) *reinterpret_cast<float4*>(yo + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ weights
+// wp rows of 32 floats: row = ((s, tap, chunk), co_pad index); mode 2: K = input channels of segment s;
+// mode 3 (data gradient of segment `seg`): K = forward output channels, rows = input channels of `seg`.
+__global__ void pack_weights_tc_kernel(const float* __restrict__ w, float* __restrict__ wp, const dvsr_wlayout wl,
+                                       int mode, int seg, int rows_pad, long long total) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int k = (int)(i & 31);
+    long long r = i >> 5;
+    const int nrow = (int)(r % rows_pad);
+    r /= rows_pad;                       // (s, tap, chunk) block index
+    float v = 0.f;
+    if (mode == 2) {
+        int s = 0, blk = (int)r;
+        for (; s < wl.nseg; ++s) {
+            const int n = wl.taps * ((wl.seg_C[s] + 31) / 32);
+            if (blk < n) break;
+            blk -= n;
+        }
+        const int chunks = (wl.seg_C[s] + 31) / 32;
+        const int tap = blk / chunks, chunk = blk - tap * chunks;
+        if (nrow < wl.Co && chunk * 32 + k < wl.seg_C[s])
+            v = w[(long long)nrow * wl.co_stride + wl.seg_base[s] + (long long)(chunk * 32 + k) * wl.ci_stride + tap];
+    } else {
+        const int chunks = (wl.Co + 31) / 32;
+        const int tap = (int)(r / chunks), chunk = (int)(r - (long long)tap * chunks);
+        if (nrow < wl.seg_C[seg] && chunk * 32 + k < wl.Co)
+            v = w[(long long)(chunk * 32 + k) * wl.co_stride + wl.seg_base[seg] + (long long)nrow * wl.ci_stride + tap];
+    }
+    wp[i] = round_tf32(v);   // round-to-nearest TF32 (the MMA would truncate)
+}
+
+// ------------------------------------------------------------------------------------------------ host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)sym;
+    }
+    return fn;
+}
+
+static int round16(int v) { return (v + 15) / 16 * 16; }
+
+}  // namespace dvsr
+
+using namespace dvsr;
+
+extern "C" int dvsr_conv_tc_supported(const dvsr_conv_desc* d) {
+    if (!d || d->deform || d->stride != 1 || d->dil != 1 || d->accumulate) return 0;
+    if (d->Co > 256 || d->Co < 16 || (d->Co & 3)) return 0;
+    if (d->shuffle && (d->Co % 32)) return 0;
+    for (int s = 0; s < d->nseg; ++s) {
+        const dvsr_conv_seg& g = d->seg[s];
+        // a partial last K chunk is zero-filled by TMA (channel coordinate out of bounds) and by the weight packer
+        if ((g.C & 3) || g.C < 16 || (g.pix_stride & 3) || (g.img_stride & 3) || ((uintptr_t)g.ptr & 15)) return 0;
+    }
+    if (((uintptr_t)d->y & 15) || (d->y_pix_stride & 3)) return 0;
+    if (d->res && ((((uintptr_t)d->res) & 15) || (d->res_pix_stride & 3))) return 0;
+    return 1;
+}
+
+extern "C" long long dvsr_conv_tc_packed_floats(const dvsr_wlayout* wl, int mode, int seg) {
+    if (!wl) return 0;
+    if (mode == 2) {
+        long long blocks = 0;
+        for (int s = 0; s < wl->nseg; ++s) blocks += (long long)wl->taps * ((wl->seg_C[s] + 31) / 32);
+        return blocks * round16(wl->Co) * 32;
+    }
+    return (long long)wl->taps * ((wl->Co + 31) / 32) * round16(wl->seg_C[seg]) * 32;
+}
+
+extern "C" int dvsr_pack_weights_tc(const float* w, float* wp, const dvsr_wlayout* wl, int mode, int seg, void* stream) {
+    DVSR_REQUIRE(w && wp && wl && (mode == 2 || mode == 3), "pack_weights_tc: bad arguments");
+    if (mode == 3) DVSR_REQUIRE(seg >= 0 && seg < wl->nseg, "pack_weights_tc: bad segment");
+    const long long total = dvsr_conv_tc_packed_floats(wl, mode, seg);
+    const int rows_pad = mode == 2 ? round16(wl->Co) : round16(wl->seg_C[seg]);
+    pack_weights_tc_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(w, wp, *wl, mode, seg, rows_pad, total);
+    return check_launch("pack_weights_tc");
+}
+
+extern "C" int dvsr_conv_tc_fprop(const dvsr_conv_desc* d, const float* wp, void* stream) {
+    DVSR_REQUIRE(d && wp && d->y, "conv_tc_fprop: null pointer");
+    DVSR_REQUIRE(dvsr_conv_tc_supported(d), "conv_tc_fprop: unsupported shape (use dvsr_conv_fprop)");
+    EncodeTiledFn encode = get_encode();
+    DVSR_REQUIRE(encode != nullptr, "conv_tc_fprop: cuTensorMapEncodeTiled is unavailable");
+    TcMaps maps;
+    TcParams p;
+    memset(&p, 0, sizeof(p));
+    p.N = d->N; p.Ho = d->Ho; p.Wo = d->Wo; p.KH = d->KH; p.KW = d->KW;
+    p.tap_sign = d->transposed ? -1 : 1;
+    p.tap_base = d->transposed ? d->pad : -d->pad;
+    p.nseg = d->nseg; p.wshare = d->wshare;
+    p.Co = d->Co; p.Co_pad = round16(d->Co);
+    p.bias = d->bias; p.act = d->act; p.slope = d->slope; p.sig_split = d->sig_split;
+    p.res = d->res; p.res_pix_stride = d->res_pix_stride; p.shuffle = d->shuffle;
+    p.y = d->y; p.y_pix_stride = d->y_pix_stride;
+    long long wrows = 0;
+    for (int s = 0; s < d->nseg; ++s) {
+        const dvsr_conv_seg& g = d->seg[s];
+        p.seg[s].C = g.C; p.seg[s].T = g.T; p.seg[s].Tsrc = g.Tsrc; p.seg[s].dt = g.dt; p.seg[s].t_fixed = g.t_fixed;
+        // number of source images addressable through this segment
+        const int T = g.T > 0 ? g.T : 1;
+        long long nsrc = ((long long)(d->N + T - 1) / T) * g.Tsrc;
+        if (nsrc < 1) nsrc = 1;
+        cuuint64_t dims[4] = {(cuuint64_t)g.C, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)nsrc};
+        long long img_stride = g.img_stride > 0 ? g.img_stride : (long long)d->H * d->W * g.pix_stride;
+        cuuint64_t strides[3] = {(cuuint64_t)g.pix_stride * 4, (cuuint64_t)d->W * g.pix_stride * 4, (cuuint64_t)img_stride * 4};
+        cuuint32_t box[4] = {TC_KC, TC_TW, TC_TH, 1};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = encode(&maps.x[s], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)g.ptr, dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        DVSR_REQUIRE(r == CUDA_SUCCESS, "conv_tc_fprop: cuTensorMapEncodeTiled(activation seg %d) failed with %d", s, (int)r);
+        if (!d->wshare || s == 0) wrows += (long long)d->KH * d->KW * ((g.C + TC_KC - 1) / TC_KC) * p.Co_pad;
+    }
+    {
+        cuuint64_t dims[2] = {TC_KC, (cuuint64_t)wrows};
+        cuuint64_t strides[1] = {TC_KC * 4};
+        cuuint32_t box[2] = {TC_KC, (cuuint32_t)p.Co_pad};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = encode(&maps.w, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)wp, dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        DVSR_REQUIRE(r == CUDA_SUCCESS, "conv_tc_fprop: cuTensorMapEncodeTiled(weights) failed with %d", (int)r);
+    }
+    const int tiles = d->N * ((d->Ho + TC_TH - 1) / TC_TH) * ((d->Wo + TC_TW - 1) / TC_TW);
+    const size_t smem = 1024 + (size_t)TC_STAGES * (TC_A_BYTES + p.Co_pad * TC_KC * 4) + 256;
+    static size_t smem_set = 0;
+    if (smem > smem_set) {
+        if (cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return check_launch("conv_tc_fprop: cudaFuncSetAttribute");
+        smem_set = smem;
+    }
+    conv_tc_kernel<<<tiles, TC_THREADS, smem, (cudaStream_t)stream>>>(maps, p);
+    return check_launch("conv_tc_fprop");
+}

@@ -100,7 +100,8 @@ def _layout(weight, seg_C, temporal):
 
 
 def _packed(weight, wl, mode, seg=0):
-    """mode 0: forward layout [K][Co]; mode 1: data-gradient layout of segment `seg` [taps*Co][C_seg]."""
+    """CUDA-core layouts -- mode 0: forward [K][Co]; mode 1: data gradient of segment `seg` [taps*Co][C_seg].
+    tcgen05 layouts (rows of 32 K-values, K-major, padded N) -- mode 2: forward; mode 3: data gradient."""
     key = (weight.data_ptr(), tuple(weight.shape), mode, seg, tuple(wl.seg_C[i] for i in range(wl.nseg)))
     ver = (weight._version, _wcache_epoch[0])
     ent = _wcache.get(key)
@@ -109,10 +110,13 @@ def _packed(weight, wl, mode, seg=0):
         return ent[1]
     if mode == 0:
         n = sum(wl.seg_C[i] for i in range(wl.nseg)) * wl.taps * wl.Co
-    else:
+    elif mode == 1:
         n = wl.seg_C[seg] * wl.taps * wl.Co
+    else:
+        n = _lib.lib().dvsr_conv_tc_packed_floats(ctypes.byref(wl), mode, seg)
     buf = ent[1] if ent is not None else torch.empty(n, device=weight.device, dtype=torch.float32)
-    call('dvsr_pack_weights', _ptr(weight), _ptr(buf), ctypes.byref(wl), mode, seg, _stream())
+    call('dvsr_pack_weights' if mode < 2 else 'dvsr_pack_weights_tc', _ptr(weight), _ptr(buf), ctypes.byref(wl),
+         mode, seg, _stream())
     _wcache[key] = (ver, buf)
     return buf
 
@@ -132,8 +136,24 @@ class _ConvSpec(object):
                  'N', 'H', 'W', 'Ho', 'Wo', 'has_res')
 
 
-def _launch_fprop(d, wp):
-    if d.Co <= 4 and d.nseg == 1 and not d.deform and not d.transposed and not d.shuffle \
+def _use_tc(d):
+    return _backend['tc'] and _lib.lib().dvsr_conv_tc_supported(ctypes.byref(d)) == 1
+
+
+def _run_conv(d, weight, wl, data_grad=False, segs=(0,)):
+    """Launch descriptor ``d`` with ``weight`` packed for the chosen kernel family.  ``data_grad`` selects
+    the mirrored (mode 1 / 3) weight layout; ``segs`` lists the forward segments whose packed blocks are
+    concatenated (one per temporal tap of a Conv3d data gradient)."""
+    tc = _use_tc(d)
+    if data_grad:
+        mode = 3 if tc else 1
+        bufs = [_packed(weight, wl, mode, sgi) for sgi in segs]
+        wp = bufs[0] if len(bufs) == 1 else torch.cat(bufs)
+    else:
+        wp = _packed(weight, wl, 2 if tc else 0)
+    if tc:
+        call('dvsr_conv_tc_fprop', ctypes.byref(d), _ptr(wp), _stream())
+    elif d.Co <= 4 and d.nseg == 1 and not d.deform and not d.transposed and not d.shuffle \
             and d.seg[0].C % 4 == 0 and d.seg[0].pix_stride % 4 == 0:
         call('dvsr_conv_small_co', ctypes.byref(d), _ptr(wp), _stream())
     else:
@@ -170,7 +190,7 @@ class _ConvFn(Function):
             assert res.is_contiguous() and res.shape == y.shape
             d.res, d.res_pix_stride = res.data_ptr(), res.shape[3]
         d.y = y.data_ptr()
-        _launch_fprop(d, _packed(weight, wl, 0))
+        _run_conv(d, weight, wl)
         ctx.spec, ctx.wl = spec, wl
         ctx.has_bias, ctx.has_res = bias is not None, res is not None
         ctx.wslot, ctx.bslot = getattr(weight, '_dvsr_grad', None), getattr(bias, '_dvsr_grad', None)
@@ -224,14 +244,11 @@ class _ConvFn(Function):
                 d.N, d.H, d.W, d.Ho, d.Wo = t.shape[0], spec.Ho, spec.Wo, spec.H, spec.W
                 d.KH, d.KW, d.stride, d.pad, d.dil, d.transposed = spec.KH, spec.KW, spec.stride, spec.pad, 1, 1
                 d.nseg = KT
-                rows = wl.taps * Co * t.shape[3]
-                wd = torch.empty(KT * rows, device=gy.device, dtype=torch.float32)
                 for kt in range(KT):
                     _fill_seg(d.seg[kt], gpre, T=m0.Tsrc, Tsrc=m0.T, dt=-kt)
-                    wd[kt * rows:(kt + 1) * rows].copy_(_packed(weight, wl, 1, kt))
                 d.Co = t.shape[3]
                 d.y, d.y_pix_stride = gx.data_ptr(), t.shape[3]
-                _launch_fprop(d, wd)
+                _run_conv(d, weight, wl, data_grad=True, segs=tuple(range(KT)))
                 gts[0] = gx
         else:
             for i, (t, m) in enumerate(zip(tensors, spec.metas)):
@@ -254,7 +271,7 @@ class _ConvFn(Function):
                     raise NotImplementedError('data gradient for segment mapping %s' % (m,))
                 d.Co = t.shape[3]
                 d.y, d.y_pix_stride = gx.data_ptr(), t.shape[3]
-                _launch_fprop(d, _packed(weight, wl, 1, i))
+                _run_conv(d, weight, wl, data_grad=True, segs=(i,))
                 gts[i] = gx
         return (None, gw, gb, gy if need_res else None) + tuple(gts)
 

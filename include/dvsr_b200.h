@@ -105,6 +105,13 @@ int dvsr_conv_fprop(const dvsr_conv_desc* d, const float* wp, void* stream);
 /* gw[PyTorch layout] += sum_pix A[pix][k] * gy[pix][co]; A described by d (deformable or plain). */
 int dvsr_conv_wgrad(const dvsr_conv_desc* d, const float* gy, int gy_pix_stride, float* gw,
                     const dvsr_wlayout* wl, void* stream);
+/* tcgen05 / TMEM / TMA implicit GEMM (conv_tc.cu): stride-1 convolutions and their data gradients with
+ * 16 <= Co <= 256; TF32 inputs, fp32 accumulation.  Weights packed by dvsr_pack_weights_tc:
+ * mode 2 = forward, mode 3 = data gradient of segment `seg`; dvsr_conv_tc_packed_floats gives the size. */
+int dvsr_conv_tc_supported(const dvsr_conv_desc* d);
+long long dvsr_conv_tc_packed_floats(const dvsr_wlayout* wl, int mode, int seg);
+int dvsr_pack_weights_tc(const float* w, float* wp, const dvsr_wlayout* wl, int mode, int seg, void* stream);
+int dvsr_conv_tc_fprop(const dvsr_conv_desc* d, const float* wp, void* stream);
 /* Small-Cout direct convolution (conv_last, 64 -> 3): one thread per output pixel. */
 int dvsr_conv_small_co(const dvsr_conv_desc* d, const float* wp, void* stream);
 

@@ -1,0 +1,110 @@
+"""tools/tc_check.py -- tcgen05 conv vs the exact-fp32 CUDA-core conv on the same inputs (prints rel errors)."""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from dynavsr_b200 import ops  # noqa: E402
+
+
+def rel(a, b):
+    return float((a.double() - b.double()).norm() / b.double().norm())
+
+
+def run(tag, fn):
+    ops.set_conv_backend(False)
+    ref = fn()
+    torch.cuda.synchronize()
+    ops.set_conv_backend(True)
+    out = fn()
+    torch.cuda.synchronize()
+    ops.set_conv_backend(False)
+    if isinstance(ref, (tuple, list)):
+        print(tag, ['%.2e' % rel(o, r) for o, r in zip(out, ref)], flush=True)
+    else:
+        print(tag, '%.2e' % rel(out, ref), 'max|ref|=%.3f' % float(ref.abs().max()), flush=True)
+
+
+def main():
+    torch.manual_seed(0)
+    dev = 'cuda'
+    for (N, H, W, Ci, Co, k) in [(1, 8, 16, 32, 64, 1), (1, 8, 16, 64, 64, 3), (2, 20, 40, 64, 64, 3), (1, 44, 80, 64, 216, 3),
+                                 (1, 16, 32, 320, 64, 1), (1, 16, 16, 64, 256, 3), (5, 11, 20, 64, 64, 3)]:
+        x = torch.randn(N, H, W, Ci, device=dev)
+        w = torch.randn(Co, Ci, k, k, device=dev) * (2.0 / (Ci * k * k)) ** 0.5
+        b = torch.randn(Co, device=dev) * 0.1
+        with torch.no_grad():
+            run('fwd N%d %dx%d %d->%d k%d' % (N, H, W, Ci, Co, k), lambda: ops.conv(x, w, b, pad=k // 2, act=ops.ACT_LRELU))
+    # two segments + broadcast + residual
+    x1, x2 = torch.randn(5, 16, 32, 64, device=dev), torch.randn(1, 16, 32, 64, device=dev)
+    w = torch.randn(64, 128, 3, 3, device=dev) * 0.03
+    b = torch.zeros(64, device=dev)
+    res = torch.randn(5, 16, 32, 64, device=dev)
+    with torch.no_grad():
+        run('cat+broadcast+res', lambda: ops.conv([x1, ops.Seg(x2, T=5, Tsrc=1, t_fixed=0)], w, b, res=res))
+    # shuffle + sigmoid split
+    x = torch.randn(1, 16, 32, 64, device=dev)
+    w = torch.randn(256, 64, 3, 3, device=dev) * 0.05
+    with torch.no_grad():
+        run('shuffle', lambda: ops.conv(x, w, None, act=ops.ACT_LRELU, shuffle=2))
+    w = torch.randn(216, 64, 3, 3, device=dev) * 0.05
+    b = torch.randn(216, device=dev)
+    with torch.no_grad():
+        run('sigmoid-split 216', lambda: ops.conv(x, w, b, act=ops.ACT_SIGMOID_SPLIT, sig_split=144))
+    # backward through TC data gradients
+    def fb():
+        xx = x1.clone().requires_grad_(True)
+        rr = x2.clone().requires_grad_(True)
+        ww = (torch.ones(64, 128, 3, 3, device=dev) * w128).requires_grad_(True)
+        y = ops.conv([xx, ops.Seg(rr, T=5, Tsrc=1, t_fixed=0)], ww, None, act=ops.ACT_LRELU)
+        return torch.autograd.grad(y, [xx, rr, ww], gy)
+    w128 = torch.randn(64, 128, 3, 3, device=dev) * 0.03
+    gy = torch.randn(5, 16, 32, 64, device=dev)
+    run('bwd (gx, gref, gw)', fb)
+    # valid conv (pad 0) as in MFDN
+    xp = torch.randn(2, 18, 34, 64, device=dev)
+    w = torch.randn(64, 64, 3, 3, device=dev) * 0.05
+    with torch.no_grad():
+        run('valid pad0', lambda: ops.conv(xp, w, None, pad=0, act=ops.ACT_LRELU))
+    print('tc_check done')
+
+
+
+
+def edvr_level():
+    """Whole-network parity of the tcgen05 path against the golden vectors of the reference."""
+    import numpy as np
+    from oracle import params as P
+    from dynavsr_b200 import adapt
+    from dynavsr_b200.models.archs import EDVR_arch, LRimg_estimator
+    gold = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tests', 'golden')
+    g = np.load(os.path.join(gold, 'edvr_m_32.npz'))
+    net = EDVR_arch.EDVR()
+    net.load_state_dict(P.make_params(P.edvr_param_shapes(), seed=int(g['seed'])))
+    net = net.cuda()
+    x = torch.from_numpy(g['x']).cuda()
+    ref = torch.from_numpy(g['out']).cuda()
+    for tc in (False, True):
+        ops.set_conv_backend(tc)
+        with torch.no_grad():
+            out = net(x)
+        print('EDVR forward vs reference golden, tc=%s: rel %.3e  maxabs %.3e' % (tc, rel(out, ref), float((out - ref).abs().max())), flush=True)
+    for tag, optimizer, crit in (('sgd2_l2', 'SGD', 'l2'), ('adam1_cb', 'Adam', 'cb')):
+        g = np.load(os.path.join(gold, 'adapt_%s.npz' % tag))
+        for tc in (False, True):
+            ops.set_conv_backend(tc)
+            netG = EDVR_arch.EDVR(); netG.load_state_dict(P.make_params(P.edvr_param_shapes(), seed=int(g['seed_G'])))
+            netE = LRimg_estimator.DirectKernelEstimatorVideo(64, 3, 4); netE.load_state_dict(P.make_params(P.mfdn_param_shapes(), seed=int(g['seed_E'])))
+            netF = LRimg_estimator.DirectKernelEstimatorVideo(64, 3, 4); netF.load_state_dict(P.make_params(P.mfdn_param_shapes(), seed=int(g['seed_E_fixed'])))
+            eng = adapt.InnerLoopAdapter(netG.cuda(), netE.cuda(), netF.cuda(), steps=int(g['steps']), lr_alpha=float(g['lr_alpha']),
+                                         optimizer=optimizer, betas=(0.9, 0.99), criterion=crit, use_graphs=False)
+            hr = eng.adapt_and_infer(torch.from_numpy(g['lr']))
+            print('adapt %s tc=%s: rel %.3e  losses %s (ref %s)' % (tag, tc, rel(hr, torch.from_numpy(g['out']).cuda()),
+                                                                     eng.last_losses.cpu().numpy(), g['losses']), flush=True)
+    ops.set_conv_backend(False)
+
+
+if __name__ == '__main__':
+    main()
+    edvr_level()
