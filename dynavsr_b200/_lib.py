@@ -59,6 +59,8 @@ SIGNATURES = {
     'dvsr_conv_tc_packed_floats': [_WP, _I, _I],
     'dvsr_pack_weights_tc': [_P, _P, _WP, _I, _I, _P],
     'dvsr_conv_tc_fprop': [_DP, _P, _P],
+    'dvsr_conv_wgrad_tc_supported': [_DP, _I],
+    'dvsr_conv_wgrad_tc': [_DP, _I, _P, _I, _P, _WP, _P],
     'dvsr_mdcn_bwd_data': [_DP, _P, _I, _P, _P, _I, _P, _I, _P, _I, _P],
     'dvsr_mdcn_workspace_bytes': [_I] * 12,
     'dvsr_mdcn_forward_nchw': [_P] * 6 + [_I] * 12 + [_P, _LL, _P],
@@ -125,12 +127,40 @@ def lib():
 
 
 COUNTER = [0]   # kernel-launching C-ABI calls issued from this process (bench.py's gpu_launches)
+PROFILE = {'on': bool(os.environ.get('DVSR_PROFILE')), 'events': [], 'tag': ''}
 
 
 def call(name, *args):
     """Invoke an int-returning entry point; raise DvsrError with the library's message on failure."""
     COUNTER[0] += 1
-    rc = getattr(lib(), name)(*args)
+    if PROFILE['on']:
+        import torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = getattr(lib(), name)(*args)
+        e1.record()
+        PROFILE['events'].append((name, PROFILE['tag'], e0, e1))
+    else:
+        rc = getattr(lib(), name)(*args)
     if rc != 0:
         msg = lib().dvsr_last_error()
         raise DvsrError('%s failed (rc=%d): %s' % (name, rc, msg.decode() if msg else '?'))
+
+
+def profile_report(top=40, by_tag=True):
+    """Aggregate the CUDA-event timings collected while PROFILE['on'] (eager mode only)."""
+    import torch
+    torch.cuda.synchronize()
+    agg = {}
+    for name, tag, e0, e1 in PROFILE['events']:
+        key = (name, tag) if by_tag else (name, '')
+        a = agg.setdefault(key, [0, 0.0])
+        a[0] += 1
+        a[1] += e0.elapsed_time(e1)
+    total = sum(v[1] for v in agg.values())
+    lines = ['%-28s %-44s %6s %10s %7s' % ('entry', 'tag', 'calls', 'total ms', 'share')]
+    for (name, tag), (c, ms) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:top]:
+        lines.append('%-28s %-44s %6d %10.3f %6.1f%%' % (name, tag, c, ms, 100 * ms / max(total, 1e-9)))
+    lines.append('total %.3f ms over %d calls' % (total, len(PROFILE['events'])))
+    PROFILE['events'].clear()
+    return '\n'.join(lines)

@@ -131,6 +131,19 @@ def set_conv_backend(tensor_cores):
     _backend['tc'] = bool(tensor_cores)
 
 
+def _run_wgrad(d, gpre, Co, gw, wl):
+    """gw += A^T gy with the tensor-core kernel when every segment qualifies, else the CUDA-core kernel."""
+    L = _lib.lib()
+    if _lib.PROFILE['on']:
+        _lib.PROFILE['tag'] = 'wgrad %dx%dx%d C%s->%d k%d s%d%s' % (d.N, d.Ho, d.Wo, '+'.join(str(d.seg[i].C) for i in range(d.nseg)),
+                                                                 d.Co, d.KH, d.stride, ' dcn' if d.deform else '')
+    if _backend['tc'] and all(L.dvsr_conv_wgrad_tc_supported(ctypes.byref(d), s) == 1 for s in range(d.nseg)):
+        for s in range(d.nseg):
+            call('dvsr_conv_wgrad_tc', ctypes.byref(d), s, _ptr(gpre), Co, _ptr(gw), ctypes.byref(wl), _stream())
+    else:
+        call('dvsr_conv_wgrad', ctypes.byref(d), _ptr(gpre), Co, _ptr(gw), ctypes.byref(wl), _stream())
+
+
 class _ConvSpec(object):
     __slots__ = ('KH', 'KW', 'stride', 'pad', 'act', 'slope', 'sig_split', 'shuffle', 'metas', 'temporal',
                  'N', 'H', 'W', 'Ho', 'Wo', 'has_res')
@@ -145,6 +158,9 @@ def _run_conv(d, weight, wl, data_grad=False, segs=(0,)):
     the mirrored (mode 1 / 3) weight layout; ``segs`` lists the forward segments whose packed blocks are
     concatenated (one per temporal tap of a Conv3d data gradient)."""
     tc = _use_tc(d)
+    if _lib.PROFILE['on']:
+        _lib.PROFILE['tag'] = '%s %dx%dx%d C%s->%d k%d s%d' % ('dgrad' if data_grad else 'fprop', d.N, d.Ho, d.Wo,
+                                                            '+'.join(str(d.seg[i].C) for i in range(d.nseg)), d.Co, d.KH, d.stride)
     if data_grad:
         mode = 3 if tc else 1
         bufs = [_packed(weight, wl, mode, sgi) for sgi in segs]
@@ -227,7 +243,7 @@ class _ConvFn(Function):
             gw = ctx.wslot if ctx.wslot is not None else torch.zeros_like(weight)
             d = _fwd_desc(spec, tensors)
             d.Co = Co
-            call('dvsr_conv_wgrad', ctypes.byref(d), _ptr(gpre), Co, _ptr(gw), ctypes.byref(wl), _stream())
+            _run_wgrad(d, gpre, Co, gw, wl)
         if ctx.wslot is not None:
             gw = None
         if ctx.bslot is not None:

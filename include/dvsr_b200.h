@@ -112,6 +112,11 @@ int dvsr_conv_tc_supported(const dvsr_conv_desc* d);
 long long dvsr_conv_tc_packed_floats(const dvsr_wlayout* wl, int mode, int seg);
 int dvsr_pack_weights_tc(const float* w, float* wp, const dvsr_wlayout* wl, int mode, int seg, void* stream);
 int dvsr_conv_tc_fprop(const dvsr_conv_desc* d, const float* wp, void* stream);
+/* Tensor-core weight gradient of segment `seg` of a stride-1 convolution (conv_wgrad_tc.cu): both operands are
+ * consumed MN-major straight from the NHWC tensors, x through one halo tile per pixel chunk. */
+int dvsr_conv_wgrad_tc_supported(const dvsr_conv_desc* d, int seg);
+int dvsr_conv_wgrad_tc(const dvsr_conv_desc* d, int seg, const float* gy, int gy_pix_stride, float* gw,
+                       const dvsr_wlayout* wl, void* stream);
 /* Small-Cout direct convolution (conv_last, 64 -> 3): one thread per output pixel. */
 int dvsr_conv_small_co(const dvsr_conv_desc* d, const float* wp, void* stream);
 

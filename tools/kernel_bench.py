@@ -56,7 +56,7 @@ def main():
         t = timeit(lambda: torch.autograd.grad(y, [x, om, w, b], gy, retain_graph=True), reps=5, warm=1)
         print(json.dumps(dict(k='mdcn_bwd_all', N=N, H=H, W=W, us=t * 1e6)), flush=True)
     # conv backward (dgrad + wgrad + act) at the inner-loop resolution
-    for (N, H, W) in [(5, 44, 80), (1, 176, 320)]:
+    for (N, H, W) in [(5, 44, 80), (1, 176, 320), (5, 176, 320)]:
         x = torch.randn(N, H, W, 64, device='cuda', requires_grad=True)
         w = (torch.randn(64, 64, 3, 3, device='cuda') * 0.05).requires_grad_(True)
         b = torch.zeros(64, device='cuda', requires_grad=True)

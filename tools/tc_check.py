@@ -62,6 +62,21 @@ def main():
     w128 = torch.randn(64, 128, 3, 3, device=dev) * 0.03
     gy = torch.randn(5, 16, 32, 64, device=dev)
     run('bwd (gx, gref, gw)', fb)
+    # backward without an activation (no sign flips): data gradients (TC dgrad) and weight gradients (TC wgrad)
+    for (N, H, W, Ci, Co, k, pad) in [(5, 16, 32, 64, 64, 3, 1), (2, 20, 24, 128, 64, 3, 1), (1, 16, 16, 64, 216, 3, 1),
+                                      (1, 16, 24, 320, 64, 1, 0), (2, 18, 34, 64, 64, 3, 0), (1, 44, 80, 64, 256, 3, 1)]:
+        xx0 = torch.randn(N, H, W, Ci, device=dev)
+        ww0 = torch.randn(Co, Ci, k, k, device=dev) * 0.05
+        Ho, Wo = H + 2 * pad - k + 1, W + 2 * pad - k + 1
+        gy0 = torch.randn(N, Ho, Wo, Co, device=dev)
+
+        def fb2():
+            xx = xx0.clone().requires_grad_(True)
+            ww = ww0.clone().requires_grad_(True)
+            bb = torch.zeros(Co, device=dev, requires_grad=True)
+            y = ops.conv(xx, ww, bb, pad=pad)
+            return torch.autograd.grad(y, [xx, ww, bb], gy0)
+        run('bwd-noact N%d %dx%d %d->%d k%d (gx, gw, gb)' % (N, H, W, Ci, Co, k), fb2)
     # valid conv (pad 0) as in MFDN
     xp = torch.randn(2, 18, 34, 64, device=dev)
     w = torch.randn(64, 64, 3, 3, device=dev) * 0.05
