@@ -33,7 +33,9 @@ class ConvDesc(ctypes.Structure):
                 ('bias', ctypes.c_void_p), ('act', ctypes.c_int), ('slope', ctypes.c_float),
                 ('sig_split', ctypes.c_int), ('res', ctypes.c_void_p), ('res_pix_stride', ctypes.c_int),
                 ('shuffle', ctypes.c_int), ('accumulate', ctypes.c_int),
-                ('y', ctypes.c_void_p), ('y_pix_stride', ctypes.c_int)]
+                ('y', ctypes.c_void_p), ('y_pix_stride', ctypes.c_int),
+                ('out_step', ctypes.c_int), ('out_off_y', ctypes.c_int), ('out_off_x', ctypes.c_int),
+                ('out_H', ctypes.c_int), ('out_W', ctypes.c_int)]
 
 
 class WLayout(ctypes.Structure):
@@ -59,6 +61,7 @@ SIGNATURES = {
     'dvsr_conv_tc_packed_floats': [_WP, _I, _I],
     'dvsr_pack_weights_tc': [_P, _P, _WP, _I, _I, _P],
     'dvsr_conv_tc_fprop': [_DP, _P, _P],
+    'dvsr_pack_weights_tc_parity': [_P, _P, _WP, _I, _I, _I, _I, _I, _P],
     'dvsr_conv_wgrad_tc_supported': [_DP, _I],
     'dvsr_conv_wgrad_tc': [_DP, _I, _P, _I, _P, _WP, _P],
     'dvsr_mdcn_bwd_data': [_DP, _P, _I, _P, _P, _I, _P, _I, _P, _I, _P],

@@ -525,6 +525,7 @@ static int validate_desc(const dvsr_conv_desc* d) {
         DVSR_REQUIRE(d->offset && d->mask, "conv: deformable sampling needs offset and mask");
     }
     if (d->shuffle) DVSR_REQUIRE(d->shuffle == 2 && d->Co % 4 == 0, "conv: only PixelShuffle(2) with Co %% 4 == 0");
+    DVSR_REQUIRE(d->out_step == 0, "conv: strided output placement is only implemented by the tensor-core path");
     return 0;
 }
 

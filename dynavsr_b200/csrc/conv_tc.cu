@@ -36,7 +36,9 @@ constexpr int TC_THREADS = 192;
 struct TcSeg { int C, T, Tsrc, dt, t_fixed; };
 struct TcParams {
     int N, Ho, Wo;                 // output images / size
-    int KH, KW, tap_sign, tap_base;  // src = o + tap_base + tap_sign * k
+    int KH, KW, tap_sign, tap_base;  // src = o * stride + tap_base + tap_sign * k
+    int stride;
+    int out_step, out_off_y, out_off_x, out_H, out_W;   // output placement (dense when out_step == 1, offsets 0)
     int nseg, wshare;
     TcSeg seg[DVSR_MAX_SEG];
     int Co, Co_pad;
@@ -118,7 +120,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
                         mbar_wait(&empty_bar[stage], phase ^ 1);
                         mbar_expect_tx(&full_bar[stage], TC_A_BYTES + b_bytes);
                         // a temporal tap outside the clip reads image index N (fully out of bounds -> zeros)
-                        tma_load_4d(&maps.x[s], &full_bar[stage], smem_a + stage * TC_A_BYTES, c * TC_KC, ox0 + dx, oy0 + dy,
+                        tma_load_4d(&maps.x[s], &full_bar[stage], smem_a + stage * TC_A_BYTES, c * TC_KC, ox0 * p.stride + dx, oy0 * p.stride + dy,
                                     img < 0 ? 0x3fffffff : img);
                         tma_load_2d(&maps.w, &full_bar[stage], smem_b + stage * b_bytes, 0, wrow * p.Co_pad);
                         if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
@@ -175,8 +177,9 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
         const int q = warp & 3;                    // TMEM lane quarter this warp may access
         const int row = q * 32 + lane;             // pixel index inside the tile: row = ty * 16 + tx
         const int oy = oy0 + row / TC_TW, ox = ox0 + row % TC_TW;
-        const bool valid = (oy < p.Ho) && (ox < p.Wo);
-        const long long pix = ((long long)n_img * p.Ho + oy) * p.Wo + ox;
+        const int py = oy * p.out_step + p.out_off_y, px = ox * p.out_step + p.out_off_x;   // placement in the output image
+        const bool valid = (oy < p.Ho) && (ox < p.Wo) && (py >= 0) && (py < p.out_H) && (px >= 0) && (px < p.out_W);
+        const long long pix = ((long long)n_img * p.out_H + py) * p.out_W + px;
         for (int c0 = 0; c0 < p.Co_pad; c0 += 32) {
             float v[32];
             tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);   // warp-collective: no divergence before it
@@ -230,8 +233,10 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
 // ------------------------------------------------------------------------------------------------ weights
 // wp rows of 32 floats: row = ((s, tap, chunk), co_pad index); mode 2: K = input channels of segment s;
 // mode 3 (data gradient of segment `seg`): K = forward output channels, rows = input channels of `seg`.
+struct TapRemap { int on, KWf, KWs, a, b; };   // packed tap (t, u) -> original tap (a + 2t) * KWf + (b + 2u)
+
 __global__ void pack_weights_tc_kernel(const float* __restrict__ w, float* __restrict__ wp, const dvsr_wlayout wl,
-                                       int mode, int seg, int rows_pad, long long total) {
+                                       int mode, int seg, int rows_pad, long long total, TapRemap rm) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     const int k = (int)(i & 31);
@@ -252,7 +257,9 @@ __global__ void pack_weights_tc_kernel(const float* __restrict__ w, float* __res
             v = w[(long long)nrow * wl.co_stride + wl.seg_base[s] + (long long)(chunk * 32 + k) * wl.ci_stride + tap];
     } else {
         const int chunks = (wl.Co + 31) / 32;
-        const int tap = (int)(r / chunks), chunk = (int)(r - (long long)tap * chunks);
+        int tap = (int)(r / chunks);
+        const int chunk = (int)(r - (long long)tap * chunks);
+        if (rm.on) tap = (rm.a + 2 * (tap / rm.KWs)) * rm.KWf + (rm.b + 2 * (tap % rm.KWs));
         if (nrow < wl.seg_C[seg] && chunk * 32 + k < wl.Co)
             v = w[(long long)(chunk * 32 + k) * wl.co_stride + wl.seg_base[seg] + (long long)nrow * wl.ci_stride + tap];
     }
@@ -278,7 +285,9 @@ static int round16(int v) { return (v + 15) / 16 * 16; }
 using namespace dvsr;
 
 extern "C" int dvsr_conv_tc_supported(const dvsr_conv_desc* d) {
-    if (!d || d->deform || d->stride != 1 || d->dil != 1 || d->accumulate) return 0;
+    if (!d || d->deform || d->dil != 1 || d->accumulate) return 0;
+    if (d->stride != 1 && (d->stride != 2 || d->transposed)) return 0;   // strided forward convs via TMA element strides
+    if (d->out_step && (d->shuffle || d->res)) return 0;
     if (d->Co > 256 || d->Co < 16 || (d->Co & 3)) return 0;
     if (d->shuffle && (d->Co % 32)) return 0;
     for (int s = 0; s < d->nseg; ++s) {
@@ -306,8 +315,22 @@ extern "C" int dvsr_pack_weights_tc(const float* w, float* wp, const dvsr_wlayou
     if (mode == 3) DVSR_REQUIRE(seg >= 0 && seg < wl->nseg, "pack_weights_tc: bad segment");
     const long long total = dvsr_conv_tc_packed_floats(wl, mode, seg);
     const int rows_pad = mode == 2 ? round16(wl->Co) : round16(wl->seg_C[seg]);
-    pack_weights_tc_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(w, wp, *wl, mode, seg, rows_pad, total);
+    TapRemap rm = {0, 0, 0, 0, 0};
+    pack_weights_tc_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(w, wp, *wl, mode, seg, rows_pad, total, rm);
     return check_launch("pack_weights_tc");
+}
+
+extern "C" int dvsr_pack_weights_tc_parity(const float* w, float* wp, const dvsr_wlayout* wl, int seg, int KHf, int KWf,
+                                           int a, int b, void* stream) {
+    DVSR_REQUIRE(w && wp && wl && seg >= 0 && seg < wl->nseg, "pack_weights_tc_parity: bad arguments");
+    DVSR_REQUIRE(KHf * KWf == wl->taps && a >= 0 && a < 2 && b >= 0 && b < 2, "pack_weights_tc_parity: bad kernel geometry");
+    const int KHs = (KHf - a + 1) / 2, KWs = (KWf - b + 1) / 2;
+    DVSR_REQUIRE(KHs > 0 && KWs > 0, "pack_weights_tc_parity: empty parity class");
+    const int rows_pad = round16(wl->seg_C[seg]);
+    const long long total = (long long)KHs * KWs * ((wl->Co + 31) / 32) * rows_pad * 32;
+    TapRemap rm = {1, KWf, KWs, a, b};
+    pack_weights_tc_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(w, wp, *wl, 3, seg, rows_pad, total, rm);
+    return check_launch("pack_weights_tc_parity");
 }
 
 extern "C" int dvsr_conv_tc_fprop(const dvsr_conv_desc* d, const float* wp, void* stream) {
@@ -319,6 +342,10 @@ extern "C" int dvsr_conv_tc_fprop(const dvsr_conv_desc* d, const float* wp, void
     TcParams p;
     memset(&p, 0, sizeof(p));
     p.N = d->N; p.Ho = d->Ho; p.Wo = d->Wo; p.KH = d->KH; p.KW = d->KW;
+    p.stride = d->stride;
+    p.out_step = d->out_step ? d->out_step : 1;
+    p.out_off_y = d->out_step ? d->out_off_y : 0; p.out_off_x = d->out_step ? d->out_off_x : 0;
+    p.out_H = d->out_step ? d->out_H : d->Ho; p.out_W = d->out_step ? d->out_W : d->Wo;
     p.tap_sign = d->transposed ? -1 : 1;
     p.tap_base = d->transposed ? d->pad : -d->pad;
     p.nseg = d->nseg; p.wshare = d->wshare;
@@ -337,8 +364,8 @@ extern "C" int dvsr_conv_tc_fprop(const dvsr_conv_desc* d, const float* wp, void
         cuuint64_t dims[4] = {(cuuint64_t)g.C, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)nsrc};
         long long img_stride = g.img_stride > 0 ? g.img_stride : (long long)d->H * d->W * g.pix_stride;
         cuuint64_t strides[3] = {(cuuint64_t)g.pix_stride * 4, (cuuint64_t)d->W * g.pix_stride * 4, (cuuint64_t)img_stride * 4};
-        cuuint32_t box[4] = {TC_KC, TC_TW, TC_TH, 1};
-        cuuint32_t estr[4] = {1, 1, 1, 1};
+        cuuint32_t box[4] = {TC_KC, (cuuint32_t)(TC_TW * d->stride), (cuuint32_t)(TC_TH * d->stride), 1};
+        cuuint32_t estr[4] = {1, (cuuint32_t)d->stride, (cuuint32_t)d->stride, 1};
         CUresult r = encode(&maps.x[s], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)g.ptr, dims, strides, box, estr,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

@@ -67,8 +67,36 @@ _SegMeta = namedtuple('_SegMeta', 'T Tsrc dt t_fixed')
 
 
 # --------------------------------------------------------------------------------------------------
-# packed-weight cache
-_wcache = {}
+# packed-weight cache: weight tensor object (weakly referenced, so an entry dies with its tensor and a recycled
+# device address can never alias a stale pack) -> {layout key: (version stamp, packed buffer)}
+import weakref
+
+
+class _WeightCache(object):
+    """id(weight) -> (weakref, {layout key: value}); identity based (tensor == is elementwise)."""
+
+    def __init__(self):
+        self._d = {}
+
+    def get(self, weight, key):
+        ent = self._d.get(id(weight))
+        if ent is None or ent[0]() is not weight:
+            return None
+        return ent[1].get(key)
+
+    def put(self, weight, key, value):
+        ent = self._d.get(id(weight))
+        if ent is None or ent[0]() is not weight:
+            wid = id(weight)
+            ent = (weakref.ref(weight, lambda _r, wid=wid, d=self._d: d.pop(wid, None)), {})
+            self._d[wid] = ent
+        ent[1][key] = value
+
+    def clear(self):
+        self._d.clear()
+
+
+_wcache = _WeightCache()
 _wcache_epoch = [0]
 
 
@@ -102,9 +130,9 @@ def _layout(weight, seg_C, temporal):
 def _packed(weight, wl, mode, seg=0):
     """CUDA-core layouts -- mode 0: forward [K][Co]; mode 1: data gradient of segment `seg` [taps*Co][C_seg].
     tcgen05 layouts (rows of 32 K-values, K-major, padded N) -- mode 2: forward; mode 3: data gradient."""
-    key = (weight.data_ptr(), tuple(weight.shape), mode, seg, tuple(wl.seg_C[i] for i in range(wl.nseg)))
-    ver = (weight._version, _wcache_epoch[0])
-    ent = _wcache.get(key)
+    key = (mode, seg, tuple(wl.seg_C[i] for i in range(wl.nseg)))
+    ver = (weight._version, _wcache_epoch[0], weight.data_ptr())
+    ent = _wcache.get(weight, key)
     capturing = torch.cuda.is_current_stream_capturing()
     if ent is not None and ent[0] == ver and not capturing:
         return ent[1]
@@ -117,8 +145,50 @@ def _packed(weight, wl, mode, seg=0):
     buf = ent[1] if ent is not None else torch.empty(n, device=weight.device, dtype=torch.float32)
     call('dvsr_pack_weights' if mode < 2 else 'dvsr_pack_weights_tc', _ptr(weight), _ptr(buf), ctypes.byref(wl),
          mode, seg, _stream())
-    _wcache[key] = (ver, buf)
+    _wcache.put(weight, key, (ver, buf))
     return buf
+
+
+def _packed_parity(weight, wl, seg, KH, KW, a, b):
+    """tcgen05 data-gradient weights restricted to the taps (a + 2t, b + 2u): one parity class of a stride-2 conv."""
+    key = ('parity', seg, a, b)
+    ver = (weight._version, _wcache_epoch[0], weight.data_ptr())
+    ent = _wcache.get(weight, key)
+    if ent is not None and ent[0] == ver and not torch.cuda.is_current_stream_capturing():
+        return ent[1]
+    KHs, KWs = (KH - a + 1) // 2, (KW - b + 1) // 2
+    n = KHs * KWs * ((wl.Co + 31) // 32) * ((wl.seg_C[seg] + 15) // 16 * 16) * 32
+    buf = ent[1] if ent is not None else torch.empty(n, device=weight.device, dtype=torch.float32)
+    call('dvsr_pack_weights_tc_parity', _ptr(weight), _ptr(buf), ctypes.byref(wl), seg, KH, KW, a, b, _stream())
+    _wcache.put(weight, key, (ver, buf))
+    return buf
+
+
+def _dgrad_stride2_tc(gpre, weight, wl, seg, shape, spec):
+    """Data gradient of a stride-2 convolution as (up to) four stride-1 tensor-core convolutions over gy, one per
+    parity class of the input pixel: gx[2i + a - pad] = sum_t gy[i - t] * W[a + 2t] (same along x)."""
+    N, H, W, C = shape
+    # a 1-wide kernel has an empty odd parity class: those input pixels receive no gradient
+    gx = (torch.zeros if (spec.KH < 2 or spec.KW < 2) else torch.empty)(shape, device=gpre.device, dtype=torch.float32)
+    for a in (0, 1):
+        for b in (0, 1):
+            KHs, KWs = (spec.KH - a + 1) // 2, (spec.KW - b + 1) // 2
+            off_y, off_x = a - spec.pad, b - spec.pad
+            Hi, Wi = (H - 1 - off_y) // 2 + 1, (W - 1 - off_x) // 2 + 1
+            if KHs == 0 or KWs == 0:
+                continue
+            d = ConvDesc()
+            d.N, d.H, d.W, d.Ho, d.Wo = N, spec.Ho, spec.Wo, Hi, Wi
+            d.KH, d.KW, d.stride, d.pad, d.dil, d.transposed = KHs, KWs, 1, 0, 1, 1
+            d.nseg = 1
+            _fill_seg(d.seg[0], gpre)
+            d.Co = C
+            d.y, d.y_pix_stride = gx.data_ptr(), C
+            d.out_step, d.out_off_y, d.out_off_x, d.out_H, d.out_W = 2, off_y, off_x, H, W
+            if _lib.PROFILE['on']:
+                _lib.PROFILE['tag'] = 'dgrad-s2[%d%d] %dx%dx%d C%d->%d k%d' % (a, b, N, Hi, Wi, gpre.shape[3], C, spec.KH)
+            call('dvsr_conv_tc_fprop', ctypes.byref(d), _ptr(_packed_parity(weight, wl, seg, spec.KH, spec.KW, a, b)), _stream())
+    return gx
 
 
 # --------------------------------------------------------------------------------------------------
@@ -269,6 +339,10 @@ class _ConvFn(Function):
         else:
             for i, (t, m) in enumerate(zip(tensors, spec.metas)):
                 if not ctx.needs_input_grad[4 + i]:
+                    continue
+                if spec.stride == 2 and _backend['tc'] and m.T == 1 and m.Tsrc == 1 and Co % 4 == 0 and Co >= 16 \
+                        and 16 <= t.shape[3] <= 256 and t.shape[3] % 4 == 0:
+                    gts[i] = _dgrad_stride2_tc(gpre, weight, wl, i, tuple(t.shape), spec)
                     continue
                 gx = torch.empty(t.shape, device=gy.device, dtype=torch.float32)
                 d = ConvDesc()

@@ -79,6 +79,10 @@ typedef struct dvsr_conv_desc {
     int shuffle;
     int accumulate;      /* y += v instead of y = v                                    */
     float* y; int y_pix_stride;
+    /* output placement (tensor-core path only; 0 = dense): produced pixel (oy, ox) is stored at
+     * (oy*out_step + out_off_y, ox*out_step + out_off_x) of an out_H x out_W image and skipped when that falls
+     * outside -- one parity class of the data gradient of a stride-2 convolution. */
+    int out_step, out_off_y, out_off_x, out_H, out_W;
 } dvsr_conv_desc;
 
 /* Where element (co, seg s, ci, tap) of a PyTorch-layout weight lives:
@@ -111,6 +115,10 @@ int dvsr_conv_wgrad(const dvsr_conv_desc* d, const float* gy, int gy_pix_stride,
 int dvsr_conv_tc_supported(const dvsr_conv_desc* d);
 long long dvsr_conv_tc_packed_floats(const dvsr_wlayout* wl, int mode, int seg);
 int dvsr_pack_weights_tc(const float* w, float* wp, const dvsr_wlayout* wl, int mode, int seg, void* stream);
+/* mode-3 packing restricted to the taps (a + 2t, b + 2u) of a KHf x KWf kernel (parity class (a, b) of a stride-2
+ * data gradient); the packed tap index is t * KWs + u with KHs = ceil((KHf-a)/2), KWs = ceil((KWf-b)/2). */
+int dvsr_pack_weights_tc_parity(const float* w, float* wp, const dvsr_wlayout* wl, int seg, int KHf, int KWf, int a,
+                                int b, void* stream);
 int dvsr_conv_tc_fprop(const dvsr_conv_desc* d, const float* wp, void* stream);
 /* Tensor-core weight gradient of segment `seg` of a stride-1 convolution (conv_wgrad_tc.cu): both operands are
  * consumed MN-major straight from the NHWC tensors, x through one halo tile per pixel chunk. */

@@ -361,3 +361,115 @@ def test_layout_roundtrip_and_cpu_rejection(ops):
     assert torch.equal(ops.to_nchw(y), x)
     with pytest.raises(NotImplementedError):
         ops.conv(torch.randn(1, 4, 4, 8), torch.randn(8, 8, 3, 3))
+
+
+# ---------------------------------------------------------------------------------------------------
+# tensor-core (tcgen05 / TMEM / TMA, TF32 operands rounded to nearest, fp32 accumulation) convolution family.
+# Per-layer tolerance 1e-3 relative L2 against the float64 CPU reference (measured ~3e-4 forward / data
+# gradient, ~8e-4 weight gradient).
+TC_TOL = 1e-3
+TC_CASES = [
+    # name, N, H, W, segC, Co, k, stride, pad, act, res, shuffle
+    ('tc_3x3_64', 2, 20, 40, [64], 64, 3, 1, 1, 0, False, 0),
+    ('tc_3x3_res', 1, 9, 13, [64], 64, 3, 1, 1, 0, True, 0),
+    ('tc_cat2', 5, 11, 20, [64, 64], 64, 3, 1, 1, 0, False, 0),
+    ('tc_offmask216', 1, 12, 20, [64], 216, 3, 1, 1, 3, False, 0),
+    ('tc_1x1_320', 1, 16, 24, [320], 64, 1, 1, 0, 0, False, 0),
+    ('tc_shuffle', 1, 8, 16, [64], 256, 3, 1, 1, 0, False, 2),
+    ('tc_valid_pad0', 2, 18, 34, [64], 64, 3, 1, 0, 0, False, 0),
+    ('tc_4x4s2', 1, 18, 34, [64], 128, 4, 2, 0, 0, False, 0),
+    ('tc_4x4s2_128', 2, 10, 18, [128], 64, 4, 2, 0, 0, False, 0),
+    ('tc_3x3s2', 2, 16, 24, [64], 64, 3, 2, 1, 0, False, 0),
+]
+
+
+@pytest.mark.parametrize('case', TC_CASES, ids=[c[0] for c in TC_CASES])
+def test_conv_tensor_core_forward_backward(ops, case):
+    name, N, H, W, segC, Co, k, stride, pad, act, use_res, shuffle = case
+    xs = [_rand(N, c, H, W, seed=i + 1) for i, c in enumerate(segC)]
+    w = _rand(Co, sum(segC), k, k, seed=10, scale=(2.0 / (sum(segC) * k * k)) ** 0.5)
+    b = _rand(Co, seed=11, scale=0.1)
+    sig_split = 144 if act == 3 else 0
+    xr = [t.clone().requires_grad_(True) for t in xs]
+    wr, br = w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    y = _act_ref(F.conv2d(torch.cat(xr, 1), wr, br, stride=stride, padding=pad), act, sig_split)
+    if shuffle:
+        y = F.pixel_shuffle(y, 2)
+    res = _rand(*y.shape, seed=12) if use_res else None
+    if use_res:
+        y = y + res
+    gy = _rand(*y.shape, seed=13)
+    grads = torch.autograd.grad(y, xr + [wr, br], gy)
+    ops.set_conv_backend(True)
+    try:
+        xd = [nhwc(_dev(t)).requires_grad_(True) for t in xs]
+        wd, bd = _dev(w).requires_grad_(True), _dev(b).requires_grad_(True)
+        resd = nhwc(_dev(res)) if use_res else None
+        n0 = ops._lib.COUNTER[0]
+        yd = ops.conv(xd, wd, bd, stride=stride, pad=pad, act=act, sig_split=sig_split, res=resd, shuffle=shuffle)
+        assert rel(nchw(yd), y) < TC_TOL, 'forward'
+        gd = torch.autograd.grad(yd, xd + [wd, bd], nhwc(_dev(gy)))
+    finally:
+        ops.set_conv_backend(False)
+    for i in range(len(xs)):
+        assert rel(nchw(gd[i]), grads[i]) < TC_TOL, 'grad input %d' % i
+    assert rel(gd[len(xs)], grads[len(xs)]) < 2 * TC_TOL, 'grad weight'
+    assert rel(gd[len(xs) + 1], grads[len(xs) + 1]) < 1e-4, 'grad bias'
+
+
+def test_conv_tensor_core_broadcast_segment(ops):
+    B, N, H, W, C = 2, 5, 12, 16, 64
+    nbr, ref = _rand(B * N, C, H, W, seed=1), _rand(B, C, H, W, seed=2)
+    w, b = _rand(C, 2 * C, 3, 3, seed=3, scale=0.03), _rand(C, seed=4, scale=0.1)
+    nr, rr, wr, br = (t.clone().requires_grad_(True) for t in (nbr, ref, w, b))
+    y = F.conv2d(torch.cat([nr, rr.repeat_interleave(N, 0)], 1), wr, br, padding=1)
+    gy = _rand(*y.shape, seed=5)
+    gr = torch.autograd.grad(y, [nr, rr, wr, br], gy)
+    ops.set_conv_backend(True)
+    try:
+        nd = nhwc(_dev(nbr)).requires_grad_(True)
+        full = torch.zeros(B, N, H, W, C, device='cuda')
+        full[:, 2] = nhwc(_dev(ref))
+        full.requires_grad_(True)
+        wd, bd = _dev(w).requires_grad_(True), _dev(b).requires_grad_(True)
+        yd = ops.conv([nd, ops.Seg(full[:, 2], T=N, Tsrc=1, t_fixed=0)], wd, bd)
+        assert rel(nchw(yd), y) < TC_TOL
+        gd = torch.autograd.grad(yd, [nd, full, wd, bd], nhwc(_dev(gy)))
+    finally:
+        ops.set_conv_backend(False)
+    assert rel(nchw(gd[0]), gr[0]) < TC_TOL
+    assert rel(nchw(gd[1][:, 2]), gr[1]) < TC_TOL
+    assert rel(gd[2], gr[2]) < 2 * TC_TOL and rel(gd[3], gr[3]) < 1e-4
+
+
+def test_conv3d_tensor_core(ops):
+    B, T, H, W, Cin, Co = 1, 5, 10, 14, 64, 64
+    x = _rand(B, Cin, T, H, W, seed=1)
+    w, b = _rand(Co, Cin, 3, 3, 3, seed=2, scale=0.03), _rand(Co, seed=3, scale=0.1)
+    xr, wr, br = (t.clone().requires_grad_(True) for t in (x, w, b))
+    y = F.conv3d(F.pad(xr, (1,) * 6, mode='replicate'), wr, br)
+    gy = _rand(*y.shape, seed=4)
+    gr = torch.autograd.grad(y, [xr, wr, br], gy)
+    ops.set_conv_backend(True)
+    try:
+        frames = _dev(x).permute(0, 2, 3, 4, 1).reshape(B * T, H, W, Cin).contiguous().requires_grad_(True)
+        wd, bd = _dev(w).requires_grad_(True), _dev(b).requires_grad_(True)
+        yd = ops.conv3d_padded(ops.pad3d_replicate(frames, T), wd, bd, T)
+        assert rel(yd, y.permute(0, 2, 3, 4, 1).reshape(B * T, H, W, Co)) < TC_TOL
+        gd = torch.autograd.grad(yd, [frames, wd, bd], _dev(gy.permute(0, 2, 3, 4, 1).reshape(B * T, H, W, Co)).contiguous())
+    finally:
+        ops.set_conv_backend(False)
+    assert rel(gd[0], gr[0].permute(0, 2, 3, 4, 1).reshape(B * T, H, W, Cin)) < TC_TOL
+    assert rel(gd[1], gr[1]) < 2 * TC_TOL and rel(gd[2], gr[2]) < 1e-4
+
+
+def test_packed_weight_cache_never_aliases_freed_weights(ops):
+    """Regression: packs are keyed by the weight OBJECT, not its device address (addresses get recycled)."""
+    x = torch.randn(1, 8, 8, 64, device='cuda')
+    outs = []
+    for seed in range(4):
+        w = _dev(_rand(64, 64, 3, 3, seed=seed, scale=0.05))    # freed after each iteration -> address reuse
+        outs.append(ops.conv(x, w).clone())
+        ref = F.conv2d(x.permute(0, 3, 1, 2).double().cpu(), w.double().cpu(), padding=1)
+        assert rel(nchw(outs[-1]), ref) < TOL
+        del w

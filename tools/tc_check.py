@@ -77,6 +77,19 @@ def main():
             y = ops.conv(xx, ww, bb, pad=pad)
             return torch.autograd.grad(y, [xx, ww, bb], gy0)
         run('bwd-noact N%d %dx%d %d->%d k%d (gx, gw, gb)' % (N, H, W, Ci, Co, k), fb2)
+    # stride-2 convolutions: forward through TMA element strides, data gradient through 4 parity classes
+    for (N, H, W, Ci, Co, k, pad) in [(2, 16, 24, 64, 64, 3, 1), (1, 18, 34, 64, 128, 4, 0), (2, 10, 18, 128, 64, 4, 0), (5, 44, 80, 64, 64, 3, 1)]:
+        xx0 = torch.randn(N, H, W, Ci, device=dev)
+        ww0 = torch.randn(Co, Ci, k, k, device=dev) * 0.05
+        Ho, Wo = (H + 2 * pad - k) // 2 + 1, (W + 2 * pad - k) // 2 + 1
+        gy0 = torch.randn(N, Ho, Wo, Co, device=dev)
+
+        def fb3():
+            xx = xx0.clone().requires_grad_(True)
+            ww = ww0.clone().requires_grad_(True)
+            y = ops.conv(xx, ww, None, stride=2, pad=pad)
+            return (y,) + tuple(torch.autograd.grad(y, [xx, ww], gy0))
+        run('stride2 N%d %dx%d %d->%d k%d (y, gx, gw)' % (N, H, W, Ci, Co, k), fb3)
     # valid conv (pad 0) as in MFDN
     xp = torch.randn(2, 18, 34, 64, device=dev)
     w = torch.randn(64, 64, 3, 3, device=dev) * 0.05
