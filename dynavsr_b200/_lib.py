@@ -62,6 +62,11 @@ SIGNATURES = {
     'dvsr_pack_weights_tc': [_P, _P, _WP, _I, _I, _P],
     'dvsr_conv_tc_fprop': [_DP, _P, _P],
     'dvsr_pack_weights_tc_parity': [_P, _P, _WP, _I, _I, _I, _I, _I, _P],
+    'dvsr_conv_tc2_supported': [_DP],
+    'dvsr_conv_tc2_packed_floats': [_WP, _I, _I, _I],
+    'dvsr_pack_weights_tc2': [_P, _P, _WP, _I, _I, _I, _P],
+    'dvsr_conv_tc2_fprop': [_DP, _P, _P, _I, _P],
+    'dvsr_conv_tc2_set_trace': [_P],
     'dvsr_conv_wgrad_tc_supported': [_DP, _I],
     'dvsr_conv_wgrad_tc': [_DP, _I, _P, _I, _P, _WP, _P],
     'dvsr_mdcn_bwd_data': [_DP, _P, _I, _P, _P, _I, _P, _I, _P, _I, _P],
@@ -94,7 +99,7 @@ SIGNATURES = {
     'dvsr_version': [],
 }
 _RESTYPE = {'dvsr_last_error': ctypes.c_char_p, 'dvsr_mdcn_workspace_bytes': ctypes.c_longlong,
-            'dvsr_conv_tc_packed_floats': ctypes.c_longlong}
+            'dvsr_conv_tc_packed_floats': ctypes.c_longlong, 'dvsr_conv_tc2_packed_floats': ctypes.c_longlong}
 
 _lib = None
 

@@ -183,25 +183,9 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
         for (int c0 = 0; c0 < p.Co_pad; c0 += 32) {
             float v[32];
             tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);   // warp-collective: no divergence before it
-            if (!valid) continue;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const int co = c0 + j;
-                float t = v[j] + ((p.bias && co < p.Co) ? __ldg(p.bias + co) : 0.f);
-                if (p.act == DVSR_ACT_SIGMOID_SPLIT) t = (co >= p.sig_split) ? sigmoidf_(t) : t;
-                else t = act_apply(t, p.act, p.slope);
-                v[j] = t;
-            }
-            if (p.res) {
-                const float* r = p.res + pix * p.res_pix_stride + c0;
-#pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    if (c0 + j < p.Co) {
-                        const float4 t = ldg4(r + j);
-                        v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
-                    }
-                }
-            }
+            if (!valid || c0 >= p.Co) continue;
+            epilogue_chunk(v, c0, p.Co, p.bias ? p.bias + c0 : nullptr, nullptr,
+                           p.res ? p.res + pix * p.res_pix_stride + c0 : nullptr, p.act, p.slope, p.sig_split);
             if (p.shuffle == 2) {
                 // out[n][2*oy + i][2*ox + jj][c] = v[4c + 2i + jj]: 8 output channels per 32-column chunk
                 const int cq = c0 >> 2;
@@ -209,10 +193,8 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
                 for (int sub = 0; sub < 4; ++sub) {
                     const long long op = ((long long)n_img * (2 * p.Ho) + 2 * oy + (sub >> 1)) * (2 * p.Wo) + 2 * ox + (sub & 1);
                     float* yo = p.y + op * p.y_pix_stride + cq;
-                    if (c0 < p.Co) {
-                        *reinterpret_cast<float4*>(yo) = make_float4(v[sub], v[4 + sub], v[8 + sub], v[12 + sub]);
-                        *reinterpret_cast<float4*>(yo + 4) = make_float4(v[16 + sub], v[20 + sub], v[24 + sub], v[28 + sub]);
-                    }
+                    *reinterpret_cast<float4*>(yo) = make_float4(v[sub], v[4 + sub], v[8 + sub], v[12 + sub]);
+                    *reinterpret_cast<float4*>(yo + 4) = make_float4(v[16 + sub], v[20 + sub], v[24 + sub], v[28 + sub]);
                 }
             } else {
                 float* yo = p.y + pix * p.y_pix_stride + c0;
@@ -297,6 +279,7 @@ extern "C" int dvsr_conv_tc_supported(const dvsr_conv_desc* d) {
     }
     if (((uintptr_t)d->y & 15) || (d->y_pix_stride & 3)) return 0;
     if (d->res && ((((uintptr_t)d->res) & 15) || (d->res_pix_stride & 3))) return 0;
+    if (d->bias && (((uintptr_t)d->bias) & 15)) return 0;
     return 1;
 }
 

@@ -1,0 +1,445 @@
+// dynavsr_b200/csrc/conv_tc2.cu
+//
+// Persistent tcgen05 implicit-GEMM convolution with SHARED-MEMORY-RESIDENT weights and halo reuse -- the
+// workhorse for EDVR's 64-channel 3x3 layers (feature extraction, PCD offset/feature convs, TSA, the
+// reconstruction trunk, HRconv) and the 1x1 fusion convs.
+//
+// conv_tc.cu (v1) re-fetches, for every 128-pixel tile, nine tap-shifted copies of the activations plus the
+// whole weight tensor from L2: 432 KB per tile, which pins it at the L2 bandwidth (~5 TB/s, ~110 TFLOP/s).
+// Here
+//   * each CTA (one per SM, persistent over tiles) loads the weights of its 64 output channels ONCE
+//     (<= 147 KB: 9 taps x 64 ci x 64 co fp32, pre-rounded to TF32) and keeps them in shared memory;
+//   * per tile and 32-channel chunk ONE halo tile ((16+KH-1) x (8+KW-1) pixels) is TMA-loaded and rounded to
+//     TF32 in place; the KH*KW tap operands are descriptors that start at different 128-byte rows of that
+//     tile (stride-byte-offset = halo row pitch; validated by tools/umma_probe.cu P1);
+//   => 46 KB of L2 traffic per tile instead of 432 KB.
+//   * two TMEM accumulators (2 x 64 columns) so the epilogue of tile i overlaps the MMAs of tile i+1.
+// Warp roles: 0 = TMA producer, 1 = MMA issuer / TMEM owner, 2-5 = TF32 rounding of the halo tile,
+// 6-9 = epilogue (bias, ReLU / LeakyReLU / sigmoid-split, residual, PixelShuffle(2), K-split accumulation).
+// Output channels are processed in groups of 64 (blockIdx.y); inputs whose weights do not fit are K-split
+// over several launches by the host wrapper (`accum_in`).
+#include "tc_common.cuh"
+
+namespace dvsr {
+
+constexpr int T2_TH = 16, T2_TW = 8;      // pixel tile (M = 128): 16 rows of 8 pixels
+constexpr int T2_NG = 64;                 // output channels per CTA
+constexpr int T2_ASTAGES = 3;
+constexpr int T2_PF = 6;                  // L2 prefetch distance in chunks
+constexpr int T2_THREADS = 320;
+constexpr int T2_MAX_BLOCKS = 18;         // resident weight blocks of 64 x 32 fp32 (8 KiB) -> 144 KiB
+
+struct T2Seg { int C, T, Tsrc, dt, t_fixed; };
+struct T2Params {
+    int N, Ho, Wo;
+    int KH, KW, tap_sign, tap_base;       // src = o + tap_base + tap_sign * k
+    int nseg, wshare;
+    T2Seg seg[DVSR_MAX_SEG];
+    int Co;                               // real output channels
+    int halo_h, halo_w, a_bytes;          // halo tile geometry / padded bytes per stage
+    int nblocks;                          // resident weight blocks ((seg, chunk), tap) of this launch
+    int tiles_total;
+    const float* bias;
+    int act; float slope; int sig_split;
+    const float* res; int res_pix_stride;
+    const float* accum_in; int accum_pix_stride;   // pre-activation addend (K-split partial sums)
+    int shuffle;
+    float* y; int y_pix_stride;
+    int y_vec8;                           // y rows are 32-byte aligned: 256-bit stores
+    long long* trace;                     // optional per-event clock64 trace of CTA (0,0): [event][chunk]
+};
+struct __align__(64) T2Maps { CUtensorMap x[DVSR_MAX_SEG]; CUtensorMap w; };
+
+__device__ __forceinline__ int t2_seg_image(const T2Seg& sg, int n) {
+    const int T = sg.T > 0 ? sg.T : 1;
+    const int q = n / T, r = n - q * T;
+    const int t = sg.t_fixed >= 0 ? sg.t_fixed : r + sg.dt;
+    if (t < 0 || t >= sg.Tsrc) return -1;
+    return q * sg.Tsrc + t;
+}
+
+#define T2_TRACE(ev, idx) do { if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && (idx) < 64) p.trace[(ev) * 64 + (idx)] = clock64(); } while (0)
+
+__global__ void __launch_bounds__(T2_THREADS, 1)
+conv_tc2_kernel(const __grid_constant__ T2Maps maps, const T2Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem_b = smem;                                        // [nblocks][64 rows x 128 B]
+    uint8_t* smem_a = smem + p.nblocks * 8192;                     // [T2_ASTAGES][a_bytes]
+    uint64_t* bars = (uint64_t*)(smem_a + T2_ASTAGES * p.a_bytes);
+    uint64_t* b_full = bars;                  // [1]
+    uint64_t* a_full = bars + 1;              // [3]
+    uint64_t* a_ready = bars + 4;             // [3]
+    uint64_t* a_empty = bars + 7;             // [3]
+    uint64_t* acc_full = bars + 10;           // [2]
+    uint64_t* acc_empty = bars + 12;          // [2]
+    uint32_t* tmem_slot = (uint32_t*)(bars + 14);
+    float* bias_s = (float*)(bars + 16);      // [64] bias of this CTA's output-channel group (zeros when absent)
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int KK = p.KH * p.KW;
+    const int ngrp = blockIdx.y;
+    const int tiles_w = (p.Wo + T2_TW - 1) / T2_TW, tiles_h = (p.Ho + T2_TH - 1) / T2_TH;
+    int chunks_total = 0;
+    for (int s = 0; s < p.nseg; ++s) chunks_total += (p.seg[s].C + 31) / 32;
+    // window offset of tap (kh, kw) inside the halo tile
+    const int min_d = p.tap_base + (p.tap_sign < 0 ? -(p.KH - 1) : 0);
+    const int min_dx = p.tap_base + (p.tap_sign < 0 ? -(p.KW - 1) : 0);
+
+    if (warp == 0 && elect_one()) {
+        for (int s = 0; s < p.nseg; ++s) prefetch_tmap(&maps.x[s]);
+        prefetch_tmap(&maps.w);
+    }
+    if (warp == 1) {
+        if (elect_one()) {
+            mbar_init(b_full, 1);
+            for (int i = 0; i < T2_ASTAGES; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_ready[i], 128); mbar_init(&a_empty[i], 1); }
+            for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(128) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (threadIdx.x >= 192 && threadIdx.x < 256) {
+        const int co = blockIdx.y * T2_NG + (threadIdx.x - 192);
+        bias_s[threadIdx.x - 192] = (p.bias && co < p.Co) ? __ldg(p.bias + co) : 0.f;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== producer =====================
+        if (elect_one()) {
+            mbar_expect_tx(b_full, (uint32_t)p.nblocks * 8192u);
+            for (int b = 0; b < p.nblocks; ++b)
+                tma_load_2d(&maps.w, b_full, smem_b + b * 8192, 0, (ngrp * p.nblocks + b) * T2_NG);
+            int stage = 0, phase = 0, trace_i = 0;
+            // L2 prefetch cursor running T2_PF chunks ahead of the shared-memory ring (the ring is only 3 deep)
+            int pf_tile = blockIdx.x, pf_s = 0, pf_c = 0;
+            auto prefetch_next = [&]() {
+                if (pf_tile >= p.tiles_total) return;
+                const int n = pf_tile / (tiles_w * tiles_h);
+                const int r = pf_tile - n * tiles_w * tiles_h;
+                const int img = t2_seg_image(p.seg[pf_s], n);
+                if (img >= 0)
+                    tma_prefetch_4d(&maps.x[pf_s], pf_c * 32, (r % tiles_w) * T2_TW + min_dx, (r / tiles_w) * T2_TH + min_d, img);
+                if (++pf_c == (p.seg[pf_s].C + 31) / 32) { pf_c = 0; if (++pf_s == p.nseg) { pf_s = 0; pf_tile += gridDim.x; } }
+            };
+            for (int i = 0; i < T2_PF; ++i) prefetch_next();
+            for (int tile = blockIdx.x; tile < p.tiles_total; tile += gridDim.x) {
+                const int n = tile / (tiles_w * tiles_h);
+                const int r = tile - n * tiles_w * tiles_h;
+                const int oy0 = (r / tiles_w) * T2_TH, ox0 = (r % tiles_w) * T2_TW;
+                for (int s = 0; s < p.nseg; ++s) {
+                    const int img = t2_seg_image(p.seg[s], n);
+                    const int chunks = (p.seg[s].C + 31) / 32;
+                    for (int c = 0; c < chunks; ++c) {
+                        prefetch_next();
+                        mbar_wait(&a_empty[stage], phase ^ 1);
+                        T2_TRACE(0, trace_i); ++trace_i;
+                        mbar_expect_tx(&a_full[stage], (uint32_t)(p.halo_h * p.halo_w * 128));
+                        tma_load_4d(&maps.x[s], &a_full[stage], smem_a + stage * p.a_bytes, c * 32, ox0 + min_dx, oy0 + min_d,
+                                    img < 0 ? 0x3fffffff : img);
+                        if (++stage == T2_ASTAGES) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        const uint32_t idesc = make_idesc_tf32(128, T2_NG);
+        // descriptor templates: only the 14-bit (address >> 4) field changes per tap / k-step
+        const uint64_t ad_const = make_desc(0, 16, (uint32_t)p.halo_w * 128u, 2);
+        const uint64_t bd_const = make_desc(0, 16, 1024, 2);
+        mbar_wait(b_full, 0);
+        int stage = 0, phase = 0, local = 0, trace_i = 0;
+        for (int tile = blockIdx.x; tile < p.tiles_total; tile += gridDim.x, ++local) {
+            const int acc = local & 1;
+            mbar_wait(&acc_empty[acc], ((local >> 1) & 1) ^ 1);      // epilogue drained this accumulator
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            int blk = 0, cidx = 0;
+            for (int s = 0; s < p.nseg; ++s) {
+                if (p.wshare) blk = 0;
+                const int chunks = (p.seg[s].C + 31) / 32;
+                for (int c = 0; c < chunks; ++c, ++cidx) {
+                    mbar_wait(&a_ready[stage], phase);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    if (elect_one()) {
+                        T2_TRACE(3, trace_i);
+                        const uint64_t ad0 = ad_const + (uint64_t)(smem_u32(smem_a + stage * p.a_bytes) >> 4);
+                        uint64_t bd = bd_const + (uint64_t)(smem_u32(smem_b + blk * 8192) >> 4);
+                        const uint32_t dcol = tmem_base + acc * T2_NG;
+                        int wy = p.tap_sign < 0 ? p.KH - 1 : 0, wx0 = p.tap_sign < 0 ? p.KW - 1 : 0, wx = wx0, kw = 0;
+                        for (int tap = 0; tap < KK; ++tap) {
+                            const uint64_t ad = ad0 + (uint64_t)((wy * p.halo_w + wx) * 8);     // 128 B per pixel = 8 x 16 B
+                            mma_tf32(dcol, ad, bd, idesc, (cidx > 0 || tap > 0) ? 1u : 0u);
+                            mma_tf32(dcol, ad + 2, bd + 2, idesc, 1u);
+                            mma_tf32(dcol, ad + 4, bd + 4, idesc, 1u);
+                            mma_tf32(dcol, ad + 6, bd + 6, idesc, 1u);
+                            bd += 512;                                                            // next 8 KiB weight block
+                            wx += p.tap_sign;
+                            if (++kw == p.KW) { kw = 0; wx = wx0; wy += p.tap_sign; }
+                        }
+                        mma_commit(&a_empty[stage]);
+                        if (cidx == chunks_total - 1) mma_commit(&acc_full[acc]);
+                        T2_TRACE(4, trace_i);
+                    }
+                    ++trace_i;
+                    blk += KK;
+                    __syncwarp();
+                    if (++stage == T2_ASTAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp < 6) {
+        // ===================== round the halo tile to nearest TF32, in place =====================
+        const int t = threadIdx.x - 64;
+        const int n16 = p.halo_h * p.halo_w * 8;        // float4 elements of the halo tile
+        int stage = 0, phase = 0, trace_i = 0;
+        for (int tile = blockIdx.x; tile < p.tiles_total; tile += gridDim.x) {
+            for (int c = 0; c < chunks_total; ++c) {
+                mbar_wait(&a_full[stage], phase);
+                if (t == 0) T2_TRACE(1, trace_i);
+                float4* a4 = reinterpret_cast<float4*>(smem_a + stage * p.a_bytes);
+                for (int i = t; i < n16; i += 128) {
+                    float4 v = a4[i];
+                    v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w);
+                    a4[i] = v;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_arrive(&a_ready[stage]);
+                if (t == 0) T2_TRACE(2, trace_i);
+                ++trace_i;
+                if (++stage == T2_ASTAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else {
+        // ===================== epilogue =====================
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        int local = 0;
+        for (int tile = blockIdx.x; tile < p.tiles_total; tile += gridDim.x, ++local) {
+            const int acc = local & 1;
+            const int n = tile / (tiles_w * tiles_h);
+            const int r = tile - n * tiles_w * tiles_h;
+            const int oy = (r / tiles_w) * T2_TH + row / T2_TW, ox = (r % tiles_w) * T2_TW + row % T2_TW;
+            const bool valid = (oy < p.Ho) && (ox < p.Wo);
+            const long long pix = ((long long)n * p.Ho + oy) * p.Wo + ox;
+            mbar_wait(&acc_full[acc], (local >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (threadIdx.x == 192) T2_TRACE(5, local);
+            float v0[32], v1[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * T2_NG), v0);
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * T2_NG + 32), v1);
+            // the accumulator is in registers: hand the TMEM buffer back to the MMA warp before the global stores
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(&acc_empty[acc]);
+            if (valid) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    float (&v)[32] = h == 0 ? v0 : v1;
+                    const int c0 = ngrp * T2_NG + h * 32;          // first global output channel of this chunk
+                    if (c0 >= p.Co) continue;
+                    epilogue_chunk(v, c0, p.Co, bias_s + h * 32, p.accum_in ? p.accum_in + pix * p.accum_pix_stride + c0 : nullptr,
+                                   p.res ? p.res + pix * p.res_pix_stride + c0 : nullptr, p.act, p.slope, p.sig_split);
+                    if (p.shuffle == 2) {
+                        const int cq = c0 >> 2;
+#pragma unroll
+                        for (int sub = 0; sub < 4; ++sub) {
+                            const long long op = ((long long)n * (2 * p.Ho) + 2 * oy + (sub >> 1)) * (2 * p.Wo) + 2 * ox + (sub & 1);
+                            float* yo = p.y + op * p.y_pix_stride + cq;
+                            if (p.y_vec8) {
+                                st_global_v8(yo, v[sub], v[4 + sub], v[8 + sub], v[12 + sub], v[16 + sub], v[20 + sub], v[24 + sub], v[28 + sub]);
+                            } else {
+                                *reinterpret_cast<float4*>(yo) = make_float4(v[sub], v[4 + sub], v[8 + sub], v[12 + sub]);
+                                *reinterpret_cast<float4*>(yo + 4) = make_float4(v[16 + sub], v[20 + sub], v[24 + sub], v[28 + sub]);
+                            }
+                        }
+                    } else {
+                        float* yo = p.y + pix * p.y_pix_stride + c0;
+                        const int nvalid = min(32, p.Co - c0);
+                        if (p.y_vec8) {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 8)
+                                if (j < nvalid) st_global_v8(yo + j, v[j], v[j + 1], v[j + 2], v[j + 3], v[j + 4], v[j + 5], v[j + 6], v[j + 7]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4)
+                                if (j < nvalid) *reinterpret_cast<float4*>(yo + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                        }
+                    }
+                }
+            }
+            if (threadIdx.x == 192) T2_TRACE(6, local);
+        }
+    }
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ weights
+// wp rows of 32 floats.  Row index = ((g * nblocks + blk) * 64 + r), blk = ((seg, chunk), tap) in launch order,
+// g = output-channel group, r = channel inside the group.  mode 5: forward (K = input channels);
+// mode 6: data gradient of segment `seg` (K = forward output channels, rows = input channels of `seg`).
+__global__ void pack_weights_tc2_kernel(const float* __restrict__ w, float* __restrict__ wp, const dvsr_wlayout wl,
+                                        int mode, int seg, int seg_lo, int seg_hi, int nblocks, int ngroups, long long total) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int k = (int)(i & 31);
+    long long r = i >> 5;
+    const int rr = (int)(r % T2_NG);
+    r /= T2_NG;
+    int blk = (int)(r % nblocks);
+    const int g = (int)(r / nblocks);
+    const int n = g * T2_NG + rr;               // output row (co for mode 5, ci for mode 6)
+    float v = 0.f;
+    if (mode == 5) {
+        int s = seg_lo;
+        for (; s < seg_hi; ++s) {
+            const int nb = wl.taps * ((wl.seg_C[s] + 31) / 32);
+            if (blk < nb) break;
+            blk -= nb;
+        }
+        const int chunk = blk / wl.taps, tap = blk - chunk * wl.taps;      // block order: chunk-major, then tap
+        const int ci = chunk * 32 + k;
+        if (n < wl.Co && ci < wl.seg_C[s])
+            v = w[(long long)n * wl.co_stride + wl.seg_base[s] + (long long)ci * wl.ci_stride + tap];
+    } else {
+        const int chunk = blk / wl.taps, tap = blk - chunk * wl.taps;
+        const int co = chunk * 32 + k;
+        if (n < wl.seg_C[seg] && co < wl.Co)
+            v = w[(long long)co * wl.co_stride + wl.seg_base[seg] + (long long)n * wl.ci_stride + tap];
+    }
+    wp[i] = round_tf32(v);
+}
+
+}  // namespace dvsr
+
+using namespace dvsr;
+
+static long long* g_t2_trace = nullptr;
+// debugging aid: device buffer of 7 x 64 clock64 stamps written by CTA (0,0) of the next launches (nullptr = off)
+extern "C" int dvsr_conv_tc2_set_trace(long long* dev_buffer) { g_t2_trace = dev_buffer; return 0; }
+
+static int t2_blocks(const dvsr_conv_desc* d) {
+    int chunks = 0;
+    for (int s = 0; s < (d->wshare ? 1 : d->nseg); ++s) chunks += (d->seg[s].C + 31) / 32;
+    return chunks * d->KH * d->KW;
+}
+
+// 1 if the WHOLE descriptor can run in one launch of the resident-weight kernel
+extern "C" int dvsr_conv_tc2_supported(const dvsr_conv_desc* d) {
+    if (!d || d->deform || d->stride != 1 || d->dil != 1 || d->accumulate || d->out_step) return 0;
+    if (d->Co < 16 || (d->Co & 3)) return 0;
+    if (d->shuffle && (d->Co % 32)) return 0;
+    if (d->KH > 5 || d->KW > 5) return 0;
+    for (int s = 0; s < d->nseg; ++s) {
+        const dvsr_conv_seg& g = d->seg[s];
+        if ((g.C & 3) || g.C < 16 || (g.pix_stride & 3) || (g.img_stride & 3) || ((uintptr_t)g.ptr & 15)) return 0;
+        if (d->wshare && g.C != d->seg[0].C) return 0;
+    }
+    if (((uintptr_t)d->y & 15) || (d->y_pix_stride & 3)) return 0;
+    if (d->res && ((((uintptr_t)d->res) & 15) || (d->res_pix_stride & 3))) return 0;
+    return t2_blocks(d) <= T2_MAX_BLOCKS;
+}
+
+extern "C" long long dvsr_conv_tc2_packed_floats(const dvsr_wlayout* wl, int mode, int seg_lo, int seg_hi) {
+    if (!wl) return 0;
+    if (mode == 5) {
+        long long nb = 0;
+        for (int s = seg_lo; s < seg_hi; ++s) nb += (long long)wl->taps * ((wl->seg_C[s] + 31) / 32);
+        return nb * ((wl->Co + T2_NG - 1) / T2_NG) * T2_NG * 32;
+    }
+    return (long long)wl->taps * ((wl->Co + 31) / 32) * ((wl->seg_C[seg_lo] + T2_NG - 1) / T2_NG) * T2_NG * 32;
+}
+
+// mode 5: forward weights of segments [seg_lo, seg_hi); mode 6: data-gradient weights of segment seg_lo
+extern "C" int dvsr_pack_weights_tc2(const float* w, float* wp, const dvsr_wlayout* wl, int mode, int seg_lo, int seg_hi, void* stream) {
+    DVSR_REQUIRE(w && wp && wl && (mode == 5 || mode == 6), "pack_weights_tc2: bad arguments");
+    DVSR_REQUIRE(seg_lo >= 0 && seg_lo < wl->nseg && (mode == 6 || (seg_hi > seg_lo && seg_hi <= wl->nseg)), "pack_weights_tc2: bad segment range");
+    int nblocks, ngroups;
+    if (mode == 5) {
+        nblocks = 0;
+        for (int s = seg_lo; s < seg_hi; ++s) nblocks += wl->taps * ((wl->seg_C[s] + 31) / 32);
+        ngroups = (wl->Co + T2_NG - 1) / T2_NG;
+    } else {
+        nblocks = wl->taps * ((wl->Co + 31) / 32);
+        ngroups = (wl->seg_C[seg_lo] + T2_NG - 1) / T2_NG;
+    }
+    const long long total = (long long)nblocks * ngroups * T2_NG * 32;
+    pack_weights_tc2_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(w, wp, *wl, mode, seg_lo, seg_lo, seg_hi, nblocks, ngroups, total);
+    return check_launch("pack_weights_tc2");
+}
+
+extern "C" int dvsr_conv_tc2_fprop(const dvsr_conv_desc* d, const float* wp, const float* accum_in, int accum_pix_stride, void* stream) {
+    DVSR_REQUIRE(d && wp && d->y, "conv_tc2_fprop: null pointer");
+    DVSR_REQUIRE(dvsr_conv_tc2_supported(d), "conv_tc2_fprop: unsupported shape");
+    EncodeTiledFn encode = get_encode_tiled();
+    DVSR_REQUIRE(encode != nullptr, "conv_tc2_fprop: cuTensorMapEncodeTiled is unavailable");
+    T2Maps maps;
+    T2Params p;
+    memset(&p, 0, sizeof(p));
+    p.N = d->N; p.Ho = d->Ho; p.Wo = d->Wo; p.KH = d->KH; p.KW = d->KW;
+    p.tap_sign = d->transposed ? -1 : 1;
+    p.tap_base = d->transposed ? d->pad : -d->pad;
+    p.nseg = d->nseg; p.wshare = d->wshare;
+    p.Co = d->Co;
+    p.halo_h = T2_TH + d->KH - 1; p.halo_w = T2_TW + d->KW - 1;
+    p.a_bytes = (p.halo_h * p.halo_w * 128 + 1023) / 1024 * 1024;
+    p.nblocks = t2_blocks(d);
+    p.bias = d->bias; p.act = d->act; p.slope = d->slope; p.sig_split = d->sig_split;
+    p.res = d->res; p.res_pix_stride = d->res_pix_stride; p.shuffle = d->shuffle;
+    p.accum_in = accum_in; p.accum_pix_stride = accum_pix_stride;
+    p.y = d->y; p.y_pix_stride = d->y_pix_stride;
+    p.y_vec8 = ((((uintptr_t)d->y) & 31) == 0) && (d->y_pix_stride % 8 == 0) && (d->Co % 8 == 0);
+    p.trace = g_t2_trace;
+    const int tiles_w = (d->Wo + T2_TW - 1) / T2_TW, tiles_h = (d->Ho + T2_TH - 1) / T2_TH;
+    p.tiles_total = d->N * tiles_w * tiles_h;
+    const int ngroups = (d->Co + T2_NG - 1) / T2_NG;
+    for (int s = 0; s < d->nseg; ++s) {
+        const dvsr_conv_seg& g = d->seg[s];
+        p.seg[s].C = g.C; p.seg[s].T = g.T; p.seg[s].Tsrc = g.Tsrc; p.seg[s].dt = g.dt; p.seg[s].t_fixed = g.t_fixed;
+        const int T = g.T > 0 ? g.T : 1;
+        long long nsrc = ((long long)(d->N + T - 1) / T) * g.Tsrc;
+        if (nsrc < 1) nsrc = 1;
+        cuuint64_t dims[4] = {(cuuint64_t)g.C, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)nsrc};
+        long long img_stride = g.img_stride > 0 ? g.img_stride : (long long)d->H * d->W * g.pix_stride;
+        cuuint64_t strides[3] = {(cuuint64_t)g.pix_stride * 4, (cuuint64_t)d->W * g.pix_stride * 4, (cuuint64_t)img_stride * 4};
+        cuuint32_t box[4] = {32, (cuuint32_t)p.halo_w, (cuuint32_t)p.halo_h, 1};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = encode(&maps.x[s], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)g.ptr, dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        DVSR_REQUIRE(r == CUDA_SUCCESS, "conv_tc2_fprop: cuTensorMapEncodeTiled(activation seg %d) failed with %d", s, (int)r);
+    }
+    {
+        cuuint64_t dims[2] = {32, (cuuint64_t)p.nblocks * ngroups * T2_NG};
+        cuuint64_t strides[1] = {128};
+        cuuint32_t box[2] = {32, T2_NG};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = encode(&maps.w, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)wp, dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        DVSR_REQUIRE(r == CUDA_SUCCESS, "conv_tc2_fprop: cuTensorMapEncodeTiled(weights) failed with %d", (int)r);
+    }
+    const size_t smem = 1024 + (size_t)p.nblocks * 8192 + (size_t)T2_ASTAGES * p.a_bytes + 512;
+    DVSR_REQUIRE(smem <= 232448, "conv_tc2_fprop: %zu B of shared memory needed", smem);
+    static size_t smem_set = 0;
+    if (smem > smem_set) {
+        if (cudaFuncSetAttribute(conv_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return check_launch("conv_tc2_fprop: cudaFuncSetAttribute");
+        smem_set = smem;
+    }
+    int ctas_x = 148 / ngroups;
+    if (ctas_x < 1) ctas_x = 1;
+    if (ctas_x > p.tiles_total) ctas_x = p.tiles_total;
+    dim3 grid(ctas_x, ngroups);
+    conv_tc2_kernel<<<grid, T2_THREADS, smem, (cudaStream_t)stream>>>(maps, p);
+    return check_launch("conv_tc2_fprop");
+}

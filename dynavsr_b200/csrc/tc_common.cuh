@@ -112,6 +112,51 @@ __device__ __forceinline__ uint32_t make_idesc_tf32_major(int M, int N, int a_mn
            ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* map, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global [%0, {%1, %2, %3, %4}];" ::"l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+// 256-bit global store (STG.E.256, sm_100+): p must be 32-byte aligned
+__device__ __forceinline__ void st_global_v8(float* p, float a, float b, float c, float d, float e, float f, float g, float h) {
+    asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d), "f"(e), "f"(f), "f"(g), "f"(h) : "memory");
+}
+
+// Epilogue math for one 32-column accumulator chunk held in registers (channels c0 .. c0+31 of one pixel):
+//   v = act(v + addend + bias) + res.  `bias32` points at 32 consecutive bias values (shared or global memory,
+//   16-byte aligned) or is null; addend / res point at this pixel's channel c0 (16-byte aligned) or are null.
+//   Channels >= Co are left untouched (they are never stored).
+__device__ __forceinline__ void epilogue_chunk(float (&v)[32], int c0, int Co, const float* bias32, const float* addend,
+                                               const float* res, int act, float slope, int sig_split) {
+    const int nvalid = min(32, Co - c0);          // multiple of 4
+    if (addend) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+            if (j < nvalid) { const float4 t = ldg4(addend + j); v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w; }
+    }
+    if (bias32) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+            if (j < nvalid) {
+                const float4 t = *reinterpret_cast<const float4*>(bias32 + j);
+                v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w;
+            }
+    }
+    if (act == DVSR_ACT_LRELU) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * slope;
+    } else if (act == DVSR_ACT_RELU) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+    } else if (act == DVSR_ACT_SIGMOID_SPLIT) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = (c0 + j >= sig_split) ? sigmoidf_(v[j]) : v[j];
+    }
+    if (res) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+            if (j < nvalid) { const float4 t = ldg4(res + j); v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w; }
+    }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);

@@ -219,6 +219,61 @@ class _ConvSpec(object):
                  'N', 'H', 'W', 'Ho', 'Wo', 'has_res')
 
 
+def _packed_tc2(weight, wl, mode, seg_lo, seg_hi):
+    """Resident-weight layout of conv_tc2.cu (mode 5 forward over segments [seg_lo, seg_hi), mode 6 data gradient)."""
+    key = ('tc2', mode, seg_lo, seg_hi, tuple(wl.seg_C[i] for i in range(wl.nseg)))
+    ver = (weight._version, _wcache_epoch[0], weight.data_ptr())
+    ent = _wcache.get(weight, key)
+    if ent is not None and ent[0] == ver and not torch.cuda.is_current_stream_capturing():
+        return ent[1]
+    n = _lib.lib().dvsr_conv_tc2_packed_floats(ctypes.byref(wl), mode, seg_lo, seg_hi)
+    buf = ent[1] if ent is not None else torch.empty(n, device=weight.device, dtype=torch.float32)
+    call('dvsr_pack_weights_tc2', _ptr(weight), _ptr(buf), ctypes.byref(wl), mode, seg_lo, seg_hi, _stream())
+    _wcache.put(weight, key, (ver, buf))
+    return buf
+
+
+def _copy_desc(d):
+    c = ConvDesc()
+    ctypes.memmove(ctypes.byref(c), ctypes.byref(d), ctypes.sizeof(ConvDesc))
+    return c
+
+
+def _try_tc2(d, weight, wl, data_grad, segs):
+    """Run ``d`` on the persistent resident-weight kernel, K-splitting over segments when the whole weight set does
+    not fit in shared memory.  Returns False if the shape is not eligible."""
+    L = _lib.lib()
+    if L.dvsr_conv_tc2_supported(ctypes.byref(d)) == 1:
+        if data_grad:
+            if len(segs) != 1:
+                return False
+            wp = _packed_tc2(weight, wl, 6, segs[0], segs[0] + 1)
+        else:
+            wp = _packed_tc2(weight, wl, 5, 0, d.nseg)
+        call('dvsr_conv_tc2_fprop', ctypes.byref(d), _ptr(wp), None, 0, _stream())
+        return True
+    if d.nseg < 2 or d.wshare or d.accumulate or d.out_step or d.deform:
+        return False
+    subs = []
+    for i in range(d.nseg):
+        sd = _copy_desc(d)
+        sd.nseg = 1
+        sd.seg[0] = d.seg[i]
+        if L.dvsr_conv_tc2_supported(ctypes.byref(sd)) != 1:
+            return False
+        subs.append(sd)
+    # K-split: partial sums of all but the last segment go to a dense scratch tensor, the last launch adds them
+    part = torch.empty(d.N * d.Ho * d.Wo * d.Co, device=weight.device, dtype=torch.float32)
+    for i, sd in enumerate(subs):
+        last = i == len(subs) - 1
+        wp = _packed_tc2(weight, wl, 6, segs[i], segs[i] + 1) if data_grad else _packed_tc2(weight, wl, 5, i, i + 1)
+        if not last:
+            sd.bias, sd.act, sd.res, sd.shuffle = None, ACT_NONE, None, 0
+            sd.y, sd.y_pix_stride = part.data_ptr(), d.Co
+        call('dvsr_conv_tc2_fprop', ctypes.byref(sd), _ptr(wp), _ptr(part) if i > 0 else None, d.Co, _stream())
+    return True
+
+
 def _use_tc(d):
     return _backend['tc'] and _lib.lib().dvsr_conv_tc_supported(ctypes.byref(d)) == 1
 
@@ -231,6 +286,8 @@ def _run_conv(d, weight, wl, data_grad=False, segs=(0,)):
     if _lib.PROFILE['on']:
         _lib.PROFILE['tag'] = '%s %dx%dx%d C%s->%d k%d s%d' % ('dgrad' if data_grad else 'fprop', d.N, d.Ho, d.Wo,
                                                             '+'.join(str(d.seg[i].C) for i in range(d.nseg)), d.Co, d.KH, d.stride)
+    if _backend['tc'] and _backend.get('tc2', True) and _try_tc2(d, weight, wl, data_grad, segs):
+        return
     if data_grad:
         mode = 3 if tc else 1
         bufs = [_packed(weight, wl, mode, sgi) for sgi in segs]

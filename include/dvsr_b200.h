@@ -120,6 +120,16 @@ int dvsr_pack_weights_tc(const float* w, float* wp, const dvsr_wlayout* wl, int 
 int dvsr_pack_weights_tc_parity(const float* w, float* wp, const dvsr_wlayout* wl, int seg, int KHf, int KWf, int a,
                                 int b, void* stream);
 int dvsr_conv_tc_fprop(const dvsr_conv_desc* d, const float* wp, void* stream);
+/* Persistent resident-weight variant (conv_tc2.cu): stride-1 convs whose packed weights for 64 output channels fit
+ * in shared memory (<= 18 blocks of (tap, 32 input channels)); halo reuse across taps.  accum_in (optional) is added
+ * before bias / activation, which lets the host split the K dimension of wider inputs over several launches.
+ * Weights: dvsr_pack_weights_tc2 mode 5 (forward, segments [seg_lo, seg_hi)) / mode 6 (data gradient of seg_lo). */
+int dvsr_conv_tc2_supported(const dvsr_conv_desc* d);
+long long dvsr_conv_tc2_packed_floats(const dvsr_wlayout* wl, int mode, int seg_lo, int seg_hi);
+int dvsr_pack_weights_tc2(const float* w, float* wp, const dvsr_wlayout* wl, int mode, int seg_lo, int seg_hi, void* stream);
+int dvsr_conv_tc2_fprop(const dvsr_conv_desc* d, const float* wp, const float* accum_in, int accum_pix_stride, void* stream);
+/* debugging aid: 7 x 64 clock64 stamps of CTA (0,0) (producer / rounding / MMA / epilogue events); NULL = off */
+int dvsr_conv_tc2_set_trace(long long* dev_buffer);
 /* Tensor-core weight gradient of segment `seg` of a stride-1 convolution (conv_wgrad_tc.cu): both operands are
  * consumed MN-major straight from the NHWC tensors, x through one halo tile per pixel chunk. */
 int dvsr_conv_wgrad_tc_supported(const dvsr_conv_desc* d, int seg);

@@ -1,0 +1,41 @@
+"""tools/one_conv.py [N H W Ci Co k] -- launch one tensor-core conv a few times (target for `ncu -k regex:conv_tc`)."""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from dynavsr_b200 import ops  # noqa: E402
+
+a = [int(v) for v in sys.argv[1:7]] if len(sys.argv) >= 7 else [5, 176, 320, 64, 64, 3]
+N, H, W, Ci, Co, k = a
+ops.set_conv_backend(True)
+x = torch.randn(N, H, W, Ci, device='cuda')
+w = torch.randn(Co, Ci, k, k, device='cuda') * 0.05
+b = torch.zeros(Co, device='cuda')
+with torch.no_grad():
+    for _ in range(5):
+        y = ops.conv(x, w, b, pad=k // 2, act=ops.ACT_LRELU)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(20):
+        y = ops.conv(x, w, b, pad=k // 2, act=ops.ACT_LRELU)
+    e1.record()
+    torch.cuda.synchronize()
+print('avg us', e0.elapsed_time(e1) / 20 * 1e3)
+
+if '--trace' in sys.argv:
+    import ctypes
+    from dynavsr_b200 import _lib
+    tr = torch.zeros(7 * 64, dtype=torch.int64, device='cuda')
+    _lib.lib().dvsr_conv_tc2_set_trace(ctypes.c_void_p(tr.data_ptr()))
+    with torch.no_grad():
+        ops.conv(x, w, b, pad=k // 2, act=ops.ACT_LRELU)
+    torch.cuda.synchronize()
+    _lib.lib().dvsr_conv_tc2_set_trace(None)
+    t = tr.view(7, 64).cpu()
+    t0 = int(t[0, 0])
+    names = ['prod:slot free', 'round:tile landed', 'round:done', 'mma:ready seen', 'mma:issued', 'epi:acc full', 'epi:done']
+    for ev in range(7):
+        print('%-18s' % names[ev], ' '.join('%6d' % (int(v) - t0) for v in t[ev, :14]))
