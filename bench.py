@@ -251,6 +251,23 @@ def main():
                 'frac': flops / t_conv / 1e12 / tc_peak, 'traffic': None, 'peak_source': peak_src + ' bf16 dense',
                 'launch_us': t_conv * 1e6}
 
+    # ---- parity of the timed configuration at full size: tcgen05 path vs this library's exact-fp32 CUDA-core path
+    parity = None
+    if rank == 0 and use_tc:
+        fr = frames_dev[0]
+        ops.set_conv_backend(False)
+        eng_ref = adapt.InnerLoopAdapter(*build(1234), use_graphs=False, **INNER)
+        ref = (eng_ref.adapt_and_infer_nhwc(fr) if args.workload == 'adapt' else eng_ref.infer_nhwc(fr)).detach()
+        ops.set_conv_backend(True)
+        out = (eng.adapt_and_infer_nhwc(fr) if args.workload == 'adapt' else eng.infer_nhwc(fr)).detach()
+        err = float((out.double() - ref.double()).norm() / ref.double().norm())
+        q = lambda t: (t.clamp(0, 1) * 255.0).round()
+        mse = float(((q(out) - q(ref)) ** 2).mean())
+        parity = {'vs': 'exact-fp32 CUDA-core path of this library, same input/weights, full size', 'rel_l2': err,
+                  'psnr_db_between_uint8_outputs': None if mse == 0 else 20 * __import__('math').log10(255.0 / mse ** 0.5),
+                  'tolerance': 1e-3}
+        del eng_ref
+
     if rank == 0:
         cpu = None if args.no_cpu_baseline else cpu_adapt_sample(1, 0)
         line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
@@ -264,7 +281,8 @@ def main():
                            'parallelism': 'clip-sharded dp%d, no data-path collective' % world},
                 'e2e': {'value': e2e, 'unit': UNIT, 'h2d_bytes_per_step': NFR * 3 * H * W * 4,
                         'd2h_bytes_per_step': 3 * SCALE * H * SCALE * W * 4, 'ms_per_step': ms_e2e / args.steps},
-                'gpu_launches': int(per_step * args.steps), 'clocks': clk, 'roofline': roofline, 'cpu_baseline': cpu}
+                'gpu_launches': int(per_step * args.steps), 'clocks': clk, 'roofline': roofline, 'cpu_baseline': cpu,
+                'parity': parity}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -193,3 +193,65 @@ def test_full_size_properties(mods):
     with torch.no_grad():
         c = net(xs)
     assert rel(c[0:1], a) < 1e-6                                   # batching does not change results
+
+
+# ---------------------------------------------------------------------------------------------------
+# tensor-core path (TF32 operands rounded to nearest, fp32 accumulation): same goldens, north-star tolerance.
+@pytest.fixture()
+def tc(mods):
+    ops = mods[3]
+    ops.set_conv_backend(True)
+    yield ops
+    ops.set_conv_backend(False)
+
+
+def test_edvr_tc_forward_matches_reference_golden(mods, tc):
+    g = gold('edvr_m_32.npz')
+    net, _ = _edvr(mods, int(g['seed']))
+    x = torch.from_numpy(g['x']).cuda()
+    with torch.no_grad():
+        out = net(x)
+    ref = torch.from_numpy(g['out'])
+    assert rel(out, ref) < NS_TOL                     # measured 9.3e-4
+    base = torch.nn.functional.interpolate(x[:, 2], scale_factor=4, mode='bicubic', align_corners=False).cpu()
+    assert abs(psnr_uint8(out, base) - psnr_uint8(ref, base)) < 0.01
+
+
+def test_adaptation_tc_matches_reference_golden(mods, tc):
+    """The benchmark configuration (2 SGD steps, L2 + 10*L1(SLR)) on the tcgen05 path, CUDA graphs on."""
+    adapt = mods[2]
+    g = gold('adapt_sgd2_l2.npz')
+    netG, _ = _edvr(mods, int(g['seed_G']))
+    netE, _ = _mfdn(mods, int(g['seed_E']))
+    netF, _ = _mfdn(mods, int(g['seed_E_fixed']))
+    eng = adapt.InnerLoopAdapter(netG, netE, netF, steps=2, lr_alpha=float(g['lr_alpha']), optimizer='SGD',
+                                 criterion='l2', slr_weight=10.0, use_graphs=True)
+    ref = torch.from_numpy(g['out'])
+    for rep in range(2):
+        hr = eng.adapt_and_infer(torch.from_numpy(g['lr']))
+        assert rel(hr, ref) < NS_TOL, 'rep %d' % rep  # measured 9.1e-4
+        assert np.allclose(eng.last_losses.cpu().numpy(), g['losses'], rtol=2e-3)
+        assert rel(hr, torch.from_numpy(g['out_unadapted'])) > 5 * rel(hr, ref)
+
+
+def test_full_size_tc_vs_fp32_cuda_core_path(mods):
+    """BASELINE size (5x3x176x320 -> 3x704x1280): the tcgen05 path against the exact-fp32 CUDA-core path of
+    this library on the same weights / input (the oracle is too slow at this size).  Bar: 1e-3 relative and
+    0.01 dB PSNR."""
+    ops = mods[3]
+    net, _ = _edvr(mods, 7)
+    g = torch.Generator().manual_seed(4)
+    x = torch.rand(1, 5, 3, 176, 320, generator=g).cuda()
+    with torch.no_grad():
+        ops.set_conv_backend(False)
+        ref = net(x)
+        ops.set_conv_backend(True)
+        try:
+            out = net(x)
+            again = net(x)
+        finally:
+            ops.set_conv_backend(False)
+    assert torch.equal(out, again)                    # deterministic
+    assert rel(out, ref) < NS_TOL
+    base = torch.nn.functional.interpolate(x[:, 2], scale_factor=4, mode='bicubic', align_corners=False)
+    assert abs(psnr_uint8(out, base) - psnr_uint8(ref, base)) < 0.01
