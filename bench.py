@@ -228,28 +228,42 @@ def main():
     # kernels launched per step: counted while the step was captured / run eagerly
     per_step = eng.launches_per_step if getattr(eng, 'launches_per_step', None) else host_launches / max(1, args.steps)
 
-    # ---- roofline of the dominant kernel: the 3x3 64->64 convolution at the trunk shape, timed alone
+    # ---- roofline of the dominant kernel: the 3x3 64->64 convolution (feature extraction / PCD / trunk shape,
+    # N frames x 176x320), timed alone on the launching stream with CUDA events.  20 back-to-back launches are
+    # replayed from a CUDA graph so that the number is the kernel's, not the Python launch path's.
     hbm_peak, tc_peak, peak_src = measured_peaks()
-    x = torch.randn(1, H, W, 64, device='cuda')
+    x = torch.randn(NFR, H, W, 64, device='cuda')
     wgt = torch.randn(64, 64, 3, 3, device='cuda') * 0.05
     bia = torch.zeros(64, device='cuda')
+    reps = 20
     with torch.no_grad():
-        for _ in range(5):
-            ops.conv(x, wgt, bia, act=ops.ACT_RELU)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                ops.conv(x, wgt, bia, act=ops.ACT_RELU)
+        torch.cuda.current_stream().wait_stream(side)
+        gconv = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gconv):
+            for _ in range(reps):
+                ops.conv(x, wgt, bia, act=ops.ACT_RELU)
+        gconv.replay()
         torch.cuda.synchronize()
-        reps = 50
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        for _ in range(reps):
-            ops.conv(x, wgt, bia, act=ops.ACT_RELU)
+        gconv.replay()
         b.record()
         torch.cuda.synchronize()
     t_conv = a.elapsed_time(b) / reps / 1000.0
-    flops = 18.0 * H * W * 64 * 64
-    roofline = {'kernel': 'conv3x3 64->64 fprop @%dx%d (%s)' % (H, W, 'tcgen05 tf32' if use_tc else 'CUDA-core fp32'),
+    flops = 18.0 * NFR * H * W * 64 * 64
+    prec = ops._backend['precision'] if use_tc else 'fp32'
+    roofline = {'kernel': 'conv3x3 64->64 fprop @%dx%dx%d (%s)' % (NFR, H, W, ('tcgen05 ' + prec) if use_tc else 'CUDA-core fp32'),
                 'bound': 'tensor', 'achieved': flops / t_conv / 1e12, 'peak': tc_peak, 'unit': 'TFLOP/s',
-                'frac': flops / t_conv / 1e12 / tc_peak, 'traffic': None, 'peak_source': peak_src + ' bf16 dense',
-                'launch_us': t_conv * 1e6}
+                'frac': flops / t_conv / 1e12 / tc_peak,
+                'traffic': None,
+                'peak_source': peak_src + ': bf16 dense burst; algorithmic FLOPs = 18*N*H*W*Cin*Cout (the BF16x3 mode issues 3x '
+                                          'that many tensor-core MACs, the TF32 mode runs at half the bf16 rate)',
+                'algorithmic_bytes': 4.0 * NFR * H * W * 128 + 36.0 * 64 * 64, 'launch_us': t_conv * 1e6}
 
     # ---- parity of the timed configuration at full size: tcgen05 path vs this library's exact-fp32 CUDA-core path
     parity = None
@@ -272,7 +286,7 @@ def main():
         cpu = None if args.no_cpu_baseline else cpu_adapt_sample(1, 0)
         line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
                 'warmup': max(args.warmup, 3), 'ms_per_step': ms / args.steps, 'higher_is_better': True,
-                'scaling': 'weak', 'vs_baseline': None, 'dtype': 'tf32 (fp32 accumulate)' if use_tc else 'f32',
+                'scaling': 'weak', 'vs_baseline': None, 'dtype': ('bf16x3 split operands, fp32 accumulate (tcgen05)' if ops._backend['precision'] == 'bf16x3' else 'tf32, fp32 accumulate (tcgen05)') if use_tc else 'f32',
                 'data': 'synthetic',
                 'config': {'workload': ('adapt2_sgd_l2+final_forward' if args.workload == 'adapt' else 'inference_only') +
                            ' EDVR-M 4x + MFDN, REDS4-shaped 5x3x180x320 window cropped to %dx%d -> 3x%dx%d' % (H, W, SCALE * H, SCALE * W),

@@ -44,6 +44,13 @@ class WLayout(ctypes.Structure):
                 ('nseg', ctypes.c_int), ('taps', ctypes.c_int), ('Co', ctypes.c_int)]
 
 
+class PackJob(ctypes.Structure):
+    _fields_ = [('w', ctypes.c_void_p), ('wp', ctypes.c_void_p), ('wl', WLayout),
+                ('mode', ctypes.c_int), ('seg', ctypes.c_int), ('seg_hi', ctypes.c_int),
+                ('a0', ctypes.c_int), ('a1', ctypes.c_int), ('a2', ctypes.c_int), ('a3', ctypes.c_int),
+                ('total', ctypes.c_longlong), ('block_start', ctypes.c_longlong)]
+
+
 ACT_NONE, ACT_RELU, ACT_LRELU, ACT_SIGMOID_SPLIT = 0, 1, 2, 3
 LOSS_L1, LOSS_L2, LOSS_CB = 0, 1, 2
 
@@ -54,6 +61,8 @@ _DP, _WP = ctypes.POINTER(ConvDesc), ctypes.POINTER(WLayout)
 # tests/test_abi.py checks that every symbol declared in the header is exported and listed here.
 SIGNATURES = {
     'dvsr_pack_weights': [_P, _P, _WP, _I, _I, _P],
+    'dvsr_pack_job_run': [ctypes.POINTER(PackJob), _P],
+    'dvsr_pack_table': [_P, _I, _LL, _P],
     'dvsr_conv_fprop': [_DP, _P, _P],
     'dvsr_conv_wgrad': [_DP, _P, _I, _P, _WP, _P],
     'dvsr_conv_small_co': [_DP, _P, _P],
@@ -67,6 +76,8 @@ SIGNATURES = {
     'dvsr_pack_weights_tc2': [_P, _P, _WP, _I, _I, _I, _P],
     'dvsr_conv_tc2_fprop': [_DP, _P, _P, _I, _P],
     'dvsr_conv_tc2_set_trace': [_P],
+    'dvsr_conv_tc2_set_precision': [_I],
+    'dvsr_conv_tc2_get_precision': [],
     'dvsr_conv_wgrad_tc_supported': [_DP, _I],
     'dvsr_conv_wgrad_tc': [_DP, _I, _P, _I, _P, _WP, _P],
     'dvsr_mdcn_bwd_data': [_DP, _P, _I, _P, _P, _I, _P, _I, _P, _I, _P],

@@ -80,14 +80,14 @@ class FlatParams(object):
         if self.m is not None:
             self.m.zero_()
             self.v.zero_()
-        ops.invalidate_weight_cache()
+        ops.invalidate_weight_cache()      # the step that follows starts with ops.repack_all()
 
     def zero_grad(self):
         self.grad.zero_()
 
     def sgd_step(self, lr0, lr1):
         call('dvsr_update_sgd', _p(self.flat), _p(self.grad), self.numel, self.split, float(lr0), float(lr1), _stream())
-        ops.invalidate_weight_cache()
+        ops.weights_updated()
 
     def adam_step(self, lr0, lr1, betas=(0.9, 0.999), eps=1e-8, step=None):
         if self.m is None:
@@ -98,7 +98,7 @@ class FlatParams(object):
         bc1, bc2 = 1.0 - betas[0] ** t, 1.0 - betas[1] ** t
         call('dvsr_update_adam', _p(self.flat), _p(self.grad), _p(self.m), _p(self.v), self.numel, self.split,
              float(lr0), float(lr1), float(betas[0]), float(betas[1]), float(eps), float(bc1), float(bc2), _stream())
-        ops.invalidate_weight_cache()
+        ops.weights_updated()
 
 
 class InnerLoopAdapter(object):
@@ -147,6 +147,7 @@ class InnerLoopAdapter(object):
 
     def _run_eager(self, frames, B):
         H, W = frames.shape[1], frames.shape[2]
+        ops.repack_all()        # weights were restored just before: refresh all kernel-layout packs in one launch
         gt = frames.view(B, self.N, H, W, 3)[:, self.center].contiguous()
         with torch.no_grad():
             slr_fixed = self.netE_fixed.forward_nhwc(frames, B, self.N)
@@ -167,6 +168,7 @@ class InnerLoopAdapter(object):
             self._run_eager(st['in'], B)
             self.flat.restore()
         torch.cuda.current_stream().wait_stream(side)
+        ops.repack_all()            # (re)build the device-side pack table now: it must not change during capture
         g = torch.cuda.CUDAGraph()
         n0 = _lib.COUNTER[0]
         with torch.cuda.graph(g):
@@ -207,5 +209,6 @@ class InnerLoopAdapter(object):
     def infer_nhwc(self, frames, B=1):
         """Plain EDVR forward with the meta-weights (no adaptation)."""
         self.flat.restore()
+        ops.repack_all()
         with torch.no_grad():
             return self.netG.forward_nhwc(frames, B, self.N)

@@ -15,7 +15,7 @@
 // Replaces: cuDNN convs at EDVR_arch.py:68-90,141-159,224-249, arch_util.py:42-43,
 //           LRimg_estimator.py:77-88 and the DCN im2col + addmm_ pair deform_conv_cuda.cpp:534-563,
 //           deform_conv_cuda_kernel.cu:569-632.
-#include "common.cuh"
+#include "pack_device.cuh"
 
 namespace dvsr {
 
@@ -429,32 +429,6 @@ conv_wgrad_kernel(const dvsr_conv_desc d, const float* __restrict__ gy, int gy_p
 }
 
 // ------------------------------------------------------------------------------------------------
-__global__ void pack_weights_kernel(const float* __restrict__ w, float* __restrict__ wp, const dvsr_wlayout wl,
-                                    int mode, int seg, long long total) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total) return;
-    if (mode == 0) {
-        // wp[k][co], k = kofs(s) + tap*C_s + ci
-        const int co = (int)(i % wl.Co);
-        long long k = i / wl.Co;
-        int s = 0;
-        for (; s < wl.nseg; ++s) {
-            long long n = (long long)wl.seg_C[s] * wl.taps;
-            if (k < n) break;
-            k -= n;
-        }
-        const int tap = (int)(k / wl.seg_C[s]), ci = (int)(k - (long long)tap * wl.seg_C[s]);
-        wp[i] = w[(long long)co * wl.co_stride + wl.seg_base[s] + (long long)ci * wl.ci_stride + tap];
-    } else {
-        // wp[tap*Co + co][ci]  (ci within segment `seg`)
-        const int C = wl.seg_C[seg];
-        const int ci = (int)(i % C);
-        const long long r = i / C;
-        const int co = (int)(r % wl.Co), tap = (int)(r / wl.Co);
-        wp[i] = w[(long long)co * wl.co_stride + wl.seg_base[seg] + (long long)ci * wl.ci_stride + tap];
-    }
-}
-
 // ------------------------------------------------------------------------------------------------
 // Small-Cout direct convolution (conv_last 64 -> 3, EDVR_arch.py:249,307): one thread per output pixel,
 // weights in shared memory, plain (non-deformable, non-transposed) taps, single segment.
@@ -552,7 +526,10 @@ extern "C" int dvsr_pack_weights(const float* w, float* wp, const dvsr_wlayout* 
         DVSR_REQUIRE(seg >= 0 && seg < wl->nseg, "pack_weights: bad segment");
         total = (long long)wl->seg_C[seg] * wl->taps * wl->Co;
     }
-    pack_weights_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(w, wp, *wl, mode, seg, total);
+    dvsr_pack_job j;
+    memset(&j, 0, sizeof(j));
+    j.w = w; j.wp = wp; j.wl = *wl; j.mode = mode; j.seg = seg; j.total = total;
+    pack_job_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(j);
     return check_launch("pack_weights");
 }
 

@@ -24,6 +24,7 @@
 //
 // Replaces cuDNN for the heavy layers of EDVR_arch.py:68-90,141-159,224-249 / arch_util.py:42-43.
 #include "tc_common.cuh"
+#include "pack_device.cuh"
 
 namespace dvsr {
 
@@ -215,39 +216,6 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
 // ------------------------------------------------------------------------------------------------ weights
 // wp rows of 32 floats: row = ((s, tap, chunk), co_pad index); mode 2: K = input channels of segment s;
 // mode 3 (data gradient of segment `seg`): K = forward output channels, rows = input channels of `seg`.
-struct TapRemap { int on, KWf, KWs, a, b; };   // packed tap (t, u) -> original tap (a + 2t) * KWf + (b + 2u)
-
-__global__ void pack_weights_tc_kernel(const float* __restrict__ w, float* __restrict__ wp, const dvsr_wlayout wl,
-                                       int mode, int seg, int rows_pad, long long total, TapRemap rm) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total) return;
-    const int k = (int)(i & 31);
-    long long r = i >> 5;
-    const int nrow = (int)(r % rows_pad);
-    r /= rows_pad;                       // (s, tap, chunk) block index
-    float v = 0.f;
-    if (mode == 2) {
-        int s = 0, blk = (int)r;
-        for (; s < wl.nseg; ++s) {
-            const int n = wl.taps * ((wl.seg_C[s] + 31) / 32);
-            if (blk < n) break;
-            blk -= n;
-        }
-        const int chunks = (wl.seg_C[s] + 31) / 32;
-        const int tap = blk / chunks, chunk = blk - tap * chunks;
-        if (nrow < wl.Co && chunk * 32 + k < wl.seg_C[s])
-            v = w[(long long)nrow * wl.co_stride + wl.seg_base[s] + (long long)(chunk * 32 + k) * wl.ci_stride + tap];
-    } else {
-        const int chunks = (wl.Co + 31) / 32;
-        int tap = (int)(r / chunks);
-        const int chunk = (int)(r - (long long)tap * chunks);
-        if (rm.on) tap = (rm.a + 2 * (tap / rm.KWs)) * rm.KWf + (rm.b + 2 * (tap % rm.KWs));
-        if (nrow < wl.seg_C[seg] && chunk * 32 + k < wl.Co)
-            v = w[(long long)(chunk * 32 + k) * wl.co_stride + wl.seg_base[seg] + (long long)nrow * wl.ci_stride + tap];
-    }
-    wp[i] = round_tf32(v);   // round-to-nearest TF32 (the MMA would truncate)
-}
-
 // ------------------------------------------------------------------------------------------------ host
 EncodeTiledFn get_encode_tiled() {
     static EncodeTiledFn fn = nullptr;
@@ -298,8 +266,10 @@ extern "C" int dvsr_pack_weights_tc(const float* w, float* wp, const dvsr_wlayou
     if (mode == 3) DVSR_REQUIRE(seg >= 0 && seg < wl->nseg, "pack_weights_tc: bad segment");
     const long long total = dvsr_conv_tc_packed_floats(wl, mode, seg);
     const int rows_pad = mode == 2 ? round16(wl->Co) : round16(wl->seg_C[seg]);
-    TapRemap rm = {0, 0, 0, 0, 0};
-    pack_weights_tc_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(w, wp, *wl, mode, seg, rows_pad, total, rm);
+    dvsr_pack_job j;
+    memset(&j, 0, sizeof(j));
+    j.w = w; j.wp = wp; j.wl = *wl; j.mode = mode; j.seg = seg; j.a0 = rows_pad; j.total = total;
+    pack_job_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(j);
     return check_launch("pack_weights_tc");
 }
 
@@ -311,8 +281,10 @@ extern "C" int dvsr_pack_weights_tc_parity(const float* w, float* wp, const dvsr
     DVSR_REQUIRE(KHs > 0 && KWs > 0, "pack_weights_tc_parity: empty parity class");
     const int rows_pad = round16(wl->seg_C[seg]);
     const long long total = (long long)KHs * KWs * ((wl->Co + 31) / 32) * rows_pad * 32;
-    TapRemap rm = {1, KWf, KWs, a, b};
-    pack_weights_tc_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(w, wp, *wl, 3, seg, rows_pad, total, rm);
+    dvsr_pack_job j;
+    memset(&j, 0, sizeof(j));
+    j.w = w; j.wp = wp; j.wl = *wl; j.mode = 4; j.seg = seg; j.a0 = rows_pad; j.a1 = KWf; j.a2 = KWs; j.a3 = 2 * a + b; j.total = total;
+    pack_job_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(j);
     return check_launch("pack_weights_tc_parity");
 }
 

@@ -19,6 +19,7 @@
 // Output channels are processed in groups of 64 (blockIdx.y); inputs whose weights do not fit are K-split
 // over several launches by the host wrapper (`accum_in`).
 #include "tc_common.cuh"
+#include "pack_device.cuh"
 
 namespace dvsr {
 
@@ -46,6 +47,7 @@ struct T2Params {
     int shuffle;
     float* y; int y_pix_stride;
     int y_vec8;                           // y rows are 32-byte aligned: 256-bit stores
+    int bf16x3;                           // 1: operands split into bf16 hi + lo, 3 products (fp32-class accuracy)
     long long* trace;                     // optional per-event clock64 trace of CTA (0,0): [event][chunk]
 };
 struct __align__(64) T2Maps { CUtensorMap x[DVSR_MAX_SEG]; CUtensorMap w; };
@@ -150,7 +152,7 @@ conv_tc2_kernel(const __grid_constant__ T2Maps maps, const T2Params p) {
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        const uint32_t idesc = make_idesc_tf32(128, T2_NG);
+        const uint32_t idesc = p.bf16x3 ? make_idesc_bf16(128, T2_NG) : make_idesc_tf32(128, T2_NG);
         // descriptor templates: only the 14-bit (address >> 4) field changes per tap / k-step
         const uint64_t ad_const = make_desc(0, 16, (uint32_t)p.halo_w * 128u, 2);
         const uint64_t bd_const = make_desc(0, 16, 1024, 2);
@@ -175,10 +177,20 @@ conv_tc2_kernel(const __grid_constant__ T2Maps maps, const T2Params p) {
                         int wy = p.tap_sign < 0 ? p.KH - 1 : 0, wx0 = p.tap_sign < 0 ? p.KW - 1 : 0, wx = wx0, kw = 0;
                         for (int tap = 0; tap < KK; ++tap) {
                             const uint64_t ad = ad0 + (uint64_t)((wy * p.halo_w + wx) * 8);     // 128 B per pixel = 8 x 16 B
-                            mma_tf32(dcol, ad, bd, idesc, (cidx > 0 || tap > 0) ? 1u : 0u);
-                            mma_tf32(dcol, ad + 2, bd + 2, idesc, 1u);
-                            mma_tf32(dcol, ad + 4, bd + 4, idesc, 1u);
-                            mma_tf32(dcol, ad + 6, bd + 6, idesc, 1u);
+                            if (!p.bf16x3) {
+                                mma_tf32(dcol, ad, bd, idesc, (cidx > 0 || tap > 0) ? 1u : 0u);
+                                mma_tf32(dcol, ad + 2, bd + 2, idesc, 1u);
+                                mma_tf32(dcol, ad + 4, bd + 4, idesc, 1u);
+                                mma_tf32(dcol, ad + 6, bd + 6, idesc, 1u);
+                            } else {
+                                // row = [hi(32 bf16) | lo(32 bf16)] for both operands; K = 16 per MMA = 32 bytes = +2
+                                mma_bf16(dcol, ad, bd, idesc, (cidx > 0 || tap > 0) ? 1u : 0u);   // x_hi . w_hi
+                                mma_bf16(dcol, ad + 2, bd + 2, idesc, 1u);
+                                mma_bf16(dcol, ad + 4, bd, idesc, 1u);                            // x_lo . w_hi
+                                mma_bf16(dcol, ad + 6, bd + 2, idesc, 1u);
+                                mma_bf16(dcol, ad, bd + 4, idesc, 1u);                            // x_hi . w_lo
+                                mma_bf16(dcol, ad + 2, bd + 6, idesc, 1u);
+                            }
                             bd += 512;                                                            // next 8 KiB weight block
                             wx += p.tap_sign;
                             if (++kw == p.KW) { kw = 0; wx = wx0; wy += p.tap_sign; }
@@ -204,10 +216,40 @@ conv_tc2_kernel(const __grid_constant__ T2Maps maps, const T2Params p) {
                 mbar_wait(&a_full[stage], phase);
                 if (t == 0) T2_TRACE(1, trace_i);
                 float4* a4 = reinterpret_cast<float4*>(smem_a + stage * p.a_bytes);
-                for (int i = t; i < n16; i += 128) {
-                    float4 v = a4[i];
-                    v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w);
-                    a4[i] = v;
+                if (!p.bf16x3) {
+                    for (int i = t; i < n16; i += 128) {
+                        float4 v = a4[i];
+                        v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w);
+                        a4[i] = v;
+                    }
+                } else {
+                    // BF16x3: rewrite every 128-byte pixel row (32 fp32 channels) in place as [32 x bf16 hi | 32 x bf16 lo].
+                    // Rows keep the 128B swizzle: logical 16-byte chunk c of row r lives at chunk c ^ ((addr >> 7) & 7).
+                    const int nrows = p.halo_h * p.halo_w;
+                    for (int r = t; r < nrows; r += 128) {
+                        uint4* row = reinterpret_cast<uint4*>(a4 + r * 8);
+                        const uint32_t ph = (smem_u32(row) >> 7) & 7;
+                        float f[32];
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) {
+                            const float4 v = *reinterpret_cast<const float4*>(row + (c ^ ph));
+                            f[4 * c] = v.x; f[4 * c + 1] = v.y; f[4 * c + 2] = v.z; f[4 * c + 3] = v.w;
+                        }
+                        uint32_t hi[16], lo[16];
+#pragma unroll
+                        for (int q2 = 0; q2 < 16; ++q2) {
+                            uint32_t h0, l0, h1, l1;
+                            split_bf16(f[2 * q2], h0, l0);
+                            split_bf16(f[2 * q2 + 1], h1, l1);
+                            hi[q2] = h0 | (h1 << 16);
+                            lo[q2] = l0 | (l1 << 16);
+                        }
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            row[c ^ ph] = make_uint4(hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
+                            row[(4 + c) ^ ph] = make_uint4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
+                        }
+                    }
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 mbar_arrive(&a_ready[stage]);
@@ -283,42 +325,6 @@ conv_tc2_kernel(const __grid_constant__ T2Maps maps, const T2Params p) {
     }
 }
 
-// ------------------------------------------------------------------------------------------------ weights
-// wp rows of 32 floats.  Row index = ((g * nblocks + blk) * 64 + r), blk = ((seg, chunk), tap) in launch order,
-// g = output-channel group, r = channel inside the group.  mode 5: forward (K = input channels);
-// mode 6: data gradient of segment `seg` (K = forward output channels, rows = input channels of `seg`).
-__global__ void pack_weights_tc2_kernel(const float* __restrict__ w, float* __restrict__ wp, const dvsr_wlayout wl,
-                                        int mode, int seg, int seg_lo, int seg_hi, int nblocks, int ngroups, long long total) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total) return;
-    const int k = (int)(i & 31);
-    long long r = i >> 5;
-    const int rr = (int)(r % T2_NG);
-    r /= T2_NG;
-    int blk = (int)(r % nblocks);
-    const int g = (int)(r / nblocks);
-    const int n = g * T2_NG + rr;               // output row (co for mode 5, ci for mode 6)
-    float v = 0.f;
-    if (mode == 5) {
-        int s = seg_lo;
-        for (; s < seg_hi; ++s) {
-            const int nb = wl.taps * ((wl.seg_C[s] + 31) / 32);
-            if (blk < nb) break;
-            blk -= nb;
-        }
-        const int chunk = blk / wl.taps, tap = blk - chunk * wl.taps;      // block order: chunk-major, then tap
-        const int ci = chunk * 32 + k;
-        if (n < wl.Co && ci < wl.seg_C[s])
-            v = w[(long long)n * wl.co_stride + wl.seg_base[s] + (long long)ci * wl.ci_stride + tap];
-    } else {
-        const int chunk = blk / wl.taps, tap = blk - chunk * wl.taps;
-        const int co = chunk * 32 + k;
-        if (n < wl.seg_C[seg] && co < wl.Co)
-            v = w[(long long)co * wl.co_stride + wl.seg_base[seg] + (long long)n * wl.ci_stride + tap];
-    }
-    wp[i] = round_tf32(v);
-}
-
 }  // namespace dvsr
 
 using namespace dvsr;
@@ -351,7 +357,7 @@ extern "C" int dvsr_conv_tc2_supported(const dvsr_conv_desc* d) {
 
 extern "C" long long dvsr_conv_tc2_packed_floats(const dvsr_wlayout* wl, int mode, int seg_lo, int seg_hi) {
     if (!wl) return 0;
-    if (mode == 5) {
+    if (mode == 5 || mode == 7) {
         long long nb = 0;
         for (int s = seg_lo; s < seg_hi; ++s) nb += (long long)wl->taps * ((wl->seg_C[s] + 31) / 32);
         return nb * ((wl->Co + T2_NG - 1) / T2_NG) * T2_NG * 32;
@@ -361,10 +367,11 @@ extern "C" long long dvsr_conv_tc2_packed_floats(const dvsr_wlayout* wl, int mod
 
 // mode 5: forward weights of segments [seg_lo, seg_hi); mode 6: data-gradient weights of segment seg_lo
 extern "C" int dvsr_pack_weights_tc2(const float* w, float* wp, const dvsr_wlayout* wl, int mode, int seg_lo, int seg_hi, void* stream) {
-    DVSR_REQUIRE(w && wp && wl && (mode == 5 || mode == 6), "pack_weights_tc2: bad arguments");
-    DVSR_REQUIRE(seg_lo >= 0 && seg_lo < wl->nseg && (mode == 6 || (seg_hi > seg_lo && seg_hi <= wl->nseg)), "pack_weights_tc2: bad segment range");
+    DVSR_REQUIRE(w && wp && wl && mode >= 5 && mode <= 8, "pack_weights_tc2: bad arguments");
+    const bool fwd = (mode == 5 || mode == 7);
+    DVSR_REQUIRE(seg_lo >= 0 && seg_lo < wl->nseg && (!fwd || (seg_hi > seg_lo && seg_hi <= wl->nseg)), "pack_weights_tc2: bad segment range");
     int nblocks, ngroups;
-    if (mode == 5) {
+    if (fwd) {
         nblocks = 0;
         for (int s = seg_lo; s < seg_hi; ++s) nblocks += wl->taps * ((wl->seg_C[s] + 31) / 32);
         ngroups = (wl->Co + T2_NG - 1) / T2_NG;
@@ -373,9 +380,17 @@ extern "C" int dvsr_pack_weights_tc2(const float* w, float* wp, const dvsr_wlayo
         ngroups = (wl->seg_C[seg_lo] + T2_NG - 1) / T2_NG;
     }
     const long long total = (long long)nblocks * ngroups * T2_NG * 32;
-    pack_weights_tc2_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(w, wp, *wl, mode, seg_lo, seg_lo, seg_hi, nblocks, ngroups, total);
+    dvsr_pack_job j;
+    memset(&j, 0, sizeof(j));
+    j.w = w; j.wp = wp; j.wl = *wl; j.mode = mode; j.seg = seg_lo; j.seg_hi = seg_hi; j.a0 = nblocks; j.total = total;
+    pack_job_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(j);
     return check_launch("pack_weights_tc2");
 }
+
+static int g_t2_bf16x3 = 1;
+// 1 (default): BF16x3 split operands (3 products, ~1e-5 per layer); 0: single-pass TF32 with round-to-nearest (~3e-4)
+extern "C" int dvsr_conv_tc2_set_precision(int bf16x3) { g_t2_bf16x3 = bf16x3 ? 1 : 0; return 0; }
+extern "C" int dvsr_conv_tc2_get_precision(void) { return g_t2_bf16x3; }
 
 extern "C" int dvsr_conv_tc2_fprop(const dvsr_conv_desc* d, const float* wp, const float* accum_in, int accum_pix_stride, void* stream) {
     DVSR_REQUIRE(d && wp && d->y, "conv_tc2_fprop: null pointer");
@@ -399,6 +414,7 @@ extern "C" int dvsr_conv_tc2_fprop(const dvsr_conv_desc* d, const float* wp, con
     p.y = d->y; p.y_pix_stride = d->y_pix_stride;
     p.y_vec8 = ((((uintptr_t)d->y) & 31) == 0) && (d->y_pix_stride % 8 == 0) && (d->Co % 8 == 0);
     p.trace = g_t2_trace;
+    p.bf16x3 = g_t2_bf16x3;
     const int tiles_w = (d->Wo + T2_TW - 1) / T2_TW, tiles_h = (d->Ho + T2_TH - 1) / T2_TH;
     p.tiles_total = d->N * tiles_w * tiles_h;
     const int ngroups = (d->Co + T2_NG - 1) / T2_NG;
@@ -419,6 +435,7 @@ extern "C" int dvsr_conv_tc2_fprop(const dvsr_conv_desc* d, const float* wp, con
         DVSR_REQUIRE(r == CUDA_SUCCESS, "conv_tc2_fprop: cuTensorMapEncodeTiled(activation seg %d) failed with %d", s, (int)r);
     }
     {
+        // the packed rows are 128 bytes either way: 32 x tf32, or [32 x bf16 hi | 32 x bf16 lo]
         cuuint64_t dims[2] = {32, (cuuint64_t)p.nblocks * ngroups * T2_NG};
         cuuint64_t strides[1] = {128};
         cuuint32_t box[2] = {32, T2_NG};

@@ -10,6 +10,7 @@
 //       4 K-rows); an M = 64 accumulator keeps row m in TMEM lane (m / 16) * 32 + m % 16.
 #pragma once
 #include <cuda.h>
+#include <cuda_bf16.h>
 
 #include "common.cuh"
 
@@ -76,6 +77,22 @@ __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
                  "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
                  ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// kind::f16 with BF16 operands, fp32 accumulation (a/b_format = 1)
+__device__ __forceinline__ uint32_t make_idesc_bf16(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// x = hi + lo with hi = bf16_rn(x), lo = bf16_rn(x - hi); returns the two bf16 bit patterns (x - hi - lo ~ 2^-17 |x|)
+__device__ __forceinline__ void split_bf16(float x, uint32_t& hi, uint32_t& lo) {
+    const __nv_bfloat16 h = __float2bfloat16_rn(x);
+    const __nv_bfloat16 l = __float2bfloat16_rn(x - __bfloat162float(h));
+    hi = (uint32_t)__bfloat16_as_ushort(h);
+    lo = (uint32_t)__bfloat16_as_ushort(l);
 }
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");

@@ -14,7 +14,7 @@ from torch.autograd import Function
 from . import _lib
 from ._lib import ACT_LRELU, ACT_NONE, ACT_RELU, ACT_SIGMOID_SPLIT, ConvDesc, WLayout, call
 
-__all__ = ['Seg', 'conv', 'conv3d_padded', 'mdcn', 'upsample', 'pool_maxavg', 'pad2d', 'pad3d_replicate',
+__all__ = ['repack_all', 'weights_updated', 'Seg', 'conv', 'conv3d_padded', 'mdcn', 'upsample', 'pool_maxavg', 'pad2d', 'pad3d_replicate',
            'tsa_temporal', 'tsa_combine', 'pixel_loss', 'to_nhwc', 'to_nchw', 'invalidate_weight_cache',
            'ACT_NONE', 'ACT_RELU', 'ACT_LRELU', 'ACT_SIGMOID_SPLIT', 'set_conv_backend']
 
@@ -101,8 +101,15 @@ _wcache_epoch = [0]
 
 
 def invalidate_weight_cache():
-    """Call after parameters were modified through raw pointers (the fused update kernels)."""
+    """Call after parameters were modified through raw pointers; packs are refreshed lazily (one launch each)."""
     _wcache_epoch[0] += 1
+
+
+def weights_updated():
+    """Call after a fused parameter update / restore: bumps the epoch and refreshes every registered pack with one
+    table-driven launch (replaces ~370 per-layer pack launches per adaptation step)."""
+    _wcache_epoch[0] += 1
+    repack_all()
 
 
 def _layout(weight, seg_C, temporal):
@@ -127,41 +134,105 @@ def _layout(weight, seg_C, temporal):
     return wl
 
 
+_pack_registry = {}        # (id(weight), key) -> entry dict; entries die with their weight (weakref callback)
+_pack_table = {'dev': None, 'n': 0, 'blocks': 0, 'dirty': True}
+
+
+def _weight_stamp(weight):
+    return (weight._version, _wcache_epoch[0], weight.data_ptr())
+
+
+def _get_pack(weight, wl, mode, seg=0, seg_hi=0, a=(0, 0, 0, 0), total=0):
+    """Packed copy of ``weight`` in the layout selected by ``mode`` (see dvsr_pack_job).  Packs lazily with one
+    launch the first time (or after an out-of-band modification of the weight); afterwards the buffer is kept fresh
+    by the table-driven single-launch ``repack_all`` that follows every fused parameter update."""
+    key = (mode, seg, seg_hi, a[1], a[2], a[3], tuple(wl.seg_C[i] for i in range(wl.nseg)))
+    ent = _wcache.get(weight, key)
+    stamp = _weight_stamp(weight)
+    if ent is not None and ent['stamp'] == stamp:
+        return ent['buf']
+    if ent is None:
+        job = _lib.PackJob()
+        ctypes.memmove(ctypes.byref(job.wl), ctypes.byref(wl), ctypes.sizeof(WLayout))
+        job.mode, job.seg, job.seg_hi = mode, seg, seg_hi
+        job.a0, job.a1, job.a2, job.a3 = a
+        job.total = total
+        buf = torch.empty(total, device=weight.device, dtype=torch.float32)
+        job.wp = buf.data_ptr()
+        ent = {'buf': buf, 'job': job, 'stamp': None, 'ref': weakref.ref(weight)}
+        _wcache.put(weight, key, ent)
+        rkey = (id(weight), key)
+        _pack_registry[rkey] = ent
+        weakref.finalize(weight, _drop_pack, rkey)
+        _pack_table['dirty'] = True
+    if ent['job'].w != weight.data_ptr():
+        ent['job'].w = weight.data_ptr()
+        _pack_table['dirty'] = True
+    call('dvsr_pack_job_run', ctypes.byref(ent['job']), _stream())
+    ent['stamp'] = stamp
+    return ent['buf']
+
+
+def _drop_pack(rkey):
+    if _pack_registry.pop(rkey, None) is not None:
+        _pack_table['dirty'] = True
+
+
+def repack_all():
+    """Re-pack every registered weight layout in ONE launch (dvsr_pack_table) and mark the packs fresh."""
+    ents = [e for e in _pack_registry.values() if e['ref']() is not None]
+    if not ents:
+        return
+    capturing = torch.cuda.is_current_stream_capturing()
+    if _pack_table['dirty'] or _pack_table['n'] != len(ents):
+        if capturing:
+            raise RuntimeError('weight-pack table changed during CUDA-graph capture (warm up the exact step first)')
+        arr = (_lib.PackJob * len(ents))()
+        blocks = 0
+        for i, e in enumerate(ents):
+            e['job'].w = e['ref']().data_ptr()
+            e['job'].block_start = blocks
+            ctypes.memmove(ctypes.byref(arr[i]), ctypes.byref(e['job']), ctypes.sizeof(_lib.PackJob))
+            blocks += (e['job'].total + 255) // 256
+        host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+        _pack_table.update(dev=host.to(ents[0]['buf'].device), n=len(ents), blocks=blocks, dirty=False, ents=ents)
+    call('dvsr_pack_table', _ptr(_pack_table['dev']), _pack_table['n'], _pack_table['blocks'], _stream())
+    for e in _pack_table['ents']:
+        w = e['ref']()
+        if w is not None:
+            e['stamp'] = _weight_stamp(w)
+
+
 def _packed(weight, wl, mode, seg=0):
     """CUDA-core layouts -- mode 0: forward [K][Co]; mode 1: data gradient of segment `seg` [taps*Co][C_seg].
     tcgen05 layouts (rows of 32 K-values, K-major, padded N) -- mode 2: forward; mode 3: data gradient."""
-    key = (mode, seg, tuple(wl.seg_C[i] for i in range(wl.nseg)))
-    ver = (weight._version, _wcache_epoch[0], weight.data_ptr())
-    ent = _wcache.get(weight, key)
-    capturing = torch.cuda.is_current_stream_capturing()
-    if ent is not None and ent[0] == ver and not capturing:
-        return ent[1]
     if mode == 0:
-        n = sum(wl.seg_C[i] for i in range(wl.nseg)) * wl.taps * wl.Co
-    elif mode == 1:
-        n = wl.seg_C[seg] * wl.taps * wl.Co
-    else:
-        n = _lib.lib().dvsr_conv_tc_packed_floats(ctypes.byref(wl), mode, seg)
-    buf = ent[1] if ent is not None else torch.empty(n, device=weight.device, dtype=torch.float32)
-    call('dvsr_pack_weights' if mode < 2 else 'dvsr_pack_weights_tc', _ptr(weight), _ptr(buf), ctypes.byref(wl),
-         mode, seg, _stream())
-    _wcache.put(weight, key, (ver, buf))
-    return buf
+        return _get_pack(weight, wl, 0, total=sum(wl.seg_C[i] for i in range(wl.nseg)) * wl.taps * wl.Co)
+    if mode == 1:
+        return _get_pack(weight, wl, 1, seg, total=wl.seg_C[seg] * wl.taps * wl.Co)
+    rows = (wl.Co if mode == 2 else wl.seg_C[seg]) + 15
+    rows = rows // 16 * 16
+    return _get_pack(weight, wl, mode, seg, a=(rows, 0, 0, 0),
+                     total=_lib.lib().dvsr_conv_tc_packed_floats(ctypes.byref(wl), mode, seg))
 
 
 def _packed_parity(weight, wl, seg, KH, KW, a, b):
     """tcgen05 data-gradient weights restricted to the taps (a + 2t, b + 2u): one parity class of a stride-2 conv."""
-    key = ('parity', seg, a, b)
-    ver = (weight._version, _wcache_epoch[0], weight.data_ptr())
-    ent = _wcache.get(weight, key)
-    if ent is not None and ent[0] == ver and not torch.cuda.is_current_stream_capturing():
-        return ent[1]
     KHs, KWs = (KH - a + 1) // 2, (KW - b + 1) // 2
-    n = KHs * KWs * ((wl.Co + 31) // 32) * ((wl.seg_C[seg] + 15) // 16 * 16) * 32
-    buf = ent[1] if ent is not None else torch.empty(n, device=weight.device, dtype=torch.float32)
-    call('dvsr_pack_weights_tc_parity', _ptr(weight), _ptr(buf), ctypes.byref(wl), seg, KH, KW, a, b, _stream())
-    _wcache.put(weight, key, (ver, buf))
-    return buf
+    rows = (wl.seg_C[seg] + 15) // 16 * 16
+    return _get_pack(weight, wl, 4, seg, a=(rows, KW, KWs, 2 * a + b), total=KHs * KWs * ((wl.Co + 31) // 32) * rows * 32)
+
+
+def _packed_tc2(weight, wl, mode, seg_lo, seg_hi):
+    """Resident-weight layout of conv_tc2.cu (mode 5 forward over segments [seg_lo, seg_hi), mode 6 data gradient)."""
+    if mode == 5:
+        nblocks = sum(wl.taps * ((wl.seg_C[s] + 31) // 32) for s in range(seg_lo, seg_hi))
+    else:
+        nblocks = wl.taps * ((wl.Co + 31) // 32)
+    if _backend['precision'] == 'bf16x3':
+        mode += 2               # 7 / 8: rows of [32 x bf16 hi | 32 x bf16 lo]
+    return _get_pack(weight, wl, mode, seg_lo, seg_hi, a=(nblocks, 0, 0, 0),
+                     total=_lib.lib().dvsr_conv_tc2_packed_floats(ctypes.byref(wl), mode, seg_lo, seg_hi))
 
 
 def _dgrad_stride2_tc(gpre, weight, wl, seg, shape, spec):
@@ -193,12 +264,18 @@ def _dgrad_stride2_tc(gpre, weight, wl, seg, shape, spec):
 
 # --------------------------------------------------------------------------------------------------
 # convolution
-_backend = {'tc': False}
+_backend = {'tc': False, 'precision': 'bf16x3'}
 
 
-def set_conv_backend(tensor_cores):
-    """Select the tcgen05 implicit-GEMM path (tf32 inputs, fp32 accumulate) for eligible layers."""
+def set_conv_backend(tensor_cores, precision=None):
+    """Select the tcgen05 implicit-GEMM path for eligible layers.  ``precision`` of the resident-weight kernel:
+    'bf16x3' (default; split operands, 3 products, fp32-class accuracy) or 'tf32' (single pass, ~3e-4 per layer)."""
     _backend['tc'] = bool(tensor_cores)
+    if precision is not None:
+        assert precision in ('bf16x3', 'tf32')
+        _backend['precision'] = precision
+    if _lib.lib().dvsr_conv_tc2_get_precision() != (1 if _backend['precision'] == 'bf16x3' else 0):
+        _lib.lib().dvsr_conv_tc2_set_precision(1 if _backend['precision'] == 'bf16x3' else 0)
 
 
 def _run_wgrad(d, gpre, Co, gw, wl):
@@ -217,20 +294,6 @@ def _run_wgrad(d, gpre, Co, gw, wl):
 class _ConvSpec(object):
     __slots__ = ('KH', 'KW', 'stride', 'pad', 'act', 'slope', 'sig_split', 'shuffle', 'metas', 'temporal',
                  'N', 'H', 'W', 'Ho', 'Wo', 'has_res')
-
-
-def _packed_tc2(weight, wl, mode, seg_lo, seg_hi):
-    """Resident-weight layout of conv_tc2.cu (mode 5 forward over segments [seg_lo, seg_hi), mode 6 data gradient)."""
-    key = ('tc2', mode, seg_lo, seg_hi, tuple(wl.seg_C[i] for i in range(wl.nseg)))
-    ver = (weight._version, _wcache_epoch[0], weight.data_ptr())
-    ent = _wcache.get(weight, key)
-    if ent is not None and ent[0] == ver and not torch.cuda.is_current_stream_capturing():
-        return ent[1]
-    n = _lib.lib().dvsr_conv_tc2_packed_floats(ctypes.byref(wl), mode, seg_lo, seg_hi)
-    buf = ent[1] if ent is not None else torch.empty(n, device=weight.device, dtype=torch.float32)
-    call('dvsr_pack_weights_tc2', _ptr(weight), _ptr(buf), ctypes.byref(wl), mode, seg_lo, seg_hi, _stream())
-    _wcache.put(weight, key, (ver, buf))
-    return buf
 
 
 def _copy_desc(d):

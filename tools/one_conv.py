@@ -39,3 +39,18 @@ if '--trace' in sys.argv:
     names = ['prod:slot free', 'round:tile landed', 'round:done', 'mma:ready seen', 'mma:issued', 'epi:acc full', 'epi:done']
     for ev in range(7):
         print('%-18s' % names[ev], ' '.join('%6d' % (int(v) - t0) for v in t[ev, :14]))
+if '--both' in sys.argv:
+    for prec in ('tf32', 'bf16x3'):
+        ops.set_conv_backend(True, prec)
+        with torch.no_grad():
+            for _ in range(3):
+                ops.conv(x, w, b, pad=k // 2, act=ops.ACT_LRELU)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(20):
+                y = ops.conv(x, w, b, pad=k // 2, act=ops.ACT_LRELU)
+            e1.record()
+            torch.cuda.synchronize()
+            ops.set_conv_backend(False)
+            ref = ops.conv(x, w, b, pad=k // 2, act=ops.ACT_LRELU)
+        print(prec, 'avg us', e0.elapsed_time(e1) / 20 * 1e3, 'rel vs fp32', float((y.double() - ref.double()).norm() / ref.double().norm()))
