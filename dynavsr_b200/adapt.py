@@ -86,6 +86,7 @@ class FlatParams(object):
         self.grad.zero_()
 
     def sgd_step(self, lr0, lr1):
+        ops.join_async()        # weight-gradient kernels run on a side stream
         call('dvsr_update_sgd', _p(self.flat), _p(self.grad), self.numel, self.split, float(lr0), float(lr1), _stream())
         ops.weights_updated()
 
@@ -93,6 +94,7 @@ class FlatParams(object):
         if self.m is None:
             self.m = torch.zeros_like(self.flat)
             self.v = torch.zeros_like(self.flat)
+        ops.join_async()
         self.step_count = self.step_count + 1 if step is None else step
         t = self.step_count
         bc1, bc2 = 1.0 - betas[0] ** t, 1.0 - betas[1] ** t

@@ -124,6 +124,17 @@ __device__ __forceinline__ float4 load_a(const dvsr_conv_desc& d, const dvsr_con
 struct KIter {
     int s, tap, c0, kbase;  // kbase = row of Wp for (s, tap, c0)
 };
+// dense variant: c0 = offset inside the segment's KH*KW*C dense K range
+__device__ __forceinline__ bool kiter_next_dense(KIter& it, const dvsr_conv_desc& d) {
+    const int kmax = d.KH * d.KW * d.seg[it.s].C;
+    it.c0 += BK;
+    if (it.c0 < kmax) { it.kbase += BK; return true; }
+    it.kbase += kmax - (it.c0 - BK);
+    it.c0 = 0;
+    it.s++;
+    if (d.wshare) it.kbase = 0;
+    return it.s < d.nseg;
+}
 __device__ __forceinline__ bool kiter_next(KIter& it, const dvsr_conv_desc& d) {
     const int KK = d.KH * d.KW;
     int C = d.seg[it.s].C;
@@ -139,7 +150,9 @@ __device__ __forceinline__ bool kiter_next(KIter& it, const dvsr_conv_desc& d) {
     return it.s < d.nseg;
 }
 
-template <int VEC, bool DEFORM>
+// DENSE (small input-channel counts, e.g. RGB): the K loop runs over the dense index tap*C + c in slices of 16
+// instead of one 16-channel slice per tap (which would be 81 % padding for C = 3).
+template <int VEC, bool DEFORM, bool DENSE = false>
 __global__ void __launch_bounds__(NT, 2) conv_fprop_kernel(const dvsr_conv_desc d, const float* __restrict__ wp) {
     __shared__ __align__(16) float As[2][BK][LDA];
     __shared__ __align__(16) float Bs[2][BK][BN];
@@ -171,6 +184,38 @@ __global__ void __launch_bounds__(NT, 2) conv_fprop_kernel(const dvsr_conv_desc 
 
     auto load_tiles = [&](const KIter& k) {
         const dvsr_conv_seg& sg = d.seg[k.s];
+        if (DENSE) {
+            // k.c0 is the dense offset tap*C + c of this slice inside segment k.s
+            const int kmax = d.KH * d.KW * sg.C;
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                float t4[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int kk = k.c0 + a_cv + j;
+                    t4[j] = 0.f;
+                    if (kk < kmax) {
+                        const int tap = kk / sg.C, c = kk - tap * sg.C;
+                        const int kh = tap / d.KW, kw = tap - kh * d.KW;
+                        t4[j] = load_a<1, false>(d, sg, ps[i], kh, kw, c).x;
+                    }
+                }
+                ra[i] = make_float4(t4[0], t4[1], t4[2], t4[3]);
+            }
+            rb = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (k.c0 + b_row < kmax) {
+                const float* p = wp + (long long)(k.kbase + b_row) * d.Co + co0 + b_col;
+                if (co_vec) {
+                    if (co0 + b_col < d.Co) rb = ldg4(p);
+                } else {
+                    if (co0 + b_col + 0 < d.Co) rb.x = __ldg(p + 0);
+                    if (co0 + b_col + 1 < d.Co) rb.y = __ldg(p + 1);
+                    if (co0 + b_col + 2 < d.Co) rb.z = __ldg(p + 2);
+                    if (co0 + b_col + 3 < d.Co) rb.w = __ldg(p + 3);
+                }
+            }
+            return;
+        }
         const int kh = k.tap / d.KW, kw = k.tap - kh * d.KW;
         if (VEC == 4 || !DEFORM) {
             ra[0] = load_a<VEC, DEFORM>(d, sg, ps[0], kh, kw, k.c0 + a_cv);
@@ -215,7 +260,7 @@ __global__ void __launch_bounds__(NT, 2) conv_fprop_kernel(const dvsr_conv_desc 
     store_tiles(0);
     __syncthreads();
     int buf = 0;
-    bool more = kiter_next(it, d);
+    bool more = DENSE ? kiter_next_dense(it, d) : kiter_next(it, d);
     while (true) {
         if (more) load_tiles(it);
 #pragma unroll
@@ -234,7 +279,7 @@ __global__ void __launch_bounds__(NT, 2) conv_fprop_kernel(const dvsr_conv_desc 
         store_tiles(buf ^ 1);
         __syncthreads();
         buf ^= 1;
-        more = kiter_next(it, d);
+        more = DENSE ? kiter_next_dense(it, d) : kiter_next(it, d);
     }
 
     // ---- epilogue
@@ -298,7 +343,7 @@ __global__ void __launch_bounds__(NT, 2) conv_fprop_kernel(const dvsr_conv_desc 
 constexpr int WK = 128;  // k rows per CTA (8 chunks of 16 channels)
 constexpr int WP = 16;   // pixels per smem stage
 
-template <int VEC, bool DEFORM>
+template <int VEC, bool DEFORM, bool DENSE = false>
 __global__ void __launch_bounds__(NT, 2)
 conv_wgrad_kernel(const dvsr_conv_desc d, const float* __restrict__ gy, int gy_pix_stride, float* __restrict__ gw,
                   const dvsr_wlayout wl, int chunks_total, long long pix_per_split) {
@@ -321,10 +366,17 @@ conv_wgrad_kernel(const dvsr_conv_desc d, const float* __restrict__ gy, int gy_p
     {
         int rem = chunk_ok ? chunk : 0;
         for (int s = 0; s < d.nseg; ++s) {
-            int per_tap = (d.seg[s].C + BK - 1) / BK;
-            int n_in_seg = per_tap * KK;
-            if (rem < n_in_seg) { cs = s; ctap = rem / per_tap; cc0 = (rem - ctap * per_tap) * BK; break; }
-            rem -= n_in_seg;
+            if (DENSE) {
+                // chunks of 16 dense K indices (tap*C + c); cc0 = dense offset of this chunk
+                int n_in_seg = (KK * d.seg[s].C + BK - 1) / BK;
+                if (rem < n_in_seg) { cs = s; cc0 = rem * BK; break; }
+                rem -= n_in_seg;
+            } else {
+                int per_tap = (d.seg[s].C + BK - 1) / BK;
+                int n_in_seg = per_tap * KK;
+                if (rem < n_in_seg) { cs = s; ctap = rem / per_tap; cc0 = (rem - ctap * per_tap) * BK; break; }
+                rem -= n_in_seg;
+            }
         }
     }
     const int a_c = cc0 + (a_kv & 3) * 4;
@@ -347,7 +399,20 @@ conv_wgrad_kernel(const dvsr_conv_desc d, const float* __restrict__ gy, int gy_p
             const long long p = p0 + a_p + 8 * i;
             if (chunk_ok && p < p_end) {
                 PixSlot ps = decode_pixel(p, M, d.Ho, d.Wo);
-                if (VEC == 4 || !DEFORM) {
+                if (DENSE) {
+                    const int C = d.seg[cs].C, kmax = KK * C;
+                    float t4[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int kk = a_c + j;
+                        t4[j] = 0.f;
+                        if (kk < kmax) {
+                            const int tap = kk / C, c = kk - tap * C;
+                            t4[j] = load_a<1, false>(d, d.seg[cs], ps, tap / d.KW, tap % d.KW, c).x;
+                        }
+                    }
+                    ra[i] = make_float4(t4[0], t4[1], t4[2], t4[3]);
+                } else if (VEC == 4 || !DEFORM) {
                     ra[i] = load_a<VEC, DEFORM>(d, d.seg[cs], ps, kh, kw, a_c);
                 } else {
                     ra[i].x = load_a<1, true>(d, d.seg[cs], ps, kh, kw, a_c + 0).x;
@@ -412,13 +477,23 @@ conv_wgrad_kernel(const dvsr_conv_desc d, const float* __restrict__ gy, int gy_p
         if (ch >= chunks_total) continue;
         int rem = ch, s = 0, tap = 0, c0 = 0;
         for (int q = 0; q < d.nseg; ++q) {
-            int per_tap = (d.seg[q].C + BK - 1) / BK;
-            int n_in_seg = per_tap * KK;
-            if (rem < n_in_seg) { s = q; tap = rem / per_tap; c0 = (rem - tap * per_tap) * BK; break; }
-            rem -= n_in_seg;
+            if (DENSE) {
+                int n_in_seg = (KK * d.seg[q].C + BK - 1) / BK;
+                if (rem < n_in_seg) { s = q; c0 = rem * BK; break; }
+                rem -= n_in_seg;
+            } else {
+                int per_tap = (d.seg[q].C + BK - 1) / BK;
+                int n_in_seg = per_tap * KK;
+                if (rem < n_in_seg) { s = q; tap = rem / per_tap; c0 = (rem - tap * per_tap) * BK; break; }
+                rem -= n_in_seg;
+            }
         }
-        const int ci = c0 + (r & 15);
-        if (ci >= d.seg[s].C) continue;
+        int ci = c0 + (r & 15);
+        if (DENSE) {
+            if (ci >= KK * d.seg[s].C) continue;
+            tap = ci / d.seg[s].C;
+            ci -= tap * d.seg[s].C;
+        } else if (ci >= d.seg[s].C) continue;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int co = co0 + tx * 4 + j;
@@ -482,6 +557,63 @@ __global__ void __launch_bounds__(128) conv_small_co_kernel(const dvsr_conv_desc
     }
 }
 
+// Coalesced variant: 4 lanes share one output pixel (each takes a quarter of the input channels), so a warp reads
+// 8 pixels x 256 B = 2 KiB contiguous per tap; partial sums are combined with two shuffles.  C % 16 == 0.
+__global__ void __launch_bounds__(256) conv_small_co4_kernel(const dvsr_conv_desc d, const float* __restrict__ wp) {
+    extern __shared__ float4 ws4[];
+    const dvsr_conv_seg& sg = d.seg[0];
+    const int KK = d.KH * d.KW;
+    const int Kt = KK * sg.C;
+    for (int i = threadIdx.x; i < Kt; i += blockDim.x) {
+        float t[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int o = 0; o < d.Co && o < SMALL_CO_MAX; ++o) t[o] = wp[(long long)i * d.Co + o];
+        ws4[i] = make_float4(t[0], t[1], t[2], t[3]);
+    }
+    __syncthreads();
+    const long long M = (long long)d.N * d.Ho * d.Wo;
+    const int sub = threadIdx.x & 3;                       // quarter of the channels
+    // persistent over pixel groups: the 9 KiB weight staging above is paid once per block, not once per 64 pixels
+    for (long long m = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 2; m < ((M + 63) / 64) * 64;
+         m += ((long long)gridDim.x * blockDim.x) >> 2) {
+    const bool valid = m < M;
+    PixSlot ps = decode_pixel(m, M, d.Ho, d.Wo);
+    const long long img_i = seg_image(sg, ps.n);
+    const float* img = sg.ptr + (img_i < 0 ? 0 : img_i) * sg.img_stride;
+    const int cq = sg.C >> 2, cb = sub * cq;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    if (valid) {
+        for (int tap = 0; tap < KK; ++tap) {
+            const int kh = tap / d.KW, kw = tap - kh * d.KW;
+            const int ih = ps.oh * d.stride - d.pad + kh * d.dil, iw = ps.ow * d.stride - d.pad + kw * d.dil;
+            if (ih < 0 || ih >= d.H || iw < 0 || iw >= d.W) continue;
+            const float* p = img + ((long long)ih * d.W + iw) * sg.pix_stride + cb;
+            const float4* wk = ws4 + tap * sg.C + cb;
+            for (int c = 0; c < cq; c += 4) {
+                const float4 x = ldg4(p + c);
+                const float xv[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float4 w = wk[c + q];
+                    a0 = fmaf(xv[q], w.x, a0); a1 = fmaf(xv[q], w.y, a1); a2 = fmaf(xv[q], w.z, a2); a3 = fmaf(xv[q], w.w, a3);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 1; o < 4; o <<= 1) {
+        a0 += __shfl_xor_sync(0xffffffffu, a0, o); a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+        a2 += __shfl_xor_sync(0xffffffffu, a2, o); a3 += __shfl_xor_sync(0xffffffffu, a3, o);
+    }
+    if (!valid || sub >= d.Co) continue;
+    // lane `sub` finishes output channel `sub`
+    float v = (sub == 0 ? a0 : sub == 1 ? a1 : sub == 2 ? a2 : a3) + (d.bias ? __ldg(d.bias + sub) : 0.f);
+    v = act_apply(v, d.act, d.slope);
+    if (d.res) v += __ldg(d.res + m * d.res_pix_stride + sub);
+    float* yp = d.y + m * d.y_pix_stride + sub;
+    *yp = d.accumulate ? (*yp + v) : v;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 static int validate_desc(const dvsr_conv_desc* d) {
     DVSR_REQUIRE(d != nullptr, "conv: null descriptor");
@@ -501,6 +633,13 @@ static int validate_desc(const dvsr_conv_desc* d) {
     if (d->shuffle) DVSR_REQUIRE(d->shuffle == 2 && d->Co % 4 == 0, "conv: only PixelShuffle(2) with Co %% 4 == 0");
     DVSR_REQUIRE(d->out_step == 0, "conv: strided output placement is only implemented by the tensor-core path");
     return 0;
+}
+
+// every segment has fewer than 16 channels (RGB inputs): use the dense-K kernels
+static bool small_c(const dvsr_conv_desc* d) {
+    for (int s = 0; s < d->nseg; ++s)
+        if (d->seg[s].C >= 16) return false;
+    return true;
 }
 
 static bool all_vec4(const dvsr_conv_desc* d) {
@@ -545,6 +684,7 @@ extern "C" int dvsr_conv_fprop(const dvsr_conv_desc* d, const float* wp, void* s
         else conv_fprop_kernel<1, true><<<grid, NT, 0, st>>>(*d, wp);
     } else {
         if (v4) conv_fprop_kernel<4, false><<<grid, NT, 0, st>>>(*d, wp);
+        else if (small_c(d)) conv_fprop_kernel<1, false, true><<<grid, NT, 0, st>>>(*d, wp);
         else conv_fprop_kernel<1, false><<<grid, NT, 0, st>>>(*d, wp);
     }
     return check_launch("conv_fprop");
@@ -556,8 +696,9 @@ extern "C" int dvsr_conv_wgrad(const dvsr_conv_desc* d, const float* gy, int gy_
     DVSR_REQUIRE(gy && gw && wl, "conv_wgrad: null pointer");
     DVSR_REQUIRE(!d->transposed, "conv_wgrad: descriptor must describe the forward op");
     const int KK = d->KH * d->KW;
+    const bool dense = !d->deform && !all_vec4(d) && small_c(d);
     int chunks = 0;
-    for (int s = 0; s < d->nseg; ++s) chunks += ((d->seg[s].C + BK - 1) / BK) * KK;
+    for (int s = 0; s < d->nseg; ++s) chunks += dense ? (KK * d->seg[s].C + BK - 1) / BK : ((d->seg[s].C + BK - 1) / BK) * KK;
     const long long M = (long long)d->N * d->Ho * d->Wo;
     const int gx = cdiv(chunks, WK / BK), gyd = cdiv(d->Co, BN);
     // enough pixel splits for ~4 waves of 148 SMs x 2 CTAs, at least 256 pixels per split
@@ -577,6 +718,7 @@ extern "C" int dvsr_conv_wgrad(const dvsr_conv_desc* d, const float* gy, int gy_
         else conv_wgrad_kernel<1, true><<<grid, NT, 0, st>>>(*d, gy, gy_pix_stride, gw, *wl, chunks, per);
     } else {
         if (v4) conv_wgrad_kernel<4, false><<<grid, NT, 0, st>>>(*d, gy, gy_pix_stride, gw, *wl, chunks, per);
+        else if (dense) conv_wgrad_kernel<1, false, true><<<grid, NT, 0, st>>>(*d, gy, gy_pix_stride, gw, *wl, chunks, per);
         else conv_wgrad_kernel<1, false><<<grid, NT, 0, st>>>(*d, gy, gy_pix_stride, gw, *wl, chunks, per);
     }
     return check_launch("conv_wgrad");
@@ -590,6 +732,11 @@ extern "C" int dvsr_conv_small_co(const dvsr_conv_desc* d, const float* wp, void
     const long long M = (long long)d->N * d->Ho * d->Wo;
     const size_t smem = (size_t)d->KH * d->KW * d->seg[0].C * 4 * sizeof(float);
     DVSR_REQUIRE(smem <= 48 * 1024, "conv_small_co: weights do not fit in shared memory");
-    conv_small_co_kernel<<<cdiv(M, 128), 128, smem, (cudaStream_t)stream>>>(*d, wp);
+    if (d->seg[0].C % 16 == 0) {
+        int blocks = cdiv(M * 4, 256);
+        if (blocks > 148 * 8) blocks = 148 * 8;
+        conv_small_co4_kernel<<<blocks, 256, smem, (cudaStream_t)stream>>>(*d, wp);
+    }
+    else conv_small_co_kernel<<<cdiv(M, 128), 128, smem, (cudaStream_t)stream>>>(*d, wp);
     return check_launch("conv_small_co");
 }

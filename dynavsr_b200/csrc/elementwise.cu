@@ -334,20 +334,27 @@ __global__ void pad3d_bwd_kernel(const float* __restrict__ gy, float* __restrict
 }
 
 // ---------------------------------------------------------------- per-image channel means
-__global__ void spatial_mean_kernel(const float* __restrict__ x, float* __restrict__ m, int HW, int C) {
-    // one block per (n, c)
-    const int n = blockIdx.x / C, c = blockIdx.x - n * C;
-    const float* s = x + (long long)n * HW * C + c;
+// m[n][c] += sum over a slice of the image / HW (m zeroed by the wrapper); grid = (slices, N), coalesced reads
+__global__ void spatial_mean_kernel(const float* __restrict__ x, float* __restrict__ m, int HW, int C, int per_block) {
+    const int n = blockIdx.y;
+    const long long total = (long long)HW * C;
+    const long long e0 = (long long)blockIdx.x * per_block * C;
+    const long long e1 = min(total, e0 + (long long)per_block * C);
+    const float* s = x + (long long)n * total;
+    // every thread keeps one running sum per channel residue it meets: element e has channel e % C; with a stride of
+    // blockDim.x*... simplest exact scheme: thread t accumulates elements t, t + T, ... and the channel of element e
+    // is e % C, so use T = blockDim.x rounded down to a multiple of C to keep each thread on ONE channel
+    const int T = (blockDim.x / C) * C;
     float acc = 0.f;
-    for (int i = threadIdx.x; i < HW; i += blockDim.x) acc += __ldg(s + (long long)i * C);
-    __shared__ float red[32];
-    acc = warp_sum(acc);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    if ((int)threadIdx.x < T)
+        for (long long e = e0 + threadIdx.x; e < e1; e += T) acc += __ldg(s + e);
+    extern __shared__ float red[];
+    red[threadIdx.x] = acc;
     __syncthreads();
-    if (threadIdx.x < 32) {
-        float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
-        v = warp_sum(v);
-        if (threadIdx.x == 0) m[blockIdx.x] = v / (float)HW;
+    if ((int)threadIdx.x < C) {
+        float v = 0.f;
+        for (int t = threadIdx.x; t < T; t += C) v += red[t];
+        atomicAdd(m + n * C + threadIdx.x, v / (float)HW);
     }
 }
 
@@ -551,7 +558,11 @@ extern "C" int dvsr_pad3d_replicate_bwd(const float* gy, float* gx, int B, int T
 
 extern "C" int dvsr_spatial_mean(const float* x, float* m, int N, int HW, int C, void* stream) {
     DVSR_REQUIRE(x && m && N > 0 && HW > 0 && C > 0, "spatial_mean: bad arguments");
-    spatial_mean_kernel<<<N * C, 256, 0, ST>>>(x, m, HW, C);
+    DVSR_REQUIRE(C <= 256, "spatial_mean: C=%d > 256", C);
+    if (cudaMemsetAsync(m, 0, sizeof(float) * (size_t)N * C, ST) != cudaSuccess) return check_launch("spatial_mean memset");
+    const int per_block = 2048;     // pixels per block
+    dim3 grid(cdiv(HW, per_block), N);
+    spatial_mean_kernel<<<grid, 256, 256 * sizeof(float), ST>>>(x, m, HW, C, per_block);
     return check_launch("spatial_mean");
 }
 extern "C" int dvsr_add_channel_bias(const float* x, const float* m, float* y, int N, int HW, int C, float sign, void* stream) {

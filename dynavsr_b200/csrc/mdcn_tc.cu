@@ -1,0 +1,290 @@
+// dynavsr_b200/csrc/mdcn_tc.cu
+//
+// Modulated deformable convolution forward (DCNv2, EDVR's PCD alignment) with the GEMM on the tcgen05 tensor
+// cores.  Replaces `modulated_deformable_im2col_gpu_kernel` + `addmm_` + bias (+ LeakyReLU)
+// (deform_conv_cuda_kernel.cu:569-632, deform_conv_cuda.cpp:534-563) without any `columns` buffer in HBM:
+//
+//   * 8 gather warps build, per 128-pixel tile, tap and 32-channel chunk, the modulated bilinear samples
+//     directly in shared memory in the K-major 128-byte-swizzled operand layout -- one thread per
+//     (pixel, deformable group): 2 offsets + 1 mask (coalesced from the fused [N,H,W,216] offset/mask tensor),
+//     4 corners x 32 contiguous bytes (8 channels of the group, NHWC), blend, split into bf16 hi + lo;
+//   * one warp issues the BF16x3 MMAs (x_hi.w_hi + x_lo.w_hi + x_hi.w_lo, fp32 accumulation in TMEM) against
+//     the weights that stay resident in shared memory for the whole kernel (persistent CTAs, one per SM);
+//   * 4 epilogue warps drain the double-buffered TMEM accumulator (bias, LeakyReLU, 256-bit stores).
+// Exact reference sampling semantics: zero outside (-1,H)x(-1,W), per-corner bounds (kernel.cu:466-496,617).
+#include "tc_common.cuh"
+
+namespace dvsr {
+
+constexpr int MD_ASTAGES = 4;
+constexpr int MD_A_BYTES = 128 * 128;     // 128 pixel rows x 128 B
+constexpr int MD_GATHER = 256;            // gather threads
+constexpr int MD_THREADS = 448;           // 1 producer + 1 MMA + 8 gather + 4 epilogue warps
+
+struct MdParams {
+    const float* x; int C, pix_stride; long long img_stride;
+    int N, H, W, Ho, Wo, KH, KW, stride, pad, dil, dg;
+    const float* offset; int off_pix_stride;
+    const float* mask; int mask_pix_stride;
+    int Co;
+    const float* bias; int act; float slope;
+    float* y; int y_pix_stride; int y_vec8;
+    int nblocks, tiles_total;
+};
+
+__global__ void __launch_bounds__(MD_THREADS, 1)
+mdcn_tc_kernel(const __grid_constant__ CUtensorMap wmap, const MdParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem_b = smem;                                    // [nblocks][64 x 128 B]
+    uint8_t* smem_a = smem + p.nblocks * 8192;                 // [MD_ASTAGES][16 KiB]
+    uint64_t* bars = (uint64_t*)(smem_a + MD_ASTAGES * MD_A_BYTES);
+    uint64_t* b_full = bars;                       // [1]
+    uint64_t* a_ready = bars + 1;                  // [4] 256 gather arrivals
+    uint64_t* a_empty = bars + 5;                  // [4] MMA commit
+    uint64_t* acc_full = bars + 9;                 // [2]
+    uint64_t* acc_empty = bars + 11;               // [2]
+    uint32_t* tmem_slot = (uint32_t*)(bars + 13);
+    float* bias_s = (float*)(bars + 16);           // [64]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int KK = p.KH * p.KW;
+    const int chunks = p.C / 32;
+    const long long M = (long long)p.N * p.Ho * p.Wo;
+    const int hw = p.Ho * p.Wo;
+
+    if (warp == 0 && elect_one()) prefetch_tmap(&wmap);
+    if (warp == 1) {
+        if (elect_one()) {
+            mbar_init(b_full, 1);
+            for (int i = 0; i < MD_ASTAGES; ++i) { mbar_init(&a_ready[i], MD_GATHER); mbar_init(&a_empty[i], 1); }
+            for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(128) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (threadIdx.x >= 320 && threadIdx.x < 384) {
+        const int co = threadIdx.x - 320;
+        bias_s[co] = (p.bias && co < p.Co) ? __ldg(p.bias + co) : 0.f;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            mbar_expect_tx(b_full, (uint32_t)p.nblocks * 8192u);
+            for (int b = 0; b < p.nblocks; ++b) tma_load_2d(&wmap, b_full, smem_b + b * 8192, 0, b * 64);
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (BF16x3) =====================
+        const uint32_t idesc = make_idesc_bf16(128, 64);
+        const uint64_t d_const = make_desc(0, 16, 1024, 2);
+        mbar_wait(b_full, 0);
+        int stage = 0, phase = 0, local = 0;
+        for (int tile = blockIdx.x; tile < p.tiles_total; tile += gridDim.x, ++local) {
+            const int acc = local & 1;
+            mbar_wait(&acc_empty[acc], ((local >> 1) & 1) ^ 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t dcol = tmem_base + acc * 64;
+            for (int it = 0; it < chunks * KK; ++it) {        // block order = chunk-major, then tap (pack mode 7)
+                mbar_wait(&a_ready[stage], phase);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (elect_one()) {
+                    const uint64_t ad = d_const + (uint64_t)(smem_u32(smem_a + stage * MD_A_BYTES) >> 4);
+                    const uint64_t bd = d_const + (uint64_t)(smem_u32(smem_b + it * 8192) >> 4);
+                    mma_bf16(dcol, ad, bd, idesc, it > 0 ? 1u : 0u);          // x_hi . w_hi
+                    mma_bf16(dcol, ad + 2, bd + 2, idesc, 1u);
+                    mma_bf16(dcol, ad + 4, bd, idesc, 1u);                    // x_lo . w_hi
+                    mma_bf16(dcol, ad + 6, bd + 2, idesc, 1u);
+                    mma_bf16(dcol, ad, bd + 4, idesc, 1u);                    // x_hi . w_lo
+                    mma_bf16(dcol, ad + 2, bd + 6, idesc, 1u);
+                    mma_commit(&a_empty[stage]);
+                    if (it == chunks * KK - 1) mma_commit(&acc_full[acc]);
+                }
+                __syncwarp();
+                if (++stage == MD_ASTAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp < 10) {
+        // ===================== gather: modulated bilinear samples -> swizzled bf16 hi|lo operand rows =====================
+        const int t = threadIdx.x - 64;                 // 0..255
+        const int gl = t & 3;                           // deformable group inside the 32-channel chunk (8 channels each)
+        int stage = 0, phase = 0;
+        for (int tile = blockIdx.x; tile < p.tiles_total; tile += gridDim.x) {
+            // the two pixels this thread serves in every stage of this tile
+            long long mlin[2]; int n_[2], oy[2], ox[2]; bool ok[2];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int prow = (t >> 2) + 64 * i;
+                mlin[i] = (long long)tile * 128 + prow;
+                ok[i] = mlin[i] < M;
+                const long long mm = ok[i] ? mlin[i] : 0;
+                n_[i] = (int)(mm / hw);
+                const int r = (int)(mm - (long long)n_[i] * hw);
+                oy[i] = r / p.Wo; ox[i] = r - oy[i] * p.Wo;
+            }
+            for (int c = 0; c < chunks; ++c) {
+                const int g = c * 4 + gl;
+                for (int tap = 0; tap < KK; ++tap) {
+                    const int kh = tap / p.KW, kw = tap - kh * p.KW;
+                    mbar_wait(&a_empty[stage], phase ^ 1);
+                    uint8_t* tile_a = smem_a + stage * MD_A_BYTES;
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        const int prow = (t >> 2) + 64 * i;
+                        float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                        if (ok[i]) {
+                            const float* op = p.offset + mlin[i] * p.off_pix_stride + (g * KK + tap) * 2;
+                            const float dy = __ldg(op), dx = __ldg(op + 1);
+                            const float mk = __ldg(p.mask + mlin[i] * p.mask_pix_stride + g * KK + tap);
+                            const float h = (float)(oy[i] * p.stride - p.pad + kh * p.dil) + dy;
+                            const float w = (float)(ox[i] * p.stride - p.pad + kw * p.dil) + dx;
+                            const BilinTap bt = make_tap(h, w, p.H, p.W);
+                            if (bt.inside) {
+                                const float* img = p.x + (long long)n_[i] * p.img_stride + g * 8;
+                                const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+                                float4 a0 = z, a1 = z, b0 = z, b1 = z, e0 = z, e1 = z, f0 = z, f1 = z;
+                                if (bt.o00 >= 0) { const float* q = img + (long long)bt.o00 * p.pix_stride; a0 = ldg4(q); a1 = ldg4(q + 4); }
+                                if (bt.o01 >= 0) { const float* q = img + (long long)bt.o01 * p.pix_stride; b0 = ldg4(q); b1 = ldg4(q + 4); }
+                                if (bt.o10 >= 0) { const float* q = img + (long long)bt.o10 * p.pix_stride; e0 = ldg4(q); e1 = ldg4(q + 4); }
+                                if (bt.o11 >= 0) { const float* q = img + (long long)bt.o11 * p.pix_stride; f0 = ldg4(q); f1 = ldg4(q + 4); }
+                                // same association as the reference: (w1*v1 + w2*v2 + w3*v3 + w4*v4) * mask
+                                v[0] = (bt.w00 * a0.x + bt.w01 * b0.x + bt.w10 * e0.x + bt.w11 * f0.x) * mk;
+                                v[1] = (bt.w00 * a0.y + bt.w01 * b0.y + bt.w10 * e0.y + bt.w11 * f0.y) * mk;
+                                v[2] = (bt.w00 * a0.z + bt.w01 * b0.z + bt.w10 * e0.z + bt.w11 * f0.z) * mk;
+                                v[3] = (bt.w00 * a0.w + bt.w01 * b0.w + bt.w10 * e0.w + bt.w11 * f0.w) * mk;
+                                v[4] = (bt.w00 * a1.x + bt.w01 * b1.x + bt.w10 * e1.x + bt.w11 * f1.x) * mk;
+                                v[5] = (bt.w00 * a1.y + bt.w01 * b1.y + bt.w10 * e1.y + bt.w11 * f1.y) * mk;
+                                v[6] = (bt.w00 * a1.z + bt.w01 * b1.z + bt.w10 * e1.z + bt.w11 * f1.z) * mk;
+                                v[7] = (bt.w00 * a1.w + bt.w01 * b1.w + bt.w10 * e1.w + bt.w11 * f1.w) * mk;
+                            }
+                        }
+                        uint32_t hi[4], lo[4];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            uint32_t h0, l0, h1, l1;
+                            split_bf16(v[2 * q], h0, l0);
+                            split_bf16(v[2 * q + 1], h1, l1);
+                            hi[q] = h0 | (h1 << 16);
+                            lo[q] = l0 | (l1 << 16);
+                        }
+                        // row prow = [hi: 4 chunks of 8 channels | lo: 4 chunks]; 128B swizzle: chunk ^ (row & 7)
+                        uint4* row = reinterpret_cast<uint4*>(tile_a + prow * 128);
+                        const int ph = prow & 7;
+                        row[gl ^ ph] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                        row[(4 + gl) ^ ph] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    mbar_arrive(&a_ready[stage]);
+                    if (++stage == MD_ASTAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else {
+        // ===================== epilogue =====================
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        int local = 0;
+        for (int tile = blockIdx.x; tile < p.tiles_total; tile += gridDim.x, ++local) {
+            const int acc = local & 1;
+            const long long pix = (long long)tile * 128 + row;
+            const bool valid = pix < M;
+            mbar_wait(&acc_full[acc], (local >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            float v0[32], v1[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 64), v0);
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 64 + 32), v1);
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(&acc_empty[acc]);
+            if (valid) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    float (&v)[32] = h == 0 ? v0 : v1;
+                    const int c0 = h * 32;
+                    if (c0 >= p.Co) continue;
+                    epilogue_chunk(v, c0, p.Co, bias_s + c0, nullptr, nullptr, p.act, p.slope, 0);
+                    float* yo = p.y + pix * p.y_pix_stride + c0;
+                    const int nvalid = min(32, p.Co - c0);
+                    if (p.y_vec8) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 8)
+                            if (j < nvalid) st_global_v8(yo + j, v[j], v[j + 1], v[j + 2], v[j + 3], v[j + 4], v[j + 5], v[j + 6], v[j + 7]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4)
+                            if (j < nvalid) *reinterpret_cast<float4*>(yo + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128) : "memory");
+    }
+}
+
+}  // namespace dvsr
+
+using namespace dvsr;
+
+extern "C" int dvsr_mdcn_tc_supported(const dvsr_conv_desc* d) {
+    if (!d || !d->deform || d->nseg != 1 || d->transposed || d->accumulate || d->shuffle || d->res || d->out_step) return 0;
+    const dvsr_conv_seg& g = d->seg[0];
+    if (g.C % 32 || d->dg <= 0 || g.C != d->dg * 8) return 0;               // 8 channels (32 bytes) per deformable group
+    if (d->KH * d->KW * (g.C / 32) > 18) return 0;                          // weights must fit in shared memory
+    if (d->Co > 64 || d->Co < 16 || (d->Co & 3)) return 0;
+    if ((g.pix_stride & 3) || (g.img_stride & 3) || ((uintptr_t)g.ptr & 15)) return 0;
+    if (g.T > 1 || g.t_fixed >= 0) return 0;
+    if (((uintptr_t)d->y & 15) || (d->y_pix_stride & 3)) return 0;
+    if (d->act == DVSR_ACT_SIGMOID_SPLIT) return 0;
+    return 1;
+}
+
+// wp: dvsr_pack_weights_tc2 mode 7 (BF16x3 rows) over the single segment
+extern "C" int dvsr_mdcn_tc_fprop(const dvsr_conv_desc* d, const float* wp, void* stream) {
+    DVSR_REQUIRE(d && wp && d->y, "mdcn_tc_fprop: null pointer");
+    DVSR_REQUIRE(dvsr_mdcn_tc_supported(d), "mdcn_tc_fprop: unsupported shape (use dvsr_conv_fprop)");
+    EncodeTiledFn encode = get_encode_tiled();
+    DVSR_REQUIRE(encode != nullptr, "mdcn_tc_fprop: cuTensorMapEncodeTiled is unavailable");
+    const dvsr_conv_seg& g = d->seg[0];
+    MdParams p;
+    memset(&p, 0, sizeof(p));
+    p.x = g.ptr; p.C = g.C; p.pix_stride = g.pix_stride;
+    p.img_stride = g.img_stride > 0 ? g.img_stride : (long long)d->H * d->W * g.pix_stride;
+    p.N = d->N; p.H = d->H; p.W = d->W; p.Ho = d->Ho; p.Wo = d->Wo;
+    p.KH = d->KH; p.KW = d->KW; p.stride = d->stride; p.pad = d->pad; p.dil = d->dil; p.dg = d->dg;
+    p.offset = d->offset; p.off_pix_stride = d->off_pix_stride; p.mask = d->mask; p.mask_pix_stride = d->mask_pix_stride;
+    p.Co = d->Co; p.bias = d->bias; p.act = d->act; p.slope = d->slope;
+    p.y = d->y; p.y_pix_stride = d->y_pix_stride;
+    p.y_vec8 = ((((uintptr_t)d->y) & 31) == 0) && (d->y_pix_stride % 8 == 0) && (d->Co % 8 == 0);
+    p.nblocks = d->KH * d->KW * (g.C / 32);
+    const long long M = (long long)d->N * d->Ho * d->Wo;
+    p.tiles_total = (int)((M + 127) / 128);
+    CUtensorMap wmap;
+    {
+        cuuint64_t dims[2] = {32, (cuuint64_t)p.nblocks * 64};
+        cuuint64_t strides[1] = {128};
+        cuuint32_t box[2] = {32, 64};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = encode(&wmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)wp, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        DVSR_REQUIRE(r == CUDA_SUCCESS, "mdcn_tc_fprop: cuTensorMapEncodeTiled(weights) failed with %d", (int)r);
+    }
+    const size_t smem = 1024 + (size_t)p.nblocks * 8192 + (size_t)MD_ASTAGES * MD_A_BYTES + 512;
+    DVSR_REQUIRE(smem <= 232448, "mdcn_tc_fprop: %zu B of shared memory needed", smem);
+    static size_t smem_set = 0;
+    if (smem > smem_set) {
+        if (cudaFuncSetAttribute(mdcn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return check_launch("mdcn_tc_fprop: cudaFuncSetAttribute");
+        smem_set = smem;
+    }
+    int ctas = p.tiles_total < 148 ? p.tiles_total : 148;
+    mdcn_tc_kernel<<<ctas, MD_THREADS, smem, (cudaStream_t)stream>>>(wmap, p);
+    return check_launch("mdcn_tc_fprop");
+}

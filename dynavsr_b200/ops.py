@@ -14,7 +14,7 @@ from torch.autograd import Function
 from . import _lib
 from ._lib import ACT_LRELU, ACT_NONE, ACT_RELU, ACT_SIGMOID_SPLIT, ConvDesc, WLayout, call
 
-__all__ = ['repack_all', 'weights_updated', 'Seg', 'conv', 'conv3d_padded', 'mdcn', 'upsample', 'pool_maxavg', 'pad2d', 'pad3d_replicate',
+__all__ = ['repack_all', 'weights_updated', 'join_async', 'Seg', 'conv', 'conv3d_padded', 'mdcn', 'upsample', 'pool_maxavg', 'pad2d', 'pad3d_replicate',
            'tsa_temporal', 'tsa_combine', 'pixel_loss', 'to_nhwc', 'to_nchw', 'invalidate_weight_cache',
            'ACT_NONE', 'ACT_RELU', 'ACT_LRELU', 'ACT_SIGMOID_SPLIT', 'set_conv_backend']
 
@@ -278,8 +278,35 @@ def set_conv_backend(tensor_cores, precision=None):
         _lib.lib().dvsr_conv_tc2_set_precision(1 if _backend['precision'] == 'bf16x3' else 0)
 
 
-def _run_wgrad(d, gpre, Co, gw, wl):
-    """gw += A^T gy with the tensor-core kernel when every segment qualifies, else the CUDA-core kernel."""
+# Weight gradients are leaves of the backward pass: when they accumulate into the flat gradient buffer nobody reads
+# them before the optimiser step, so they run on a side stream, concurrently with the data-gradient chain (the small
+# inner-loop layers use 30-120 CTAs each and leave most SMs idle).  join_async() is called before the update.
+_async = {'on': True, 'stream': None, 'pending': []}
+
+
+def _side_stream():
+    if _async['stream'] is None:
+        _async['stream'] = torch.cuda.Stream()
+    return _async['stream']
+
+
+def join_async():
+    """Make the current stream wait for every weight-gradient kernel issued on the side stream."""
+    if _async['pending']:
+        torch.cuda.current_stream().wait_stream(_side_stream())
+        _async['pending'].clear()
+
+
+def _run_wgrad(d, gpre, Co, gw, wl, keep=None):
+    """gw += A^T gy with the tensor-core kernel when every segment qualifies, else the CUDA-core kernel.
+    ``keep`` (tensors the kernel reads) switches on side-stream execution; they stay referenced until join_async()."""
+    if keep is not None and _async['on'] and not _lib.PROFILE['on']:
+        side = _side_stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            _run_wgrad(d, gpre, Co, gw, wl)
+        _async['pending'].append(keep)
+        return
     L = _lib.lib()
     if _lib.PROFILE['on']:
         _lib.PROFILE['tag'] = 'wgrad %dx%dx%d C%s->%d k%d s%d%s' % (d.N, d.Ho, d.Wo, '+'.join(str(d.seg[i].C) for i in range(d.nseg)),
@@ -433,7 +460,7 @@ class _ConvFn(Function):
             gw = ctx.wslot if ctx.wslot is not None else torch.zeros_like(weight)
             d = _fwd_desc(spec, tensors)
             d.Co = Co
-            _run_wgrad(d, gpre, Co, gw, wl)
+            _run_wgrad(d, gpre, Co, gw, wl, keep=(gpre, gy, tensors) if ctx.wslot is not None else None)
         if ctx.wslot is not None:
             gw = None
         if ctx.bslot is not None:
@@ -548,7 +575,15 @@ class _MdcnFn(Function):
         d.act, d.slope = act, slope
         y = torch.empty(N, Ho, Wo, Co, device=x.device, dtype=torch.float32)
         d.y, d.y_pix_stride = y.data_ptr(), Co
-        call('dvsr_conv_fprop', ctypes.byref(d), _ptr(_packed(weight, wl, 0)), _stream())
+        if _lib.PROFILE['on']:
+            _lib.PROFILE['tag'] = 'mdcn fwd %dx%dx%d C%d->%d' % (N, Ho, Wo, C, Co)
+        if _backend['tc'] and _lib.lib().dvsr_mdcn_tc_supported(ctypes.byref(d)) == 1:
+            nblocks = KK * ((C + 31) // 32)
+            wp = _get_pack(weight, wl, 7, 0, 1, a=(nblocks, 0, 0, 0),
+                           total=_lib.lib().dvsr_conv_tc2_packed_floats(ctypes.byref(wl), 7, 0, 1))
+            call('dvsr_mdcn_tc_fprop', ctypes.byref(d), _ptr(wp), _stream())
+        else:
+            call('dvsr_conv_fprop', ctypes.byref(d), _ptr(_packed(weight, wl, 0)), _stream())
         ctx.cfg = (dg, stride, pad, dil, act, slope, Ho, Wo, bias is not None)
         ctx.wl = wl
         ctx.wslot, ctx.bslot = getattr(weight, '_dvsr_grad', None), getattr(bias, '_dvsr_grad', None)
@@ -601,7 +636,7 @@ class _MdcnFn(Function):
                  _ptr(gx), C, ctypes.c_void_p(goff_p), om.shape[3], ctypes.c_void_p(gmask_p), om.shape[3], _stream())
         if ctx.needs_input_grad[2]:
             gw = ctx.wslot if ctx.wslot is not None else torch.zeros_like(weight)
-            call('dvsr_conv_wgrad', ctypes.byref(d), _ptr(gpre), Co, _ptr(gw), ctypes.byref(wl), _stream())
+            _run_wgrad(d, gpre, Co, gw, wl, keep=(gpre, gy, x, om) if ctx.wslot is not None else None)
         if ctx.wslot is not None:
             gw = None
         if ctx.bslot is not None:

@@ -168,6 +168,11 @@ int dvsr_mdcn_bwd_data(const dvsr_conv_desc* d, const float* gy, int gy_pix_stri
                        float* gx, int gx_pix_stride, float* goff, int goff_pix_stride,
                        float* gmask, int gmask_pix_stride, void* stream);
 
+/* Tensor-core forward (mdcn_tc.cu): gather warps build the modulated bilinear samples as BF16x3 operand rows in shared
+ * memory, resident weights (pack mode 7), persistent CTAs.  8 channels per deformable group, C*KH*KW <= 576, Co <= 64. */
+int dvsr_mdcn_tc_supported(const dvsr_conv_desc* d);
+int dvsr_mdcn_tc_fprop(const dvsr_conv_desc* d, const float* wp, void* stream);
+
 /* Reference operator boundary, NCHW fp32 (deform_conv_cuda.cpp:486-492, :566-573).  groups must be 1
  * (no YML of the reference uses groups != 1).  Workspace: dvsr_mdcn_workspace_bytes() bytes. */
 long long dvsr_mdcn_workspace_bytes(int B, int C, int H, int W, int Co, int kh, int kw, int stride,

@@ -90,6 +90,14 @@ def main():
             y = ops.conv(xx, ww, None, stride=2, pad=pad)
             return (y,) + tuple(torch.autograd.grad(y, [xx, ww], gy0))
         run('stride2 N%d %dx%d %d->%d k%d (y, gx, gw)' % (N, H, W, Ci, Co, k), fb3)
+    # modulated deformable conv forward on tensor cores
+    for (N, H, W) in [(1, 11, 13), (5, 44, 80), (2, 90, 160)]:
+        xd = torch.randn(N, H, W, 64, device=dev)
+        om = torch.cat([torch.randn(N, H, W, 144, device=dev) * 3.0, torch.rand(N, H, W, 72, device=dev)], 3).contiguous()
+        wd = torch.randn(64, 64, 3, 3, device=dev) * 0.05
+        bd = torch.randn(64, device=dev) * 0.1
+        with torch.no_grad():
+            run('mdcn fwd N%d %dx%d' % (N, H, W), lambda: ops.mdcn(xd, om, wd, bd, 8, 1, 1, 1, ops.ACT_LRELU))
     # valid conv (pad 0) as in MFDN
     xp = torch.randn(2, 18, 34, 64, device=dev)
     w = torch.randn(64, 64, 3, 3, device=dev) * 0.05
