@@ -36,6 +36,7 @@ def parse():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='adapt', choices=['adapt', 'infer'])
     ap.add_argument('--no-graphs', action='store_true')
+    ap.add_argument('--pipelines', type=int, default=3, help='independent frames kept in flight per GPU (adapt.AdaptationPool)')
     ap.add_argument('--no-tc', action='store_true', help='exact-fp32 CUDA-core convolutions only')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--height', type=int, default=LR_H)
@@ -45,19 +46,8 @@ def parse():
 
 # ---------------------------------------------------------------------------------------------------
 def synth_clip(seed, H, W, nfr=NFR):
-    """Seeded band-limited noise with a global translation of <= 2 px/frame, in [0, 1], quantised to
-    8 bits like the reference pipeline (vsrbase.py:188).  [1, nfr, 3, H, W] float32 (CPU)."""
-    import torch
-    import torch.nn.functional as F
-    g = torch.Generator().manual_seed(seed)
-    base = torch.rand(1, 3, H // 4 + 8, W // 4 + 8, generator=g)
-    base = F.interpolate(base, scale_factor=4, mode='bicubic', align_corners=False).clamp(0, 1)
-    frames = []
-    for t in range(nfr):
-        dy, dx = 8 + (t * 2) % 5, 8 + (t * 3) % 7
-        frames.append(base[:, :, dy:dy + H, dx:dx + W])
-    clip = torch.stack(frames, 1)
-    return (clip * 255).round() / 255
+    from dynavsr_b200.synth import synth_clip as f
+    return f(seed, H, W, nfr)
 
 
 class ClockSampler(threading.Thread):
@@ -169,8 +159,8 @@ def main():
         return
     import torch
     import torch.distributed as dist
-    from oracle import params as P          # weights only (seeded generator); no oracle compute on this path
     from dynavsr_b200 import _lib, adapt, ops
+    from dynavsr_b200.synth import seed_parameters
     from dynavsr_b200.models.archs import EDVR_arch, LRimg_estimator
     if not torch.cuda.is_available():
         raise SystemExit('bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm')
@@ -182,33 +172,45 @@ def main():
     ops.set_conv_backend(use_tc)
 
     def build(seedG):
-        netG = EDVR_arch.EDVR(nf=64, nframes=NFR, groups=8, front_RBs=5, back_RBs=10, scale=SCALE)
-        netG.load_state_dict(P.make_params(P.edvr_param_shapes(), seed=seedG))
-        netE = LRimg_estimator.DirectKernelEstimatorVideo(64, 3, SCALE)
-        netE.load_state_dict(P.make_params(P.mfdn_param_shapes(), seed=77))
-        netF = LRimg_estimator.DirectKernelEstimatorVideo(64, 3, SCALE)
-        netF.load_state_dict(P.make_params(P.mfdn_param_shapes(), seed=78))
+        netG = seed_parameters(EDVR_arch.EDVR(nf=64, nframes=NFR, groups=8, front_RBs=5, back_RBs=10, scale=SCALE), seedG)
+        netE = seed_parameters(LRimg_estimator.DirectKernelEstimatorVideo(64, 3, SCALE), 77)
+        netF = seed_parameters(LRimg_estimator.DirectKernelEstimatorVideo(64, 3, SCALE), 78)
         return netG.cuda(), netE.cuda(), netF.cuda()
 
-    netG, netE, netF = build(1234)
-    eng = adapt.InnerLoopAdapter(netG, netE, netF, use_graphs=not args.no_graphs, **INNER)
+    P = max(1, args.pipelines)
+    pool = adapt.AdaptationPool(*build(1234), pipelines=P, use_graphs=not args.no_graphs, **INNER)
+    eng = pool.engines[0]
     # distinct windows per step and per rank (clip sharding: frame i -> rank i % world, train_dynavsr.py:509)
     n_clips = 4
     clips_host = [synth_clip(100 + rank * n_clips + i, H, W).pin_memory() for i in range(n_clips)]
     frames_dev = [ops.to_nhwc(c.cuda().reshape(NFR, 3, H, W)) for c in clips_host]
-    hr_host = torch.empty(1, 3, SCALE * H, SCALE * W).pin_memory()
+    hr_host = [torch.empty(1, 3, SCALE * H, SCALE * W).pin_memory() for _ in range(P)]
+    done = [None] * P
+    if args.workload == 'adapt' and not args.no_graphs:
+        pool.warm(frames_dev[0])        # capture every pipeline's CUDA graphs outside the timed regions
+
+    def run(e, fr):
+        return e.adapt_and_infer_nhwc(fr) if args.workload == 'adapt' else e.infer_nhwc(fr)
 
     def step_dev(i):
-        if args.workload == 'adapt':
-            return eng.adapt_and_infer_nhwc(frames_dev[i % n_clips])
-        return eng.infer_nhwc(frames_dev[i % n_clips])
+        # frame i goes to pipeline i % P (its own stream, parameter copy and graphs); inputs already resident in HBM
+        pool.submit(lambda e: run(e, frames_dev[i % n_clips]))
 
     def step_e2e(i):
-        x = clips_host[i % n_clips].cuda(non_blocking=True).reshape(NFR, 3, H, W)
-        fr = ops.to_nhwc(x)
-        hr = eng.adapt_and_infer_nhwc(fr) if args.workload == 'adapt' else eng.infer_nhwc(fr)
-        hr_host.copy_(ops.to_nchw(hr), non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        # the user-facing call with HOST buffers: H2D of the pinned LR window, adapt + super-resolve, D2H of the HR frame,
+        # all on the frame's pipeline stream; the host takes delivery of a pipeline's previous frame before reusing its
+        # pinned output buffer
+        k = i % P
+        if done[k] is not None:
+            done[k].synchronize()
+
+        def work(e):
+            x = clips_host[i % n_clips].cuda(non_blocking=True).reshape(NFR, 3, H, W)
+            hr_host[k].copy_(ops.to_nchw(run(e, ops.to_nhwc(x))), non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            return ev
+        done[k] = pool.submit(work, pipeline=k)[1]
 
     def barrier():
         if world > 1:
@@ -218,12 +220,14 @@ def main():
     def timed(fn, steps, warmup):
         for i in range(warmup):
             fn(i)
+        pool.join()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         _lib.COUNTER[0] = 0
         e0.record()
         for i in range(steps):
             fn(warmup + i)
+        pool.join()
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -243,7 +247,8 @@ def main():
     value = world * args.steps / (ms / 1000.0)
     e2e = world * args.steps / (ms_e2e / 1000.0)
     # kernels launched per step: counted while the step was captured / run eagerly
-    per_step = eng.launches_per_step if getattr(eng, 'launches_per_step', None) else host_launches / max(1, args.steps)
+    per_step = eng.launches_per_step if (getattr(eng, 'launches_per_step', None) and args.workload == 'adapt') \
+        else host_launches / max(1, args.steps)
 
     # ---- roofline of the dominant kernel: the 3x3 64->64 convolution (feature extraction / PCD / trunk shape,
     # N frames x 176x320), timed alone on the launching stream with CUDA events.  20 back-to-back launches are
@@ -311,6 +316,7 @@ def main():
                 'config': {'workload': ('adapt2_sgd_l2+final_forward' if args.workload == 'adapt' else 'inference_only') +
                            ' EDVR-M 4x + MFDN, REDS4-shaped 5x3x180x320 window cropped to %dx%d -> 3x%dx%d' % (H, W, SCALE * H, SCALE * W),
                            'inner': INNER, 'clips_per_rank': n_clips, 'cuda_graphs': not args.no_graphs,
+                           'frames_in_flight_per_gpu': P,
                            'l2': 'per-step working set (activations ~GBs) exceeds the 126 MB L2; inputs rotate over %d clips' % n_clips,
                            'parallelism': 'clip-sharded dp%d, no data-path collective' % world},
                 'e2e': {'value': e2e, 'unit': UNIT, 'h2d_bytes_per_step': NFR * 3 * H * W * 4,

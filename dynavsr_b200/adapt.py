@@ -14,8 +14,8 @@ optimiser step a single kernel launch (dvsr_update_sgd / dvsr_update_adam) inste
 launches; weight-gradient kernels accumulate straight into the flat gradient buffer.  The whole
 step (forward, backward, update) and the final forward are captured in CUDA graphs per input shape.
 """
+import copy
 import ctypes
-import math
 
 import torch
 
@@ -39,7 +39,8 @@ class FlatParams(object):
     """
     ALIGN = 64  # floats (256 B)
 
-    def __init__(self, modules, device=None):
+    def __init__(self, modules, device=None, scope=None):
+        self.scope = scope or ops._default_scope
         params = []
         self.split = None
         offsets = []
@@ -65,10 +66,11 @@ class FlatParams(object):
                 p.data = view
                 p.grad = None
                 p._dvsr_grad = self.grad[o:o + p.numel()].view(p.shape)   # kernels accumulate here directly
+                p._dvsr_scope = self.scope
         self.meta = self.flat.clone()       # the meta-weights every frame restarts from
         self.m = self.v = None
         self.step_count = 0
-        ops.invalidate_weight_cache()
+        ops.invalidate_weight_cache(self.scope)
 
     def snapshot(self):
         self.meta.copy_(self.flat)
@@ -80,7 +82,7 @@ class FlatParams(object):
         if self.m is not None:
             self.m.zero_()
             self.v.zero_()
-        ops.invalidate_weight_cache()      # the step that follows starts with ops.repack_all()
+        ops.invalidate_weight_cache(self.scope)      # the step that follows starts with ops.repack_all()
 
     def zero_grad(self):
         self.grad.zero_()
@@ -123,9 +125,11 @@ class InnerLoopAdapter(object):
         self.lr_alpha_est = lr_alpha if lr_alpha_est is None else lr_alpha_est
         self.slr_weight, self.pixel_weight = slr_weight, pixel_weight
         self.use_graphs = use_graphs
-        self.flat = FlatParams([netG, netE])
+        self.scope = ops.new_scope()        # this engine's weight packs / pack table / weight-gradient side stream
+        self.flat = FlatParams([netG, netE], scope=self.scope)
         for p in netE_fixed.parameters():
             p.requires_grad_(False)
+            p._dvsr_scope = self.scope
         self.N = netG.nframes
         self.center = netG.center
         self._graphs = {}
@@ -189,17 +193,18 @@ class InnerLoopAdapter(object):
         if H % (4 * s) or W % (4 * s):
             raise RuntimeError('adaptation runs EDVR on LR/scale: H and W must be multiples of %d, got %dx%d '
                                '(the reference dataset crops for this: video_test_dataset_int.py:185-189)' % (4 * s, H, W))
-        if not self.use_graphs:
+        with ops.scope(self.scope):
+            if not self.use_graphs:
+                self.flat.restore()
+                hr, losses = self._run_eager(frames, B)
+                self.last_losses = torch.stack(losses) if losses else None
+                return hr
+            st = self._graphs.get((tuple(frames.shape), B)) or self._build_graphs(frames, B)
+            st['in'].copy_(frames, non_blocking=True)
             self.flat.restore()
-            hr, losses = self._run_eager(frames, B)
-            self.last_losses = torch.stack(losses) if losses else None
-            return hr
-        st = self._graphs.get((tuple(frames.shape), B)) or self._build_graphs(frames, B)
-        st['in'].copy_(frames, non_blocking=True)
-        self.flat.restore()
-        st['graph'].replay()
-        self.last_losses = st['losses']
-        return st['hr']
+            st['graph'].replay()
+            self.last_losses = st['losses']
+            return st['hr']
 
     def adapt_and_infer(self, lr_clip):
         """lr_clip: [B, N, 3, H, W] (reference tensor layout, host or device) -> HR [B, 3, sH, sW]."""
@@ -210,7 +215,73 @@ class InnerLoopAdapter(object):
 
     def infer_nhwc(self, frames, B=1):
         """Plain EDVR forward with the meta-weights (no adaptation)."""
-        self.flat.restore()
-        ops.repack_all()
-        with torch.no_grad():
-            return self.netG.forward_nhwc(frames, B, self.N)
+        with ops.scope(self.scope):
+            self.flat.restore()
+            ops.repack_all()
+            with torch.no_grad():
+                return self.netG.forward_nhwc(frames, B, self.N)
+
+
+class AdaptationPool(object):
+    """P independent ``InnerLoopAdapter`` pipelines on P CUDA streams of ONE GPU.
+
+    Output frames are independent units of work: every frame restarts from the same meta-weights and reads only its own
+    window (test_dynavsr.py:208), which is why the path shards over GPUs with no collective (train_dynavsr.py:509).  The
+    same property lets one GPU keep several frames in flight: the inner adaptation steps run EDVR on the 4x smaller SLR
+    window (44x80 -> 28-140 CTAs per kernel, a dependent chain of ~400 launches), which leaves most of the 148 SMs idle;
+    a second and third frame's kernels fill them.  Each pipeline owns its parameter copy (flat buffer), weight packs,
+    CUDA graphs and streams; nothing is shared but the (read-only) meta-weights they were cloned from.
+    """
+
+    def __init__(self, netG, netE, netE_fixed, pipelines=3, **kw):
+        assert pipelines >= 1
+        nets = [(netG, netE, netE_fixed)]
+        for _ in range(pipelines - 1):          # clone BEFORE any engine re-homes the parameters
+            nets.append((copy.deepcopy(netG), copy.deepcopy(netE), copy.deepcopy(netE_fixed)))
+        self.engines = [InnerLoopAdapter(g, e, f, **kw) for g, e, f in nets]
+        self.streams = [torch.cuda.Stream() for _ in self.engines]
+        self._next = 0
+        self.scale = netG.scale
+
+    def __len__(self):
+        return len(self.engines)
+
+    @property
+    def launches_per_step(self):
+        return self.engines[0].launches_per_step
+
+    def warm(self, frames, B=1):
+        """Capture every pipeline's CUDA graphs for this window shape (sequentially, on the current stream)."""
+        for eng in self.engines:
+            eng.adapt_and_infer_nhwc(frames, B)
+        torch.cuda.current_stream().synchronize()
+
+    def submit(self, fn, pipeline=None):
+        """Run ``fn(engine)`` on the next pipeline's stream (round robin) after everything already enqueued on the
+        caller's stream; returns (pipeline index, result of fn).  Nothing is synchronised: results are ordered on that
+        pipeline's stream -- consume them there (``fn`` may include the device-to-host copy) or call ``join()``."""
+        i = self._next if pipeline is None else pipeline
+        self._next = (i + 1) % len(self.engines)
+        s = self.streams[i]
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            out = fn(self.engines[i])
+        return i, out
+
+    def join(self):
+        """Make the caller's stream wait for every pipeline."""
+        cur = torch.cuda.current_stream()
+        for s in self.streams:
+            cur.wait_stream(s)
+
+    def adapt_and_infer_many(self, windows):
+        """windows: iterable of [N, H, W, 3] device tensors (LR windows, channels-last) -> list of HR [1, sH, sW, 3]."""
+        outs = []
+        for w in windows:
+            w.record_stream(self.streams[self._next])           # allocator: w is consumed on the pipeline's stream
+            _, hr = self.submit(lambda eng, w=w: eng.adapt_and_infer_nhwc(w).clone())
+            outs.append(hr)
+        self.join()
+        for hr in outs:
+            hr.record_stream(torch.cuda.current_stream())
+        return outs

@@ -48,6 +48,8 @@ struct T2Params {
     float* y; int y_pix_stride;
     int y_vec8;                           // y rows are 32-byte aligned: 256-bit stores
     int bf16x3;                           // 1: operands split into bf16 hi + lo, 3 products (fp32-class accuracy)
+    int n_mma;                            // MMA N (16..64): output channels of this launch's widest group, rounded up to 16
+    int scalar_out;                       // narrow / unaligned outputs (conv_last 64 -> 3): scalar epilogue, Co <= 32
     long long* trace;                     // optional per-event clock64 trace of CTA (0,0): [event][chunk]
 };
 struct __align__(64) T2Maps { CUtensorMap x[DVSR_MAX_SEG]; CUtensorMap w; };
@@ -152,7 +154,7 @@ conv_tc2_kernel(const __grid_constant__ T2Maps maps, const T2Params p) {
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        const uint32_t idesc = p.bf16x3 ? make_idesc_bf16(128, T2_NG) : make_idesc_tf32(128, T2_NG);
+        const uint32_t idesc = p.bf16x3 ? make_idesc_bf16(128, p.n_mma) : make_idesc_tf32(128, p.n_mma);
         // descriptor templates: only the 14-bit (address >> 4) field changes per tap / k-step
         const uint64_t ad_const = make_desc(0, 16, (uint32_t)p.halo_w * 128u, 2);
         const uint64_t bd_const = make_desc(0, 16, 1024, 2);
@@ -275,6 +277,23 @@ conv_tc2_kernel(const __grid_constant__ T2Maps maps, const T2Params p) {
             if (threadIdx.x == 192) T2_TRACE(5, local);
             float v0[32], v1[32];
             tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * T2_NG), v0);
+            if (p.scalar_out) {
+                // narrow output (Co <= 32, any alignment): one 32-column read, per-channel loads / stores
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                mbar_arrive(&acc_empty[acc]);
+                if (valid) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        if (j >= p.Co) break;
+                        float t = v0[j] + bias_s[j];
+                        if (p.accum_in) t += __ldg(p.accum_in + pix * p.accum_pix_stride + j);
+                        t = (p.act == DVSR_ACT_SIGMOID_SPLIT) ? (j >= p.sig_split ? sigmoidf_(t) : t) : act_apply(t, p.act, p.slope);
+                        if (p.res) t += __ldg(p.res + pix * p.res_pix_stride + j);
+                        p.y[pix * p.y_pix_stride + j] = t;
+                    }
+                }
+                continue;
+            }
             tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * T2_NG + 32), v1);
             // the accumulator is in registers: hand the TMEM buffer back to the MMA warp before the global stores
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -342,7 +361,10 @@ static int t2_blocks(const dvsr_conv_desc* d) {
 // 1 if the WHOLE descriptor can run in one launch of the resident-weight kernel
 extern "C" int dvsr_conv_tc2_supported(const dvsr_conv_desc* d) {
     if (!d || d->deform || d->stride != 1 || d->dil != 1 || d->accumulate || d->out_step) return 0;
-    if (d->Co < 16 || (d->Co & 3)) return 0;
+    const bool narrow = d->Co <= 32 && (d->Co < 16 || (d->Co & 3) || (d->y_pix_stride & 3) || ((uintptr_t)d->y & 15) ||
+                                        (d->res && ((((uintptr_t)d->res) & 15) || (d->res_pix_stride & 3))));
+    if (narrow && d->shuffle) return 0;
+    if (!narrow && (d->Co < 16 || (d->Co & 3))) return 0;
     if (d->shuffle && (d->Co % 32)) return 0;
     if (d->KH > 5 || d->KW > 5) return 0;
     for (int s = 0; s < d->nseg; ++s) {
@@ -350,8 +372,10 @@ extern "C" int dvsr_conv_tc2_supported(const dvsr_conv_desc* d) {
         if ((g.C & 3) || g.C < 16 || (g.pix_stride & 3) || (g.img_stride & 3) || ((uintptr_t)g.ptr & 15)) return 0;
         if (d->wshare && g.C != d->seg[0].C) return 0;
     }
-    if (((uintptr_t)d->y & 15) || (d->y_pix_stride & 3)) return 0;
-    if (d->res && ((((uintptr_t)d->res) & 15) || (d->res_pix_stride & 3))) return 0;
+    if (!narrow) {
+        if (((uintptr_t)d->y & 15) || (d->y_pix_stride & 3)) return 0;
+        if (d->res && ((((uintptr_t)d->res) & 15) || (d->res_pix_stride & 3))) return 0;
+    }
     return t2_blocks(d) <= T2_MAX_BLOCKS;
 }
 
@@ -415,6 +439,9 @@ extern "C" int dvsr_conv_tc2_fprop(const dvsr_conv_desc* d, const float* wp, con
     p.y_vec8 = ((((uintptr_t)d->y) & 31) == 0) && (d->y_pix_stride % 8 == 0) && (d->Co % 8 == 0);
     p.trace = g_t2_trace;
     p.bf16x3 = g_t2_bf16x3;
+    p.scalar_out = d->Co <= 32 && (d->Co < 16 || (d->Co & 3) || (d->y_pix_stride & 3) || ((uintptr_t)d->y & 15) ||
+                                   (d->res && ((((uintptr_t)d->res) & 15) || (d->res_pix_stride & 3))));
+    p.n_mma = d->Co >= T2_NG ? T2_NG : (d->Co + 15) / 16 * 16;
     const int tiles_w = (d->Wo + T2_TW - 1) / T2_TW, tiles_h = (d->Ho + T2_TH - 1) / T2_TH;
     p.tiles_total = d->N * tiles_w * tiles_h;
     const int ngroups = (d->Co + T2_NG - 1) / T2_NG;

@@ -1,6 +1,7 @@
 // dynavsr_b200/csrc/conv_wgrad_tc.cu
 //
-// Weight gradient of a stride-1 convolution on the tcgen05 tensor cores, straight from the NHWC tensors:
+// Weight gradient of a stride-1 (or, by parity decomposition, stride-2) convolution on the tcgen05 tensor cores,
+// straight from the NHWC tensors:
 //
 //   gw[co][ci][tap] += sum_{pixels p} x[p + tap][ci] * gy[p][co]
 //
@@ -15,6 +16,10 @@
 // -layout gradient with red.global.add.f32.  Grid = (pixel splits, tap groups, ci tiles).
 // TF32 operands are used as stored (hardware truncation): a weight gradient is a leaf, its ~1e-3 relative
 // error does not compound through layers.
+// Stride 2 (MFDN's 4x4/s2 convs LRimg_estimator.py:79-82, fea_L{2,3}_conv1 EDVR_arch.py:229,231): tap kh = a + 2t reads
+// input row 2(oy + t) + a - pad, so each parity class (a, b) is a stride-1 weight gradient with ceil((KH-a)/2) x
+// ceil((KW-b)/2) taps over the 2x-subsampled input x[2i + a - pad][2j + b - pad] -- which TMA delivers directly
+// (element strides 2, negative / out-of-range coordinates zero-filled).  One launch per parity class.
 #include "tc_common.cuh"
 
 namespace dvsr {
@@ -24,7 +29,9 @@ constexpr int WG_TW = 8;                 // chunk width in pixels (one K=8 MMA p
 
 struct WgParams {
     int N, Ho, Wo;                       // gy images / size
-    int KH, KW, pad;
+    int KH, KW;                          // taps of this launch (a parity class of the full kernel when xs == 2)
+    int xs, x_org_y, x_org_x;            // input pixel of output (oy, ox), tap (kh, kw): (oy + kh) * xs + x_org_y, ...
+    int tap_a, tap_b, KWf;               // full-kernel tap of local tap (kh, kw): (tap_a + xs*kh) * KWf + tap_b + xs*kw
     int T, Tsrc, dt, t_fixed;            // source-image rule of the segment
     int C, c_tile0, Mtile;               // segment channels; first channel and size (64/128) of this CTA's M tile
     int Co, Npad;
@@ -97,7 +104,8 @@ conv_wgrad_tc_kernel(const __grid_constant__ WgMaps maps, const WgParams p) {
                 uint8_t* sa = smem + stage * stage_bytes;
                 uint8_t* sb = sa + a_bytes;
                 for (int b = 0; b < mblk; ++b)
-                    tma_load_4d(&maps.x, &full_bar[stage], sa + b * p.a_blk_bytes, c_tile + b * 32, ox0 - p.pad, oy0 - p.pad, img);
+                    tma_load_4d(&maps.x, &full_bar[stage], sa + b * p.a_blk_bytes, c_tile + b * 32, ox0 * p.xs + p.x_org_x,
+                                oy0 * p.xs + p.x_org_y, img);
                 for (int b = 0; b < nblk; ++b)
                     tma_load_4d(&maps.gy, &full_bar[stage], sb + b * p.b_blk_bytes, b * 32, ox0, oy0, n);
                 if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -138,7 +146,8 @@ conv_wgrad_tc_kernel(const __grid_constant__ WgMaps maps, const WgParams p) {
         const int ci = c_tile + m;
         const bool row_ok = (m >= 0) && (m < Mt) && (ci < p.C);
         for (int tl = 0; tl < ntaps; ++tl) {
-            const int tap = tap0 + tl;
+            const int ltap = tap0 + tl, lkh = ltap / p.KW, lkw = ltap - lkh * p.KW;
+            const int tap = (p.tap_a + p.xs * lkh) * p.KWf + p.tap_b + p.xs * lkw;
             for (int c0 = 0; c0 < p.Npad; c0 += 32) {
                 float v[32];
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(tl * p.Npad + c0), v);
@@ -168,7 +177,7 @@ using namespace dvsr;
 
 // Is segment `seg` of forward descriptor `d` eligible for the tensor-core weight gradient?
 extern "C" int dvsr_conv_wgrad_tc_supported(const dvsr_conv_desc* d, int seg) {
-    if (!d || d->deform || d->transposed || d->stride != 1 || d->dil != 1) return 0;
+    if (!d || d->deform || d->transposed || (d->stride != 1 && d->stride != 2) || d->dil != 1) return 0;
     if (seg < 0 || seg >= d->nseg) return 0;
     if (d->Co < 16 || d->Co > 256 || (d->Co & 3)) return 0;
     const dvsr_conv_seg& g = d->seg[seg];
@@ -185,14 +194,22 @@ extern "C" int dvsr_conv_wgrad_tc(const dvsr_conv_desc* d, int seg, const float*
     EncodeTiledFn encode = get_encode_tiled();
     DVSR_REQUIRE(encode != nullptr, "conv_wgrad_tc: cuTensorMapEncodeTiled is unavailable");
     const dvsr_conv_seg& g = d->seg[seg];
+    const int xs = d->stride;
+    static size_t smem_set = 0;
+    for (int pa = 0; pa < xs; ++pa)
+    for (int pb = 0; pb < xs; ++pb) {
     WgParams p;
     memset(&p, 0, sizeof(p));
-    p.N = d->N; p.Ho = d->Ho; p.Wo = d->Wo; p.KH = d->KH; p.KW = d->KW; p.pad = d->pad;
+    const int KHs = (d->KH - pa + xs - 1) / xs, KWs = (d->KW - pb + xs - 1) / xs;   // taps of this parity class
+    if (KHs <= 0 || KWs <= 0) continue;
+    p.N = d->N; p.Ho = d->Ho; p.Wo = d->Wo; p.KH = KHs; p.KW = KWs;
+    p.xs = xs; p.x_org_y = pa - d->pad; p.x_org_x = pb - d->pad;
+    p.tap_a = pa; p.tap_b = pb; p.KWf = d->KW;
     p.T = g.T; p.Tsrc = g.Tsrc; p.dt = g.dt; p.t_fixed = g.t_fixed;
     p.C = g.C; p.c_tile0 = 0;
     p.Mtile = g.C >= 128 ? 128 : 64;
     p.Co = d->Co; p.Npad = round_up(d->Co, 16);
-    const int KK = d->KH * d->KW;
+    const int KK = KHs * KWs;
     // TMEM budget: taps_per_group * Npad <= 512 columns
     p.taps_per_group = 512 / p.Npad;
     if (p.taps_per_group > KK) p.taps_per_group = KK;
@@ -203,7 +220,7 @@ extern "C" int dvsr_conv_wgrad_tc(const dvsr_conv_desc* d, int seg, const float*
     // chunk rows: 8 if three stages fit in ~200 KB, else 4
     int CH = 8, stages = 0;
     for (;; CH = 4) {
-        p.a_blk_bytes = round_up((CH + d->KH - 1) * (WG_TW + d->KW - 1) * 128, 1024);
+        p.a_blk_bytes = round_up((CH + KHs - 1) * (WG_TW + KWs - 1) * 128, 1024);
         p.b_blk_bytes = CH * WG_TW * 128;
         const int stage_bytes = mblk * p.a_blk_bytes + nblk * p.b_blk_bytes;
         stages = (200 * 1024) / stage_bytes;
@@ -233,8 +250,8 @@ extern "C" int dvsr_conv_wgrad_tc(const dvsr_conv_desc* d, int seg, const float*
         long long img_stride = g.img_stride > 0 ? g.img_stride : (long long)d->H * d->W * g.pix_stride;
         cuuint64_t dims[4] = {(cuuint64_t)g.C, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)nsrc};
         cuuint64_t strides[3] = {(cuuint64_t)g.pix_stride * 4, (cuuint64_t)d->W * g.pix_stride * 4, (cuuint64_t)img_stride * 4};
-        cuuint32_t box[4] = {32, (cuuint32_t)(WG_TW + d->KW - 1), (cuuint32_t)(CH + d->KH - 1), 1};
-        cuuint32_t es[4] = {1, 1, 1, 1};
+        cuuint32_t box[4] = {32, (cuuint32_t)((WG_TW + KWs - 1) * xs), (cuuint32_t)((CH + KHs - 1) * xs), 1};
+        cuuint32_t es[4] = {1, (cuuint32_t)xs, (cuuint32_t)xs, 1};
         CUresult r = encode(&maps.x, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)g.ptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                             CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         DVSR_REQUIRE(r == CUDA_SUCCESS, "conv_wgrad_tc: cuTensorMapEncodeTiled(x) failed with %d", (int)r);
@@ -250,7 +267,6 @@ extern "C" int dvsr_conv_wgrad_tc(const dvsr_conv_desc* d, int seg, const float*
         DVSR_REQUIRE(r == CUDA_SUCCESS, "conv_wgrad_tc: cuTensorMapEncodeTiled(gy) failed with %d", (int)r);
     }
     const size_t smem = 1024 + (size_t)stages * (mblk * p.a_blk_bytes + nblk * p.b_blk_bytes) + 256;
-    static size_t smem_set = 0;
     if (smem > smem_set) {
         if (cudaFuncSetAttribute(conv_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
             return check_launch("conv_wgrad_tc: cudaFuncSetAttribute");
@@ -258,5 +274,7 @@ extern "C" int dvsr_conv_wgrad_tc(const dvsr_conv_desc* d, int seg, const float*
     }
     dim3 grid(splits, groups, ztiles);
     conv_wgrad_tc_kernel<<<grid, WG_THREADS, smem, (cudaStream_t)stream>>>(maps, p);
+    if (int rc = check_launch("conv_wgrad_tc")) return rc;
+    }
     return check_launch("conv_wgrad_tc");
 }

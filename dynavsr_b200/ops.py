@@ -14,7 +14,7 @@ from torch.autograd import Function
 from . import _lib
 from ._lib import ACT_LRELU, ACT_NONE, ACT_RELU, ACT_SIGMOID_SPLIT, ConvDesc, WLayout, call
 
-__all__ = ['repack_all', 'weights_updated', 'join_async', 'Seg', 'conv', 'conv3d_padded', 'mdcn', 'upsample', 'pool_maxavg', 'pad2d', 'pad3d_replicate',
+__all__ = ['PackScope', 'new_scope', 'scope', 'repack_all', 'weights_updated', 'join_async', 'Seg', 'conv', 'conv3d_padded', 'mdcn', 'upsample', 'pool_maxavg', 'pad2d', 'pad3d_replicate',
            'tsa_temporal', 'tsa_combine', 'pixel_loss', 'to_nhwc', 'to_nchw', 'invalidate_weight_cache',
            'ACT_NONE', 'ACT_RELU', 'ACT_LRELU', 'ACT_SIGMOID_SPLIT', 'set_conv_backend']
 
@@ -97,18 +97,60 @@ class _WeightCache(object):
 
 
 _wcache = _WeightCache()
-_wcache_epoch = [0]
 
 
-def invalidate_weight_cache():
+class PackScope(object):
+    """Bookkeeping of ONE adaptation engine: its registered weight packs + device-side pack table, the epoch that marks
+    packs stale after an out-of-band parameter write, and the side stream its weight-gradient kernels run on.
+    Several engines (adapt.AdaptationPool: independent frames in flight on separate streams) each own a scope, so one
+    engine's single-launch re-pack never touches another engine's buffers.  Weights are bound to a scope with the
+    ``_dvsr_scope`` attribute (adapt.FlatParams); untagged weights live in the process-wide default scope."""
+
+    def __init__(self):
+        self.registry = {}      # (id(weight), key) -> entry dict; entries die with their weight (weakref callback)
+        self.table = {'dev': None, 'n': 0, 'blocks': 0, 'dirty': True}
+        self.epoch = 0
+        self.side = None
+        self.pending = []
+
+
+_default_scope = PackScope()
+_current_scope = [_default_scope]
+
+
+def new_scope():
+    return PackScope()
+
+
+class scope(object):
+    """``with ops.scope(s):`` -- makes ``s`` the scope repack_all / weights_updated / join_async act on."""
+
+    def __init__(self, s):
+        self.s = s
+
+    def __enter__(self):
+        self.prev = _current_scope[0]
+        _current_scope[0] = self.s
+        return self.s
+
+    def __exit__(self, *exc):
+        _current_scope[0] = self.prev
+        return False
+
+
+def _scope_of(weight):
+    return getattr(weight, '_dvsr_scope', None) or _default_scope
+
+
+def invalidate_weight_cache(s=None):
     """Call after parameters were modified through raw pointers; packs are refreshed lazily (one launch each)."""
-    _wcache_epoch[0] += 1
+    (s or _current_scope[0]).epoch += 1
 
 
 def weights_updated():
     """Call after a fused parameter update / restore: bumps the epoch and refreshes every registered pack with one
     table-driven launch (replaces ~370 per-layer pack launches per adaptation step)."""
-    _wcache_epoch[0] += 1
+    _current_scope[0].epoch += 1
     repack_all()
 
 
@@ -134,12 +176,8 @@ def _layout(weight, seg_C, temporal):
     return wl
 
 
-_pack_registry = {}        # (id(weight), key) -> entry dict; entries die with their weight (weakref callback)
-_pack_table = {'dev': None, 'n': 0, 'blocks': 0, 'dirty': True}
-
-
 def _weight_stamp(weight):
-    return (weight._version, _wcache_epoch[0], weight.data_ptr())
+    return (weight._version, _scope_of(weight).epoch, weight.data_ptr())
 
 
 def _get_pack(weight, wl, mode, seg=0, seg_hi=0, a=(0, 0, 0, 0), total=0):
@@ -159,28 +197,33 @@ def _get_pack(weight, wl, mode, seg=0, seg_hi=0, a=(0, 0, 0, 0), total=0):
         job.total = total
         buf = torch.empty(total, device=weight.device, dtype=torch.float32)
         job.wp = buf.data_ptr()
-        ent = {'buf': buf, 'job': job, 'stamp': None, 'ref': weakref.ref(weight)}
+        sc = _scope_of(weight)
+        ent = {'buf': buf, 'job': job, 'stamp': None, 'ref': weakref.ref(weight), 'scope': sc}
         _wcache.put(weight, key, ent)
         rkey = (id(weight), key)
-        _pack_registry[rkey] = ent
-        weakref.finalize(weight, _drop_pack, rkey)
-        _pack_table['dirty'] = True
+        sc.registry[rkey] = ent
+        weakref.finalize(weight, _drop_pack, weakref.ref(sc), rkey)
+        sc.table['dirty'] = True
     if ent['job'].w != weight.data_ptr():
         ent['job'].w = weight.data_ptr()
-        _pack_table['dirty'] = True
+        ent['scope'].table['dirty'] = True
     call('dvsr_pack_job_run', ctypes.byref(ent['job']), _stream())
     ent['stamp'] = stamp
     return ent['buf']
 
 
-def _drop_pack(rkey):
-    if _pack_registry.pop(rkey, None) is not None:
-        _pack_table['dirty'] = True
+def _drop_pack(scope_ref, rkey):
+    sc = scope_ref()
+    if sc is not None and sc.registry.pop(rkey, None) is not None:
+        sc.table['dirty'] = True
 
 
 def repack_all():
-    """Re-pack every registered weight layout in ONE launch (dvsr_pack_table) and mark the packs fresh."""
-    ents = [e for e in _pack_registry.values() if e['ref']() is not None]
+    """Re-pack every weight layout registered in the current scope in ONE launch (dvsr_pack_table) and mark the packs
+    fresh."""
+    sc = _current_scope[0]
+    _pack_table = sc.table
+    ents = [e for e in sc.registry.values() if e['ref']() is not None]
     if not ents:
         return
     capturing = torch.cuda.is_current_stream_capturing()
@@ -281,20 +324,22 @@ def set_conv_backend(tensor_cores, precision=None):
 # Weight gradients are leaves of the backward pass: when they accumulate into the flat gradient buffer nobody reads
 # them before the optimiser step, so they run on a side stream, concurrently with the data-gradient chain (the small
 # inner-loop layers use 30-120 CTAs each and leave most SMs idle).  join_async() is called before the update.
-_async = {'on': True, 'stream': None, 'pending': []}
+_async = {'on': True}
 
 
 def _side_stream():
-    if _async['stream'] is None:
-        _async['stream'] = torch.cuda.Stream()
-    return _async['stream']
+    sc = _current_scope[0]
+    if sc.side is None:
+        sc.side = torch.cuda.Stream()
+    return sc.side
 
 
 def join_async():
-    """Make the current stream wait for every weight-gradient kernel issued on the side stream."""
-    if _async['pending']:
+    """Make the current stream wait for every weight-gradient kernel issued on the (current scope's) side stream."""
+    sc = _current_scope[0]
+    if sc.pending:
         torch.cuda.current_stream().wait_stream(_side_stream())
-        _async['pending'].clear()
+        sc.pending.clear()
 
 
 def _run_wgrad(d, gpre, Co, gw, wl, keep=None):
@@ -305,7 +350,7 @@ def _run_wgrad(d, gpre, Co, gw, wl, keep=None):
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             _run_wgrad(d, gpre, Co, gw, wl)
-        _async['pending'].append(keep)
+        _current_scope[0].pending.append(keep)
         return
     L = _lib.lib()
     if _lib.PROFILE['on']:

@@ -18,8 +18,8 @@ def _fresh_weight_cache():
         from dynavsr_b200 import ops
         ops.invalidate_weight_cache()
         ops._wcache.clear()
-        ops._pack_registry.clear()
-        ops._pack_table.update(dev=None, n=0, blocks=0, dirty=True)
+        ops._default_scope.registry.clear()
+        ops._default_scope.table.update(dev=None, n=0, blocks=0, dirty=True)
     except Exception:
         pass
     yield

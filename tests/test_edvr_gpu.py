@@ -174,6 +174,29 @@ def test_adaptation_matches_reference_golden(mods, tag, optimizer, crit, graphs)
     assert rel(nchw(eng.infer_nhwc(frames)), torch.from_numpy(g['out_unadapted'])) < NS_TOL
 
 
+def test_adaptation_pool_frames_in_flight_match_golden(mods):
+    """adapt.AdaptationPool: 3 pipelines (own parameter copy / packs / graphs / streams) process 7 windows concurrently;
+    every output must equal the reference golden of its window, and the windows must not bleed into each other."""
+    adapt = mods[2]
+    g = gold('adapt_sgd2_l2.npz')
+    netG, _ = _edvr(mods, int(g['seed_G']))
+    netE, _ = _mfdn(mods, int(g['seed_E']))
+    netF, _ = _mfdn(mods, int(g['seed_E_fixed']))
+    pool = adapt.AdaptationPool(netG, netE, netF, pipelines=3, steps=int(g['steps']), lr_alpha=float(g['lr_alpha']),
+                                optimizer='SGD', criterion='l2', slr_weight=10.0, use_graphs=True)
+    lr = torch.from_numpy(g['lr'])
+    ref = torch.from_numpy(g['out'])
+    fr = nhwc(lr.reshape(5, 3, *lr.shape[-2:]).cuda())
+    other = fr.flip(0).contiguous()                     # a different window (reversed frame order)
+    single = nchw(pool.engines[0].adapt_and_infer_nhwc(other).clone())
+    outs = pool.adapt_and_infer_many([fr, other, fr, fr, other, fr, other])
+    torch.cuda.synchronize()
+    for i, o in enumerate(outs):
+        want = ref if i in (0, 2, 3, 5) else single
+        assert rel(nchw(o), want) < (NS_TOL if want is ref else 1e-5), 'window %d' % i
+    assert rel(single, ref) > 1e-2                      # the two windows really differ
+
+
 def test_full_size_properties(mods):
     """BASELINE size (5x3x180x320 -> 3x720x1280): properties that need no oracle run --
     determinism, batch-vs-single consistency of the batched PCD pass, and shape."""

@@ -367,6 +367,9 @@ def test_layout_roundtrip_and_cpu_rejection(ops):
 # tensor-core (tcgen05 / TMEM / TMA, TF32 operands rounded to nearest, fp32 accumulation) convolution family.
 # Per-layer tolerance 1e-3 relative L2 against the float64 CPU reference (measured ~3e-4 forward / data
 # gradient, ~8e-4 weight gradient).
+# Backward cases use act = 0 (or the smooth sigmoid): with a ReLU-family activation a pre-activation within the TF32 error of
+# zero flips the derivative mask relative to the fp32 CPU reference (about one element per 5 000 outputs), which is a
+# property of the comparison, not of the kernels; activation derivatives are covered by the exact-fp32 cases above.
 TC_TOL = 1e-3
 TC_CASES = [
     # name, N, H, W, segC, Co, k, stride, pad, act, res, shuffle
@@ -380,6 +383,11 @@ TC_CASES = [
     ('tc_4x4s2', 1, 18, 34, [64], 128, 4, 2, 0, 0, False, 0),
     ('tc_4x4s2_128', 2, 10, 18, [128], 64, 4, 2, 0, 0, False, 0),
     ('tc_3x3s2', 2, 16, 24, [64], 64, 3, 2, 1, 0, False, 0),
+    ('tc_4x4s2_p1', 1, 16, 24, [64], 128, 4, 2, 1, 0, False, 0),
+    ('tc_3x3s2_odd', 1, 15, 21, [64], 64, 3, 2, 1, 0, False, 0),
+    ('tc_last_64to3_res', 1, 24, 40, [64], 3, 3, 1, 1, 0, True, 0),       # conv_last + bilinear skip: narrow scalar epilogue
+    ('tc_1x1_64to3', 2, 9, 13, [64], 3, 1, 1, 0, 0, False, 0),            # MFDN conv6
+    ('tc_3x3_64to24', 1, 10, 12, [64], 24, 3, 1, 1, 0, False, 0),
 ]
 
 

@@ -10,12 +10,12 @@ import torch  # noqa: E402
 from bench import INNER, LR_H, LR_W, NFR, SCALE, synth_clip  # noqa: E402
 from dynavsr_b200 import _lib, adapt, ops  # noqa: E402
 from dynavsr_b200.models.archs import EDVR_arch, LRimg_estimator  # noqa: E402
-from oracle import params as P  # noqa: E402
+from dynavsr_b200.synth import seed_parameters  # noqa: E402
 
 ops.set_conv_backend('--no-tc' not in sys.argv)
-netG = EDVR_arch.EDVR(); netG.load_state_dict(P.make_params(P.edvr_param_shapes(), seed=1234))
-netE = LRimg_estimator.DirectKernelEstimatorVideo(64, 3, SCALE); netE.load_state_dict(P.make_params(P.mfdn_param_shapes(), seed=77))
-netF = LRimg_estimator.DirectKernelEstimatorVideo(64, 3, SCALE); netF.load_state_dict(P.make_params(P.mfdn_param_shapes(), seed=78))
+netG = seed_parameters(EDVR_arch.EDVR(), 1234)
+netE = seed_parameters(LRimg_estimator.DirectKernelEstimatorVideo(64, 3, SCALE), 77)
+netF = seed_parameters(LRimg_estimator.DirectKernelEstimatorVideo(64, 3, SCALE), 78)
 eng = adapt.InnerLoopAdapter(netG.cuda(), netE.cuda(), netF.cuda(), use_graphs=False, **INNER)
 fr = ops.to_nhwc(synth_clip(1, LR_H, LR_W).cuda().reshape(NFR, 3, LR_H, LR_W))
 for _ in range(2):
