@@ -63,6 +63,7 @@ SIGNATURES = {
     'dvsr_pack_weights': [_P, _P, _WP, _I, _I, _P],
     'dvsr_pack_job_run': [ctypes.POINTER(PackJob), _P],
     'dvsr_pack_table': [_P, _I, _LL, _P],
+    'dvsr_pack_table_copy': [_P, _I, _LL, _P, _I, _P],
     'dvsr_conv_fprop': [_DP, _P, _P],
     'dvsr_conv_wgrad': [_DP, _P, _I, _P, _WP, _P],
     'dvsr_conv_small_co': [_DP, _P, _P],

@@ -74,6 +74,7 @@ class FlatParams(object):
 
     def snapshot(self):
         self.meta.copy_(self.flat)
+        ops.invalidate_pack_snapshot(self.scope)
 
     def restore(self):
         """test_dynavsr.py:208 -- one D2D copy instead of two module deep-copies."""
@@ -151,9 +152,17 @@ class InnerLoopAdapter(object):
             self.flat.adam_step(self.lr_alpha, self.lr_alpha_est, self.betas, step=step_idx + 1)
         return loss.detach()
 
+    def _restore_packs(self):
+        """The weights were restored to the meta-weights just before: bring the kernel-layout packs back too -- a copy
+        of their snapshot when there is one, else one table-driven re-pack launch (whose result becomes the snapshot)."""
+        if not ops.restore_packs():
+            ops.repack_all()
+            if not torch.cuda.is_current_stream_capturing():
+                ops.snapshot_packs()
+
     def _run_eager(self, frames, B):
         H, W = frames.shape[1], frames.shape[2]
-        ops.repack_all()        # weights were restored just before: refresh all kernel-layout packs in one launch
+        self._restore_packs()
         gt = frames.view(B, self.N, H, W, 3)[:, self.center].contiguous()
         with torch.no_grad():
             slr_fixed = self.netE_fixed.forward_nhwc(frames, B, self.N)
@@ -175,6 +184,7 @@ class InnerLoopAdapter(object):
             self.flat.restore()
         torch.cuda.current_stream().wait_stream(side)
         ops.repack_all()            # (re)build the device-side pack table now: it must not change during capture
+        ops.snapshot_packs()        # packs of the meta-weights: every replay restores them with one copy
         g = torch.cuda.CUDAGraph()
         n0 = _lib.COUNTER[0]
         with torch.cuda.graph(g):
@@ -200,6 +210,12 @@ class InnerLoopAdapter(object):
                 self.last_losses = torch.stack(losses) if losses else None
                 return hr
             st = self._graphs.get((tuple(frames.shape), B)) or self._build_graphs(frames, B)
+            if not self.scope.arena_valid:
+                # the meta-weights changed since the graphs were captured (FlatParams.snapshot): refresh the pack
+                # snapshot the captured restore-copy reads, in place
+                self.flat.restore()
+                ops.repack_all()
+                ops.snapshot_packs()
             st['in'].copy_(frames, non_blocking=True)
             self.flat.restore()
             st['graph'].replay()
@@ -217,7 +233,7 @@ class InnerLoopAdapter(object):
         """Plain EDVR forward with the meta-weights (no adaptation)."""
         with ops.scope(self.scope):
             self.flat.restore()
-            ops.repack_all()
+            self._restore_packs()
             with torch.no_grad():
                 return self.netG.forward_nhwc(frames, B, self.N)
 

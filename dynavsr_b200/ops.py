@@ -14,7 +14,7 @@ from torch.autograd import Function
 from . import _lib
 from ._lib import ACT_LRELU, ACT_NONE, ACT_RELU, ACT_SIGMOID_SPLIT, ConvDesc, WLayout, call
 
-__all__ = ['PackScope', 'new_scope', 'scope', 'repack_all', 'weights_updated', 'join_async', 'Seg', 'conv', 'conv3d_padded', 'mdcn', 'upsample', 'pool_maxavg', 'pad2d', 'pad3d_replicate',
+__all__ = ['PackScope', 'new_scope', 'scope', 'repack_all', 'snapshot_packs', 'restore_packs', 'invalidate_pack_snapshot', 'weights_updated', 'join_async', 'Seg', 'conv', 'conv3d_padded', 'mdcn', 'upsample', 'pool_maxavg', 'pad2d', 'pad3d_replicate',
            'tsa_temporal', 'tsa_combine', 'pixel_loss', 'to_nhwc', 'to_nchw', 'invalidate_weight_cache',
            'ACT_NONE', 'ACT_RELU', 'ACT_LRELU', 'ACT_SIGMOID_SPLIT', 'set_conv_backend']
 
@@ -112,6 +112,8 @@ class PackScope(object):
         self.epoch = 0
         self.side = None
         self.pending = []
+        self.arena = None       # snapshot of every pack buffer (the packs of the meta-weights), see snapshot_packs()
+        self.arena_valid = False
 
 
 _default_scope = PackScope()
@@ -239,11 +241,50 @@ def repack_all():
             blocks += (e['job'].total + 255) // 256
         host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
         _pack_table.update(dev=host.to(ents[0]['buf'].device), n=len(ents), blocks=blocks, dirty=False, ents=ents)
+        sc.arena_valid = False
     call('dvsr_pack_table', _ptr(_pack_table['dev']), _pack_table['n'], _pack_table['blocks'], _stream())
     for e in _pack_table['ents']:
         w = e['ref']()
         if w is not None:
             e['stamp'] = _weight_stamp(w)
+
+
+def snapshot_packs():
+    """Save every registered pack of the current scope (they must be fresh: call right after repack_all) into one arena,
+    so that the next frame can restore them with restore_packs() -- a copy -- instead of re-deriving them."""
+    sc = _current_scope[0]
+    t = sc.table
+    if t['dev'] is None or t['dirty']:
+        return False
+    n = t['blocks'] * 256
+    if sc.arena is None or sc.arena.numel() != n:
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError('pack arena must be allocated before CUDA-graph capture')
+        sc.arena = torch.empty(n, device=t['dev'].device, dtype=torch.float32)
+    call('dvsr_pack_table_copy', _ptr(t['dev']), t['n'], t['blocks'], _ptr(sc.arena), 0, _stream())
+    sc.arena_valid = True
+    return True
+
+
+def restore_packs():
+    """Bring every pack of the current scope back to the snapshot (one copy launch).  Returns False when there is no
+    valid snapshot (new layers were registered, or the meta-weights changed): the caller re-packs instead."""
+    sc = _current_scope[0]
+    t = sc.table
+    ents = [e for e in sc.registry.values() if e['ref']() is not None]
+    if not sc.arena_valid or t['dirty'] or t['dev'] is None or t['n'] != len(ents):
+        sc.arena_valid = False
+        return False
+    call('dvsr_pack_table_copy', _ptr(t['dev']), t['n'], t['blocks'], _ptr(sc.arena), 1, _stream())
+    for e in t['ents']:
+        w = e['ref']()
+        if w is not None:
+            e['stamp'] = _weight_stamp(w)
+    return True
+
+
+def invalidate_pack_snapshot(s=None):
+    (s or _current_scope[0]).arena_valid = False
 
 
 def _packed(weight, wl, mode, seg=0):

@@ -120,6 +120,11 @@ int dvsr_pack_weights(const float* w, float* wp, const dvsr_wlayout* wl, int mod
 int dvsr_pack_job_run(const dvsr_pack_job* job, void* stream);
 /* Re-pack every job of a DEVICE-resident table in one launch (after a fused parameter update). */
 int dvsr_pack_table(const dvsr_pack_job* table_dev, int n_jobs, long long total_blocks, void* stream);
+/* Copy every packed buffer of the table to (to_packs = 0) / from (to_packs = 1) one arena of total_blocks * 256 floats
+ * (job j lives at arena + block_start * 256): restoring the packs of the meta-weights for the next frame
+ * (test_dynavsr.py:208) is then one copy launch instead of a re-pack. */
+int dvsr_pack_table_copy(const dvsr_pack_job* table_dev, int n_jobs, long long total_blocks, float* arena, int to_packs,
+                         void* stream);
 /* y = epilogue(conv(x, wp)); wp packed with mode 0 (or mode 1 together with d->transposed). */
 int dvsr_conv_fprop(const dvsr_conv_desc* d, const float* wp, void* stream);
 /* gw[PyTorch layout] += sum_pix A[pix][k] * gy[pix][co]; A described by d (deformable or plain). */
