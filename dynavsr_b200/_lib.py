@@ -52,7 +52,7 @@ class PackJob(ctypes.Structure):
 
 
 ACT_NONE, ACT_RELU, ACT_LRELU, ACT_SIGMOID_SPLIT = 0, 1, 2, 3
-LOSS_L1, LOSS_L2, LOSS_CB = 0, 1, 2
+LOSS_L1, LOSS_L2, LOSS_CB, LOSS_HUBER = 0, 1, 2, 3
 
 _I, _LL, _F, _P = ctypes.c_int, ctypes.c_longlong, ctypes.c_float, ctypes.c_void_p
 _DP, _WP = ctypes.POINTER(ConvDesc), ctypes.POINTER(WLayout)
@@ -106,8 +106,8 @@ SIGNATURES = {
     'dvsr_tsa_combine_bwd': [_P, _P, _P, _P, _P, _LL, _P],
     'dvsr_loss_fwd': [_P, _P, _P, _P, _LL, _I, _F, _F, _P],
     'dvsr_scale_by_device_scalar': [_P, _P, _P, _LL, _P],
-    'dvsr_update_sgd': [_P, _P, _LL, _LL, _F, _F, _P],
-    'dvsr_update_adam': [_P, _P, _P, _P, _LL, _LL, _F, _F, _F, _F, _F, _F, _F, _P],
+    'dvsr_update_sgd': [_P, _P, _LL, _LL, _F, _F, _F, _P],
+    'dvsr_update_adam': [_P, _P, _P, _P, _LL, _LL, _F, _F, _F, _F, _F, _F, _F, _F, _P],
     'dvsr_abs_sum': [_P, _P, _LL, _I, _I, _I, _P],
     'dvsr_last_error': [],
     'dvsr_version': [],

@@ -40,6 +40,8 @@ class FlatParams(object):
     ALIGN = 64  # floats (256 B)
 
     def __init__(self, modules, device=None, scope=None):
+        """``modules``: list of nn.Modules, or list of parameter lists (explicit groups, e.g. the optimiser param groups
+        of Video_base_model.py:57-126); the second entry starts the second learning-rate group."""
         self.scope = scope or ops._default_scope
         params = []
         self.split = None
@@ -48,7 +50,7 @@ class FlatParams(object):
         for mi, m in enumerate(modules):
             if mi == 1:
                 self.split = n
-            for p in m.parameters():
+            for p in (m.parameters() if hasattr(m, 'parameters') else m):
                 offsets.append(n)
                 params.append(p)
                 n += (p.numel() + self.ALIGN - 1) // self.ALIGN * self.ALIGN
@@ -88,12 +90,13 @@ class FlatParams(object):
     def zero_grad(self):
         self.grad.zero_()
 
-    def sgd_step(self, lr0, lr1):
+    def sgd_step(self, lr0, lr1, weight_decay=0.0):
         ops.join_async()        # weight-gradient kernels run on a side stream
-        call('dvsr_update_sgd', _p(self.flat), _p(self.grad), self.numel, self.split, float(lr0), float(lr1), _stream())
+        call('dvsr_update_sgd', _p(self.flat), _p(self.grad), self.numel, self.split, float(lr0), float(lr1),
+             float(weight_decay), _stream())
         ops.weights_updated()
 
-    def adam_step(self, lr0, lr1, betas=(0.9, 0.999), eps=1e-8, step=None):
+    def adam_step(self, lr0, lr1, betas=(0.9, 0.999), eps=1e-8, step=None, weight_decay=0.0):
         if self.m is None:
             self.m = torch.zeros_like(self.flat)
             self.v = torch.zeros_like(self.flat)
@@ -102,7 +105,8 @@ class FlatParams(object):
         t = self.step_count
         bc1, bc2 = 1.0 - betas[0] ** t, 1.0 - betas[1] ** t
         call('dvsr_update_adam', _p(self.flat), _p(self.grad), _p(self.m), _p(self.v), self.numel, self.split,
-             float(lr0), float(lr1), float(betas[0]), float(betas[1]), float(eps), float(bc1), float(bc2), _stream())
+             float(lr0), float(lr1), float(betas[0]), float(betas[1]), float(eps), float(bc1), float(bc2),
+             float(weight_decay), _stream())
         ops.weights_updated()
 
 

@@ -19,7 +19,12 @@ __global__ void loss_kernel(const float* __restrict__ a, const float* __restrict
         float v, g;
         if (kind == DVSR_LOSS_L1) { v = fabsf(d); g = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f); }
         else if (kind == DVSR_LOSS_L2) { v = d * d; g = 2.f * d; }
-        else { const float r = sqrtf(d * d + eps); v = r; g = d / r; }
+        else if (kind == DVSR_LOSS_CB) { const float r = sqrtf(d * d + eps); v = r; g = d / r; }
+        else {  // Huber with delta = eps (loss.py:5-17): 0.5 d^2 inside, delta |d| - 0.5 delta^2 outside
+            const float ad = fabsf(d);
+            if (ad <= eps) { v = 0.5f * d * d; g = d; }
+            else { v = eps * ad - 0.5f * eps * eps; g = d > 0.f ? eps : -eps; }
+        }
         acc += v;
         if (ga) ga[i] = weight * inv_n * g;
     }
@@ -40,25 +45,30 @@ __global__ void scale_kernel(const float* __restrict__ x, const float* __restric
         y[i] = x[i] * k;
 }
 
-__global__ void sgd_kernel(float* __restrict__ p, const float* __restrict__ g, long long n, long long split, float lr0, float lr1) {
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-        p[i] = p[i] - (i < split ? lr0 : lr1) * g[i];
+__global__ void sgd_kernel(float* __restrict__ p, const float* __restrict__ g, long long n, long long split, float lr0, float lr1,
+                           float wd) {
+    // torch.optim.SGD without momentum: g += wd * p (L2 weight decay); p -= lr * g
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float pi = p[i];
+        p[i] = pi - (i < split ? lr0 : lr1) * (g[i] + wd * pi);
+    }
 }
 
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                             long long n, long long split, float lr0, float lr1, float b1, float b2, float eps,
-                            float bc1, float bc2) {
+                            float bc1, float bc2, float wd) {
     // torch.optim.Adam (single-tensor path): m = b1 m + (1-b1) g ; v = b2 v + (1-b2) g^2 ;
     // p -= (lr / bc1) * m / (sqrt(v) / sqrt(bc2) + eps)
     const float rs = 1.f / sqrtf(bc2);
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        const float gi = g[i];
+        const float pi = p[i];
+        const float gi = g[i] + wd * pi;         // torch.optim.Adam: L2 weight decay folded into the gradient
         const float mi = b1 * m[i] + (1.f - b1) * gi;
         const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
         m[i] = mi;
         v[i] = vi;
         const float lr = i < split ? lr0 : lr1;
-        p[i] = p[i] - (lr / bc1) * (mi / (sqrtf(vi) * rs + eps));
+        p[i] = pi - (lr / bc1) * (mi / (sqrtf(vi) * rs + eps));
     }
 }
 
@@ -97,7 +107,7 @@ using namespace dvsr;
 extern "C" int dvsr_loss_fwd(const float* a, const float* b, float* loss, float* ga, long long n, int kind, float weight,
                              float eps, void* stream) {
     DVSR_REQUIRE(a && b && loss && n > 0, "loss_fwd: bad arguments");
-    DVSR_REQUIRE(kind >= DVSR_LOSS_L1 && kind <= DVSR_LOSS_CB, "loss_fwd: unknown loss kind %d", kind);
+    DVSR_REQUIRE(kind >= DVSR_LOSS_L1 && kind <= DVSR_LOSS_HUBER, "loss_fwd: unknown loss kind %d", kind);
     loss_kernel<<<blocks_for(n), 256, 0, ST>>>(a, b, loss, ga, n, kind, weight, eps);
     return check_launch("loss_fwd");
 }
@@ -106,15 +116,16 @@ extern "C" int dvsr_scale_by_device_scalar(const float* x, const float* s, float
     scale_kernel<<<blocks_for(n), 256, 0, ST>>>(x, s, y, n);
     return check_launch("scale_by_device_scalar");
 }
-extern "C" int dvsr_update_sgd(float* p, const float* g, long long n, long long split, float lr0, float lr1, void* stream) {
+extern "C" int dvsr_update_sgd(float* p, const float* g, long long n, long long split, float lr0, float lr1, float wd,
+                               void* stream) {
     DVSR_REQUIRE(p && g && n > 0, "update_sgd: bad arguments");
-    sgd_kernel<<<blocks_for(n), 256, 0, ST>>>(p, g, n, split, lr0, lr1);
+    sgd_kernel<<<blocks_for(n), 256, 0, ST>>>(p, g, n, split, lr0, lr1, wd);
     return check_launch("update_sgd");
 }
 extern "C" int dvsr_update_adam(float* p, const float* g, float* m, float* v, long long n, long long split, float lr0,
-                                float lr1, float b1, float b2, float eps, float bc1, float bc2, void* stream) {
+                                float lr1, float b1, float b2, float eps, float bc1, float bc2, float wd, void* stream) {
     DVSR_REQUIRE(p && g && m && v && n > 0, "update_adam: bad arguments");
-    adam_kernel<<<blocks_for(n), 256, 0, ST>>>(p, g, m, v, n, split, lr0, lr1, b1, b2, eps, bc1, bc2);
+    adam_kernel<<<blocks_for(n), 256, 0, ST>>>(p, g, m, v, n, split, lr0, lr1, b1, b2, eps, bc1, bc2, wd);
     return check_launch("update_adam");
 }
 extern "C" int dvsr_abs_sum(const float* x, float* out, long long npix, int pix_stride, int c0, int c1, void* stream) {

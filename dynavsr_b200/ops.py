@@ -895,7 +895,7 @@ def tsa_combine(fea, att, att_add):
 
 # --------------------------------------------------------------------------------------------------
 # losses
-_LOSS_KIND = {'l1': _lib.LOSS_L1, 'l2': _lib.LOSS_L2, 'cb': _lib.LOSS_CB}
+_LOSS_KIND = {'l1': _lib.LOSS_L1, 'l2': _lib.LOSS_L2, 'cb': _lib.LOSS_CB, 'huber': _lib.LOSS_HUBER}
 
 
 class _LossFn(Function):
@@ -921,7 +921,7 @@ class _LossFn(Function):
 
 
 def pixel_loss(a, b, kind='l2', weight=1.0, eps=1e-6):
-    """weight * mean(f(a - b)), f in {l1, l2, Charbonnier}; gradient flows to ``a`` only
+    """weight * mean(f(a - b)), f in {l1, l2, Charbonnier (eps), Huber (delta = eps)}; gradient flows to ``a`` only
     (Video_base_model.py:39-50, loss.py:19-30, test_dynavsr.py:274)."""
     return _LossFn.apply(a, b, _LOSS_KIND[kind], float(weight), float(eps))
 

@@ -235,18 +235,20 @@ int dvsr_tsa_combine_bwd(const float* fea, const float* att, const float* gout, 
 #define DVSR_LOSS_L1 0
 #define DVSR_LOSS_L2 1
 #define DVSR_LOSS_CB 2
+#define DVSR_LOSS_HUBER 3 /* delta passed in `eps` (loss.py:5-17, default 1e-2) */
 /* loss[0] (+)= weight * mean(f(a - b)).  `loss` must be zeroed by the caller when accumulate == 0 is not
  * wanted; ga (optional) = weight * f'(a-b) / n  (caller multiplies by the upstream scalar). */
 int dvsr_loss_fwd(const float* a, const float* b, float* loss, float* ga, long long n, int kind, float weight,
                   float eps, void* stream);
 /* y = x * s[0] (device scalar) */
 int dvsr_scale_by_device_scalar(const float* x, const float* s, float* y, long long n, void* stream);
-/* p[i] -= lr(i) * g[i], lr(i) = lr0 for i < split else lr1 (two param groups: test_dynavsr.py:213-231,
+/* p[i] -= lr(i) * (g[i] + wd * p[i]), lr(i) = lr0 for i < split else lr1 (two param groups: test_dynavsr.py:213-231,
  * train_dynavsr.py:335-344).  One launch for the whole flat EDVR+MFDN parameter buffer. */
-int dvsr_update_sgd(float* p, const float* g, long long n, long long split, float lr0, float lr1, void* stream);
-/* torch.optim.Adam semantics (no weight decay / amsgrad); bias corrections bc1 = 1-b1^t, bc2 = 1-b2^t. */
+int dvsr_update_sgd(float* p, const float* g, long long n, long long split, float lr0, float lr1, float wd, void* stream);
+/* torch.optim.Adam semantics (L2 weight decay wd folded into the gradient, no amsgrad; Video_base_model.py:128-135);
+ * bias corrections bc1 = 1-b1^t, bc2 = 1-b2^t. */
 int dvsr_update_adam(float* p, const float* g, float* m, float* v, long long n, long long split, float lr0,
-                     float lr1, float b1, float b2, float eps, float bc1, float bc2, void* stream);
+                     float lr1, float b1, float b2, float eps, float bc1, float bc2, float wd, void* stream);
 /* sum |x| over channels [c0, c1) of an NHWC tensor -> out[0] (+=); the `offset_mean > 100` check of
  * deform_conv.py:285-287 without a host sync per call. */
 int dvsr_abs_sum(const float* x, float* out, long long npix, int pix_stride, int c0, int c1, void* stream);

@@ -160,7 +160,7 @@ def mfdn_forward(sd, x, scale=4):
 
 
 def pixel_loss(kind, a, b):
-    """Video_base_model.py:39-50, loss.py:19-30."""
+    """Video_base_model.py:39-50, loss.py:5-30."""
     if kind == 'l1':
         return (a - b).abs().mean()
     if kind == 'l2':
@@ -168,6 +168,10 @@ def pixel_loss(kind, a, b):
     if kind == 'cb':
         d = a - b
         return torch.sqrt(d * d + 1e-6).mean()
+    if kind == 'huber':                       # loss.py:5-17, delta = 1e-2
+        delta = 1e-2
+        diff = (a - b).abs()
+        return torch.where(diff > delta, delta * diff - 0.5 * delta * delta, 0.5 * diff * diff).mean()
     raise NotImplementedError(kind)
 
 

@@ -1,0 +1,127 @@
+"""The reference's model-wrapper API on the CUDA path (Video_base_model.py:16-251, LRestimator_model.py:28-171,
+models/__init__.py:5-37): ``create_model`` list order, ``feed_data`` / ``optimize_parameters`` / ``calculate_loss`` /
+``test`` against the CPU oracle (plain-PyTorch restatement + torch.optim) on the same seeded weights and inputs."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from util import rel
+
+pytestmark = pytest.mark.gpu
+
+
+def _opt(model='video_base+lrimgestimator', **train):
+    from dynavsr_b200.options import dict_to_nonedict
+    t = dict(pixel_criterion='cb', pixel_weight=1.0, optim='Adam', lr_G=1e-4, beta1=0.9, beta2=0.99, lr_scheme='MultiStepLR',
+             lr_steps=[2, 4], lr_gamma=0.5, loss_ftn='l1', lr_C=1e-4)
+    t.update(train)
+    return dict_to_nonedict({
+        'model': model, 'scale': 4, 'gpu_ids': [0], 'dist': False, 'is_train': True,
+        'network_G': {'which_model_G': 'EDVR', 'nf': 64, 'nframes': 5, 'groups': 8, 'front_RBs': 5, 'back_RBs': 10,
+                      'predeblur': False, 'HR_in': False, 'w_TSA': True},
+        'network_E': {'which_model_E': 'MFDN', 'mode': 'video', 'nf': 64, 'in_nc': 3},
+        'path': {'strict_load': True}, 'train': t})
+
+
+@pytest.fixture(scope='module')
+def P():
+    if not torch.cuda.is_available():
+        pytest.skip('no CUDA device')
+    from oracle import params
+    return params
+
+
+def test_create_model_order_and_state_dict_contract(P):
+    from dynavsr_b200.models import create_model
+    from dynavsr_b200.models.Video_base_model import VideoBaseModel
+    from dynavsr_b200.models.LRestimator_model import LRimgestimator_Model
+    model, est = create_model(_opt())                         # test_dynavsr.py:105-109 unpack order
+    assert isinstance(model, VideoBaseModel) and isinstance(est, LRimgestimator_Model)
+    assert list(model.netG.module.state_dict().keys()) == list(P.edvr_param_shapes().keys())
+    assert list(est.netE.module.state_dict().keys()) == list(P.mfdn_param_shapes().keys())
+    assert all(k.startswith('module.') for k in model.netG.state_dict().keys())     # DataParallel-style prefix
+    with pytest.raises(NotImplementedError):
+        create_model(_opt(pixel_criterion='nope'))
+    opt = _opt()
+    opt['model'] = 'srgan'
+    with pytest.raises(NotImplementedError):
+        create_model(opt)
+
+
+@pytest.mark.parametrize('optim,crit,groups', [('SGD', 'l2', None), ('Adam', 'cb', 'small_offset_lr'), ('SGD', 'huber', 'ft_tsa_only')])
+def test_video_base_model_train_step_vs_oracle(P, optim, crit, groups):
+    from oracle import edvr_oracle as O
+    from dynavsr_b200.models import create_model
+    lr = 1e-3 if optim == 'SGD' else 1e-4
+    extra = {groups: True} if groups else {}
+    model = create_model(_opt('video_base', pixel_criterion=crit, optim=optim, lr_G=lr, **extra))
+    sd = P.make_params(P.edvr_param_shapes(), seed=11)
+    model.netG.module.load_state_dict(sd, strict=True)
+    g = torch.Generator().manual_seed(3)
+    data = {'LQs': torch.rand(1, 5, 3, 32, 32, generator=g), 'GT': torch.rand(1, 3, 128, 128, generator=g)}
+    # ---- oracle: same groups, torch.optim
+    ref = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    if groups == 'small_offset_lr':
+        sel = lambda k: any(t in k for t in ('pcd_align', 'fea_L', 'feature_extraction', 'conv_first'))
+        pg = [{'params': [v for k, v in ref.items() if not sel(k)], 'lr': lr}, {'params': [v for k, v in ref.items() if sel(k)], 'lr': lr * 0.1}]
+    elif groups == 'ft_tsa_only':
+        sel = lambda k: 'tsa_fusion' in k
+        pg = [{'params': [v for k, v in ref.items() if not sel(k)], 'lr': lr}, {'params': [v for k, v in ref.items() if sel(k)], 'lr': lr}]
+    else:
+        pg = list(ref.values())
+    topt = torch.optim.SGD(pg, lr=lr) if optim == 'SGD' else torch.optim.Adam(pg, lr=lr, betas=(0.9, 0.99))
+    losses_ref, losses = [], []
+    for step in range(2):
+        topt.zero_grad()
+        l = O.pixel_loss(crit, O.edvr_forward(ref, data['LQs']), data['GT'])
+        l.backward()
+        topt.step()
+        losses_ref.append(float(l))
+        model.feed_data(data)
+        model.optimize_parameters(step + 1)
+        losses.append(model.get_current_log()['l_pix'])
+    assert losses == pytest.approx(losses_ref, rel=1e-4)
+    new = model.netG.module.state_dict()
+    for k in ('conv_first.weight', 'pcd_align.L1_dcnpack.conv_offset_mask.weight', 'tsa_fusion.fea_fusion.weight',
+              'recon_trunk.9.conv2.bias', 'conv_last.weight'):
+        d_ref, d = ref[k].detach() - sd[k], new[k].cpu() - sd[k]
+        assert rel(d, d_ref) < (1e-3 if optim == 'SGD' else 3e-2), k
+    # calculate_loss / test keep the reference's contract
+    model.feed_data(data)
+    l = model.calculate_loss()
+    assert l.requires_grad and model.fake_H.shape == (1, 3, 128, 128)
+    with torch.no_grad():
+        want = O.pixel_loss(crit, O.edvr_forward({k: v.detach() for k, v in ref.items()}, data['LQs']), data['GT'])
+    assert float(l) == pytest.approx(float(want), rel=1e-4)
+    model.test()
+    assert not model.fake_H.requires_grad
+    assert model.get_current_learning_rate()[0] == pytest.approx(lr)        # milestones at 2 and 4 scheduler steps: none taken
+
+
+def test_lrimgestimator_model_vs_oracle(P):
+    from oracle import edvr_oracle as O
+    from dynavsr_b200.models import create_model
+    est = create_model(_opt('lrimgestimator', loss_ftn='l1', lr_C=1e-4))
+    sd = P.make_params(P.mfdn_param_shapes(), seed=5)
+    est.netE.module.load_state_dict(sd, strict=True)
+    g = torch.Generator().manual_seed(4)
+    data = {'LQs': torch.rand(2, 5, 3, 32, 48, generator=g), 'SuperLQs': torch.rand(2, 5, 3, 8, 12, generator=g)}
+    est.feed_data(data)
+    est.forward_without_optim()
+    want = O.mfdn_forward(sd, data['LQs'].transpose(1, 2)).transpose(1, 2)
+    assert est.fake_L.shape == (2, 5, 3, 8, 12) and est.fake_L.requires_grad
+    assert rel(est.fake_L, want) < 1e-4
+    est.test()
+    assert not est.fake_L.requires_grad and rel(est.fake_L, want) < 1e-4
+    ref = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    topt = torch.optim.Adam(list(ref.values()), lr=1e-4)
+    for _ in range(2):
+        topt.zero_grad()
+        l = F.l1_loss(O.mfdn_forward(ref, data['LQs'].transpose(1, 2)).transpose(1, 2), data['SuperLQs'])
+        l.backward()
+        topt.step()
+        est.feed_data(data)
+        est.optimize_parameters()
+        assert est.get_current_log()['l_pix'] == pytest.approx(float(l), rel=1e-4)
+    d_ref = ref['conv6.weight'].detach() - sd['conv6.weight']
+    assert rel(est.netE.module.conv6.weight.detach().cpu() - sd['conv6.weight'], d_ref) < 3e-2

@@ -311,15 +311,16 @@ def test_tsa_temporal_and_combine(ops):
         assert rel(gd[i], gr[i]) < TOL
 
 
-@pytest.mark.parametrize('kind', ['l1', 'l2', 'cb'])
+@pytest.mark.parametrize('kind', ['l1', 'l2', 'cb', 'huber'])
 def test_pixel_loss(ops, kind):
-    a, b = _rand(2, 8, 9, 3, seed=1), _rand(2, 8, 9, 3, seed=2)
+    from oracle import edvr_oracle as O
+    sc = 0.02 if kind == 'huber' else 1.0        # straddle the Huber delta (1e-2, loss.py:8)
+    a, b = _rand(2, 8, 9, 3, seed=1) * sc, _rand(2, 8, 9, 3, seed=2) * sc
     ar = a.clone().requires_grad_(True)
-    d = ar - b
-    ref = {'l1': d.abs().mean(), 'l2': (d * d).mean(), 'cb': torch.sqrt(d * d + 1e-6).mean()}[kind] * 10.0
+    ref = O.pixel_loss(kind, ar, b) * 10.0
     gr, = torch.autograd.grad(ref * 3.0, ar)
     ad = _dev(a).requires_grad_(True)
-    l = ops.pixel_loss(ad, _dev(b), kind, 10.0)
+    l = ops.pixel_loss(ad, _dev(b), kind, 10.0, 1e-2 if kind == 'huber' else 1e-6)
     assert abs(float(l) - float(ref)) < 1e-5 * abs(float(ref))
     gd, = torch.autograd.grad(l * 3.0, ad)
     assert rel(gd, gr) < TOL
@@ -331,12 +332,13 @@ def test_fused_updates_match_torch_optim(ops):
     m1, m2 = torch.nn.Conv2d(8, 8, 3).cuda(), torch.nn.Conv2d(8, 4, 1).cuda()
     r1, r2 = torch.nn.Conv2d(8, 8, 3).cuda(), torch.nn.Conv2d(8, 4, 1).cuda()
     r1.load_state_dict(m1.state_dict()); r2.load_state_dict(m2.state_dict())
-    for opt_name in ('SGD', 'Adam'):
+    for opt_name, wd in (('SGD', 0.0), ('Adam', 0.0), ('SGD', 0.05), ('Adam', 0.05)):
         flat = FlatParams([m1, m2])
         if opt_name == 'SGD':
-            ref = torch.optim.SGD([{'params': r1.parameters(), 'lr': 0.1}, {'params': r2.parameters(), 'lr': 0.01}])
+            ref = torch.optim.SGD([{'params': r1.parameters(), 'lr': 0.1}, {'params': r2.parameters(), 'lr': 0.01}], weight_decay=wd)
         else:
-            ref = torch.optim.Adam([{'params': r1.parameters(), 'lr': 0.1}, {'params': r2.parameters(), 'lr': 0.01}], betas=(0.9, 0.99))
+            ref = torch.optim.Adam([{'params': r1.parameters(), 'lr': 0.1}, {'params': r2.parameters(), 'lr': 0.01}], betas=(0.9, 0.99),
+                                   weight_decay=wd)
         for step in range(3):
             flat.zero_grad()
             for (p, q) in zip(list(m1.parameters()) + list(m2.parameters()), list(r1.parameters()) + list(r2.parameters())):
@@ -344,9 +346,9 @@ def test_fused_updates_match_torch_optim(ops):
                 p._dvsr_grad.copy_(g)
                 q.grad = g.clone()
             if opt_name == 'SGD':
-                flat.sgd_step(0.1, 0.01)
+                flat.sgd_step(0.1, 0.01, weight_decay=wd)
             else:
-                flat.adam_step(0.1, 0.01, (0.9, 0.99))
+                flat.adam_step(0.1, 0.01, (0.9, 0.99), weight_decay=wd)
             ref.step()
         for (p, q) in zip(list(m1.parameters()) + list(m2.parameters()), list(r1.parameters()) + list(r2.parameters())):
             assert rel(p, q) < 1e-5, opt_name
