@@ -578,19 +578,21 @@ extern "C" int dvsr_act_bwd(const float* gy, const float* y, const float* res, f
     DVSR_REQUIRE(act == DVSR_ACT_NONE || y, "act_bwd: activation derivative needs the saved output");
     DVSR_REQUIRE(shuffle == 0 || (shuffle == 2 && C % 4 == 0 && gpre && gpre != gy && !res), "act_bwd: bad shuffle arguments");
     const bool v4 = (C % 4 == 0) && (C / 4 <= 256) && A16(gy) && (!y || A16(y)) && (!res || A16(res)) && (!gpre || A16(gpre)) && shuffle == 0;
-    DVSR_REQUIRE(v4 || C <= 256, "act_bwd: C=%d too wide for the scalar path", C);
     const int vec = v4 ? 4 : 1;
-    const int rows = 256 / (C / vec);
+    const int cw = C / vec;
+    const int threads = cw <= 256 ? 256 : (cw + 31) / 32 * 32;      // one thread per channel vector of a pixel row
+    DVSR_REQUIRE(threads <= 1024, "act_bwd: C=%d too wide", C);
+    const int rows = threads / cw;
     long long blocks = (npix + (long long)rows * 8 - 1) / ((long long)rows * 8);
     if (blocks > 148 * 8) blocks = 148 * 8;
     if (blocks < 1) blocks = 1;
     long long per = (npix + blocks - 1) / blocks;
     per = (per + rows - 1) / rows * rows;
     blocks = (npix + per - 1) / per;
-    const size_t smem = gbias ? sizeof(float) * 256 * vec : 0;
-    if (v4) act_bwd_kernel<4><<<(int)blocks, 256, smem, ST>>>(gy, y, res, gpre, gbias, npix, C, act, slope, sig_split, shuffle, Ho, Wo, per);
+    const size_t smem = gbias ? sizeof(float) * threads * vec : 0;
+    if (v4) act_bwd_kernel<4><<<(int)blocks, threads, smem, ST>>>(gy, y, res, gpre, gbias, npix, C, act, slope, sig_split, shuffle, Ho, Wo, per);
     else {
-        act_bwd_kernel<1><<<(int)blocks, 256, smem, ST>>>(gy, y, res, gpre, gbias, npix, C, act, slope, sig_split, shuffle, Ho, Wo, per);
+        act_bwd_kernel<1><<<(int)blocks, threads, smem, ST>>>(gy, y, res, gpre, gbias, npix, C, act, slope, sig_split, shuffle, Ho, Wo, per);
     }
     return check_launch("act_bwd");
 }

@@ -1,0 +1,157 @@
+"""Outer (meta) step of DynaVSR training -- codes/train_dynavsr.py:252-438 -- on the CUDA path.
+
+Per outer step every rank loops over its own tasks (clips; DistIterSampler sharding, dist.dist_iter_sampler_indices):
+
+    theta' <- theta                                    (:322  deepcopy(model.netG), deepcopy(est_model.netE))
+    K times:  SLR = MFDN'(LR);  L = w*cri(EDVR'(SLR), LR_c) + L1(SLR, SLR_true);  backward;  inner Adam/SGD on theta'
+                                                       (:355-399; two lr groups lr_alpha / lr_alpha_est :335-344)
+    L_q = w*cri(EDVR'(LR), HR_c);   meta_grad[G] += grad(L_q / B)            (:404-415)
+    L_e = loss_e(MFDN'(LR), SLR_true);  meta_grad[E] += grad(L_e / (10 B))   (:417-426)
+  one all-reduce (mean) of the FLAT meta-gradient over ranks, then ONE fused Adam/SGD launch on theta   (:438)
+
+This is first-order MAML, the evident intent of the reference (its validation loop :633-677 and test_dynavsr.py:233-277
+adapt the working copy exactly like this).  AS WRITTEN the training loop binds the inner optimiser to the copy but the
+loss to the original (:322-399), so nothing is ever adapted and the inner losses' gradients leak, unscaled, into the
+outer gradient; ``reference_quirk=True`` reproduces that accumulation (meta_grad = sum_tasks [K*grad L_inner(theta) +
+grad L_q(theta)/B + grad L_e(theta)/(10B)]) for a numerical side-by-side on one GPU.
+
+B200-first structure: theta' (EDVR u MFDN) is one flat buffer, so "deepcopy" = one D2D copy, the inner update = one launch,
+``meta_grad += grad`` = one axpy over the flat gradient (kernels accumulate weight gradients straight into it), the
+exchange step = ONE NCCL all-reduce of 15 MB (EDVR-M) / 84 MB (EDVR-L) over NVLink instead of DDP's bucketed hooks
+firing inside the inner loop, and the outer update = one launch on the flat meta-weights.
+"""
+import ctypes
+
+import torch
+
+from . import dist as ddist
+from . import ops
+from ._lib import call
+from .adapt import FlatParams
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class MetaLearner(object):
+    """netG: models.archs.EDVR_arch.EDVR, netE: models.archs.LRimg_estimator.DirectKernelEstimatorVideo (both on cuda).
+    Their parameters become views of the working copy theta'; ``self.theta`` holds the meta-weights."""
+
+    def __init__(self, netG, netE, inner_steps=1, lr_alpha=1e-5, lr_alpha_est=None, inner_optimizer='Adam',
+                 inner_betas=(0.9, 0.99), criterion='cb', pixel_weight=1.0, est_loss='l1', outer_optimizer='Adam',
+                 lr_outer=1e-5, outer_betas=(0.9, 0.99), reference_quirk=False):
+        if inner_optimizer not in ('SGD', 'Adam') or outer_optimizer not in ('SGD', 'Adam'):
+            raise NotImplementedError()
+        if criterion not in ('l1', 'l2', 'cb', 'huber'):
+            raise NotImplementedError('Loss type [%s] is not recognized.' % criterion)
+        self.netG, self.netE = netG, netE
+        self.K, self.lr_alpha = inner_steps, lr_alpha
+        self.lr_alpha_est = lr_alpha if lr_alpha_est is None else lr_alpha_est
+        self.inner_optimizer, self.inner_betas = inner_optimizer, inner_betas
+        self.criterion, self.pixel_weight, self.est_loss = criterion, pixel_weight, est_loss
+        self.outer_optimizer, self.lr_outer, self.outer_betas = outer_optimizer, lr_outer, outer_betas
+        self.reference_quirk = reference_quirk
+        self.scope = ops.new_scope()
+        self.work = FlatParams([netG, netE], scope=self.scope)      # theta' (+ its gradient buffer)
+        self.theta = self.work.meta                                  # theta: restored into theta' per task
+        self.meta_grad = torch.zeros_like(self.theta)
+        self.m = torch.zeros_like(self.theta) if outer_optimizer == 'Adam' else None
+        self.v = torch.zeros_like(self.theta) if outer_optimizer == 'Adam' else None
+        self.outer_steps = 0
+        self.N, self.center = netG.nframes, netG.center
+        self.last = {}
+
+    def _eps(self):
+        return 1e-2 if self.criterion == 'huber' else 1e-6
+
+    # ------------------------------------------------------------------ one task
+    def _task(self, task, n_tasks):
+        """task: dict of device tensors  LQs [1, N, 3, h, w], GT [1, N, 3, sh, sw] or [1, 3, sh, sw], SuperLQs [1, N, 3, h/s, w/s]."""
+        LQs, GT, SLQ = task['LQs'], task['GT'], task['SuperLQs']
+        B, N, C, h, w = LQs.shape
+        gt_hr = GT[:, self.center] if GT.dim() == 5 else GT
+        frames = ops.to_nhwc(LQs.reshape(B * N, C, h, w))
+        lr_c = frames.view(B, N, h, w, C)[:, self.center].contiguous()             # meta_train GT = LR centre (:292)
+        slr_true = ops.to_nhwc(SLQ.reshape(B * N, C, SLQ.shape[-2], SLQ.shape[-1]))
+        hr_c = ops.to_nhwc(gt_hr)
+        fl = self.work
+        if not self.reference_quirk:
+            fl.restore()                                                            # theta' <- theta (:322)
+            ops.repack_all()
+        inner = []
+        for k in range(self.K):
+            if not self.reference_quirk:
+                fl.zero_grad()
+            slr = self.netE.forward_nhwc(frames, B, N)                              # :360-363
+            sr = self.netG.forward_nhwc(slr, B, N)                                  # :384-385
+            loss = ops.pixel_loss(sr, lr_c, self.criterion, self.pixel_weight, self._eps()) + \
+                ops.pixel_loss(slr, slr_true, 'l1', 1.0)                            # :395
+            loss.backward()                                                         # :397
+            inner.append(loss.detach())
+            if not self.reference_quirk:                                            # :399 (a no-op as written)
+                if self.inner_optimizer == 'SGD':
+                    fl.sgd_step(self.lr_alpha, self.lr_alpha_est)
+                else:
+                    fl.adam_step(self.lr_alpha, self.lr_alpha_est, self.inner_betas, step=k + 1)
+        if not self.reference_quirk:
+            fl.zero_grad()
+        # meta test at theta' (:404-426); the two losses touch disjoint halves of the flat gradient
+        sr = self.netG.forward_nhwc(frames, B, N)
+        loss_q = ops.pixel_loss(sr, hr_c, self.criterion, self.pixel_weight, self._eps())
+        (loss_q / n_tasks).backward()
+        slr = self.netE.forward_nhwc(frames, B, N)
+        loss_e = ops.pixel_loss(slr, slr_true, self.est_loss, 1.0)
+        (loss_e / (n_tasks * 10)).backward()
+        ops.join_async()
+        if not self.reference_quirk:
+            self.meta_grad.add_(fl.grad)
+        return loss_q.detach(), loss_e.detach(), inner
+
+    # ------------------------------------------------------------------ one outer step
+    def outer_step(self, tasks, lr=None):
+        """tasks: this rank's clips for the step.  Returns the summed query loss / B (the reference's ``total_loss_q``)."""
+        fl = self.work
+        with ops.scope(self.scope):
+            self.meta_grad.zero_()
+            if self.reference_quirk:
+                fl.restore()
+                ops.repack_all()
+                fl.zero_grad()                     # optimizer.zero_grad() (:270): grads then pile up across tasks
+            if fl.m is not None:
+                fl.m.zero_(); fl.v.zero_()
+            lq, le, inner = [], [], []
+            for t in tasks:
+                if self.inner_optimizer == 'Adam' and fl.m is not None:
+                    fl.m.zero_(); fl.v.zero_()     # a fresh inner optimiser per task (:346-353)
+                a, b, c = self._task(t, len(tasks))
+                lq.append(a); le.append(b); inner.append(c)
+            if self.reference_quirk:
+                self.meta_grad.copy_(fl.grad)
+            # ---- the single exchange step: mean of the flat meta-gradient over ranks (NCCL over NVLink)
+            ddist.allreduce_flat_gradient(self.meta_grad, average=True)
+            # ---- outer update on theta (:438), one launch
+            lr = self.lr_outer if lr is None else lr
+            self.outer_steps += 1
+            n = self.theta.numel()
+            if self.outer_optimizer == 'SGD':
+                call('dvsr_update_sgd', _p(self.theta), _p(self.meta_grad), n, n, float(lr), float(lr), 0.0, _stream())
+            else:
+                b1, b2 = self.outer_betas
+                t = self.outer_steps
+                call('dvsr_update_adam', _p(self.theta), _p(self.meta_grad), _p(self.m), _p(self.v), n, n, float(lr), float(lr),
+                     float(b1), float(b2), 1e-8, float(1 - b1 ** t), float(1 - b2 ** t), 0.0, _stream())
+            ops.invalidate_pack_snapshot(self.scope)
+            fl.restore()                           # the modules now hold the updated meta-weights
+            ops.repack_all()
+        self.last = {'loss_q': torch.stack(lq), 'loss_e': torch.stack(le), 'inner': inner}
+        return torch.stack(lq).sum() / len(tasks)
+
+    def state_dicts(self):
+        """(EDVR state_dict, MFDN state_dict) of the meta-weights, reference key names (checkpoint contract)."""
+        return ({k: v.detach().clone() for k, v in self.netG.state_dict().items()},
+                {k: v.detach().clone() for k, v in self.netE.state_dict().items()})
