@@ -1,6 +1,7 @@
-"""Mirror of codes/models/archs/dcn/__init__.py:1-7 (DCNv2 exports; DCNv1 is not on the hot path)."""
-from .deform_conv import (ModulatedDeformConv, ModulatedDeformConvFunction, ModulatedDeformConvPack,
+"""Mirror of codes/models/archs/dcn/__init__.py:1-7 (same export list)."""
+from .deform_conv import (DeformConv, DeformConvPack, ModulatedDeformConv, ModulatedDeformConvPack, deform_conv,
                           modulated_deform_conv)
+from .deform_conv import DeformConvFunction, ModulatedDeformConvFunction  # noqa: F401
 
-__all__ = ['ModulatedDeformConv', 'ModulatedDeformConvPack', 'ModulatedDeformConvFunction',
+__all__ = ['DeformConv', 'DeformConvPack', 'ModulatedDeformConv', 'ModulatedDeformConvPack', 'deform_conv',
            'modulated_deform_conv']

@@ -1,4 +1,5 @@
-"""Mirror of codes/models/archs/dcn/deform_conv.py:97-291 (modulated deformable convolution, DCNv2).
+"""Mirror of codes/models/archs/dcn/deform_conv.py:15-291 (deformable convolution: DCNv2 = modulated, on the EDVR hot
+path; DCNv1 = the same sampling without the modulation mask, exported by the reference but used by no YML).
 
 Two entry levels:
   * ``modulated_deform_conv(input, offset, mask, weight, bias, stride, padding, dilation, groups,
@@ -97,6 +98,112 @@ class ModulatedDeformConvFunction(Function):
 
 
 modulated_deform_conv = ModulatedDeformConvFunction.apply
+
+
+def _one(v, what):
+    a, b = _pair(v)
+    if a != b:
+        raise NotImplementedError('%s must be the same along H and W (got %s)' % (what, (a, b)))
+    return a
+
+
+class DeformConvFunction(Function):
+    """DCNv1 (deform_conv.py:15-94): y = W * bilinear(x, p + dk + offset).  Runs on the modulated kernels with a mask of
+    ones -- the sampling rule of deformable_im2col (deform_conv_cuda_kernel.cu:189-262) is the modulated one
+    (:569-632) without the multiply; the offset layout [dg][k][(dh, dw)] is the same.  ``im2col_step`` only sets the
+    reference's scratch batching and is accepted for signature parity."""
+
+    @staticmethod
+    def forward(ctx, input, offset, weight, stride=1, padding=0, dilation=1, groups=1, deformable_groups=1, im2col_step=64):
+        if input is not None and input.dim() != 4:
+            raise ValueError("Expected 4D tensor as input, got {}D tensor instead.".format(input.dim()))
+        if not input.is_cuda:
+            raise NotImplementedError
+        cur_im2col_step = min(im2col_step, input.shape[0])
+        assert (input.shape[0] % cur_im2col_step) == 0, 'im2col step must divide batchsize'
+        stride, padding, dilation = _one(stride, 'stride'), _one(padding, 'padding'), _one(dilation, 'dilation')
+        kh, kw = weight.shape[2:]
+        B = input.shape[0]
+        Ho = (input.shape[2] + 2 * padding - (dilation * (kh - 1) + 1)) // stride + 1
+        Wo = (input.shape[3] + 2 * padding - (dilation * (kw - 1) + 1)) // stride + 1
+        if Ho <= 0 or Wo <= 0:
+            raise ValueError("convolution input is too small (output would be {})".format('x'.join(map(str, (B, weight.shape[0], Ho, Wo)))))
+        mask = input.new_ones((B, deformable_groups * kh * kw, Ho, Wo))
+        ctx.cfg = (stride, padding, dilation, groups, deformable_groups)
+        ctx.save_for_backward(input, offset, weight, mask)
+        with torch.no_grad():
+            return ModulatedDeformConvFunction.apply(input, offset, mask, weight, None, stride, padding, dilation, groups,
+                                                     deformable_groups)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_output):
+        if not grad_output.is_cuda:
+            raise NotImplementedError
+        input, offset, weight, mask = ctx.saved_tensors
+        stride, padding, dilation, groups, dg = ctx.cfg
+        B, C, H, W = input.shape
+        Co, _, kh, kw = weight.shape
+        input, offset, weight, grad_output = (t.contiguous() for t in (input, offset, weight, grad_output))
+        grad_input, grad_offset, grad_mask = torch.empty_like(input), torch.empty_like(offset), torch.empty_like(mask)
+        grad_weight = torch.empty_like(weight)
+        nbytes = ops._lib.lib().dvsr_mdcn_workspace_bytes(B, C, H, W, Co, kh, kw, stride, padding, dilation, dg, 1)
+        ws = _workspace(nbytes, input.device)
+        call('dvsr_mdcn_backward_nchw', _p(input), _p(offset), _p(mask), _p(weight), _p(grad_output),
+             _p(grad_input), _p(grad_offset), _p(grad_mask), _p(grad_weight), None,
+             B, C, H, W, Co, kh, kw, stride, padding, dilation, groups, dg, _p(ws), ws.numel(), _stream())
+        return (grad_input, grad_offset, grad_weight, None, None, None, None, None, None)
+
+
+deform_conv = DeformConvFunction.apply
+
+
+class DeformConv(nn.Module):
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, groups=1,
+                 deformable_groups=1, bias=False):
+        super(DeformConv, self).__init__()
+        assert not bias
+        assert in_channels % groups == 0, 'in_channels {} cannot be divisible by groups {}'.format(in_channels, groups)
+        assert out_channels % groups == 0, 'out_channels {} cannot be divisible by groups {}'.format(out_channels, groups)
+        self.in_channels = in_channels
+        self.out_channels = out_channels
+        self.kernel_size = _pair(kernel_size)
+        self.stride = _pair(stride)
+        self.padding = _pair(padding)
+        self.dilation = _pair(dilation)
+        self.groups = groups
+        self.deformable_groups = deformable_groups
+        self.weight = nn.Parameter(torch.Tensor(out_channels, in_channels // self.groups, *self.kernel_size))
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        n = self.in_channels
+        for k in self.kernel_size:
+            n *= k
+        stdv = 1. / math.sqrt(n)
+        self.weight.data.uniform_(-stdv, stdv)
+
+    def forward(self, x, offset):
+        return deform_conv(x, offset, self.weight, self.stride, self.padding, self.dilation, self.groups,
+                           self.deformable_groups)
+
+
+class DeformConvPack(DeformConv):
+    def __init__(self, *args, **kwargs):
+        super(DeformConvPack, self).__init__(*args, **kwargs)
+        self.conv_offset = nn.Conv2d(self.in_channels, self.deformable_groups * 2 * self.kernel_size[0] * self.kernel_size[1],
+                                     kernel_size=self.kernel_size, stride=_pair(self.stride), padding=_pair(self.padding), bias=True)
+        self.init_offset()
+
+    def init_offset(self):
+        self.conv_offset.weight.data.zero_()
+        self.conv_offset.bias.data.zero_()
+
+    def forward(self, x):
+        m = self.conv_offset
+        offset = ops.to_nchw(ops.conv(ops.to_nhwc(x), m.weight, m.bias, stride=m.stride[0], pad=m.padding[0]))
+        return deform_conv(x, offset, self.weight, self.stride, self.padding, self.dilation, self.groups,
+                           self.deformable_groups)
 
 
 class ModulatedDeformConv(nn.Module):

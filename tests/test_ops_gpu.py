@@ -223,6 +223,75 @@ def test_dcn_pack_module_matches_oracle(ops):
     assert rel(y, ref) < TOL
 
 
+def _dcn_v1_case(seed=3):
+    from oracle.torch_ops import mdcn_torch
+    x, w = _rand(2, 16, 9, 11, seed=seed), _rand(12, 16, 3, 3, seed=seed + 1, scale=0.2)
+    off = _rand(2, 2 * 2 * 9, 9, 11, seed=seed + 2, scale=1.5)
+    gy = _rand(2, 12, 9, 11, seed=seed + 3)
+    leaves = [t.clone().requires_grad_(True) for t in (x, off, w)]
+    y = mdcn_torch(leaves[0], leaves[1], torch.ones(2, 18, 9, 11, dtype=x.dtype), leaves[2], None, 1, 1, 1, 1, 2)   # DCNv1 = mask of ones
+    return x, off, w, gy, y.detach(), torch.autograd.grad(y, leaves, gy)
+
+
+def test_dcn_v1_function_and_modules_vs_oracle(ops):
+    """DeformConv* (deform_conv.py:15-94,161-218; kernel.cu:189-464): exported by the reference, used by no YML."""
+    from dynavsr_b200.models.archs.dcn import DeformConv, DeformConvPack, deform_conv
+    x, off, w, gy, y_ref, g_ref = _dcn_v1_case()
+    leaves = [_dev(t).requires_grad_(True) for t in (x, off, w)]
+    y = deform_conv(leaves[0], leaves[1], leaves[2], 1, 1, 1, 1, 2)
+    assert rel(y, y_ref) < TOL
+    for name, a, b in zip(('gx', 'goffset', 'gweight'), torch.autograd.grad(y, leaves, _dev(gy)), g_ref):
+        assert rel(a, b) < GTOL, name
+    m = DeformConv(16, 12, 3, stride=1, padding=1, deformable_groups=2).cuda()
+    assert list(m.state_dict().keys()) == ['weight']
+    m.weight.data.copy_(_dev(w))
+    assert rel(m(_dev(x), _dev(off)), y_ref) < TOL
+    pk = DeformConvPack(16, 12, 3, stride=1, padding=1, deformable_groups=2).cuda()
+    assert list(pk.state_dict().keys()) == ['weight', 'conv_offset.weight', 'conv_offset.bias']
+    assert float(pk.conv_offset.weight.abs().max()) == 0.0                                    # zero init -> plain convolution
+    pk.weight.data.copy_(_dev(w))
+    assert rel(pk(_dev(x)), F.conv2d(x, w, None, 1, 1)) < TOL
+    with pytest.raises(NotImplementedError):
+        deform_conv(x.float(), off.float(), w.float(), 1, 1, 1, 1, 2)
+    with pytest.raises(ValueError):
+        deform_conv(_dev(x)[0], _dev(off), _dev(w))
+
+
+def test_legacy_deform_conv_cuda_module(ops):
+    """The five pybind names of the reference extension (deform_conv_cuda.cpp:681-695) with their positional signatures,
+    caller-allocated outputs and accumulate-into-gradient behaviour."""
+    from dynavsr_b200.models.archs.dcn import deform_conv_cuda as D
+    g = gold('dcn_small.npz')
+    t = {k: torch.from_numpy(g[k]).cuda() for k in ('x', 'offset', 'mask', 'weight', 'bias', 'gy')}
+    dg = int(g['dg'])
+    empty = t['x'].new_empty(0)
+    out = t['x'].new_empty(tuple(g['y'].shape))
+    D.modulated_deform_conv_cuda_forward(t['x'], t['weight'], t['bias'], empty, t['offset'], t['mask'], out, empty,
+                                         3, 3, 1, 1, 1, 1, 1, 1, 1, dg, True)
+    assert rel(out, torch.from_numpy(g['y'])) < TOL
+    gi, gw, gb = torch.zeros_like(t['x']), torch.ones_like(t['weight']), torch.zeros_like(t['bias'])
+    go, gm = torch.zeros_like(t['offset']), torch.zeros_like(t['mask'])
+    D.modulated_deform_conv_cuda_backward(t['x'], t['weight'], t['bias'], empty, t['offset'], t['mask'], empty, gi, gw, gb, go, gm,
+                                          t['gy'], 3, 3, 1, 1, 1, 1, 1, 1, 1, dg, True)
+    for name, a in (('gx', gi), ('goffset', go), ('gmask', gm), ('gbias', gb)):
+        assert rel(a, torch.from_numpy(g[name])) < GTOL, name
+    assert rel(gw - 1.0, torch.from_numpy(g['gweight'])) < GTOL                               # accumulated onto the caller's values
+    with pytest.raises(RuntimeError):                                                         # AT_CHECK(is_contiguous)
+        D.modulated_deform_conv_cuda_forward(t['x'].transpose(2, 3), t['weight'], t['bias'], empty, t['offset'], t['mask'], out,
+                                             empty, 3, 3, 1, 1, 1, 1, 1, 1, 1, dg, True)
+    # DCNv1 trio
+    x, off, w, gy, y_ref, g_ref = _dcn_v1_case(7)
+    xd, od, wd, gyd = _dev(x), _dev(off), _dev(w), _dev(gy)
+    out = xd.new_empty(0)
+    D.deform_conv_forward_cuda(xd, wd, od, out, empty, empty, 3, 3, 1, 1, 1, 1, 1, 1, 1, 2, 2)
+    assert tuple(out.shape) == tuple(y_ref.shape) and rel(out, y_ref) < TOL
+    gi, go, gw = torch.zeros_like(xd), torch.zeros_like(od), torch.zeros_like(wd)
+    D.deform_conv_backward_input_cuda(xd, od, gyd, gi, go, wd, empty, 3, 3, 1, 1, 1, 1, 1, 1, 1, 2, 2)
+    D.deform_conv_backward_parameters_cuda(xd, od, gyd, gw, empty, empty, 3, 3, 1, 1, 1, 1, 1, 1, 1, 2, 1, 2)
+    for name, a, b in zip(('gx', 'goffset', 'gweight'), (gi, go, gw), g_ref):
+        assert rel(a, b) < GTOL, name
+
+
 @pytest.mark.parametrize('scale,C,mul', [(2, 64, 1.0), (2, 64, 2.0), (4, 3, 1.0), (2, 6, 1.0)])
 def test_upsample(ops, scale, C, mul):
     x = _rand(2, C, 7, 9, seed=1)

@@ -27,7 +27,8 @@ def main():
     tc = '--tc' in sys.argv
     ops.set_conv_backend(tc)
     out = []
-    for (N, H, W) in [(1, 176, 320), (5, 176, 320), (5, 88, 160), (5, 44, 80), (1, 704, 1280), (5, 44, 80)]:
+    conv_shapes = [] if '--only-mdcn' in sys.argv else [(1, 176, 320), (5, 176, 320), (5, 88, 160), (5, 44, 80), (1, 704, 1280), (5, 44, 80)]
+    for (N, H, W) in conv_shapes:
         for (Ci, Co) in [(64, 64), (128, 64), (64, 216), (64, 256)]:
             if H >= 704 and Co != 64:
                 continue
@@ -56,7 +57,7 @@ def main():
         t = timeit(lambda: torch.autograd.grad(y, [x, om, w, b], gy, retain_graph=True), reps=5, warm=1)
         print(json.dumps(dict(k='mdcn_bwd_all', N=N, H=H, W=W, us=t * 1e6)), flush=True)
     # conv backward (dgrad + wgrad + act) at the inner-loop resolution
-    for (N, H, W) in [(5, 44, 80), (1, 176, 320), (5, 176, 320)]:
+    for (N, H, W) in ([] if '--only-mdcn' in sys.argv else [(5, 44, 80), (1, 176, 320), (5, 176, 320)]):
         x = torch.randn(N, H, W, 64, device='cuda', requires_grad=True)
         w = (torch.randn(64, 64, 3, 3, device='cuda') * 0.05).requires_grad_(True)
         b = torch.zeros(64, device='cuda', requires_grad=True)
