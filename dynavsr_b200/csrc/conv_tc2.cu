@@ -38,7 +38,10 @@ struct T2Params {
     T2Seg seg[DVSR_MAX_SEG];
     int Co;                               // real output channels
     int halo_h, halo_w, a_bytes;          // halo tile geometry / padded bytes per stage
-    int nblocks;                          // resident weight blocks ((seg, chunk), tap) of this launch
+    int nblocks;                          // resident weight blocks of this launch: TF32 -- ((seg, chunk), tap) blocks of 64 rows
+                                          // (8 KiB); BF16x3 -- ((seg, 64-channel pair), tap) blocks of 128 rows (16 KiB)
+    int wblk_bytes, wblk_rows;
+    int seg_blk0[DVSR_MAX_SEG];           // first weight block of each segment
     int tiles_total;
     const float* bias;
     int act; float slope; int sig_split;
@@ -68,8 +71,8 @@ __global__ void __launch_bounds__(T2_THREADS, 1)
 conv_tc2_kernel(const __grid_constant__ T2Maps maps, const T2Params p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    uint8_t* smem_b = smem;                                        // [nblocks][64 rows x 128 B]
-    uint8_t* smem_a = smem + p.nblocks * 8192;                     // [T2_ASTAGES][a_bytes]
+    uint8_t* smem_b = smem;                                        // [nblocks][wblk_rows x 128 B]
+    uint8_t* smem_a = smem + p.nblocks * p.wblk_bytes;             // [T2_ASTAGES][a_bytes]
     uint64_t* bars = (uint64_t*)(smem_a + T2_ASTAGES * p.a_bytes);
     uint64_t* b_full = bars;                  // [1]
     uint64_t* a_full = bars + 1;              // [3]
@@ -102,7 +105,7 @@ conv_tc2_kernel(const __grid_constant__ T2Maps maps, const T2Params p) {
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(128) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (threadIdx.x >= 192 && threadIdx.x < 256) {
@@ -117,9 +120,9 @@ conv_tc2_kernel(const __grid_constant__ T2Maps maps, const T2Params p) {
     if (warp == 0) {
         // ===================== producer =====================
         if (elect_one()) {
-            mbar_expect_tx(b_full, (uint32_t)p.nblocks * 8192u);
+            mbar_expect_tx(b_full, (uint32_t)(p.nblocks * p.wblk_bytes));
             for (int b = 0; b < p.nblocks; ++b)
-                tma_load_2d(&maps.w, b_full, smem_b + b * 8192, 0, (ngrp * p.nblocks + b) * T2_NG);
+                tma_load_2d(&maps.w, b_full, smem_b + b * p.wblk_bytes, 0, (ngrp * p.nblocks + b) * p.wblk_rows);
             int stage = 0, phase = 0, trace_i = 0;
             // L2 prefetch cursor running T2_PF chunks ahead of the shared-memory ring (the ring is only 3 deep)
             int pf_tile = blockIdx.x, pf_s = 0, pf_c = 0;
@@ -155,6 +158,8 @@ conv_tc2_kernel(const __grid_constant__ T2Maps maps, const T2Params p) {
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         const uint32_t idesc = p.bf16x3 ? make_idesc_bf16(128, p.n_mma) : make_idesc_tf32(128, p.n_mma);
+        const uint32_t idesc_wide = make_idesc_bf16(128, 2 * T2_NG);      // [w_hi | w_lo] stacked along N (BF16x3, full groups)
+        const bool wide = p.bf16x3 && p.n_mma == T2_NG;
         // descriptor templates: only the 14-bit (address >> 4) field changes per tap / k-step
         const uint64_t ad_const = make_desc(0, 16, (uint32_t)p.halo_w * 128u, 2);
         const uint64_t bd_const = make_desc(0, 16, 1024, 2);
@@ -164,9 +169,8 @@ conv_tc2_kernel(const __grid_constant__ T2Maps maps, const T2Params p) {
             const int acc = local & 1;
             mbar_wait(&acc_empty[acc], ((local >> 1) & 1) ^ 1);      // epilogue drained this accumulator
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            int blk = 0, cidx = 0;
+            int cidx = 0;
             for (int s = 0; s < p.nseg; ++s) {
-                if (p.wshare) blk = 0;
                 const int chunks = (p.seg[s].C + 31) / 32;
                 for (int c = 0; c < chunks; ++c, ++cidx) {
                     mbar_wait(&a_ready[stage], phase);
@@ -174,26 +178,35 @@ conv_tc2_kernel(const __grid_constant__ T2Maps maps, const T2Params p) {
                     if (elect_one()) {
                         T2_TRACE(3, trace_i);
                         const uint64_t ad0 = ad_const + (uint64_t)(smem_u32(smem_a + stage * p.a_bytes) >> 4);
-                        uint64_t bd = bd_const + (uint64_t)(smem_u32(smem_b + blk * 8192) >> 4);
-                        const uint32_t dcol = tmem_base + acc * T2_NG;
+                        // first weight block of this chunk; BF16x3 blocks hold a PAIR of chunks (64 K-channels per row)
+                        const int blk = p.seg_blk0[s] + (p.bf16x3 ? (c >> 1) : c) * KK;
+                        uint64_t bd = bd_const + (uint64_t)((smem_u32(smem_b + blk * p.wblk_bytes) + (p.bf16x3 ? (c & 1) * 64 : 0)) >> 4);
+                        const uint32_t dcol = tmem_base + acc * (2 * T2_NG);
                         int wy = p.tap_sign < 0 ? p.KH - 1 : 0, wx0 = p.tap_sign < 0 ? p.KW - 1 : 0, wx = wx0, kw = 0;
                         for (int tap = 0; tap < KK; ++tap) {
                             const uint64_t ad = ad0 + (uint64_t)((wy * p.halo_w + wx) * 8);     // 128 B per pixel = 8 x 16 B
+                            const uint32_t first = (cidx > 0 || tap > 0) ? 1u : 0u;
                             if (!p.bf16x3) {
-                                mma_tf32(dcol, ad, bd, idesc, (cidx > 0 || tap > 0) ? 1u : 0u);
+                                mma_tf32(dcol, ad, bd, idesc, first);
                                 mma_tf32(dcol, ad + 2, bd + 2, idesc, 1u);
                                 mma_tf32(dcol, ad + 4, bd + 4, idesc, 1u);
                                 mma_tf32(dcol, ad + 6, bd + 6, idesc, 1u);
-                            } else {
-                                // row = [hi(32 bf16) | lo(32 bf16)] for both operands; K = 16 per MMA = 32 bytes = +2
-                                mma_bf16(dcol, ad, bd, idesc, (cidx > 0 || tap > 0) ? 1u : 0u);   // x_hi . w_hi
-                                mma_bf16(dcol, ad + 2, bd + 2, idesc, 1u);
-                                mma_bf16(dcol, ad + 4, bd, idesc, 1u);                            // x_lo . w_hi
+                            } else if (wide) {
+                                // activation row = [hi(32 bf16) | lo(32 bf16)]; weight rows 0-63 = hi, 64-127 = lo; K = 16 = +2
+                                mma_bf16(dcol, ad, bd, idesc_wide, first);            // x_hi . [w_hi | w_lo] -> columns [0,64) | [64,128)
+                                mma_bf16(dcol, ad + 2, bd + 2, idesc_wide, 1u);
+                                mma_bf16(dcol, ad + 4, bd, idesc, 1u);                // x_lo . w_hi         -> columns [0,64)
                                 mma_bf16(dcol, ad + 6, bd + 2, idesc, 1u);
-                                mma_bf16(dcol, ad, bd + 4, idesc, 1u);                            // x_hi . w_lo
-                                mma_bf16(dcol, ad + 2, bd + 6, idesc, 1u);
+                            } else {
+                                // narrow output group (N < 64): three N-wide products; the lo rows start 64 rows (8 KiB) further
+                                mma_bf16(dcol, ad, bd, idesc, first);                 // x_hi . w_hi
+                                mma_bf16(dcol, ad + 2, bd + 2, idesc, 1u);
+                                mma_bf16(dcol, ad + 4, bd, idesc, 1u);                // x_lo . w_hi
+                                mma_bf16(dcol, ad + 6, bd + 2, idesc, 1u);
+                                mma_bf16(dcol, ad, bd + 512, idesc, 1u);              // x_hi . w_lo
+                                mma_bf16(dcol, ad + 2, bd + 514, idesc, 1u);
                             }
-                            bd += 512;                                                            // next 8 KiB weight block
+                            bd += (uint64_t)(p.wblk_bytes >> 4);                      // next tap's weight block
                             wx += p.tap_sign;
                             if (++kw == p.KW) { kw = 0; wx = wx0; wy += p.tap_sign; }
                         }
@@ -202,7 +215,6 @@ conv_tc2_kernel(const __grid_constant__ T2Maps maps, const T2Params p) {
                         T2_TRACE(4, trace_i);
                     }
                     ++trace_i;
-                    blk += KK;
                     __syncwarp();
                     if (++stage == T2_ASTAGES) { stage = 0; phase ^= 1; }
                 }
@@ -239,13 +251,7 @@ conv_tc2_kernel(const __grid_constant__ T2Maps maps, const T2Params p) {
                         }
                         uint32_t hi[16], lo[16];
 #pragma unroll
-                        for (int q2 = 0; q2 < 16; ++q2) {
-                            uint32_t h0, l0, h1, l1;
-                            split_bf16(f[2 * q2], h0, l0);
-                            split_bf16(f[2 * q2 + 1], h1, l1);
-                            hi[q2] = h0 | (h1 << 16);
-                            lo[q2] = l0 | (l1 << 16);
-                        }
+                        for (int q2 = 0; q2 < 16; ++q2) split_bf16x2(f[2 * q2], f[2 * q2 + 1], hi[q2], lo[q2]);
 #pragma unroll
                         for (int c = 0; c < 4; ++c) {
                             row[c ^ ph] = make_uint4(hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
@@ -276,7 +282,9 @@ conv_tc2_kernel(const __grid_constant__ T2Maps maps, const T2Params p) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (threadIdx.x == 192) T2_TRACE(5, local);
             float v0[32], v1[32];
-            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * T2_NG), v0);
+            const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 2 * T2_NG);
+            const bool wide = p.bf16x3 && p.n_mma == T2_NG;     // columns [64,128) hold the x_hi . w_lo partial sums
+            tmem_ld32(tacc, v0);
             if (p.scalar_out) {
                 // narrow output (Co <= 32, any alignment): one 32-column read, per-channel loads / stores
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -294,10 +302,20 @@ conv_tc2_kernel(const __grid_constant__ T2Maps maps, const T2Params p) {
                 }
                 continue;
             }
-            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * T2_NG + 32), v1);
+            tmem_ld32(tacc + 32, v1);
+            if (wide) {
+                float t[32];
+                tmem_ld32(tacc + 64, t);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v0[j] += t[j];
+                tmem_ld32(tacc + 96, t);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v1[j] += t[j];
+            }
             // the accumulator is in registers: hand the TMEM buffer back to the MMA warp before the global stores
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             mbar_arrive(&acc_empty[acc]);
+            if (threadIdx.x == 192) T2_TRACE(7, local);
             if (valid) {
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
@@ -340,7 +358,7 @@ conv_tc2_kernel(const __grid_constant__ T2Maps maps, const T2Params p) {
     __syncthreads();
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256) : "memory");
     }
 }
 
@@ -349,13 +367,17 @@ conv_tc2_kernel(const __grid_constant__ T2Maps maps, const T2Params p) {
 using namespace dvsr;
 
 static long long* g_t2_trace = nullptr;
-// debugging aid: device buffer of 7 x 64 clock64 stamps written by CTA (0,0) of the next launches (nullptr = off)
+// debugging aid: device buffer of 8 x 64 clock64 stamps written by CTA (0,0) of the next launches (nullptr = off)
 extern "C" int dvsr_conv_tc2_set_trace(long long* dev_buffer) { g_t2_trace = dev_buffer; return 0; }
 
+static int g_t2_bf16x3 = 1;
+// resident weight footprint in 8 KiB units: TF32 -- one 64-row block per (32-channel chunk, tap); BF16x3 -- one 128-row
+// (16 KiB) block per (64-channel pair, tap)
 static int t2_blocks(const dvsr_conv_desc* d) {
-    int chunks = 0;
-    for (int s = 0; s < (d->wshare ? 1 : d->nseg); ++s) chunks += (d->seg[s].C + 31) / 32;
-    return chunks * d->KH * d->KW;
+    int n = 0;
+    for (int s = 0; s < (d->wshare ? 1 : d->nseg); ++s)
+        n += g_t2_bf16x3 ? 2 * ((d->seg[s].C + 63) / 64) : (d->seg[s].C + 31) / 32;
+    return n * d->KH * d->KW;
 }
 
 // 1 if the WHOLE descriptor can run in one launch of the resident-weight kernel
@@ -381,6 +403,12 @@ extern "C" int dvsr_conv_tc2_supported(const dvsr_conv_desc* d) {
 
 extern "C" long long dvsr_conv_tc2_packed_floats(const dvsr_wlayout* wl, int mode, int seg_lo, int seg_hi) {
     if (!wl) return 0;
+    if (mode == 9) {
+        long long nb = 0;
+        for (int s = seg_lo; s < seg_hi; ++s) nb += (long long)wl->taps * ((wl->seg_C[s] + 63) / 64);
+        return nb * ((wl->Co + T2_NG - 1) / T2_NG) * 128 * 32;
+    }
+    if (mode == 10) return (long long)wl->taps * ((wl->Co + 63) / 64) * ((wl->seg_C[seg_lo] + T2_NG - 1) / T2_NG) * 128 * 32;
     if (mode == 5 || mode == 7) {
         long long nb = 0;
         for (int s = seg_lo; s < seg_hi; ++s) nb += (long long)wl->taps * ((wl->seg_C[s] + 31) / 32);
@@ -391,19 +419,20 @@ extern "C" long long dvsr_conv_tc2_packed_floats(const dvsr_wlayout* wl, int mod
 
 // mode 5: forward weights of segments [seg_lo, seg_hi); mode 6: data-gradient weights of segment seg_lo
 extern "C" int dvsr_pack_weights_tc2(const float* w, float* wp, const dvsr_wlayout* wl, int mode, int seg_lo, int seg_hi, void* stream) {
-    DVSR_REQUIRE(w && wp && wl && mode >= 5 && mode <= 8, "pack_weights_tc2: bad arguments");
-    const bool fwd = (mode == 5 || mode == 7);
+    DVSR_REQUIRE(w && wp && wl && mode >= 5 && mode <= 10, "pack_weights_tc2: bad arguments");
+    const bool fwd = (mode == 5 || mode == 7 || mode == 9);
+    const int kdiv = mode >= 9 ? 64 : 32, rows = mode >= 9 ? 128 : T2_NG;
     DVSR_REQUIRE(seg_lo >= 0 && seg_lo < wl->nseg && (!fwd || (seg_hi > seg_lo && seg_hi <= wl->nseg)), "pack_weights_tc2: bad segment range");
     int nblocks, ngroups;
     if (fwd) {
         nblocks = 0;
-        for (int s = seg_lo; s < seg_hi; ++s) nblocks += wl->taps * ((wl->seg_C[s] + 31) / 32);
+        for (int s = seg_lo; s < seg_hi; ++s) nblocks += wl->taps * ((wl->seg_C[s] + kdiv - 1) / kdiv);
         ngroups = (wl->Co + T2_NG - 1) / T2_NG;
     } else {
-        nblocks = wl->taps * ((wl->Co + 31) / 32);
+        nblocks = wl->taps * ((wl->Co + kdiv - 1) / kdiv);
         ngroups = (wl->seg_C[seg_lo] + T2_NG - 1) / T2_NG;
     }
-    const long long total = (long long)nblocks * ngroups * T2_NG * 32;
+    const long long total = (long long)nblocks * ngroups * rows * 32;
     dvsr_pack_job j;
     memset(&j, 0, sizeof(j));
     j.w = w; j.wp = wp; j.wl = *wl; j.mode = mode; j.seg = seg_lo; j.seg_hi = seg_hi; j.a0 = nblocks; j.total = total;
@@ -411,7 +440,6 @@ extern "C" int dvsr_pack_weights_tc2(const float* w, float* wp, const dvsr_wlayo
     return check_launch("pack_weights_tc2");
 }
 
-static int g_t2_bf16x3 = 1;
 // 1 (default): BF16x3 split operands (3 products, ~1e-5 per layer); 0: single-pass TF32 with round-to-nearest (~3e-4)
 extern "C" int dvsr_conv_tc2_set_precision(int bf16x3) { g_t2_bf16x3 = bf16x3 ? 1 : 0; return 0; }
 extern "C" int dvsr_conv_tc2_get_precision(void) { return g_t2_bf16x3; }
@@ -431,14 +459,24 @@ extern "C" int dvsr_conv_tc2_fprop(const dvsr_conv_desc* d, const float* wp, con
     p.Co = d->Co;
     p.halo_h = T2_TH + d->KH - 1; p.halo_w = T2_TW + d->KW - 1;
     p.a_bytes = (p.halo_h * p.halo_w * 128 + 1023) / 1024 * 1024;
-    p.nblocks = t2_blocks(d);
+    p.bf16x3 = g_t2_bf16x3;
+    p.wblk_rows = p.bf16x3 ? 128 : T2_NG;
+    p.wblk_bytes = p.wblk_rows * 128;
+    {
+        int b = 0;
+        for (int s = 0; s < d->nseg; ++s) {
+            const int nb = (p.bf16x3 ? (d->seg[s].C + 63) / 64 : (d->seg[s].C + 31) / 32) * d->KH * d->KW;
+            p.seg_blk0[s] = d->wshare ? 0 : b;          // wshare: every segment reads segment 0's blocks
+            if (!d->wshare || s == 0) b += nb;
+        }
+        p.nblocks = b;
+    }
     p.bias = d->bias; p.act = d->act; p.slope = d->slope; p.sig_split = d->sig_split;
     p.res = d->res; p.res_pix_stride = d->res_pix_stride; p.shuffle = d->shuffle;
     p.accum_in = accum_in; p.accum_pix_stride = accum_pix_stride;
     p.y = d->y; p.y_pix_stride = d->y_pix_stride;
     p.y_vec8 = ((((uintptr_t)d->y) & 31) == 0) && (d->y_pix_stride % 8 == 0) && (d->Co % 8 == 0);
     p.trace = g_t2_trace;
-    p.bf16x3 = g_t2_bf16x3;
     p.scalar_out = d->Co <= 32 && (d->Co < 16 || (d->Co & 3) || (d->y_pix_stride & 3) || ((uintptr_t)d->y & 15) ||
                                    (d->res && ((((uintptr_t)d->res) & 15) || (d->res_pix_stride & 3))));
     p.n_mma = d->Co >= T2_NG ? T2_NG : (d->Co + 15) / 16 * 16;
@@ -463,16 +501,16 @@ extern "C" int dvsr_conv_tc2_fprop(const dvsr_conv_desc* d, const float* wp, con
     }
     {
         // the packed rows are 128 bytes either way: 32 x tf32, or [32 x bf16 hi | 32 x bf16 lo]
-        cuuint64_t dims[2] = {32, (cuuint64_t)p.nblocks * ngroups * T2_NG};
+        cuuint64_t dims[2] = {32, (cuuint64_t)p.nblocks * ngroups * p.wblk_rows};
         cuuint64_t strides[1] = {128};
-        cuuint32_t box[2] = {32, T2_NG};
+        cuuint32_t box[2] = {32, (cuuint32_t)p.wblk_rows};
         cuuint32_t estr[2] = {1, 1};
         CUresult r = encode(&maps.w, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)wp, dims, strides, box, estr,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         DVSR_REQUIRE(r == CUDA_SUCCESS, "conv_tc2_fprop: cuTensorMapEncodeTiled(weights) failed with %d", (int)r);
     }
-    const size_t smem = 1024 + (size_t)p.nblocks * 8192 + (size_t)T2_ASTAGES * p.a_bytes + 512;
+    const size_t smem = 1024 + (size_t)p.nblocks * p.wblk_bytes + (size_t)T2_ASTAGES * p.a_bytes + 512;
     DVSR_REQUIRE(smem <= 232448, "conv_tc2_fprop: %zu B of shared memory needed", smem);
     static size_t smem_set = 0;
     if (smem > smem_set) {

@@ -20,7 +20,6 @@
 // input row 2(oy + t) + a - pad, so each parity class (a, b) is a stride-1 weight gradient with ceil((KH-a)/2) x
 // ceil((KW-b)/2) taps over the 2x-subsampled input x[2i + a - pad][2j + b - pad] -- which TMA delivers directly
 // (element strides 2, negative / out-of-range coordinates zero-filled).  One launch per parity class.
-#include <cstdlib>
 #include "tc_common.cuh"
 
 namespace dvsr {
@@ -42,7 +41,6 @@ struct WgParams {
     int a_blk_bytes, b_blk_bytes, stages;
     long long co_stride, ci_stride, seg_base;   // dvsr_wlayout addressing
     float* gw;
-    int debug;
 };
 struct __align__(64) WgMaps { CUtensorMap x; CUtensorMap gy; };
 
@@ -158,7 +156,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ WgMaps maps, const WgParams p) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                     const int co = c0 + j;
-                    if (co < p.Co && !(p.debug & 1)) atomicAdd(dst + (long long)co * p.co_stride, v[j]);
+                    if (co < p.Co) atomicAdd(dst + (long long)co * p.co_stride, v[j]);
                 }
             }
         }
@@ -239,7 +237,6 @@ extern "C" int dvsr_conv_wgrad_tc(const dvsr_conv_desc* d, int seg, const float*
     if (splits < 1) splits = 1;
     int per = (p.chunks_total + splits - 1) / splits;
     if (per < 4) per = 4;
-    { const char* e = getenv("DVSR_WG_PER"); if (e) per = atoi(e); const char* f = getenv("DVSR_WG_DEBUG"); p.debug = f ? atoi(f) : 0; }
     p.chunks_per_cta = per;
     splits = (p.chunks_total + per - 1) / per;
     p.co_stride = wl->co_stride; p.ci_stride = wl->ci_stride; p.seg_base = wl->seg_base[seg];

@@ -165,13 +165,7 @@ mdcn_tc_kernel(const __grid_constant__ CUtensorMap wmap, const MdParams p) {
                         }
                         uint32_t hi[4], lo[4];
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            uint32_t h0, l0, h1, l1;
-                            split_bf16(v[2 * q], h0, l0);
-                            split_bf16(v[2 * q + 1], h1, l1);
-                            hi[q] = h0 | (h1 << 16);
-                            lo[q] = l0 | (l1 << 16);
-                        }
+                        for (int q = 0; q < 4; ++q) split_bf16x2(v[2 * q], v[2 * q + 1], hi[q], lo[q]);
                         // row prow = [hi: 4 chunks of 8 channels | lo: 4 chunks]; 128B swizzle: chunk ^ (row & 7)
                         uint4* row = reinterpret_cast<uint4*>(tile_a + prow * 128);
                         const int ph = prow & 7;

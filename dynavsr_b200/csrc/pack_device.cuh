@@ -19,7 +19,11 @@ __device__ __forceinline__ float pack_round_tf32(float x) {
 //                taps (a + 2t, b + 2u): a1 = KWf, a2 = KWs, a3 = 2a + b
 //   mode 5 / 6 : resident-weight tcgen05 layouts (conv_tc2.cu)  a0 = blocks per output group, seg..seg_hi = segments
 //   mode 7 / 8 : same block structure as 5 / 6 for the BF16x3 split: each 128-byte row holds 32 channels as
-//                [hi: 32 x bf16 | lo: 32 x bf16]; one float slot of wp carries two consecutive bf16 values
+//                [hi: 32 x bf16 | lo: 32 x bf16]; one float slot of wp carries two consecutive bf16 values (mdcn_tc.cu)
+//   mode 9 / 10: BF16x3 layout of conv_tc2.cu with hi and lo parts stacked along N: 16 KiB blocks of 128 rows x 128 B per
+//                (64-channel pair of K, tap); rows 0-63 = hi part of output channel g*64 + r, rows 64-127 = lo part; a row
+//                holds 64 K-channels as bf16.  One N = 128 MMA then yields x_hi.w_hi and x_hi.w_lo from a single read of
+//                the activation operand.  a0 = blocks per output group.
 __device__ __forceinline__ float pack_value(const dvsr_pack_job& j, long long i) {
     const dvsr_wlayout& wl = j.wl;
     const float* __restrict__ w = j.w;
@@ -41,6 +45,44 @@ __device__ __forceinline__ float pack_value(const dvsr_pack_job& j, long long i)
         const long long r = i / C;
         const int co = (int)(r % wl.Co), tap = (int)(r / wl.Co);
         return w[(long long)co * wl.co_stride + wl.seg_base[j.seg] + (long long)ci * wl.ci_stride + tap];
+    }
+    if (j.mode >= 9) {
+        const int k2 = (int)(i & 31);
+        long long r = i >> 5;
+        const int row = (int)(r % 128);
+        r /= 128;
+        const int nblocks = j.a0;
+        int blk = (int)(r % nblocks);
+        const int g = (int)(r / nblocks);
+        const int n = g * 64 + (row & 63);
+        const bool want_lo = row >= 64;
+        uint32_t out = 0;
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int ch = 2 * k2 + e;            // channel inside the 64-channel pair
+            float v = 0.f;
+            if (j.mode == 9) {
+                int s = j.seg, b2 = blk;
+                for (; s < j.seg_hi; ++s) {
+                    const int nb = wl.taps * ((wl.seg_C[s] + 63) / 64);
+                    if (b2 < nb) break;
+                    b2 -= nb;
+                }
+                const int pair = b2 / wl.taps, tap = b2 - pair * wl.taps;
+                const int ci = pair * 64 + ch;
+                if (n < wl.Co && ci < wl.seg_C[s])
+                    v = w[(long long)n * wl.co_stride + wl.seg_base[s] + (long long)ci * wl.ci_stride + tap];
+            } else {
+                const int pair = blk / wl.taps, tap = blk - pair * wl.taps;
+                const int co = pair * 64 + ch;
+                if (n < wl.seg_C[j.seg] && co < wl.Co)
+                    v = w[(long long)co * wl.co_stride + wl.seg_base[j.seg] + (long long)n * wl.ci_stride + tap];
+            }
+            const __nv_bfloat16 h = __float2bfloat16_rn(v);
+            const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
+            out |= (uint32_t)__bfloat16_as_ushort(want_lo ? l : h) << (16 * e);
+        }
+        return __uint_as_float(out);
     }
     if (j.mode >= 7) {
         // slot k2 of the 32-slot row: elements 2*k2, 2*k2+1 of [hi(32) | lo(32)]

@@ -51,7 +51,7 @@ extern "C" int dvsr_pack_table_copy(const dvsr_pack_job* table_dev, int n_jobs, 
 }
 
 extern "C" int dvsr_pack_job_run(const dvsr_pack_job* job, void* stream) {
-    DVSR_REQUIRE(job && job->w && job->wp && job->total > 0 && job->mode >= 0 && job->mode <= 8, "pack_job: bad job");
+    DVSR_REQUIRE(job && job->w && job->wp && job->total > 0 && job->mode >= 0 && job->mode <= 10, "pack_job: bad job");
     pack_job_kernel<<<cdiv(job->total, 256), 256, 0, (cudaStream_t)stream>>>(*job);
     return check_launch("pack_job");
 }

@@ -94,6 +94,16 @@ __device__ __forceinline__ void split_bf16(float x, uint32_t& hi, uint32_t& lo) 
     hi = (uint32_t)__bfloat16_as_ushort(h);
     lo = (uint32_t)__bfloat16_as_ushort(l);
 }
+// the same split for two values at once with the packed converters (F2FP.BF16.PACK_AB): hi = {bf16(x1), bf16(x0)},
+// lo = {bf16(x1 - hi1), bf16(x0 - hi0)}; x0 lands in the low half-word (element order of a K-major row)
+__device__ __forceinline__ void split_bf16x2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    const float r0 = x0 - __uint_as_float(hi << 16);
+    const float r1 = x1 - __uint_as_float(hi & 0xffff0000u);
+    const __nv_bfloat162 l = __floats2bfloat162_rn(r0, r1);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+}
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }

@@ -308,13 +308,16 @@ def _packed_parity(weight, wl, seg, KH, KW, a, b):
 
 
 def _packed_tc2(weight, wl, mode, seg_lo, seg_hi):
-    """Resident-weight layout of conv_tc2.cu (mode 5 forward over segments [seg_lo, seg_hi), mode 6 data gradient)."""
+    """Resident-weight layout of conv_tc2.cu (mode 5 forward over segments [seg_lo, seg_hi), mode 6 data gradient).
+    BF16x3 precision uses modes 9 / 10: 16 KiB blocks per (64-channel pair, tap) with the hi and lo parts stacked along N."""
+    bf = _backend['precision'] == 'bf16x3'
+    kdiv = 64 if bf else 32
     if mode == 5:
-        nblocks = sum(wl.taps * ((wl.seg_C[s] + 31) // 32) for s in range(seg_lo, seg_hi))
+        nblocks = sum(wl.taps * ((wl.seg_C[s] + kdiv - 1) // kdiv) for s in range(seg_lo, seg_hi))
     else:
-        nblocks = wl.taps * ((wl.Co + 31) // 32)
-    if _backend['precision'] == 'bf16x3':
-        mode += 2               # 7 / 8: rows of [32 x bf16 hi | 32 x bf16 lo]
+        nblocks = wl.taps * ((wl.Co + kdiv - 1) // kdiv)
+    if bf:
+        mode += 4               # 9 / 10
     return _get_pack(weight, wl, mode, seg_lo, seg_hi, a=(nblocks, 0, 0, 0),
                      total=_lib.lib().dvsr_conv_tc2_packed_floats(ctypes.byref(wl), mode, seg_lo, seg_hi))
 

@@ -99,7 +99,7 @@ typedef struct dvsr_wlayout {
 
 /* One weight-packing job (pack_table.cu).  mode 0/1: CUDA-core layouts; 2/3/4: streaming tcgen05 layouts (a0 = padded
  * rows; mode 4: parity-restricted taps, a1 = KWf, a2 = KWs, a3 = 2a+b); 5/6: resident-weight tcgen05 layouts (a0 =
- * weight blocks per 64-channel output group; segments [seg, seg_hi)).  block_start is only used by dvsr_pack_table. */
+ * weight blocks per 64-channel output group; segments [seg, seg_hi)); 7-10: BF16x3 variants of 5/6.  block_start is only used by dvsr_pack_table. */
 typedef struct dvsr_pack_job {
     const float* w;
     float* wp;
@@ -144,18 +144,20 @@ int dvsr_conv_tc_fprop(const dvsr_conv_desc* d, const float* wp, void* stream);
 /* Persistent resident-weight variant (conv_tc2.cu): stride-1 convs whose packed weights for 64 output channels fit
  * in shared memory (<= 18 blocks of (tap, 32 input channels)); halo reuse across taps.  accum_in (optional) is added
  * before bias / activation, which lets the host split the K dimension of wider inputs over several launches.
- * Weights: dvsr_pack_weights_tc2 mode 5 / 7 (forward, segments [seg_lo, seg_hi)), mode 6 / 8 (data gradient of seg_lo);
- * 5 / 6 = TF32 rows, 7 / 8 = BF16x3 rows (see dvsr_conv_tc2_set_precision). */
+ * Weights: dvsr_pack_weights_tc2 mode 5 / 9 (forward, segments [seg_lo, seg_hi)), mode 6 / 10 (data gradient of seg_lo);
+ * 5 / 6 = TF32 rows (8 KiB blocks per (32-channel chunk, tap)); 9 / 10 = BF16x3 (16 KiB blocks per (64-channel pair, tap):
+ * rows 0-63 hold the bf16 hi parts of 64 output channels, rows 64-127 the lo parts, so ONE N = 128 MMA gives x_hi.w_hi and
+ * x_hi.w_lo); modes 7 / 8 are the [hi | lo]-per-row variant read by dvsr_mdcn_tc_fprop (see dvsr_conv_tc2_set_precision). */
 int dvsr_conv_tc2_supported(const dvsr_conv_desc* d);
 long long dvsr_conv_tc2_packed_floats(const dvsr_wlayout* wl, int mode, int seg_lo, int seg_hi);
 int dvsr_pack_weights_tc2(const float* w, float* wp, const dvsr_wlayout* wl, int mode, int seg_lo, int seg_hi, void* stream);
 int dvsr_conv_tc2_fprop(const dvsr_conv_desc* d, const float* wp, const float* accum_in, int accum_pix_stride, void* stream);
 /* Operand precision of conv_tc2: 1 (default) = BF16x3 -- activations and weights are split into bf16 hi + lo parts and
- * the three significant products are accumulated in fp32 (per-layer error ~1e-5, weights packed with mode 7 / 8);
+ * the three significant products are accumulated in fp32 (per-layer error ~1e-5, weights packed with mode 9 / 10);
  * 0 = single-pass TF32 with operands rounded to nearest (~3e-4 per layer, weights packed with mode 5 / 6). */
 int dvsr_conv_tc2_set_precision(int bf16x3);
 int dvsr_conv_tc2_get_precision(void);
-/* debugging aid: 7 x 64 clock64 stamps of CTA (0,0) (producer / rounding / MMA / epilogue events); NULL = off */
+/* debugging aid: 8 x 64 clock64 stamps of CTA (0,0) (producer / rounding / MMA / epilogue events); NULL = off */
 int dvsr_conv_tc2_set_trace(long long* dev_buffer);
 /* Tensor-core weight gradient of segment `seg` of a stride-1 convolution (conv_wgrad_tc.cu): both operands are
  * consumed MN-major straight from the NHWC tensors, x through one halo tile per pixel chunk. */

@@ -28,16 +28,16 @@ print('avg us', e0.elapsed_time(e1) / 20 * 1e3)
 if '--trace' in sys.argv:
     import ctypes
     from dynavsr_b200 import _lib
-    tr = torch.zeros(7 * 64, dtype=torch.int64, device='cuda')
+    tr = torch.zeros(8 * 64, dtype=torch.int64, device='cuda')
     _lib.lib().dvsr_conv_tc2_set_trace(ctypes.c_void_p(tr.data_ptr()))
     with torch.no_grad():
         ops.conv(x, w, b, pad=k // 2, act=ops.ACT_LRELU)
     torch.cuda.synchronize()
     _lib.lib().dvsr_conv_tc2_set_trace(None)
-    t = tr.view(7, 64).cpu()
+    t = tr.view(8, 64).cpu()
     t0 = int(t[0, 0])
-    names = ['prod:slot free', 'round:tile landed', 'round:done', 'mma:ready seen', 'mma:issued', 'epi:acc full', 'epi:done']
-    for ev in range(7):
+    names = ['prod:slot free', 'round:tile landed', 'round:done', 'mma:ready seen', 'mma:issued', 'epi:acc full', 'epi:done', 'epi:tmem read']
+    for ev in range(8):
         print('%-18s' % names[ev], ' '.join('%6d' % (int(v) - t0) for v in t[ev, :14]))
 if '--both' in sys.argv:
     for prec in ('tf32', 'bf16x3'):
