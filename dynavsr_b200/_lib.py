@@ -41,7 +41,8 @@ class ConvDesc(ctypes.Structure):
 class WLayout(ctypes.Structure):
     _fields_ = [('co_stride', ctypes.c_longlong), ('ci_stride', ctypes.c_longlong),
                 ('seg_base', ctypes.c_longlong * MAX_SEG), ('seg_C', ctypes.c_int * MAX_SEG),
-                ('nseg', ctypes.c_int), ('taps', ctypes.c_int), ('Co', ctypes.c_int)]
+                ('nseg', ctypes.c_int), ('taps', ctypes.c_int), ('Co', ctypes.c_int),
+                ('ci_bits', ctypes.c_int), ('ci_lo_valid', ctypes.c_int), ('ci_hi_stride', ctypes.c_longlong)]
 
 
 class PackJob(ctypes.Structure):
@@ -97,6 +98,7 @@ SIGNATURES = {
     'dvsr_pad2d_bwd': [_P, _P, _I, _I, _I, _I, _I, _I, _P],
     'dvsr_pad3d_replicate': [_P, _P, _I, _I, _I, _I, _I, _P],
     'dvsr_pad3d_replicate_bwd': [_P, _P, _I, _I, _I, _I, _I, _P],
+    'dvsr_tcat_pad3': [_P, _P, _I, _I, _I, _I, _I, _P],
     'dvsr_spatial_mean': [_P, _P, _I, _I, _I, _P],
     'dvsr_add_channel_bias': [_P, _P, _P, _I, _I, _I, _F, _P],
     'dvsr_act_bwd': [_P, _P, _P, _P, _P, _LL, _I, _I, _F, _I, _I, _I, _I, _P],

@@ -391,7 +391,7 @@ extern "C" int dvsr_conv_tc2_supported(const dvsr_conv_desc* d) {
     if (d->KH > 5 || d->KW > 5) return 0;
     for (int s = 0; s < d->nseg; ++s) {
         const dvsr_conv_seg& g = d->seg[s];
-        if ((g.C & 3) || g.C < 16 || (g.pix_stride & 3) || (g.img_stride & 3) || ((uintptr_t)g.ptr & 15)) return 0;
+        if ((g.C & 3) || g.C < 4 || (g.pix_stride & 3) || (g.img_stride & 3) || ((uintptr_t)g.ptr & 15)) return 0;
         if (d->wshare && g.C != d->seg[0].C) return 0;
     }
     if (!narrow) {

@@ -40,6 +40,7 @@ struct WgParams {
     int chunks_total, chunks_per_cta;
     int a_blk_bytes, b_blk_bytes, stages;
     long long co_stride, ci_stride, seg_base;   // dvsr_wlayout addressing
+    int ci_bits, ci_lo_valid; long long ci_hi_stride;   // interleaved channels (0 = plain)
     float* gw;
 };
 struct __align__(64) WgMaps { CUtensorMap x; CUtensorMap gy; };
@@ -144,7 +145,13 @@ conv_wgrad_tc_kernel(const __grid_constant__ WgMaps maps, const WgParams p) {
         if (Mt == 128) m = tl_lane;
         else if (lane < 16) m = q * 16 + lane;
         const int ci = c_tile + m;
-        const bool row_ok = (m >= 0) && (m < Mt) && (ci < p.C);
+        bool row_ok = (m >= 0) && (m < Mt) && (ci < p.C);
+        long long ci_off = (long long)ci * p.ci_stride;
+        if (p.ci_bits) {
+            const int lo = ci & ((1 << p.ci_bits) - 1);
+            row_ok = row_ok && lo < p.ci_lo_valid;
+            ci_off = (long long)lo * p.ci_stride + (long long)(ci >> p.ci_bits) * p.ci_hi_stride;
+        }
         for (int tl = 0; tl < ntaps; ++tl) {
             const int ltap = tap0 + tl, lkh = ltap / p.KW, lkw = ltap - lkh * p.KW;
             const int tap = (p.tap_a + p.xs * lkh) * p.KWf + p.tap_b + p.xs * lkw;
@@ -152,7 +159,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ WgMaps maps, const WgParams p) {
                 float v[32];
                 tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(tl * p.Npad + c0), v);
                 if (!row_ok) continue;
-                float* dst = p.gw + p.seg_base + (long long)ci * p.ci_stride + tap;
+                float* dst = p.gw + p.seg_base + ci_off + tap;
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                     const int co = c0 + j;
@@ -181,7 +188,7 @@ extern "C" int dvsr_conv_wgrad_tc_supported(const dvsr_conv_desc* d, int seg) {
     if (seg < 0 || seg >= d->nseg) return 0;
     if (d->Co < 16 || d->Co > 256 || (d->Co & 3)) return 0;
     const dvsr_conv_seg& g = d->seg[seg];
-    if (g.C < 64 || (g.C % 64) || (g.pix_stride & 3) || (g.img_stride & 3) || ((uintptr_t)g.ptr & 15)) return 0;
+    if ((g.C % 64 && (g.C > 32 || (g.C & 3))) || (g.pix_stride & 3) || (g.img_stride & 3) || ((uintptr_t)g.ptr & 15)) return 0;
     if (d->KH > 5 || d->KW > 5) return 0;
     return 1;
 }
@@ -240,6 +247,7 @@ extern "C" int dvsr_conv_wgrad_tc(const dvsr_conv_desc* d, int seg, const float*
     p.chunks_per_cta = per;
     splits = (p.chunks_total + per - 1) / per;
     p.co_stride = wl->co_stride; p.ci_stride = wl->ci_stride; p.seg_base = wl->seg_base[seg];
+    p.ci_bits = wl->ci_bits; p.ci_lo_valid = wl->ci_lo_valid; p.ci_hi_stride = wl->ci_hi_stride;
     p.gw = gw;
 
     WgMaps maps;

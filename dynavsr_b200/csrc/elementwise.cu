@@ -545,6 +545,39 @@ extern "C" int dvsr_pad3d_replicate(const float* x, float* y, int B, int T, int 
     });
     return check_launch("pad3d_replicate");
 }
+// Replication pad + temporal taps folded into channels (see dvsr_tcat_pad3 in the header): one thread per output pixel.
+__global__ void tcat_pad3_kernel(const float* __restrict__ x, float* __restrict__ y, int B, int T, int H, int W, int C) {
+    const int Ho = H + 2, Wo = W + 2;
+    const long long total = (long long)B * T * Ho * Wo;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        long long q = i;
+        const int ow = (int)(q % Wo); q /= Wo;
+        const int oh = (int)(q % Ho); q /= Ho;
+        const int t = (int)(q % T);
+        const int b = (int)(q / T);
+        const int ih = min(max(oh - 1, 0), H - 1), iw = min(max(ow - 1, 0), W - 1);
+        float4* o = reinterpret_cast<float4*>(y + i * 12);
+#pragma unroll
+        for (int kt = 0; kt < 3; ++kt) {
+            const int it = min(max(t + kt - 1, 0), T - 1);
+            const float* s = x + ((((long long)b * T + it) * H + ih) * W + iw) * C;
+            float v[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int c = 0; c < C; ++c) v[c] = __ldg(s + c);
+            o[kt] = make_float4(v[0], v[1], v[2], v[3]);
+        }
+    }
+}
+
+extern "C" int dvsr_tcat_pad3(const float* x, float* y, int B, int T, int H, int W, int C, void* stream) {
+    DVSR_REQUIRE(x && y && B > 0 && T > 0 && H > 0 && W > 0 && C > 0 && C <= 4, "tcat_pad3: bad arguments (C <= 4)");
+    DVSR_REQUIRE(A16(y), "tcat_pad3: output must be 16-byte aligned");
+    const long long total = (long long)B * T * (H + 2) * (W + 2);
+    long long blocks = (total + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    tcat_pad3_kernel<<<(int)blocks, 256, 0, ST>>>(x, y, B, T, H, W, C);
+    return check_launch("tcat_pad3");
+}
+
 extern "C" int dvsr_pad3d_replicate_bwd(const float* gy, float* gx, int B, int T, int H, int W, int C, void* stream) {
     DVSR_REQUIRE(gy && gx && B > 0 && T > 0 && H > 0 && W > 0 && C > 0, "pad3d_replicate_bwd: bad arguments");
     const bool v4 = (C % 4 == 0) && A16(gy) && A16(gx);

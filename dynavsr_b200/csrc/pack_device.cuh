@@ -13,6 +13,14 @@ __device__ __forceinline__ float pack_round_tf32(float x) {
     return __uint_as_float(u);
 }
 
+// Offset of kernel channel `ci` inside a weight row (dvsr_wlayout: plain or interleaved channels); -1 = no such element.
+__device__ __forceinline__ long long wl_ci_offset(const dvsr_wlayout& wl, int ci) {
+    if (wl.ci_bits == 0) return (long long)ci * wl.ci_stride;
+    const int lo = ci & ((1 << wl.ci_bits) - 1), hi = ci >> wl.ci_bits;
+    if (lo >= wl.ci_lo_valid) return -1;
+    return (long long)lo * wl.ci_stride + (long long)hi * wl.ci_hi_stride;
+}
+
 // Element `i` of the packed buffer described by job `j` (see dvsr_pack_job in include/dvsr_b200.h).
 //   mode 0 / 1 : CUDA-core layouts            (conv_simt.cu)   exact fp32
 //   mode 2 / 3 : streaming tcgen05 layouts     (conv_tc.cu)     a0 = padded rows;  mode 4 = mode 3 restricted to the
@@ -70,8 +78,8 @@ __device__ __forceinline__ float pack_value(const dvsr_pack_job& j, long long i)
                 }
                 const int pair = b2 / wl.taps, tap = b2 - pair * wl.taps;
                 const int ci = pair * 64 + ch;
-                if (n < wl.Co && ci < wl.seg_C[s])
-                    v = w[(long long)n * wl.co_stride + wl.seg_base[s] + (long long)ci * wl.ci_stride + tap];
+                const long long co_ = (n < wl.Co && ci < wl.seg_C[s]) ? wl_ci_offset(wl, ci) : -1;
+                if (co_ >= 0) v = w[(long long)n * wl.co_stride + wl.seg_base[s] + co_ + tap];
             } else {
                 const int pair = blk / wl.taps, tap = blk - pair * wl.taps;
                 const int co = pair * 64 + ch;
@@ -166,8 +174,8 @@ __device__ __forceinline__ float pack_value(const dvsr_pack_job& j, long long i)
             }
             const int chunk = blk / wl.taps, tap = blk - chunk * wl.taps;
             const int ci = chunk * 32 + k;
-            if (n < wl.Co && ci < wl.seg_C[s])
-                v = w[(long long)n * wl.co_stride + wl.seg_base[s] + (long long)ci * wl.ci_stride + tap];
+            const long long co_ = (n < wl.Co && ci < wl.seg_C[s]) ? wl_ci_offset(wl, ci) : -1;
+            if (co_ >= 0) v = w[(long long)n * wl.co_stride + wl.seg_base[s] + co_ + tap];
         } else {
             const int chunk = blk / wl.taps, tap = blk - chunk * wl.taps;
             const int co = chunk * 32 + k;

@@ -81,7 +81,11 @@ class DirectKernelEstimatorVideo(nn.Module):
         c2 = lambda t, m: ops.conv(ops.pad2d(t, 1, 'reflect'), m.weight, m.bias, stride=m.stride[0], pad=0, act=L)
         m = frame_mean(frames.detach())
         x = _AddFrameMean.apply(frames, m, -1.0)
-        x = ops.conv3d_padded(ops.pad3d_replicate(x, T), self.conv0.weight, self.conv0.bias, T, act=L)
+        if ops._backend['tc'] and x.shape[3] <= 4 and not x.requires_grad:
+            # RGB clip: temporal taps folded into channels, one tensor-core conv (ops.conv3d_rgb)
+            x = ops.conv3d_rgb(x, self.conv0.weight, self.conv0.bias, T, act=L)
+        else:
+            x = ops.conv3d_padded(ops.pad3d_replicate(x, T), self.conv0.weight, self.conv0.bias, T, act=L)
         fea = c2(x, self.conv1)
         fea = c2(fea, self.conv2)
         fea = c2(fea, self.conv3)

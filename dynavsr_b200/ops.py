@@ -14,7 +14,7 @@ from torch.autograd import Function
 from . import _lib
 from ._lib import ACT_LRELU, ACT_NONE, ACT_RELU, ACT_SIGMOID_SPLIT, ConvDesc, WLayout, call
 
-__all__ = ['PackScope', 'new_scope', 'scope', 'repack_all', 'snapshot_packs', 'restore_packs', 'invalidate_pack_snapshot', 'weights_updated', 'join_async', 'Seg', 'conv', 'conv3d_padded', 'mdcn', 'upsample', 'pool_maxavg', 'pad2d', 'pad3d_replicate',
+__all__ = ['conv3d_rgb', 'PackScope', 'new_scope', 'scope', 'repack_all', 'snapshot_packs', 'restore_packs', 'invalidate_pack_snapshot', 'weights_updated', 'join_async', 'Seg', 'conv', 'conv3d_padded', 'mdcn', 'upsample', 'pool_maxavg', 'pad2d', 'pad3d_replicate',
            'tsa_temporal', 'tsa_combine', 'pixel_loss', 'to_nhwc', 'to_nchw', 'invalidate_weight_cache',
            'ACT_NONE', 'ACT_RELU', 'ACT_LRELU', 'ACT_SIGMOID_SPLIT', 'set_conv_backend']
 
@@ -386,21 +386,21 @@ def join_async():
         sc.pending.clear()
 
 
-def _run_wgrad(d, gpre, Co, gw, wl, keep=None):
+def _run_wgrad(d, gpre, Co, gw, wl, keep=None, force_tc=False):
     """gw += A^T gy with the tensor-core kernel when every segment qualifies, else the CUDA-core kernel.
     ``keep`` (tensors the kernel reads) switches on side-stream execution; they stay referenced until join_async()."""
     if keep is not None and _async['on'] and not _lib.PROFILE['on']:
         side = _side_stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
-            _run_wgrad(d, gpre, Co, gw, wl)
+            _run_wgrad(d, gpre, Co, gw, wl, force_tc=force_tc)
         _current_scope[0].pending.append(keep)
         return
     L = _lib.lib()
     if _lib.PROFILE['on']:
         _lib.PROFILE['tag'] = 'wgrad %dx%dx%d C%s->%d k%d s%d%s' % (d.N, d.Ho, d.Wo, '+'.join(str(d.seg[i].C) for i in range(d.nseg)),
                                                                  d.Co, d.KH, d.stride, ' dcn' if d.deform else '')
-    if _backend['tc'] and all(L.dvsr_conv_wgrad_tc_supported(ctypes.byref(d), s) == 1 for s in range(d.nseg)):
+    if (_backend['tc'] or force_tc) and all(L.dvsr_conv_wgrad_tc_supported(ctypes.byref(d), s) == 1 for s in range(d.nseg)):
         for s in range(d.nseg):
             call('dvsr_conv_wgrad_tc', ctypes.byref(d), s, _ptr(gpre), Co, _ptr(gw), ctypes.byref(wl), _stream())
     else:
@@ -643,6 +643,83 @@ def conv3d_padded(xpad, weight, bias, T, act=ACT_NONE, slope=0.1):
     spec.Ho, spec.Wo = spec.H - KH + 1, spec.W - KW + 1
     # the same tensor feeds every temporal tap; autograd sees it once (data gradient is returned for slot 0)
     return _ConvFn.apply(spec, weight, bias, None, xpad, *([xpad.detach()] * (KT - 1)))
+
+
+class _Conv3dRgbFn(Function):
+    """Conv3d(C <= 4 -> Co, 3x3x3) over a replication-padded clip (MFDN conv0, LRimg_estimator.py:75-77,100-102) as ONE
+    tensor-core 3x3 conv: ``dvsr_tcat_pad3`` folds the three temporal taps into the channel axis of a [B*T, H+2, W+2, 12]
+    tensor (channel 4*kt + c) and the weight is addressed through an interleaved-channel ``dvsr_wlayout``.  The weight
+    gradient runs on the tensor-core kernel over the same tensor; the clip itself gets no gradient (it is input data)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, T, act, slope):
+        _check_cuda(x, weight, bias)
+        x = x.contiguous()
+        BT, H, W, C = x.shape
+        Co, Ci, KT, KH, KW = weight.shape
+        assert Ci == C and C <= 4 and (KT, KH, KW) == (3, 3, 3) and BT % T == 0
+        xc = torch.empty(BT, H + 2, W + 2, 12, device=x.device, dtype=torch.float32)
+        call('dvsr_tcat_pad3', _ptr(x), _ptr(xc), BT // T, T, H, W, C, _stream())
+        wl = WLayout()
+        wl.co_stride, wl.ci_stride, wl.ci_hi_stride = Ci * 27, 27, 9
+        wl.ci_bits, wl.ci_lo_valid = 2, C
+        wl.seg_base[0], wl.seg_C[0] = 0, 12
+        wl.nseg, wl.taps, wl.Co = 1, 9, Co
+        d = ConvDesc()
+        d.N, d.H, d.W, d.Ho, d.Wo = BT, H + 2, W + 2, H, W
+        d.KH, d.KW, d.stride, d.pad, d.dil = 3, 3, 1, 0, 1
+        d.nseg = 1
+        _fill_seg(d.seg[0], xc)
+        d.Co = Co
+        d.bias = bias.data_ptr() if bias is not None else None
+        d.act, d.slope = act, slope
+        y = torch.empty(BT, H, W, Co, device=x.device, dtype=torch.float32)
+        d.y, d.y_pix_stride = y.data_ptr(), Co
+        if _lib.PROFILE['on']:
+            _lib.PROFILE['tag'] = 'fprop conv3d-rgb %dx%dx%d C12->%d' % (BT, H, W, Co)
+        if _lib.lib().dvsr_conv_tc2_supported(ctypes.byref(d)) != 1:
+            raise RuntimeError('conv3d_rgb: shape not supported by the resident-weight tensor-core kernel')
+        call('dvsr_conv_tc2_fprop', ctypes.byref(d), _ptr(_packed_tc2(weight, wl, 5, 0, 1)), None, 0, _stream())
+        ctx.cfg = (act, slope, BT, H, W, Co, bias is not None)
+        ctx.wl = wl
+        ctx.wslot, ctx.bslot = getattr(weight, '_dvsr_grad', None), getattr(bias, '_dvsr_grad', None)
+        ctx.save_for_backward(xc, weight, y if act != ACT_NONE else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        if ctx.needs_input_grad[0]:
+            raise NotImplementedError('conv3d_rgb: no gradient w.r.t. the input clip (use conv3d_padded)')
+        xc, weight, y = ctx.saved_tensors
+        act, slope, BT, H, W, Co, has_bias = ctx.cfg
+        gy = gy.contiguous()
+        need_b = has_bias and ctx.needs_input_grad[2]
+        gb = (ctx.bslot if ctx.bslot is not None else torch.zeros(Co, device=gy.device, dtype=torch.float32)) if need_b else None
+        if act != ACT_NONE:
+            gpre = torch.empty_like(gy)
+            call('dvsr_act_bwd', _ptr(gy), _ptr(y), None, _ptr(gpre), _ptr(gb), BT * H * W, Co, act, slope, 0, 0, H, W, _stream())
+        else:
+            gpre = gy
+            if need_b:
+                call('dvsr_act_bwd', _ptr(gy), None, None, None, _ptr(gb), BT * H * W, Co, ACT_NONE, 0.0, 0, 0, H, W, _stream())
+        gw = None
+        if ctx.needs_input_grad[1]:
+            gw = ctx.wslot if ctx.wslot is not None else torch.zeros_like(weight)
+            d = ConvDesc()
+            d.N, d.H, d.W, d.Ho, d.Wo = BT, H + 2, W + 2, H, W
+            d.KH, d.KW, d.stride, d.pad, d.dil = 3, 3, 1, 0, 1
+            d.nseg = 1
+            _fill_seg(d.seg[0], xc)
+            d.Co = Co
+            if _lib.lib().dvsr_conv_wgrad_tc_supported(ctypes.byref(d), 0) != 1:
+                raise RuntimeError('conv3d_rgb: weight gradient shape not supported')
+            _run_wgrad(d, gpre, Co, gw, ctx.wl, keep=(gpre, gy, xc) if ctx.wslot is not None else None, force_tc=True)
+        return None, (None if ctx.wslot is not None else gw), (None if ctx.bslot is not None else gb), None, None, None
+
+
+def conv3d_rgb(x, weight, bias, T, act=ACT_NONE, slope=0.1):
+    """Conv3d(C <= 4 -> Co, 3^3, replication padding 1) on clip frames [B*T, H, W, C] -> [B*T, H, W, Co] (tensor cores)."""
+    return _Conv3dRgbFn.apply(x, weight, bias, T, act, slope)
 
 
 # --------------------------------------------------------------------------------------------------

@@ -89,12 +89,19 @@ typedef struct dvsr_conv_desc {
  *   co * co_stride + seg_base[s] + ci * ci_stride + tap
  * Conv2d [Co, Cin, KH, KW] with cat-segments: co_stride = Cin*KH*KW, ci_stride = KH*KW,
  * seg_base[s] = (channel offset of s) * KH*KW.  Conv3d [Co, Ci, KT, KH, KW] with one segment per kt:
- * ci_stride = KT*KH*KW, seg_base[kt] = kt*KH*KW. */
+ * ci_stride = KT*KH*KW, seg_base[kt] = kt*KH*KW.
+ *
+ * Interleaved channels (ci_bits > 0): kernel channel ci = (hi << ci_bits) | lo addresses weight element
+ *   co * co_stride + seg_base[s] + lo * ci_stride + hi * ci_hi_stride + tap      and exists only for lo < ci_lo_valid.
+ * Used by the RGB Conv3d of MFDN (LRimg_estimator.py:77): its three temporal taps are folded into the channel axis of ONE
+ * tensor-core conv over a [.., 12] tensor (channel 4*kt + c, c < 3), ci_stride = KT*KH*KW, ci_hi_stride = KH*KW. */
 typedef struct dvsr_wlayout {
     long long co_stride, ci_stride;
     long long seg_base[DVSR_MAX_SEG];
     int seg_C[DVSR_MAX_SEG];
     int nseg, taps, Co;
+    int ci_bits, ci_lo_valid;
+    long long ci_hi_stride;
 } dvsr_wlayout;
 
 /* One weight-packing job (pack_table.cu).  mode 0/1: CUDA-core layouts; 2/3/4: streaming tcgen05 layouts (a0 = padded
@@ -210,6 +217,10 @@ int dvsr_pad2d(const float* x, float* y, int N, int H, int W, int C, int p, int 
 int dvsr_pad2d_bwd(const float* gy, float* gx, int N, int H, int W, int C, int p, int mode, void* stream);
 int dvsr_pad3d_replicate(const float* x, float* y, int B, int T, int H, int W, int C, void* stream);
 int dvsr_pad3d_replicate_bwd(const float* gy, float* gx, int B, int T, int H, int W, int C, void* stream);
+/* Replication-padded clip with the KT = 3 temporal taps folded into channels: x [B*T, H, W, C] (C <= 4) ->
+ * y [B*T, H+2, W+2, 12], y[.., 4*kt + c] = x[b, clamp(t + kt - 1), clamp(h - 1), clamp(w - 1), c], zero for c >= C.
+ * A Conv3d(C -> Co, 3^3) over the padded clip is then ONE 3x3 conv over y (LRimg_estimator.py:75-77,100-102). */
+int dvsr_tcat_pad3(const float* x, float* y, int B, int T, int H, int W, int C, void* stream);
 /* per-image per-channel spatial mean: m[n][c]; y = x - m (sign=-1) or x + m (sign=+1) */
 int dvsr_spatial_mean(const float* x, float* m, int N, int HW, int C, void* stream);
 int dvsr_add_channel_bias(const float* x, const float* m, float* y, int N, int HW, int C, float sign, void* stream);

@@ -542,6 +542,30 @@ def test_conv3d_tensor_core(ops):
     assert rel(gd[1], gr[1]) < 2 * TC_TOL and rel(gd[2], gr[2]) < 1e-4
 
 
+def test_conv3d_rgb_tensor_core(ops):
+    """MFDN conv0 (Conv3d 3 -> 64 over the replication-padded RGB clip): temporal taps folded into channels."""
+    B, T, H, W, Cin, Co = 2, 5, 12, 18, 3, 64
+    x = _rand(B, Cin, T, H, W, seed=1)
+    w, b = _rand(Co, Cin, 3, 3, 3, seed=2, scale=0.1), _rand(Co, seed=3, scale=0.1)
+    wr, br = (t.clone().requires_grad_(True) for t in (w, b))
+    y = F.conv3d(F.pad(x, (1,) * 6, mode='replicate'), wr, br)
+    gy = _rand(*y.shape, seed=4)
+    gr = torch.autograd.grad(y, [wr, br], gy)
+    frames = _dev(x).permute(0, 2, 3, 4, 1).reshape(B * T, H, W, Cin).contiguous()
+    wd, bd = _dev(w).requires_grad_(True), _dev(b).requires_grad_(True)
+    ops.set_conv_backend(True)
+    try:
+        yd = ops.conv3d_rgb(frames, wd, bd, T)
+        assert rel(yd, y.permute(0, 2, 3, 4, 1).reshape(B * T, H, W, Co)) < 1e-4        # BF16x3: fp32-class
+        gd = torch.autograd.grad(yd, [wd, bd], _dev(gy.permute(0, 2, 3, 4, 1).reshape(B * T, H, W, Co)).contiguous())
+        with pytest.raises(NotImplementedError):
+            f2 = frames.clone().requires_grad_(True)
+            torch.autograd.grad(ops.conv3d_rgb(f2, wd, bd, T).sum(), [f2])
+    finally:
+        ops.set_conv_backend(False)
+    assert rel(gd[0], gr[0]) < 2 * TC_TOL and rel(gd[1], gr[1]) < 1e-4
+
+
 def test_packed_weight_cache_never_aliases_freed_weights(ops):
     """Regression: packs are keyed by the weight OBJECT, not its device address (addresses get recycled)."""
     x = torch.randn(1, 8, 8, 64, device='cuda')
