@@ -31,12 +31,14 @@ INNER = dict(steps=2, lr_alpha=1e-5, optimizer='SGD', criterion='l2', slr_weight
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--steps', type=int, default=60)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='adapt', choices=['adapt', 'infer'])
     ap.add_argument('--no-graphs', action='store_true')
-    ap.add_argument('--pipelines', type=int, default=3, help='independent frames kept in flight per GPU (adapt.AdaptationPool)')
+    ap.add_argument('--cta-budget', type=int, default=None, help='CTAs per launch of the persistent kernels (default: AdaptationPool policy)')
+    ap.add_argument('--min-tiles', type=int, default=None, help='conv_tc2 grid policy: tiles per CTA (default: AdaptationPool policy)')
+    ap.add_argument('--pipelines', type=int, default=None, help='independent frames kept in flight per GPU (adapt.AdaptationPool)')
     ap.add_argument('--no-tc', action='store_true', help='exact-fp32 CUDA-core convolutions only')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--height', type=int, default=LR_H)
@@ -177,8 +179,11 @@ def main():
         netF = seed_parameters(LRimg_estimator.DirectKernelEstimatorVideo(64, 3, SCALE), 78)
         return netG.cuda(), netE.cuda(), netF.cuda()
 
-    P = max(1, args.pipelines)
-    pool = adapt.AdaptationPool(*build(1234), pipelines=P, use_graphs=not args.no_graphs, **INNER)
+    # frames in flight: 6 for the adaptation workload (latency-bound inner steps), 2 for plain inference (GPU-filling kernels)
+    P = max(1, args.pipelines if args.pipelines is not None else (6 if args.workload == 'adapt' else 2))
+    pool = adapt.AdaptationPool(*build(1234), pipelines=P, cta_budget=args.cta_budget, min_tiles_per_cta=args.min_tiles,
+                                use_graphs=not args.no_graphs, **INNER)
+    min_tiles, budget = pool.min_tiles_per_cta, pool.cta_budget
     eng = pool.engines[0]
     # distinct windows per step and per rank (clip sharding: frame i -> rank i % world, train_dynavsr.py:509)
     n_clips = 4
@@ -241,9 +246,9 @@ def main():
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
-    ms, host_launches = timed(step_dev, args.steps, max(args.warmup, 3))
+    ms, host_launches = timed(step_dev, args.steps, max(args.warmup, 3, P))
     clk = clocks.stop() if rank == 0 else None
-    ms_e2e, _ = timed(step_e2e, args.steps, 2)
+    ms_e2e, _ = timed(step_e2e, args.steps, max(2, P))
     value = world * args.steps / (ms / 1000.0)
     e2e = world * args.steps / (ms_e2e / 1000.0)
     # kernels launched per step: counted while the step was captured / run eagerly
@@ -258,6 +263,8 @@ def main():
     wgt = torch.randn(64, 64, 3, 3, device='cuda') * 0.05
     bia = torch.zeros(64, device='cuda')
     reps = 20
+    _lib.lib().dvsr_set_cta_budget(148)                        # the kernel alone: whole GPU, one tile per CTA
+    _lib.lib().dvsr_conv_tc2_set_min_tiles_per_cta(1)
     with torch.no_grad():
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
@@ -277,6 +284,8 @@ def main():
         b.record()
         torch.cuda.synchronize()
     t_conv = a.elapsed_time(b) / reps / 1000.0
+    _lib.lib().dvsr_set_cta_budget(budget)
+    _lib.lib().dvsr_conv_tc2_set_min_tiles_per_cta(min_tiles)
     flops = 18.0 * NFR * H * W * 64 * 64
     prec = ops._backend['precision'] if use_tc else 'fp32'
     roofline = {'kernel': 'conv3x3 64->64 fprop @%dx%dx%d (%s)' % (NFR, H, W, ('tcgen05 ' + prec) if use_tc else 'CUDA-core fp32'),
@@ -310,13 +319,13 @@ def main():
     if rank == 0:
         cpu = None if args.no_cpu_baseline else cpu_adapt_sample(2, 1, budget_s=40.0)
         line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
-                'warmup': max(args.warmup, 3), 'ms_per_step': ms / args.steps, 'higher_is_better': True,
+                'warmup': max(args.warmup, 3, P), 'ms_per_step': ms / args.steps, 'higher_is_better': True,
                 'scaling': 'weak', 'vs_baseline': None, 'dtype': ('bf16x3 split operands, fp32 accumulate (tcgen05)' if ops._backend['precision'] == 'bf16x3' else 'tf32, fp32 accumulate (tcgen05)') if use_tc else 'f32',
                 'data': 'synthetic',
                 'config': {'workload': ('adapt2_sgd_l2+final_forward' if args.workload == 'adapt' else 'inference_only') +
                            ' EDVR-M 4x + MFDN, REDS4-shaped 5x3x180x320 window cropped to %dx%d -> 3x%dx%d' % (H, W, SCALE * H, SCALE * W),
                            'inner': INNER, 'clips_per_rank': n_clips, 'cuda_graphs': not args.no_graphs,
-                           'frames_in_flight_per_gpu': P,
+                           'frames_in_flight_per_gpu': P, 'conv_min_tiles_per_cta': min_tiles, 'cta_budget_per_launch': budget,
                            'l2': 'per-step working set (activations ~GBs) exceeds the 126 MB L2; inputs rotate over %d clips' % n_clips,
                            'parallelism': 'clip-sharded dp%d, no data-path collective' % world},
                 'e2e': {'value': e2e, 'unit': UNIT, 'h2d_bytes_per_step': NFR * 3 * H * W * 4,

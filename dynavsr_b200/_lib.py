@@ -80,6 +80,7 @@ SIGNATURES = {
     'dvsr_conv_tc2_set_trace': [_P],
     'dvsr_conv_tc2_set_precision': [_I],
     'dvsr_conv_tc2_get_precision': [],
+    'dvsr_conv_tc2_set_min_tiles_per_cta': [_I],
     'dvsr_conv_wgrad_tc_supported': [_DP, _I],
     'dvsr_conv_wgrad_tc': [_DP, _I, _P, _I, _P, _WP, _P],
     'dvsr_mdcn_bwd_data': [_DP, _P, _I, _P, _P, _I, _P, _I, _P, _I, _P],
@@ -111,6 +112,8 @@ SIGNATURES = {
     'dvsr_update_sgd': [_P, _P, _LL, _LL, _F, _F, _F, _P],
     'dvsr_update_adam': [_P, _P, _P, _P, _LL, _LL, _F, _F, _F, _F, _F, _F, _F, _F, _P],
     'dvsr_abs_sum': [_P, _P, _LL, _I, _I, _I, _P],
+    'dvsr_set_cta_budget': [_I],
+    'dvsr_get_cta_budget': [],
     'dvsr_last_error': [],
     'dvsr_version': [],
 }

@@ -253,8 +253,15 @@ class AdaptationPool(object):
     CUDA graphs and streams; nothing is shared but the (read-only) meta-weights they were cloned from.
     """
 
-    def __init__(self, netG, netE, netE_fixed, pipelines=3, **kw):
+    def __init__(self, netG, netE, netE_fixed, pipelines=6, cta_budget=None, min_tiles_per_cta=None, **kw):
         assert pipelines >= 1
+        # Launch policy of the persistent kernels while several frames share the GPU (measured on B200, bench.py sweep):
+        # a launch is held to ~1/4 of the SMs and every conv CTA takes >= 2 tiles, so the pipelines' launches run side by
+        # side instead of queueing behind each other's 148-CTA grids.  One pipeline keeps the whole GPU per launch.
+        self.cta_budget = cta_budget if cta_budget is not None else (148 if pipelines == 1 else (74 if pipelines < 4 else 37))
+        self.min_tiles_per_cta = min_tiles_per_cta if min_tiles_per_cta is not None else (1 if pipelines == 1 else 2)
+        _lib.lib().dvsr_set_cta_budget(self.cta_budget)
+        _lib.lib().dvsr_conv_tc2_set_min_tiles_per_cta(self.min_tiles_per_cta)
         nets = [(netG, netE, netE_fixed)]
         for _ in range(pipelines - 1):          # clone BEFORE any engine re-homes the parameters
             nets.append((copy.deepcopy(netG), copy.deepcopy(netE), copy.deepcopy(netE_fixed)))

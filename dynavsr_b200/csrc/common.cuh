@@ -11,6 +11,7 @@ namespace dvsr {
 // ---- error plumbing: every extern "C" entry returns 0 or a negative code; message via dvsr_last_error()
 void set_error(const char* fmt, ...);
 int check_launch(const char* what);   // cudaGetLastError() -> code
+int cta_budget();                     // CTAs one launch of a persistent kernel may use (dvsr_set_cta_budget)
 
 #define DVSR_REQUIRE(cond, ...)                 \
     do {                                        \

@@ -367,6 +367,10 @@ conv_tc2_kernel(const __grid_constant__ T2Maps maps, const T2Params p) {
 using namespace dvsr;
 
 static long long* g_t2_trace = nullptr;
+static int g_t2_min_tiles = 1;
+// Grid policy: 1 (default) = one tile per CTA until the GPU is full (lowest latency of a single launch); n > 1 = at least n
+// tiles per CTA (fewer, longer-lived CTAs: less SM-time per launch when several streams share the GPU).
+extern "C" int dvsr_conv_tc2_set_min_tiles_per_cta(int n) { g_t2_min_tiles = n < 1 ? 1 : n; return 0; }
 // debugging aid: device buffer of 8 x 64 clock64 stamps written by CTA (0,0) of the next launches (nullptr = off)
 extern "C" int dvsr_conv_tc2_set_trace(long long* dev_buffer) { g_t2_trace = dev_buffer; return 0; }
 
@@ -518,8 +522,12 @@ extern "C" int dvsr_conv_tc2_fprop(const dvsr_conv_desc* d, const float* wp, con
             return check_launch("conv_tc2_fprop: cudaFuncSetAttribute");
         smem_set = smem;
     }
-    int ctas_x = 148 / ngroups;
+    int ctas_x = cta_budget() / ngroups;
     if (ctas_x < 1) ctas_x = 1;
+    // throughput mode: at least g_t2_min_tiles tiles per CTA, so that the per-CTA fixed cost (147 KB of weights, pipeline
+    // fill) is amortised and the SMs left free serve the other frames in flight (adapt.AdaptationPool)
+    const int want = (p.tiles_total + g_t2_min_tiles - 1) / g_t2_min_tiles;
+    if (ctas_x > want) ctas_x = want;
     if (ctas_x > p.tiles_total) ctas_x = p.tiles_total;
     dim3 grid(ctas_x, ngroups);
     conv_tc2_kernel<<<grid, T2_THREADS, smem, (cudaStream_t)stream>>>(maps, p);

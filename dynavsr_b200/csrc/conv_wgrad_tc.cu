@@ -240,7 +240,7 @@ extern "C" int dvsr_conv_wgrad_tc(const dvsr_conv_desc* d, int seg, const float*
     p.chunks_total = d->N * tiles_w * tiles_h;
     const int ztiles = (g.C + 127) / 128;
     // enough pixel splits to fill the GPU once (1 CTA per SM), at least 4 chunks per CTA
-    int splits = 148 / (groups * ztiles);
+    int splits = cta_budget() / (groups * ztiles);
     if (splits < 1) splits = 1;
     int per = (p.chunks_total + splits - 1) / splits;
     if (per < 4) per = 4;

@@ -278,7 +278,7 @@ extern "C" int dvsr_mdcn_tc_fprop(const dvsr_conv_desc* d, const float* wp, void
             return check_launch("mdcn_tc_fprop: cudaFuncSetAttribute");
         smem_set = smem;
     }
-    int ctas = p.tiles_total < 148 ? p.tiles_total : 148;
+    int ctas = p.tiles_total < cta_budget() ? p.tiles_total : cta_budget();
     mdcn_tc_kernel<<<ctas, MD_THREADS, smem, (cudaStream_t)stream>>>(wmap, p);
     return check_launch("mdcn_tc_fprop");
 }

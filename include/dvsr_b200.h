@@ -119,6 +119,10 @@ typedef struct dvsr_pack_job {
 
 const char* dvsr_last_error(void);
 int dvsr_version(void);
+/* SM budget of one launch of the persistent kernels (conv_tc2, conv_wgrad_tc, mdcn_tc), 1..148 (default 148 = whole GPU).
+ * With P independent frames in flight on P streams, ~148 / P lets their launches run side by side. */
+int dvsr_set_cta_budget(int n);
+int dvsr_get_cta_budget(void);
 
 /* ---- convolution family (conv_simt.cu; tensor-core fast path in conv_tc.cu) ---------------------- */
 /* Packed layouts.  mode 0 (forward):  wp[k][co],  k = kofs(s) + tap*C_s + ci.
@@ -164,6 +168,10 @@ int dvsr_conv_tc2_fprop(const dvsr_conv_desc* d, const float* wp, const float* a
  * 0 = single-pass TF32 with operands rounded to nearest (~3e-4 per layer, weights packed with mode 5 / 6). */
 int dvsr_conv_tc2_set_precision(int bf16x3);
 int dvsr_conv_tc2_get_precision(void);
+/* Grid policy of conv_tc2: at least n tiles (128 output pixels each) per persistent CTA.  1 (default) spreads a small
+ * launch over as many SMs as it has tiles (lowest single-launch latency); n > 1 amortises the per-CTA cost (resident
+ * weights, pipeline fill) and leaves SMs to the other frames in flight -- less SM-time per launch, higher throughput. */
+int dvsr_conv_tc2_set_min_tiles_per_cta(int n);
 /* debugging aid: 8 x 64 clock64 stamps of CTA (0,0) (producer / rounding / MMA / epilogue events); NULL = off */
 int dvsr_conv_tc2_set_trace(long long* dev_buffer);
 /* Tensor-core weight gradient of segment `seg` of a stride-1 convolution (conv_wgrad_tc.cu): both operands are
