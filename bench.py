@@ -168,7 +168,7 @@ def main():
         raise SystemExit('bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm')
     torch.cuda.set_device(local)
     if world > 1:
-        dist.init_process_group('nccl', rank=rank, world_size=world)
+        dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', local))
     H, W = args.height, args.width
     use_tc = (not args.no_tc) and hasattr(_lib.lib(), 'dvsr_conv_tc_fprop')
     ops.set_conv_backend(use_tc)
