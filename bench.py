@@ -36,6 +36,7 @@ def parse():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='adapt', choices=['adapt', 'infer'])
     ap.add_argument('--no-graphs', action='store_true')
+    ap.add_argument('--inner-steps', type=int, default=None, help='diagnostic only: override the 2 inner adaptation steps of the metric')
     ap.add_argument('--cta-budget', type=int, default=None, help='CTAs per launch of the persistent kernels (default: AdaptationPool policy)')
     ap.add_argument('--min-tiles', type=int, default=None, help='conv_tc2 grid policy: tiles per CTA (default: AdaptationPool policy)')
     ap.add_argument('--pipelines', type=int, default=None, help='independent frames kept in flight per GPU (adapt.AdaptationPool)')
@@ -153,6 +154,8 @@ def run_reference(args, rank):
 # ---------------------------------------------------------------------------------------------------
 def main():
     args = parse()
+    if args.inner_steps is not None:
+        INNER['steps'] = args.inner_steps
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
     local = int(os.environ.get('LOCAL_RANK', 0))

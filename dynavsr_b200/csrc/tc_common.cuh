@@ -173,9 +173,12 @@ __device__ __forceinline__ void epilogue_chunk(float (&v)[32], int c0, int Co, c
     } else if (act == DVSR_ACT_RELU) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-    } else if (act == DVSR_ACT_SIGMOID_SPLIT) {
+    } else if (act == DVSR_ACT_SIGMOID_SPLIT && c0 + 32 > sig_split) {
+        // only the chunks that reach into the mask channels pay for the sigmoid; ex2 + fast reciprocal (2 MUFU ops) instead
+        // of an IEEE division per element -- the epilogue of the 64 -> 216 offset/mask conv was its bottleneck
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = (c0 + j >= sig_split) ? sigmoidf_(v[j]) : v[j];
+        for (int j = 0; j < 32; ++j)
+            if (c0 + j >= sig_split && j < nvalid) v[j] = __fdividef(1.f, 1.f + __expf(-v[j]));
     }
     if (res) {
 #pragma unroll
