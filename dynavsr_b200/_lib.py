@@ -100,6 +100,7 @@ SIGNATURES = {
     'dvsr_pad3d_replicate': [_P, _P, _I, _I, _I, _I, _I, _P],
     'dvsr_pad3d_replicate_bwd': [_P, _P, _I, _I, _I, _I, _I, _P],
     'dvsr_tcat_pad3': [_P, _P, _I, _I, _I, _I, _I, _P],
+    'dvsr_degrade': [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     'dvsr_spatial_mean': [_P, _P, _I, _I, _I, _P],
     'dvsr_add_channel_bias': [_P, _P, _P, _I, _I, _I, _F, _P],
     'dvsr_act_bwd': [_P, _P, _P, _P, _P, _LL, _I, _I, _F, _I, _I, _I, _I, _P],

@@ -568,6 +568,49 @@ __global__ void tcat_pad3_kernel(const float* __restrict__ x, float* __restrict_
     }
 }
 
+// Blur-and-subsample degradation HR -> LR (random_kernel_generator.py:83-130): reflection pad L/2, depthwise L x L kernel
+// (the same for every channel, optionally one per frame), stride `scale`, optional 8-bit quantisation (vsrbase.py:188).
+// One thread per output pixel; the kernel taps sit in shared memory, the HR reads are served by L1 / L2.
+__global__ void degrade_kernel(const float* __restrict__ x, const float* __restrict__ k, float* __restrict__ y, int T, int H, int W,
+                               int C, int L, int scale, int Tk, int kmode, int Ho, int Wo, int quantize) {
+    extern __shared__ float ks[];            // [L*L] of this block's frame
+    const int t = blockIdx.z;
+    const int ki = kmode == 0 ? 0 : (kmode == 1 ? t : ((t - 1) % Tk + Tk) % Tk);
+    for (int i = threadIdx.y * blockDim.x + threadIdx.x; i < L * L; i += blockDim.x * blockDim.y) ks[i] = __ldg(k + (long long)ki * L * L + i);
+    __syncthreads();
+    const int ox = blockIdx.x * blockDim.x + threadIdx.x, oy = blockIdx.y * blockDim.y + threadIdx.y;
+    if (ox >= Wo || oy >= Ho) return;
+    const int p = L / 2;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    const float* img = x + (long long)t * H * W * C;
+    for (int a = 0; a < L; ++a) {
+        int iy = oy * scale - p + a;
+        iy = iy < 0 ? -iy : (iy >= H ? 2 * (H - 1) - iy : iy);          // ReflectionPad2d
+        const float* row = img + (long long)iy * W * C;
+        for (int b = 0; b < L; ++b) {
+            int ix = ox * scale - p + b;
+            ix = ix < 0 ? -ix : (ix >= W ? 2 * (W - 1) - ix : ix);
+            const float w = ks[a * L + b];
+            const float* q = row + ix * C;
+            for (int c = 0; c < C; ++c) acc[c] = fmaf(w, __ldg(q + c), acc[c]);
+        }
+    }
+    float* o = y + (((long long)t * Ho + oy) * Wo + ox) * C;
+    for (int c = 0; c < C; ++c) o[c] = quantize ? rintf(acc[c] * 255.f) / 255.f : acc[c];
+}
+
+extern "C" int dvsr_degrade(const float* x, const float* k, float* y, int T, int H, int W, int C, int L, int scale, int Tk,
+                            int kmode, int quantize, void* stream) {
+    DVSR_REQUIRE(x && k && y && T > 0 && H > 0 && W > 0 && C > 0 && C <= 4 && L > 0 && scale > 0 && Tk > 0, "degrade: bad arguments");
+    DVSR_REQUIRE(L / 2 < H && L / 2 < W, "degrade: reflection padding %d needs an image larger than that", L / 2);
+    DVSR_REQUIRE(kmode >= 0 && kmode <= 2 && (size_t)L * L * sizeof(float) <= 48 * 1024, "degrade: bad kernel arguments");
+    const int Ho = (H + 2 * (L / 2) - L) / scale + 1, Wo = (W + 2 * (L / 2) - L) / scale + 1;
+    DVSR_REQUIRE(Ho > 0 && Wo > 0 && T <= 65535, "degrade: empty output");
+    dim3 block(32, 8), grid((Wo + 31) / 32, (Ho + 7) / 8, T);
+    degrade_kernel<<<grid, block, (size_t)L * L * sizeof(float), ST>>>(x, k, y, T, H, W, C, L, scale, Tk, kmode, Ho, Wo, quantize);
+    return check_launch("degrade");
+}
+
 extern "C" int dvsr_tcat_pad3(const float* x, float* y, int B, int T, int H, int W, int C, void* stream) {
     DVSR_REQUIRE(x && y && B > 0 && T > 0 && H > 0 && W > 0 && C > 0 && C <= 4, "tcat_pad3: bad arguments (C <= 4)");
     DVSR_REQUIRE(A16(y), "tcat_pad3: output must be 16-byte aligned");

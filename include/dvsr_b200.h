@@ -229,6 +229,12 @@ int dvsr_pad3d_replicate_bwd(const float* gy, float* gx, int B, int T, int H, in
  * y [B*T, H+2, W+2, 12], y[.., 4*kt + c] = x[b, clamp(t + kt - 1), clamp(h - 1), clamp(w - 1), c], zero for c >= C.
  * A Conv3d(C -> Co, 3^3) over the padded clip is then ONE 3x3 conv over y (LRimg_estimator.py:75-77,100-102). */
 int dvsr_tcat_pad3(const float* x, float* y, int B, int T, int H, int W, int C, void* stream);
+/* Blur-and-subsample degradation HR -> LR on NHWC frames x [T, H, W, C] (C <= 4), Degradation.apply of
+ * random_kernel_generator.py:83-130: reflection pad L/2, depthwise L x L kernel k (already centre-shifted; [Tk, L, L]),
+ * stride `scale`; kmode 0 = one kernel, 1 = kernel t per frame, 2 = kernel (t - 1) mod Tk (the T == Tk + 2 rule, :113-116);
+ * quantize != 0 applies round(y * 255) / 255 (vsrbase.py:188).  y: [T, Ho, Wo, C], Ho = (H + 2*(L/2) - L) / scale + 1. */
+int dvsr_degrade(const float* x, const float* k, float* y, int T, int H, int W, int C, int L, int scale, int Tk, int kmode,
+                 int quantize, void* stream);
 /* per-image per-channel spatial mean: m[n][c]; y = x - m (sign=-1) or x + m (sign=+1) */
 int dvsr_spatial_mean(const float* x, float* m, int N, int HW, int C, void* stream);
 int dvsr_add_channel_bias(const float* x, const float* m, float* y, int N, int HW, int C, float sign, void* stream);
