@@ -32,6 +32,56 @@ def _c(x, m, act=ops.ACT_NONE, res=None, stride=None, shuffle=0):
                     act=act, slope=0.1, res=res, shuffle=shuffle)
 
 
+class _Stem(object):
+    """Shared by EDVR and Predeblur: ``conv_first`` or, for HR-sized inputs, the three-conv 4x down-sampling stem
+    (EDVR_arch.py:21-26,45-50 / :224-229,266-272)."""
+
+    @staticmethod
+    def build(mod, nf, HR_in):
+        if HR_in:
+            mod.conv_first_1 = nn.Conv2d(3, nf, 3, 1, 1, bias=True)
+            mod.conv_first_2 = nn.Conv2d(nf, nf, 3, 2, 1, bias=True)
+            mod.conv_first_3 = nn.Conv2d(nf, nf, 3, 2, 1, bias=True)
+        else:
+            mod.conv_first = nn.Conv2d(3, nf, 3, 1, 1, bias=True)
+
+    @staticmethod
+    def run(mod, frames, HR_in):
+        if HR_in:
+            x = _c(frames, mod.conv_first_1, ACT_LRELU)
+            x = _c(x, mod.conv_first_2, ACT_LRELU)
+            return _c(x, mod.conv_first_3, ACT_LRELU)
+        return _c(frames, mod.conv_first, ACT_LRELU)
+
+
+class Predeblur_ResNet_Pyramid(nn.Module):
+    """Pre-deblur pyramid of EDVR_arch.py:13-57 (same parameter names; used by no YML of the reference)."""
+
+    def __init__(self, nf=128, HR_in=False):
+        super(Predeblur_ResNet_Pyramid, self).__init__()
+        self.HR_in = True if HR_in else False
+        _Stem.build(self, nf, self.HR_in)
+        basic_block = functools.partial(arch_util.ResidualBlock_noBN, nf=nf)
+        for name in ('RB_L1_1', 'RB_L1_2', 'RB_L1_3', 'RB_L1_4', 'RB_L1_5', 'RB_L2_1', 'RB_L2_2', 'RB_L3_1'):
+            setattr(self, name, basic_block())
+        self.deblur_L2_conv = nn.Conv2d(nf, nf, 3, 2, 1, bias=True)
+        self.deblur_L3_conv = nn.Conv2d(nf, nf, 3, 2, 1, bias=True)
+        self.lrelu = nn.LeakyReLU(negative_slope=0.1, inplace=True)
+
+    def forward(self, x):
+        return ops.to_nchw(self.forward_nhwc(ops.to_nhwc(x)))
+
+    def forward_nhwc(self, frames):
+        L1 = _Stem.run(self, frames, self.HR_in)
+        L2 = _c(L1, self.deblur_L2_conv, ACT_LRELU)
+        L3 = _c(L2, self.deblur_L3_conv, ACT_LRELU)
+        L3 = ops.upsample(self.RB_L3_1(L3), 2)
+        L2 = self.RB_L2_1(L2) + L3
+        L2 = ops.upsample(self.RB_L2_2(L2), 2)
+        L1 = self.RB_L1_2(self.RB_L1_1(L1)) + L2
+        return self.RB_L1_5(self.RB_L1_4(self.RB_L1_3(L1)))
+
+
 class PCD_Align(nn.Module):
     """Alignment module using Pyramid, Cascading and Deformable convolution with 3 pyramid levels
     (EDVR_arch.py:60-128)."""
@@ -147,21 +197,24 @@ class EDVR(nn.Module):
     def __init__(self, nf=64, nframes=5, groups=8, front_RBs=5, back_RBs=10, center=None, predeblur=False,
                  HR_in=False, w_TSA=True, scale=4):
         super(EDVR, self).__init__()
-        if predeblur or HR_in or not w_TSA:
-            # no YML of the reference enables these
-            raise NotImplementedError('predeblur / HR_in / w_TSA=False variants are not on the DynaVSR hot path')
         if scale not in (2, 4):
             raise NotImplementedError('scale must be 2 or 4')
         self.nf = nf
         self.nframes = nframes
         self.center = nframes // 2 if center is None else center
-        self.is_predeblur = False
-        self.HR_in = False
+        self.is_predeblur = True if predeblur else False
+        self.HR_in = True if HR_in else False
         self.w_TSA = w_TSA
         self.scale = scale
+        if not w_TSA and nframes > 5:
+            raise NotImplementedError('w_TSA=False reads the aligned frames as K-segments: at most 5 frames')
         ResidualBlock_noBN_f = functools.partial(arch_util.ResidualBlock_noBN, nf=nf)
 
-        self.conv_first = nn.Conv2d(3, nf, 3, 1, 1, bias=True)
+        if self.is_predeblur:
+            self.pre_deblur = Predeblur_ResNet_Pyramid(nf=nf, HR_in=self.HR_in)
+            self.conv_1x1 = nn.Conv2d(nf, nf, 1, 1, bias=True)
+        else:
+            _Stem.build(self, nf, self.HR_in)
         self.feature_extraction = arch_util.make_layer(ResidualBlock_noBN_f, front_RBs)
         self.fea_L2_conv1 = nn.Conv2d(nf, nf, 3, 2, 1, bias=True)
         self.fea_L2_conv2 = nn.Conv2d(nf, nf, 3, 1, 1, bias=True)
@@ -169,7 +222,10 @@ class EDVR(nn.Module):
         self.fea_L3_conv2 = nn.Conv2d(nf, nf, 3, 1, 1, bias=True)
 
         self.pcd_align = PCD_Align(nf=nf, groups=groups)
-        self.tsa_fusion = TSA_Fusion(nf=nf, nframes=nframes, center=self.center)
+        if self.w_TSA:
+            self.tsa_fusion = TSA_Fusion(nf=nf, nframes=nframes, center=self.center)
+        else:
+            self.tsa_fusion = nn.Conv2d(nframes * nf, nf, 1, 1, bias=True)
 
         self.recon_trunk = arch_util.make_layer(ResidualBlock_noBN_f, back_RBs)
         if self.scale == 4:
@@ -192,10 +248,14 @@ class EDVR(nn.Module):
         """frames: [B*N, H, W, 3] channels-last -> [B, scale*H, scale*W, 3]."""
         L = ACT_LRELU
         _, H, W, C = frames.shape
-        if H % 4 or W % 4:
-            raise RuntimeError('EDVR needs H and W to be multiples of 4, got %dx%d' % (H, W))
+        need = 16 if self.HR_in else 4
+        if H % need or W % need:
+            raise RuntimeError('EDVR needs H and W to be multiples of %d, got %dx%d' % (need, H, W))
         # ---- per-frame feature pyramid (EDVR_arch.py:272-283), all N frames batched
-        L1 = _c(frames, self.conv_first, L)
+        if self.is_predeblur:
+            L1 = _c(self.pre_deblur.forward_nhwc(frames), self.conv_1x1)
+        else:
+            L1 = _Stem.run(self, frames, self.HR_in)
         L1 = self.feature_extraction(L1)
         L2 = _c(_c(L1, self.fea_L2_conv1, L), self.fea_L2_conv2, L)
         L3 = _c(_c(L2, self.fea_L3_conv1, L), self.fea_L3_conv2, L)
@@ -203,12 +263,17 @@ class EDVR(nn.Module):
         ref = [Seg(t.view(B, N, *t.shape[1:])[:, self.center], T=N, Tsrc=1, t_fixed=0) for t in (L1, L2, L3)]
         aligned = self.pcd_align.forward_nhwc([L1, L2, L3], ref, stats=self.offset_stats)
         # ---- TSA fusion, reconstruction trunk, PixelShuffle head (:299-312)
-        fea = self.tsa_fusion.forward_nhwc(aligned, B, N)
+        if self.w_TSA:
+            fea = self.tsa_fusion.forward_nhwc(aligned, B, N)
+        else:
+            # aligned_fea.view(B, -1, H, W) -> 1x1 conv (:299-301): the N frames are the K-segments of the conv, read in place
+            al = aligned.view(B, N, *aligned.shape[1:])
+            fea = _c([al[:, i] for i in range(N)], self.tsa_fusion)
         out = self.recon_trunk(fea)
         if self.scale == 4:
             out = _c(out, self.upconv1, L, shuffle=2)   # lrelu commutes with the PixelShuffle permutation
         out = _c(out, self.upconv2, L, shuffle=2)
         out = _c(out, self.HRconv, L)
         x_center = frames.view(B, N, H, W, C)[:, self.center]
-        base = ops.upsample(x_center, self.scale)
+        base = x_center.contiguous() if self.HR_in else ops.upsample(x_center, self.scale)     # :308-311
         return _c(out, self.conv_last, res=base)        # conv_last(out) + bilinear(x_center)

@@ -102,13 +102,40 @@ def tsa_fusion(sd, p, aligned, center):
     return fea * torch.sigmoid(att) * 2 + att_add
 
 
+def _first(sd, p, x, HR_in):
+    """EDVR_arch.py:45-50 / :266-272: conv_first, or the three-conv 4x down-sampling stem of HR-sized inputs."""
+    if HR_in:
+        x = _lrelu(_conv(sd, p + 'conv_first_1', x))
+        x = _lrelu(_conv(sd, p + 'conv_first_2', x, stride=2))
+        return _lrelu(_conv(sd, p + 'conv_first_3', x, stride=2))
+    return _lrelu(_conv(sd, p + 'conv_first', x))
+
+
+def predeblur(sd, p, x, HR_in):
+    """Predeblur_ResNet_Pyramid.forward, EDVR_arch.py:43-57."""
+    L1 = _first(sd, p, x, HR_in)
+    L2 = _lrelu(_conv(sd, p + 'deblur_L2_conv', L1, stride=2))
+    L3 = _lrelu(_conv(sd, p + 'deblur_L3_conv', L2, stride=2))
+    L3 = _up2(res_block(sd, p + 'RB_L3_1', L3))
+    L2 = res_block(sd, p + 'RB_L2_1', L2) + L3
+    L2 = _up2(res_block(sd, p + 'RB_L2_2', L2))
+    L1 = res_block(sd, p + 'RB_L1_2', res_block(sd, p + 'RB_L1_1', L1)) + L2
+    return res_block(sd, p + 'RB_L1_5', res_block(sd, p + 'RB_L1_4', res_block(sd, p + 'RB_L1_3', L1)))
+
+
 def edvr_forward(sd, x, nf=64, nframes=5, groups=8, front_RBs=5, back_RBs=10, center=None, scale=4,
-                 return_intermediates=False):
-    """EDVR_arch.py:254-313 (predeblur=False, HR_in=False, w_TSA=True: the only variant any YML uses)."""
+                 return_intermediates=False, predeblur_=False, HR_in=False, w_TSA=True):
+    """EDVR_arch.py:254-313.  Every shipped YML uses predeblur=False, HR_in=False, w_TSA=True; the other variants of the
+    constructor (:208-239) are restated too."""
     B, N, C, H, W = x.shape
     center = N // 2 if center is None else center
     inter = {}
-    f1 = _lrelu(_conv(sd, 'conv_first', x.reshape(-1, C, H, W)))
+    if predeblur_:
+        f1 = _conv(sd, 'conv_1x1', predeblur(sd, 'pre_deblur.', x.reshape(-1, C, H, W), HR_in), padding=0)
+    else:
+        f1 = _first(sd, '', x.reshape(-1, C, H, W), HR_in)
+    if HR_in:
+        H, W = H // 4, W // 4
     for i in range(front_RBs):
         f1 = res_block(sd, 'feature_extraction.%d' % i, f1)
     f2 = _lrelu(_conv(sd, 'fea_L2_conv2', _lrelu(_conv(sd, 'fea_L2_conv1', f1, stride=2))))
@@ -121,7 +148,10 @@ def edvr_forward(sd, x, nf=64, nframes=5, groups=8, front_RBs=5, back_RBs=10, ce
     aligned = torch.stack([pcd_align(sd, 'pcd_align.', [f1[:, i], f2[:, i], f3[:, i]], ref, groups)
                            for i in range(N)], 1)
     inter['aligned'] = aligned
-    fea = tsa_fusion(sd, 'tsa_fusion.', aligned, center)
+    if w_TSA:
+        fea = tsa_fusion(sd, 'tsa_fusion.', aligned, center)
+    else:
+        fea = _conv(sd, 'tsa_fusion', aligned.reshape(B, -1, H, W), padding=0)          # :299-301
     inter['tsa'] = fea
     out = fea
     for i in range(back_RBs):
@@ -132,7 +162,10 @@ def edvr_forward(sd, x, nf=64, nframes=5, groups=8, front_RBs=5, back_RBs=10, ce
     out = _lrelu(F.pixel_shuffle(_conv(sd, 'upconv2', out), 2))
     out = _lrelu(_conv(sd, 'HRconv', out))
     out = _conv(sd, 'conv_last', out)
-    out = out + F.interpolate(x[:, center], scale_factor=scale, mode='bilinear', align_corners=False)
+    if HR_in:
+        out = out + x[:, center]                                                         # :308-309
+    else:
+        out = out + F.interpolate(x[:, center], scale_factor=scale, mode='bilinear', align_corners=False)
     if return_intermediates:
         return out, inter
     return out

@@ -21,9 +21,28 @@ def _conv(d, name, co, ci, k, k2=None):
     d[name + '.bias'] = (co,)
 
 
-def edvr_param_shapes(nf=64, nframes=5, groups=8, front_RBs=5, back_RBs=10, scale=4):
+def edvr_param_shapes(nf=64, nframes=5, groups=8, front_RBs=5, back_RBs=10, scale=4, predeblur=False, HR_in=False,
+                      w_TSA=True):
     d = OrderedDict()
-    _conv(d, 'conv_first', nf, 3, 3)
+
+    def first(prefix):                      # EDVR_arch.py:21-26 / :224-229
+        if HR_in:
+            _conv(d, prefix + 'conv_first_1', nf, 3, 3)
+            _conv(d, prefix + 'conv_first_2', nf, nf, 3)
+            _conv(d, prefix + 'conv_first_3', nf, nf, 3)
+        else:
+            _conv(d, prefix + 'conv_first', nf, 3, 3)
+
+    if predeblur:                           # Predeblur_ResNet_Pyramid, EDVR_arch.py:13-39, + conv_1x1 :221
+        first('pre_deblur.')
+        for rb in ('RB_L1_1', 'RB_L1_2', 'RB_L1_3', 'RB_L1_4', 'RB_L1_5', 'RB_L2_1', 'RB_L2_2', 'RB_L3_1'):
+            _conv(d, 'pre_deblur.%s.conv1' % rb, nf, nf, 3)
+            _conv(d, 'pre_deblur.%s.conv2' % rb, nf, nf, 3)
+        _conv(d, 'pre_deblur.deblur_L2_conv', nf, nf, 3)
+        _conv(d, 'pre_deblur.deblur_L3_conv', nf, nf, 3)
+        _conv(d, 'conv_1x1', nf, nf, 1)
+    else:
+        first('')
     for i in range(front_RBs):
         _conv(d, 'feature_extraction.%d.conv1' % i, nf, nf, 3)
         _conv(d, 'feature_extraction.%d.conv2' % i, nf, nf, 3)
@@ -53,19 +72,22 @@ def edvr_param_shapes(nf=64, nframes=5, groups=8, front_RBs=5, back_RBs=10, scal
     _conv(d, p + 'cas_offset_conv2', nf, nf, 3)
     dcn(p + 'cas_dcnpack')
     t = 'tsa_fusion.'
-    _conv(d, t + 'tAtt_1', nf, nf, 3)
-    _conv(d, t + 'tAtt_2', nf, nf, 3)
-    _conv(d, t + 'fea_fusion', nf, nframes * nf, 1)
-    _conv(d, t + 'sAtt_1', nf, nframes * nf, 1)
-    _conv(d, t + 'sAtt_2', nf, 2 * nf, 1)
-    _conv(d, t + 'sAtt_3', nf, nf, 3)
-    _conv(d, t + 'sAtt_4', nf, nf, 1)
-    _conv(d, t + 'sAtt_5', nf, nf, 3)
-    _conv(d, t + 'sAtt_L1', nf, nf, 1)
-    _conv(d, t + 'sAtt_L2', nf, 2 * nf, 3)
-    _conv(d, t + 'sAtt_L3', nf, nf, 3)
-    _conv(d, t + 'sAtt_add_1', nf, nf, 1)
-    _conv(d, t + 'sAtt_add_2', nf, nf, 1)
+    if not w_TSA:                           # EDVR_arch.py:239: a plain 1x1 fusion conv
+        _conv(d, 'tsa_fusion', nf, nframes * nf, 1)
+    else:
+        _conv(d, t + 'tAtt_1', nf, nf, 3)
+        _conv(d, t + 'tAtt_2', nf, nf, 3)
+        _conv(d, t + 'fea_fusion', nf, nframes * nf, 1)
+        _conv(d, t + 'sAtt_1', nf, nframes * nf, 1)
+        _conv(d, t + 'sAtt_2', nf, 2 * nf, 1)
+        _conv(d, t + 'sAtt_3', nf, nf, 3)
+        _conv(d, t + 'sAtt_4', nf, nf, 1)
+        _conv(d, t + 'sAtt_5', nf, nf, 3)
+        _conv(d, t + 'sAtt_L1', nf, nf, 1)
+        _conv(d, t + 'sAtt_L2', nf, 2 * nf, 3)
+        _conv(d, t + 'sAtt_L3', nf, nf, 3)
+        _conv(d, t + 'sAtt_add_1', nf, nf, 1)
+        _conv(d, t + 'sAtt_add_2', nf, nf, 1)
     for i in range(back_RBs):
         _conv(d, 'recon_trunk.%d.conv1' % i, nf, nf, 3)
         _conv(d, 'recon_trunk.%d.conv2' % i, nf, nf, 3)
@@ -106,7 +128,7 @@ def make_params(shapes, seed, residual_scale=0.1, offset_std=0.02, dtype=torch.f
             for s in shp[1:]:
                 fan_in *= s
             std = math.sqrt(2.0 / fan_in)
-            if 'feature_extraction' in k or 'recon_trunk' in k:
+            if 'feature_extraction' in k or 'recon_trunk' in k or '.RB_L' in k:
                 std *= residual_scale
             if 'conv_offset_mask' in k:
                 std = offset_std

@@ -82,8 +82,15 @@ def test_reference_api_surface():
     assert float(m.conv_offset_mask.weight.abs().sum()) == 0 and float(m.bias.abs().sum()) == 0
     rb = arch_util.ResidualBlock_noBN(64)
     assert 0.3 * 0.1 * (2 / 576) ** 0.5 < float(rb.conv1.weight.std()) < 3 * 0.1 * (2 / 576) ** 0.5
+    from oracle import params as P
+    for kw in (dict(predeblur=True), dict(HR_in=True, w_TSA=False), dict(predeblur=True, HR_in=True)):
+        v = EDVR_arch.EDVR(front_RBs=1, back_RBs=1, **kw)           # constructor variants of EDVR_arch.py:208-239
+        full = dict(predeblur=False, HR_in=False, w_TSA=True)
+        full.update(kw)
+        want = P.edvr_param_shapes(front_RBs=1, back_RBs=1, **full)
+        assert [(k, tuple(t.shape)) for k, t in v.state_dict().items()] == [(k, tuple(sh)) for k, sh in want.items()]
     with pytest.raises(NotImplementedError):
-        EDVR_arch.EDVR(predeblur=True)
+        EDVR_arch.EDVR(scale=3)
 
 
 def test_cpu_tensors_are_rejected_not_emulated():

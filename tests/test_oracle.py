@@ -102,3 +102,16 @@ def test_param_inventory_counts():
     assert (n(P.mfdn_param_shapes()), len(P.mfdn_param_shapes())) == (452291, 14)
     L = P.edvr_param_shapes(nf=128, back_RBs=40)
     assert (n(L), len(L)) == (20633827, 264)
+
+
+@pytest.mark.parametrize('tag,kw', [('predeblur', dict(predeblur=True, HR_in=False, w_TSA=True)),
+                                    ('hrin_notsa', dict(predeblur=False, HR_in=True, w_TSA=False)),
+                                    ('predeblur_hrin', dict(predeblur=True, HR_in=True, w_TSA=True))])
+def test_edvr_variant_oracle_matches_reference_golden(tag, kw):
+    """predeblur / HR_in / w_TSA=False (EDVR_arch.py:13-57,208-239) through the unmodified reference module."""
+    g = gold('edvr_variants.npz')
+    cfg = dict(nf=64, nframes=5, groups=8, front_RBs=1, back_RBs=1, scale=4)
+    sd = P.make_params(P.edvr_param_shapes(**cfg, **kw), seed=int(g[tag + '_seed']))
+    y = O.edvr_forward(sd, torch.from_numpy(g[tag + '_x']), front_RBs=1, back_RBs=1, predeblur_=kw['predeblur'],
+                       HR_in=kw['HR_in'], w_TSA=kw['w_TSA'])
+    assert torch.equal(y, torch.from_numpy(g[tag + '_out']))
