@@ -54,35 +54,62 @@ def synth_clip(seed, H, W, nfr=NFR):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md recipe): NVML polled every 20 ms when
+    nvidia_ml_py is importable, else one nvidia-smi query per ~0.3 s."""
     Q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+    NAMES = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
 
     def __init__(self, index=0):
         super().__init__(daemon=True)
-        self.index, self.samples, self._stop_evt = index, [], threading.Event()
+        self.index, self.sm, self.mx, self.reasons, self._stop_evt = index, [], [], set(), threading.Event()
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+            phys = int(vis.split(',')[index]) if vis and vis.split(',')[index].isdigit() else index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _poll_nvml(self):
+        n = self.nvml
+        self.sm.append(int(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)))
+        self.mx.append(int(n.nvmlDeviceGetMaxClockInfo(self.h, n.NVML_CLOCK_SM)))
+        r = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.h)) if hasattr(n, 'nvmlDeviceGetCurrentClocksEventReasons') \
+            else int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+        for name, bit in (('hw_slowdown', 0x8), ('hw_thermal_slowdown', 0x40), ('sw_thermal_slowdown', 0x20), ('sw_power_cap', 0x4)):
+            if r & bit:
+                self.reasons.add(name)
+
+    def _poll_smi(self):
+        out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits'],
+                             stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=5).stdout.strip()
+        v = [t.strip() for t in out.split(',')] if out else []
+        if len(v) >= 2 and v[0].isdigit():
+            self.sm.append(int(v[0]))
+            self.mx.append(int(v[1]) if v[1].isdigit() else 0)
+            for i, name in enumerate(self.NAMES):
+                if len(v) > 2 + i and v[2 + i].lower().startswith('active'):
+                    self.reasons.add(name)
 
     def run(self):
         while not self._stop_evt.is_set():
             try:
-                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
-                                      '--format=csv,noheader,nounits'], stdout=subprocess.PIPE,
-                                     stderr=subprocess.DEVNULL, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([v.strip() for v in out.split(',')])
+                self._poll_nvml() if self.nvml else self._poll_smi()
             except Exception:
                 pass
-            self._stop_evt.wait(0.2)
+            self._stop_evt.wait(0.02 if self.nvml else 0.2)
 
     def stop(self):
         self._stop_evt.set()
         self.join(timeout=6)
-        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
-        mx = [int(s[1]) for s in self.samples if s[1].isdigit()]
-        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        reasons = [n for i, n in enumerate(names) if any(len(s) > 2 + i and s[2 + i].lower().startswith('active') for s in self.samples)]
-        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(mx) if mx else None,
-                'reasons': reasons, 'samples': len(self.samples)}
+        sm = sorted(self.sm)
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(self.mx) if self.mx else None,
+                'reasons': [n for n in self.NAMES if n in self.reasons], 'samples': len(sm),
+                'source': 'nvml' if self.nvml else 'nvidia-smi'}
 
 
 def measured_peaks():

@@ -32,6 +32,12 @@ __device__ __forceinline__ float act_apply(float v, int act, float slope) {
 __device__ __forceinline__ float sigmoidf_(float v) { return 1.f / (1.f + __expf(-v)); }
 
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+// 256-bit read-only load (LDG.E.256.CONSTANT, sm_100): p must be 32-byte aligned.  One request per 8-channel deformable
+// group corner instead of two -- the DCN gather is bound by L1 wavefronts, not by bytes.
+__device__ __forceinline__ void ldg8(const float* p, float4& a, float4& b) {
+    asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

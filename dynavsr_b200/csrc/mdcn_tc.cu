@@ -127,10 +127,30 @@ mdcn_tc_kernel(const __grid_constant__ CUtensorMap wmap, const MdParams p) {
                 const int r = (int)(mm - (long long)n_[i] * hw);
                 oy[i] = r / p.Wo; ox[i] = r - oy[i] * p.Wo;
             }
+            // offsets / mask of stage it + 1 are fetched while stage it gathers: one dependent memory round trip per stage
+            // (offset -> corner addresses) instead of two
+            float ody[2], odx[2], omk[2], ndy[2] = {0.f, 0.f}, ndx[2] = {0.f, 0.f}, nmk[2] = {0.f, 0.f};
+            auto load_off = [&](int c, int tap, float (&dy)[2], float (&dx)[2], float (&mk)[2]) {
+                const int g = c * 4 + gl;
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    dy[i] = dx[i] = mk[i] = 0.f;
+                    if (ok[i]) {
+                        const float* op = p.offset + mlin[i] * p.off_pix_stride + (g * KK + tap) * 2;
+                        dy[i] = __ldg(op); dx[i] = __ldg(op + 1);
+                        mk[i] = __ldg(p.mask + mlin[i] * p.mask_pix_stride + g * KK + tap);
+                    }
+                }
+            };
+            load_off(0, 0, ody, odx, omk);
             for (int c = 0; c < chunks; ++c) {
                 const int g = c * 4 + gl;
                 for (int tap = 0; tap < KK; ++tap) {
                     const int kh = tap / p.KW, kw = tap - kh * p.KW;
+                    {
+                        const int tn = tap + 1 < KK ? tap + 1 : 0, cn = tap + 1 < KK ? c : c + 1;
+                        if (cn < chunks) load_off(cn, tn, ndy, ndx, nmk);
+                    }
                     mbar_wait(&a_empty[stage], phase ^ 1);
                     uint8_t* tile_a = smem_a + stage * MD_A_BYTES;
 #pragma unroll
@@ -138,9 +158,7 @@ mdcn_tc_kernel(const __grid_constant__ CUtensorMap wmap, const MdParams p) {
                         const int prow = (t >> 2) + 64 * i;
                         float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
                         if (ok[i]) {
-                            const float* op = p.offset + mlin[i] * p.off_pix_stride + (g * KK + tap) * 2;
-                            const float dy = __ldg(op), dx = __ldg(op + 1);
-                            const float mk = __ldg(p.mask + mlin[i] * p.mask_pix_stride + g * KK + tap);
+                            const float dy = ody[i], dx = odx[i], mk = omk[i];
                             const float h = (float)(oy[i] * p.stride - p.pad + kh * p.dil) + dy;
                             const float w = (float)(ox[i] * p.stride - p.pad + kw * p.dil) + dx;
                             const BilinTap bt = make_tap(h, w, p.H, p.W);
@@ -148,10 +166,10 @@ mdcn_tc_kernel(const __grid_constant__ CUtensorMap wmap, const MdParams p) {
                                 const float* img = p.x + (long long)n_[i] * p.img_stride + g * 8;
                                 const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
                                 float4 a0 = z, a1 = z, b0 = z, b1 = z, e0 = z, e1 = z, f0 = z, f1 = z;
-                                if (bt.o00 >= 0) { const float* q = img + (long long)bt.o00 * p.pix_stride; a0 = ldg4(q); a1 = ldg4(q + 4); }
-                                if (bt.o01 >= 0) { const float* q = img + (long long)bt.o01 * p.pix_stride; b0 = ldg4(q); b1 = ldg4(q + 4); }
-                                if (bt.o10 >= 0) { const float* q = img + (long long)bt.o10 * p.pix_stride; e0 = ldg4(q); e1 = ldg4(q + 4); }
-                                if (bt.o11 >= 0) { const float* q = img + (long long)bt.o11 * p.pix_stride; f0 = ldg4(q); f1 = ldg4(q + 4); }
+                                if (bt.o00 >= 0) ldg8(img + (long long)bt.o00 * p.pix_stride, a0, a1);
+                                if (bt.o01 >= 0) ldg8(img + (long long)bt.o01 * p.pix_stride, b0, b1);
+                                if (bt.o10 >= 0) ldg8(img + (long long)bt.o10 * p.pix_stride, e0, e1);
+                                if (bt.o11 >= 0) ldg8(img + (long long)bt.o11 * p.pix_stride, f0, f1);
                                 // same association as the reference: (w1*v1 + w2*v2 + w3*v3 + w4*v4) * mask
                                 v[0] = (bt.w00 * a0.x + bt.w01 * b0.x + bt.w10 * e0.x + bt.w11 * f0.x) * mk;
                                 v[1] = (bt.w00 * a0.y + bt.w01 * b0.y + bt.w10 * e0.y + bt.w11 * f0.y) * mk;
@@ -175,6 +193,8 @@ mdcn_tc_kernel(const __grid_constant__ CUtensorMap wmap, const MdParams p) {
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     mbar_arrive(&a_ready[stage]);
                     if (++stage == MD_ASTAGES) { stage = 0; phase ^= 1; }
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) { ody[i] = ndy[i]; odx[i] = ndx[i]; omk[i] = nmk[i]; }
                 }
             }
         }
@@ -233,7 +253,7 @@ extern "C" int dvsr_mdcn_tc_supported(const dvsr_conv_desc* d) {
     if (g.C % 32 || d->dg <= 0 || g.C != d->dg * 8) return 0;               // 8 channels (32 bytes) per deformable group
     if (d->KH * d->KW * (g.C / 32) > 18) return 0;                          // weights must fit in shared memory
     if (d->Co > 64 || d->Co < 16 || (d->Co & 3)) return 0;
-    if ((g.pix_stride & 3) || (g.img_stride & 3) || ((uintptr_t)g.ptr & 15)) return 0;
+    if ((g.pix_stride & 7) || (g.img_stride & 7) || ((uintptr_t)g.ptr & 31)) return 0;       // 256-bit corner loads
     if (g.T > 1 || g.t_fixed >= 0) return 0;
     if (((uintptr_t)d->y & 15) || (d->y_pix_stride & 3)) return 0;
     if (d->act == DVSR_ACT_SIGMOID_SPLIT) return 0;
