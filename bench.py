@@ -38,6 +38,7 @@ def parse():
     ap.add_argument('--no-graphs', action='store_true')
     ap.add_argument('--inner-steps', type=int, default=None, help='diagnostic only: override the 2 inner adaptation steps of the metric')
     ap.add_argument('--cta-budget', type=int, default=None, help='CTAs per launch of the persistent kernels (default: AdaptationPool policy)')
+    ap.add_argument('--wg-chunks', type=int, default=None, help='wgrad split-K policy: min chunks per CTA')
     ap.add_argument('--min-tiles', type=int, default=None, help='conv_tc2 grid policy: tiles per CTA (default: AdaptationPool policy)')
     ap.add_argument('--pipelines', type=int, default=None, help='independent frames kept in flight per GPU (adapt.AdaptationPool)')
     ap.add_argument('--no-tc', action='store_true', help='exact-fp32 CUDA-core convolutions only')
@@ -214,6 +215,8 @@ def main():
     pool = adapt.AdaptationPool(*build(1234), pipelines=P, cta_budget=args.cta_budget, min_tiles_per_cta=args.min_tiles,
                                 use_graphs=not args.no_graphs, **INNER)
     min_tiles, budget = pool.min_tiles_per_cta, pool.cta_budget
+    if args.wg_chunks is not None:
+        _lib.lib().dvsr_conv_wgrad_tc_set_min_chunks_per_cta(args.wg_chunks)
     eng = pool.engines[0]
     # distinct windows per step and per rank (clip sharding: frame i -> rank i % world, train_dynavsr.py:509)
     n_clips = 4

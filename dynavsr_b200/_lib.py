@@ -82,6 +82,7 @@ SIGNATURES = {
     'dvsr_conv_tc2_get_precision': [],
     'dvsr_conv_tc2_set_min_tiles_per_cta': [_I],
     'dvsr_conv_wgrad_tc_supported': [_DP, _I],
+    'dvsr_conv_wgrad_tc_set_min_chunks_per_cta': [_I],
     'dvsr_conv_wgrad_tc': [_DP, _I, _P, _I, _P, _WP, _P],
     'dvsr_mdcn_bwd_data': [_DP, _P, _I, _P, _P, _I, _P, _I, _P, _I, _P],
     'dvsr_mdcn_tc_supported': [_DP],

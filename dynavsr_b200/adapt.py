@@ -262,6 +262,7 @@ class AdaptationPool(object):
         self.min_tiles_per_cta = min_tiles_per_cta if min_tiles_per_cta is not None else (1 if pipelines == 1 else 2)
         _lib.lib().dvsr_set_cta_budget(self.cta_budget)
         _lib.lib().dvsr_conv_tc2_set_min_tiles_per_cta(self.min_tiles_per_cta)
+        _lib.lib().dvsr_conv_wgrad_tc_set_min_chunks_per_cta(4 if pipelines == 1 else 24)   # fewer split-K partial sums
         nets = [(netG, netE, netE_fixed)]
         for _ in range(pipelines - 1):          # clone BEFORE any engine re-homes the parameters
             nets.append((copy.deepcopy(netG), copy.deepcopy(netE), copy.deepcopy(netE_fixed)))

@@ -668,8 +668,7 @@ extern "C" int dvsr_pack_weights(const float* w, float* wp, const dvsr_wlayout* 
     dvsr_pack_job j;
     memset(&j, 0, sizeof(j));
     j.w = w; j.wp = wp; j.wl = *wl; j.mode = mode; j.seg = seg; j.total = total;
-    pack_job_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(j);
-    return check_launch("pack_weights");
+    return dvsr_pack_job_run(&j, stream);      // the kernel lives in pack_table.cu (no cross-TU device linking)
 }
 
 extern "C" int dvsr_conv_fprop(const dvsr_conv_desc* d, const float* wp, void* stream) {

@@ -269,8 +269,7 @@ extern "C" int dvsr_pack_weights_tc(const float* w, float* wp, const dvsr_wlayou
     dvsr_pack_job j;
     memset(&j, 0, sizeof(j));
     j.w = w; j.wp = wp; j.wl = *wl; j.mode = mode; j.seg = seg; j.a0 = rows_pad; j.total = total;
-    pack_job_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(j);
-    return check_launch("pack_weights_tc");
+    return dvsr_pack_job_run(&j, stream);      // the kernel lives in pack_table.cu (no cross-TU device linking)
 }
 
 extern "C" int dvsr_pack_weights_tc_parity(const float* w, float* wp, const dvsr_wlayout* wl, int seg, int KHf, int KWf,
@@ -284,8 +283,7 @@ extern "C" int dvsr_pack_weights_tc_parity(const float* w, float* wp, const dvsr
     dvsr_pack_job j;
     memset(&j, 0, sizeof(j));
     j.w = w; j.wp = wp; j.wl = *wl; j.mode = 4; j.seg = seg; j.a0 = rows_pad; j.a1 = KWf; j.a2 = KWs; j.a3 = 2 * a + b; j.total = total;
-    pack_job_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(j);
-    return check_launch("pack_weights_tc_parity");
+    return dvsr_pack_job_run(&j, stream);      // the kernel lives in pack_table.cu (no cross-TU device linking)
 }
 
 extern "C" int dvsr_conv_tc_fprop(const dvsr_conv_desc* d, const float* wp, void* stream) {

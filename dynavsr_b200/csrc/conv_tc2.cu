@@ -440,8 +440,7 @@ extern "C" int dvsr_pack_weights_tc2(const float* w, float* wp, const dvsr_wlayo
     dvsr_pack_job j;
     memset(&j, 0, sizeof(j));
     j.w = w; j.wp = wp; j.wl = *wl; j.mode = mode; j.seg = seg_lo; j.seg_hi = seg_hi; j.a0 = nblocks; j.total = total;
-    pack_job_kernel<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(j);
-    return check_launch("pack_weights_tc2");
+    return dvsr_pack_job_run(&j, stream);      // the kernel lives in pack_table.cu (no cross-TU device linking)
 }
 
 // 1 (default): BF16x3 split operands (3 products, ~1e-5 per layer); 0: single-pass TF32 with round-to-nearest (~3e-4)

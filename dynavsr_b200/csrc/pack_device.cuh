@@ -186,6 +186,5 @@ __device__ __forceinline__ float pack_value(const dvsr_pack_job& j, long long i)
     return pack_round_tf32(v);   // the MMA would truncate; weights are rounded to nearest TF32 once, here
 }
 
-__global__ void pack_job_kernel(const dvsr_pack_job j);
 
 }  // namespace dvsr

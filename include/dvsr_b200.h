@@ -177,6 +177,9 @@ int dvsr_conv_tc2_set_trace(long long* dev_buffer);
 /* Tensor-core weight gradient of segment `seg` of a stride-1 convolution (conv_wgrad_tc.cu): both operands are
  * consumed MN-major straight from the NHWC tensors, x through one halo tile per pixel chunk. */
 int dvsr_conv_wgrad_tc_supported(const dvsr_conv_desc* d, int seg);
+/* Split-K policy of the tensor-core weight gradient: at least n pixel chunks per CTA (default 4; larger = fewer CTAs and
+ * fewer atomically added partial sums per launch: less SM-time per launch when several streams share the GPU). */
+int dvsr_conv_wgrad_tc_set_min_chunks_per_cta(int n);
 int dvsr_conv_wgrad_tc(const dvsr_conv_desc* d, int seg, const float* gy, int gy_pix_stride, float* gw,
                        const dvsr_wlayout* wl, void* stream);
 /* Small-Cout direct convolution (conv_last, 64 -> 3): one thread per output pixel. */
