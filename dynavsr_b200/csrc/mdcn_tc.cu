@@ -30,6 +30,8 @@ struct MdParams {
     const float* bias; int act; float slope;
     float* y; int y_pix_stride; int y_vec8;
     int nblocks, tiles_total;
+    // staged variant (mdcn_tcs_kernel): 2-D output tiles of 16 x 8 pixels, input window of win_h x win_w pixels per chunk
+    int tiles_w, tiles_h, margin, win_h, win_w, win_bytes;
 };
 
 __global__ void __launch_bounds__(MD_THREADS, 1)
@@ -243,6 +245,259 @@ mdcn_tc_kernel(const __grid_constant__ CUtensorMap wmap, const MdParams p) {
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------------
+// Staged variant (3x3, stride 1, dilation 1 -- every DCN of EDVR): per 16 x 8 output tile and 32-channel chunk ONE TMA box
+// brings the input window (tile + 1-pixel tap ring + `margin` pixels for the learned offsets; 24 x 16 pixels x 128 B = 48 KB)
+// into shared memory, and the 9 taps x 4 corners x 128 pixels x 4 groups bilinear reads of that chunk are served from there
+// (swizzled LDS.128 pairs) instead of L1/L2 -- 48 KB of L2 traffic per chunk-tile instead of ~590 KB.  Corners that a large
+// offset pushes outside the window fall back to the global 256-bit load, so the result is exact for any offset.
+constexpr int MDS_ASTAGES = 2;
+
+__device__ __forceinline__ void lds8(uint32_t addr0, uint32_t addr1, float4& a, float4& b) {
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "r"(addr0));
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "r"(addr1));
+}
+
+__global__ void __launch_bounds__(MD_THREADS, 1)
+mdcn_tcs_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__ CUtensorMap xmap, const MdParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem_b = smem;                                    // [nblocks][64 x 128 B] resident weights
+    uint8_t* smem_w = smem + p.nblocks * 8192;                 // input window [win_h * win_w][128 B], 128B-swizzled by TMA
+    uint8_t* smem_a = smem_w + p.win_bytes;                    // [MDS_ASTAGES][16 KiB]
+    uint64_t* bars = (uint64_t*)(smem_a + MDS_ASTAGES * MD_A_BYTES);
+    uint64_t* b_full = bars;                       // [1]
+    uint64_t* a_ready = bars + 1;                  // [2] 256 gather arrivals
+    uint64_t* a_empty = bars + 3;                  // [2] MMA commit
+    uint64_t* acc_full = bars + 5;                 // [2]
+    uint64_t* acc_empty = bars + 7;                // [2]
+    uint64_t* win_full = bars + 9;                 // [1] TMA
+    uint64_t* win_empty = bars + 10;               // [1] 256 gather arrivals
+    uint32_t* tmem_slot = (uint32_t*)(bars + 12);
+    float* bias_s = (float*)(bars + 14);           // [64]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int KK = 9;
+    const int chunks = p.C / 32;
+    const int tiles_per_img = p.tiles_w * p.tiles_h;
+
+    if (warp == 0 && elect_one()) { prefetch_tmap(&wmap); prefetch_tmap(&xmap); }
+    if (warp == 1) {
+        if (elect_one()) {
+            mbar_init(b_full, 1);
+            for (int i = 0; i < MDS_ASTAGES; ++i) { mbar_init(&a_ready[i], MD_GATHER); mbar_init(&a_empty[i], 1); }
+            for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
+            mbar_init(win_full, 1);
+            mbar_init(win_empty, MD_GATHER);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(128) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (threadIdx.x >= 320 && threadIdx.x < 384) {
+        const int co = threadIdx.x - 320;
+        bias_s[co] = (p.bias && co < p.Co) ? __ldg(p.bias + co) : 0.f;
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== producer: weights once, then one input window per (tile, chunk) =====================
+        if (elect_one()) {
+            mbar_expect_tx(b_full, (uint32_t)p.nblocks * 8192u);
+            for (int b = 0; b < p.nblocks; ++b) tma_load_2d(&wmap, b_full, smem_b + b * 8192, 0, b * 64);
+            int wphase = 0;
+            for (int tile = blockIdx.x; tile < p.tiles_total; tile += gridDim.x) {
+                const int tn = tile / tiles_per_img, tr = tile - tn * tiles_per_img;
+                const int oy0 = (tr / p.tiles_w) * 16, ox0 = (tr % p.tiles_w) * 8;
+                for (int c = 0; c < chunks; ++c) {
+                    mbar_wait(win_empty, wphase ^ 1);
+                    mbar_expect_tx(win_full, (uint32_t)p.win_bytes);
+                    tma_load_4d(&xmap, win_full, smem_w, c * 32, ox0 - 1 - p.margin, oy0 - 1 - p.margin, tn);
+                    wphase ^= 1;
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (BF16x3) =====================
+        const uint32_t idesc = make_idesc_bf16(128, 64);
+        const uint64_t d_const = make_desc(0, 16, 1024, 2);
+        mbar_wait(b_full, 0);
+        int stage = 0, phase = 0, local = 0;
+        for (int tile = blockIdx.x; tile < p.tiles_total; tile += gridDim.x, ++local) {
+            const int acc = local & 1;
+            mbar_wait(&acc_empty[acc], ((local >> 1) & 1) ^ 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t dcol = tmem_base + acc * 64;
+            for (int it = 0; it < chunks * KK; ++it) {        // block order = chunk-major, then tap (pack mode 7)
+                mbar_wait(&a_ready[stage], phase);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (elect_one()) {
+                    const uint64_t ad = d_const + (uint64_t)(smem_u32(smem_a + stage * MD_A_BYTES) >> 4);
+                    const uint64_t bd = d_const + (uint64_t)(smem_u32(smem_b + it * 8192) >> 4);
+                    mma_bf16(dcol, ad, bd, idesc, it > 0 ? 1u : 0u);          // x_hi . w_hi
+                    mma_bf16(dcol, ad + 2, bd + 2, idesc, 1u);
+                    mma_bf16(dcol, ad + 4, bd, idesc, 1u);                    // x_lo . w_hi
+                    mma_bf16(dcol, ad + 6, bd + 2, idesc, 1u);
+                    mma_bf16(dcol, ad, bd + 4, idesc, 1u);                    // x_hi . w_lo
+                    mma_bf16(dcol, ad + 2, bd + 6, idesc, 1u);
+                    mma_commit(&a_empty[stage]);
+                    if (it == chunks * KK - 1) mma_commit(&acc_full[acc]);
+                }
+                __syncwarp();
+                if (++stage == MDS_ASTAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp < 10) {
+        // ===================== gather from the staged window =====================
+        const int t = threadIdx.x - 64;                 // 0..255
+        const int gl = t & 3;                           // deformable group inside the 32-channel chunk
+        const uint32_t win_s = smem_u32(smem_w);
+        int stage = 0, phase = 0, wphase = 0;
+        for (int tile = blockIdx.x; tile < p.tiles_total; tile += gridDim.x) {
+            const int tn = tile / tiles_per_img, tr = tile - tn * tiles_per_img;
+            const int oy0 = (tr / p.tiles_w) * 16, ox0 = (tr % p.tiles_w) * 8;
+            const int wy0 = oy0 - 1 - p.margin, wx0 = ox0 - 1 - p.margin;       // image coordinates of window pixel (0, 0)
+            long long mlin[2]; int oy[2], ox[2]; bool ok[2];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int prow = (t >> 2) + 64 * i;
+                oy[i] = oy0 + (prow >> 3);
+                ox[i] = ox0 + (prow & 7);
+                ok[i] = oy[i] < p.Ho && ox[i] < p.Wo;
+                mlin[i] = ((long long)tn * p.Ho + (ok[i] ? oy[i] : 0)) * p.Wo + (ok[i] ? ox[i] : 0);
+            }
+            const float* img0 = p.x + (long long)tn * p.img_stride;
+            for (int c = 0; c < chunks; ++c) {
+                const int g = c * 4 + gl;
+                // all 9 taps' offsets / masks of this thread's two pixels: independent loads in flight while the window lands
+                float ody[2][9], odx[2][9], omk[2][9];
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const float* op = p.offset + mlin[i] * p.off_pix_stride + g * KK * 2;
+                    const float* mp = p.mask + mlin[i] * p.mask_pix_stride + g * KK;
+#pragma unroll
+                    for (int tap = 0; tap < 9; ++tap) {
+                        // (dy, dx) pairs are 8-byte aligned ([dg][k][2] layout, even pixel stride): one 64-bit request per tap
+                        const float2 o2 = ok[i] ? __ldg(reinterpret_cast<const float2*>(op) + tap) : make_float2(0.f, 0.f);
+                        ody[i][tap] = o2.x;
+                        odx[i][tap] = o2.y;
+                        omk[i][tap] = ok[i] ? __ldg(mp + tap) : 0.f;
+                    }
+                }
+                mbar_wait(win_full, wphase);
+                wphase ^= 1;
+#pragma unroll
+                for (int tap = 0; tap < 9; ++tap) {
+                    const int kh = tap / 3, kw = tap - kh * 3;
+                    mbar_wait(&a_empty[stage], phase ^ 1);
+                    uint8_t* tile_a = smem_a + stage * MD_A_BYTES;
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        const int prow = (t >> 2) + 64 * i;
+                        float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                        const float h = (float)(oy[i] - 1 + kh) + ody[i][tap];
+                        const float w = (float)(ox[i] - 1 + kw) + odx[i][tap];
+                        if (ok[i] && h > -1.f && w > -1.f && h < (float)p.H && w < (float)p.W) {
+                            const float hf = floorf(h), wf = floorf(w);
+                            const int h0 = (int)hf, w0 = (int)wf;
+                            const float lh = h - hf, lw = w - wf, hh = 1.f - lh, hw = 1.f - lw;
+                            const float mk = omk[i][tap];
+                            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+                            float4 q0[4], q1[4];
+#pragma unroll
+                            for (int cr = 0; cr < 4; ++cr) {
+                                const int hc = h0 + (cr >> 1), wc = w0 + (cr & 1);
+                                q0[cr] = z; q1[cr] = z;
+                                if (hc >= 0 && hc <= p.H - 1 && wc >= 0 && wc <= p.W - 1) {      // kernel.cu:478-490 corner rule
+                                    const int wy = hc - wy0, wx = wc - wx0;
+                                    if (wy >= 0 && wy < p.win_h && wx >= 0 && wx < p.win_w) {
+                                        const int row = wy * p.win_w + wx;
+                                        const uint32_t ra = win_s + (uint32_t)row * 128u;
+                                        const uint32_t sw = (uint32_t)(row & 7);
+                                        lds8(ra + (((uint32_t)(gl * 2) ^ sw) << 4), ra + (((uint32_t)(gl * 2 + 1) ^ sw) << 4), q0[cr], q1[cr]);
+                                    } else {
+                                        ldg8(img0 + ((long long)hc * p.W + wc) * p.pix_stride + g * 8, q0[cr], q1[cr]);
+                                    }
+                                }
+                            }
+                            const float w00 = hh * hw, w01 = hh * lw, w10 = lh * hw, w11 = lh * lw;
+                            // same association as the reference: (w1*v1 + w2*v2 + w3*v3 + w4*v4) * mask
+                            v[0] = (w00 * q0[0].x + w01 * q0[1].x + w10 * q0[2].x + w11 * q0[3].x) * mk;
+                            v[1] = (w00 * q0[0].y + w01 * q0[1].y + w10 * q0[2].y + w11 * q0[3].y) * mk;
+                            v[2] = (w00 * q0[0].z + w01 * q0[1].z + w10 * q0[2].z + w11 * q0[3].z) * mk;
+                            v[3] = (w00 * q0[0].w + w01 * q0[1].w + w10 * q0[2].w + w11 * q0[3].w) * mk;
+                            v[4] = (w00 * q1[0].x + w01 * q1[1].x + w10 * q1[2].x + w11 * q1[3].x) * mk;
+                            v[5] = (w00 * q1[0].y + w01 * q1[1].y + w10 * q1[2].y + w11 * q1[3].y) * mk;
+                            v[6] = (w00 * q1[0].z + w01 * q1[1].z + w10 * q1[2].z + w11 * q1[3].z) * mk;
+                            v[7] = (w00 * q1[0].w + w01 * q1[1].w + w10 * q1[2].w + w11 * q1[3].w) * mk;
+                        }
+                        uint32_t hi[4], lo[4];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) split_bf16x2(v[2 * q], v[2 * q + 1], hi[q], lo[q]);
+                        uint4* row = reinterpret_cast<uint4*>(tile_a + prow * 128);
+                        const int ph = prow & 7;
+                        row[gl ^ ph] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                        row[(4 + gl) ^ ph] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    mbar_arrive(&a_ready[stage]);
+                    if (++stage == MDS_ASTAGES) { stage = 0; phase ^= 1; }
+                }
+                mbar_arrive(win_empty);                 // this thread is done reading the window of (tile, chunk)
+            }
+        }
+    } else {
+        // ===================== epilogue =====================
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        int local = 0;
+        for (int tile = blockIdx.x; tile < p.tiles_total; tile += gridDim.x, ++local) {
+            const int acc = local & 1;
+            const int tn = tile / tiles_per_img, tr = tile - tn * tiles_per_img;
+            const int eoy = (tr / p.tiles_w) * 16 + (row >> 3), eox = (tr % p.tiles_w) * 8 + (row & 7);
+            const bool valid = eoy < p.Ho && eox < p.Wo;
+            const long long pix = ((long long)tn * p.Ho + eoy) * p.Wo + eox;
+            mbar_wait(&acc_full[acc], (local >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            float v0[32], v1[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 64), v0);
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 64 + 32), v1);
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(&acc_empty[acc]);
+            if (valid) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    float (&v)[32] = h == 0 ? v0 : v1;
+                    const int c0 = h * 32;
+                    if (c0 >= p.Co) continue;
+                    epilogue_chunk(v, c0, p.Co, bias_s + c0, nullptr, nullptr, p.act, p.slope, 0);
+                    float* yo = p.y + pix * p.y_pix_stride + c0;
+                    const int nvalid = min(32, p.Co - c0);
+                    if (p.y_vec8) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 8)
+                            if (j < nvalid) st_global_v8(yo + j, v[j], v[j + 1], v[j + 2], v[j + 3], v[j + 4], v[j + 5], v[j + 6], v[j + 7]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4)
+                            if (j < nvalid) *reinterpret_cast<float4*>(yo + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128) : "memory");
+    }
+}
+
 }  // namespace dvsr
 
 using namespace dvsr;
@@ -259,6 +514,11 @@ extern "C" int dvsr_mdcn_tc_supported(const dvsr_conv_desc* d) {
     if (d->act == DVSR_ACT_SIGMOID_SPLIT) return 0;
     return 1;
 }
+
+static int g_mdcn_staged = 1;
+// 1 (default): large 3x3 / stride 1 launches use the staged-window kernel; 0: always the direct-gather kernel; 2: staged at
+// every size (A/B measurements, tests)
+extern "C" int dvsr_mdcn_tc_set_staged(int on) { g_mdcn_staged = on < 0 ? 0 : on; return 0; }
 
 // wp: dvsr_pack_weights_tc2 mode 7 (BF16x3 rows) over the single segment
 extern "C" int dvsr_mdcn_tc_fprop(const dvsr_conv_desc* d, const float* wp, void* stream) {
@@ -297,6 +557,41 @@ extern "C" int dvsr_mdcn_tc_fprop(const dvsr_conv_desc* d, const float* wp, void
         if (cudaFuncSetAttribute(mdcn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
             return check_launch("mdcn_tc_fprop: cudaFuncSetAttribute");
         smem_set = smem;
+    }
+    // staged-window variant for the EDVR geometry (3x3, stride 1, pad 1, dilation 1); launches with fewer than ~2 tiles per SM
+    // keep the direct kernel: one window load per CTA would not be amortised
+    if (g_mdcn_staged && d->KH == 3 && d->KW == 3 && d->stride == 1 && d->dil == 1 && d->pad == 1 && d->Ho == d->H && d->Wo == d->W &&
+        (g_mdcn_staged > 1 || (long long)d->N * ((d->Wo + 7) / 8) * ((d->Ho + 15) / 16) >= 296) &&
+        (((uintptr_t)d->offset & 7) == 0) && ((d->off_pix_stride & 1) == 0)) {
+        p.margin = 3;
+        p.win_h = 16 + 2 + 2 * p.margin;
+        p.win_w = 8 + 2 + 2 * p.margin;
+        p.win_bytes = (p.win_h * p.win_w * 128 + 1023) / 1024 * 1024;
+        p.tiles_w = (d->Wo + 7) / 8;
+        p.tiles_h = (d->Ho + 15) / 16;
+        p.tiles_total = d->N * p.tiles_w * p.tiles_h;
+        CUtensorMap xmap;
+        cuuint64_t dims[4] = {(cuuint64_t)g.C, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->N};
+        cuuint64_t strides[3] = {(cuuint64_t)g.pix_stride * 4, (cuuint64_t)d->W * g.pix_stride * 4, (cuuint64_t)p.img_stride * 4};
+        cuuint32_t box[4] = {32, (cuuint32_t)p.win_w, (cuuint32_t)p.win_h, 1};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = encode(&xmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)g.ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        DVSR_REQUIRE(r == CUDA_SUCCESS, "mdcn_tc_fprop: cuTensorMapEncodeTiled(input window) failed with %d", (int)r);
+        const size_t smem_s = 1024 + (size_t)p.nblocks * 8192 + (size_t)p.win_bytes + (size_t)MDS_ASTAGES * MD_A_BYTES + 512;
+        if (smem_s <= 232448) {
+            static size_t smem_set_s = 0;
+            if (smem_s > smem_set_s) {
+                if (cudaFuncSetAttribute(mdcn_tcs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s) != cudaSuccess)
+                    return check_launch("mdcn_tc_fprop: cudaFuncSetAttribute");
+                smem_set_s = smem_s;
+            }
+            const int ctas_s = p.tiles_total < cta_budget() ? p.tiles_total : cta_budget();
+            mdcn_tcs_kernel<<<ctas_s, MD_THREADS, smem_s, (cudaStream_t)stream>>>(wmap, xmap, p);
+            return check_launch("mdcn_tc_fprop (staged)");
+        }
+        const long long M2 = (long long)d->N * d->Ho * d->Wo;
+        p.tiles_total = (int)((M2 + 127) / 128);
     }
     int ctas = p.tiles_total < cta_budget() ? p.tiles_total : cta_budget();
     mdcn_tc_kernel<<<ctas, MD_THREADS, smem, (cudaStream_t)stream>>>(wmap, p);

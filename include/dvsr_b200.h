@@ -197,6 +197,11 @@ int dvsr_mdcn_bwd_data(const dvsr_conv_desc* d, const float* gy, int gy_pix_stri
  * memory, resident weights (pack mode 7), persistent CTAs.  8 channels per deformable group, C*KH*KW <= 576, Co <= 64. */
 int dvsr_mdcn_tc_supported(const dvsr_conv_desc* d);
 int dvsr_mdcn_tc_fprop(const dvsr_conv_desc* d, const float* wp, void* stream);
+/* 3x3 / stride-1 / pad-1 launches (every DCN of EDVR) stage a 24 x 16-pixel input window per 16 x 8 output tile and 32-channel
+ * chunk in shared memory with one TMA box and gather the 36 corners per pixel from there (global fallback for corners a large
+ * offset pushes outside the window) when the launch has at least two tiles per SM.  on = 0 forces the direct-gather kernel,
+ * on = 2 the staged one at every size (A/B measurements, tests). */
+int dvsr_mdcn_tc_set_staged(int on);
 
 /* Reference operator boundary, NCHW fp32 (deform_conv_cuda.cpp:486-492, :566-573).  groups must be 1
  * (no YML of the reference uses groups != 1).  Workspace: dvsr_mdcn_workspace_bytes() bytes. */

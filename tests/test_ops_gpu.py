@@ -170,6 +170,30 @@ def test_mdcn_nhwc(ops, cfg):
     _mdcn_case(ops, N, C, H, W, Co, dg, s, act, seed=7)
 
 
+@pytest.mark.parametrize('staged', [2, 0], ids=['staged_window', 'direct_gather'])
+@pytest.mark.parametrize('shape,off_scale', [((2, 19, 21), 1.0), ((1, 33, 40), 3.0), ((1, 16, 8), 12.0), ((5, 44, 80), 2.0)],
+                         ids=['small_offsets', 'edge_of_window', 'mostly_outside_window', 'slr_size'])
+def test_mdcn_tensor_core_forward(ops, staged, shape, off_scale):
+    """tcgen05 DCN forward, both gather variants, against the float64 oracle: offsets inside the staged window (margin 3),
+    straddling it, and far outside (global fallback + out-of-image corners)."""
+    from oracle.torch_ops import mdcn_torch
+    N, H, W = shape
+    x = _rand(N, 64, H, W, seed=1)
+    off = _rand(N, 144, H, W, seed=2, scale=off_scale)
+    m = torch.sigmoid(_rand(N, 72, H, W, seed=3))
+    w, b = _rand(64, 64, 3, 3, seed=4, scale=0.1), _rand(64, seed=5, scale=0.1)
+    y = F.leaky_relu(mdcn_torch(x, off, m, w, b, 1, 1, 1, 1, 8), 0.1)
+    om = torch.cat([nhwc(_dev(off)), nhwc(_dev(m))], 3).contiguous()
+    ops.set_conv_backend(True)
+    ops._lib.lib().dvsr_mdcn_tc_set_staged(staged)
+    try:
+        yd = ops.mdcn(nhwc(_dev(x)), om, _dev(w), _dev(b), 8, 1, 1, 1, ops.ACT_LRELU)
+    finally:
+        ops._lib.lib().dvsr_mdcn_tc_set_staged(1)
+        ops.set_conv_backend(False)
+    assert rel(nchw(yd), y) < 1e-4          # BF16x3: fp32-class
+
+
 def test_mdcn_all_taps_outside_gives_bias(ops):
     x = nhwc(_dev(_rand(1, 64, 5, 5)))
     om = torch.cat([torch.full((1, 5, 5, 144), 100.0), torch.ones(1, 5, 5, 72)], 3).cuda()
