@@ -89,11 +89,11 @@ mdcn_tc_kernel(const __grid_constant__ CUtensorMap wmap, const MdParams p) {
         int stage = 0, phase = 0, local = 0;
         for (int tile = blockIdx.x; tile < p.tiles_total; tile += gridDim.x, ++local) {
             const int acc = local & 1;
-            mbar_wait(&acc_empty[acc], ((local >> 1) & 1) ^ 1);
+            mbar_wait_relaxed(&acc_empty[acc], ((local >> 1) & 1) ^ 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t dcol = tmem_base + acc * 64;
             for (int it = 0; it < chunks * KK; ++it) {        // block order = chunk-major, then tap (pack mode 7)
-                mbar_wait(&a_ready[stage], phase);
+                mbar_wait_relaxed(&a_ready[stage], phase, 64);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (elect_one()) {
                     const uint64_t ad = d_const + (uint64_t)(smem_u32(smem_a + stage * MD_A_BYTES) >> 4);
@@ -209,7 +209,7 @@ mdcn_tc_kernel(const __grid_constant__ CUtensorMap wmap, const MdParams p) {
             const int acc = local & 1;
             const long long pix = (long long)tile * 128 + row;
             const bool valid = pix < M;
-            mbar_wait(&acc_full[acc], (local >> 1) & 1);
+            mbar_wait_relaxed(&acc_full[acc], (local >> 1) & 1, 256);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             float v0[32], v1[32];
             tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 64), v0);
@@ -315,7 +315,7 @@ mdcn_tcs_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant_
                 const int tn = tile / tiles_per_img, tr = tile - tn * tiles_per_img;
                 const int oy0 = (tr / p.tiles_w) * 16, ox0 = (tr % p.tiles_w) * 8;
                 for (int c = 0; c < chunks; ++c) {
-                    mbar_wait(win_empty, wphase ^ 1);
+                    mbar_wait_relaxed(win_empty, wphase ^ 1);
                     mbar_expect_tx(win_full, (uint32_t)p.win_bytes);
                     tma_load_4d(&xmap, win_full, smem_w, c * 32, ox0 - 1 - p.margin, oy0 - 1 - p.margin, tn);
                     wphase ^= 1;
@@ -330,11 +330,11 @@ mdcn_tcs_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant_
         int stage = 0, phase = 0, local = 0;
         for (int tile = blockIdx.x; tile < p.tiles_total; tile += gridDim.x, ++local) {
             const int acc = local & 1;
-            mbar_wait(&acc_empty[acc], ((local >> 1) & 1) ^ 1);
+            mbar_wait_relaxed(&acc_empty[acc], ((local >> 1) & 1) ^ 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t dcol = tmem_base + acc * 64;
             for (int it = 0; it < chunks * KK; ++it) {        // block order = chunk-major, then tap (pack mode 7)
-                mbar_wait(&a_ready[stage], phase);
+                mbar_wait_relaxed(&a_ready[stage], phase, 64);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (elect_one()) {
                     const uint64_t ad = d_const + (uint64_t)(smem_u32(smem_a + stage * MD_A_BYTES) >> 4);
@@ -462,7 +462,7 @@ mdcn_tcs_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant_
             const int eoy = (tr / p.tiles_w) * 16 + (row >> 3), eox = (tr % p.tiles_w) * 8 + (row & 7);
             const bool valid = eoy < p.Ho && eox < p.Wo;
             const long long pix = ((long long)tn * p.Ho + eoy) * p.Wo + eox;
-            mbar_wait(&acc_full[acc], (local >> 1) & 1);
+            mbar_wait_relaxed(&acc_full[acc], (local >> 1) & 1, 256);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             float v0[32], v1[32];
             tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 64), v0);

@@ -45,6 +45,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
                      : "=r"(done) : "r"(a), "r"(parity) : "memory");
     }
 }
+// Same wait with a sleep between polls, for warps that wait long and are not on the critical path (epilogue, producer, MMA
+// issuer of a gather-bound kernel): a tight try_wait / branch loop competes for issue slots with the working warps of the
+// same scheduler (ncu: 40 % of the instructions of the DCN kernel were such polls).
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity, uint32_t ns = 128) {
+    uint32_t done = 0;
+    const uint32_t a = smem_u32(bar);
+    for (;;) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(a), "r"(parity) : "memory");
+        if (done) break;
+        __nanosleep(ns);
+    }
+}
 __device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3) {
     asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
                  ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
