@@ -325,10 +325,10 @@ def main():
                 'bound': 'tensor', 'achieved': flops / t_conv / 1e12, 'peak': tc_peak, 'unit': 'TFLOP/s',
                 'frac': flops / t_conv / 1e12 / tc_peak,
                 # dram__bytes_read.sum + dram__bytes_write.sum of this very launch shape from the committed ncu --set full
-                # capture profiles/r1_conv_tc2_ncu_full.csv (72.3 MB read + 29.6 MB written; the rest of y stays in L2)
-                'traffic': 101.9e6 if (use_tc and prec == 'bf16x3' and (H, W) == (LR_H, LR_W)) else None,
+                # capture profiles/r1_ncu_tc2.csv (72.3 MB read + 29.8 MB written; the rest of y stays in L2)
+                'traffic': 102.1e6 if (use_tc and prec == 'bf16x3' and (H, W) == (LR_H, LR_W)) else None,
                 'peak_source': peak_src + ': bf16 dense burst; algorithmic FLOPs = 18*N*H*W*Cin*Cout (the BF16x3 mode issues 3x '
-                                          'that many tensor-core MACs, the TF32 mode runs at half the bf16 rate)',
+                                          'that many tensor-core MACs and is bounded by the 128 B/clk shared-memory operand path: DESIGN.md section 3)',
                 'algorithmic_bytes': 4.0 * NFR * H * W * 128 + 36.0 * 64 * 64, 'launch_us': t_conv * 1e6,
                 'tensor_macs_issued_x': 3 if prec == 'bf16x3' else 1}
 
