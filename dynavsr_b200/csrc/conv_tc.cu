@@ -118,7 +118,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
                     const int kh = tap / p.KW, kw = tap - kh * p.KW;
                     const int dy = p.tap_base + p.tap_sign * kh, dx = p.tap_base + p.tap_sign * kw;
                     for (int c = 0; c < chunks; ++c, ++wrow) {
-                        mbar_wait(&empty_bar[stage], phase ^ 1);
+                        mbar_wait_relaxed(&empty_bar[stage], phase ^ 1, 64);
                         mbar_expect_tx(&full_bar[stage], TC_A_BYTES + b_bytes);
                         // a temporal tap outside the clip reads image index N (fully out of bounds -> zeros)
                         tma_load_4d(&maps.x[s], &full_bar[stage], smem_a + stage * TC_A_BYTES, c * TC_KC, ox0 * p.stride + dx, oy0 * p.stride + dy,
@@ -159,7 +159,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
             int stage = 0, phase = 0, total = 0;
             for (int s = 0; s < p.nseg; ++s) total += KK * ((p.seg[s].C + TC_KC - 1) / TC_KC);
             for (int it = 0; it < total; ++it) {
-                mbar_wait(&full_bar[stage], phase);
+                mbar_wait_relaxed(&full_bar[stage], phase, 32);
                 float4* a4 = reinterpret_cast<float4*>(smem_a + stage * TC_A_BYTES);
 #pragma unroll
                 for (int i = 0; i < TC_A_BYTES / 16 / 128; ++i) {
@@ -173,7 +173,7 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
             }
         }
         // ===================== epilogue: 4 warps, one TMEM lane (= output pixel) per thread =====================
-        mbar_wait(accum_bar, 0);
+        mbar_wait_relaxed(accum_bar, 0, 256);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int q = warp & 3;                    // TMEM lane quarter this warp may access
         const int row = q * 32 + lane;             // pixel index inside the tile: row = ty * 16 + tx

@@ -145,7 +145,7 @@ conv_tc2_kernel(const __grid_constant__ T2Maps maps, const T2Params p) {
                     const int chunks = (p.seg[s].C + 31) / 32;
                     for (int c = 0; c < chunks; ++c) {
                         prefetch_next();
-                        mbar_wait(&a_empty[stage], phase ^ 1);
+                        mbar_wait_relaxed(&a_empty[stage], phase ^ 1, 64);
                         T2_TRACE(0, trace_i); ++trace_i;
                         mbar_expect_tx(&a_full[stage], (uint32_t)(p.halo_h * p.halo_w * 128));
                         tma_load_4d(&maps.x[s], &a_full[stage], smem_a + stage * p.a_bytes, c * 32, ox0 + min_dx, oy0 + min_d,
@@ -227,7 +227,7 @@ conv_tc2_kernel(const __grid_constant__ T2Maps maps, const T2Params p) {
         int stage = 0, phase = 0, trace_i = 0;
         for (int tile = blockIdx.x; tile < p.tiles_total; tile += gridDim.x) {
             for (int c = 0; c < chunks_total; ++c) {
-                mbar_wait(&a_full[stage], phase);
+                mbar_wait_relaxed(&a_full[stage], phase, 32);
                 if (t == 0) T2_TRACE(1, trace_i);
                 float4* a4 = reinterpret_cast<float4*>(smem_a + stage * p.a_bytes);
                 if (!p.bf16x3) {
@@ -278,7 +278,7 @@ conv_tc2_kernel(const __grid_constant__ T2Maps maps, const T2Params p) {
             const int oy = (r / tiles_w) * T2_TH + row / T2_TW, ox = (r % tiles_w) * T2_TW + row % T2_TW;
             const bool valid = (oy < p.Ho) && (ox < p.Wo);
             const long long pix = ((long long)n * p.Ho + oy) * p.Wo + ox;
-            mbar_wait(&acc_full[acc], (local >> 1) & 1);
+            mbar_wait_relaxed(&acc_full[acc], (local >> 1) & 1, 128);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (threadIdx.x == 192) T2_TRACE(5, local);
             float v0[32], v1[32];

@@ -99,7 +99,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ WgMaps maps, const WgParams p) {
                 const int q = n / T, rr = n - q * T;
                 const int t = p.t_fixed >= 0 ? p.t_fixed : rr + p.dt;
                 const int img = (t < 0 || t >= p.Tsrc) ? 0x3fffffff : q * p.Tsrc + t;
-                mbar_wait(&empty_bar[stage], phase ^ 1);
+                mbar_wait_relaxed(&empty_bar[stage], phase ^ 1, 64);
                 // a halo block is (CH+KH-1) x halo_w pixels x 128 B; TMA always delivers the full box
                 mbar_expect_tx(&full_bar[stage], (uint32_t)(mblk * (p.CH + p.KH - 1) * halo_w * 128 + nblk * p.CH * WG_TW * 128));
                 uint8_t* sa = smem + stage * stage_bytes;
@@ -136,7 +136,7 @@ conv_wgrad_tc_kernel(const __grid_constant__ WgMaps maps, const WgParams p) {
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
     } else if (chunk_begin < chunk_end) {
-        mbar_wait(accum_bar, 0);
+        mbar_wait_relaxed(accum_bar, 0, 256);      // the epilogue warps idle for the whole main loop
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int q = warp & 3;
         const int tl_lane = q * 32 + lane;
