@@ -114,6 +114,7 @@ SIGNATURES = {
     'dvsr_scale_by_device_scalar': [_P, _P, _P, _LL, _P],
     'dvsr_update_sgd': [_P, _P, _LL, _LL, _F, _F, _F, _P],
     'dvsr_update_adam': [_P, _P, _P, _P, _LL, _LL, _F, _F, _F, _F, _F, _F, _F, _F, _P],
+    'dvsr_update_peers': [_P, _P, _I, _LL, _F, _P, _P, _LL, _LL, _F, _F, _F, _F, _F, _F, _F, _F, _I, _P],
     'dvsr_abs_sum': [_P, _P, _LL, _I, _I, _I, _P],
     'dvsr_set_cta_budget': [_I],
     'dvsr_get_cta_budget': [],

@@ -72,6 +72,45 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
     }
 }
 
+// Exchange step of meta-training fused with the outer update (train_dynavsr.py:438 + the gradient averaging DDP would do):
+// every rank reads the flat meta-gradient of ALL ranks straight from their HBM over NVLink (peer pointers of a symmetric-memory
+// allocation), sums them in rank order (bit-identical on every rank), scales by 1/world and applies Adam / SGD to its copy of the
+// meta-weights -- one pass, no reduced gradient buffer, no separate all-reduce launch.  Loads are cache-volatile: the peers
+// rewrite these buffers every outer step.
+template <bool ADAM>
+__global__ void update_peers_kernel(float* __restrict__ p, const float* const* __restrict__ grads, int n_peers, long long goff, float scale,
+                                    float* __restrict__ m, float* __restrict__ v, long long n, long long split, float lr0, float lr1,
+                                    float b1, float b2, float eps, float bc1, float bc2, float wd) {
+    const float rs = ADAM ? 1.f / sqrtf(bc2) : 0.f;
+    const long long n4 = n >> 2;
+    for (long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i4 < n4; i4 += (long long)gridDim.x * blockDim.x) {
+        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int r = 0; r < n_peers; ++r) {
+            const float4 t = __ldcv(reinterpret_cast<const float4*>(grads[r] + goff) + i4);
+            g.x += t.x; g.y += t.y; g.z += t.z; g.w += t.w;
+        }
+        float gv[4] = {g.x * scale, g.y * scale, g.z * scale, g.w * scale};
+        float4 pv4 = reinterpret_cast<float4*>(p)[i4];
+        float pv[4] = {pv4.x, pv4.y, pv4.z, pv4.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const long long i = i4 * 4 + k;
+            const float lr = i < split ? lr0 : lr1;
+            const float gi = gv[k] + wd * pv[k];
+            if (ADAM) {
+                const float mi = b1 * m[i] + (1.f - b1) * gi;
+                const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+                m[i] = mi;
+                v[i] = vi;
+                pv[k] = pv[k] - (lr / bc1) * (mi / (sqrtf(vi) * rs + eps));
+            } else {
+                pv[k] = pv[k] - lr * gi;
+            }
+        }
+        reinterpret_cast<float4*>(p)[i4] = make_float4(pv[0], pv[1], pv[2], pv[3]);
+    }
+}
+
 __global__ void abs_sum_kernel(const float* __restrict__ x, float* __restrict__ out, long long npix, int pix_stride, int c0, int c1) {
     const int w = c1 - c0;
     const long long total = npix * w;
@@ -127,6 +166,16 @@ extern "C" int dvsr_update_adam(float* p, const float* g, float* m, float* v, lo
     DVSR_REQUIRE(p && g && m && v && n > 0, "update_adam: bad arguments");
     adam_kernel<<<blocks_for(n), 256, 0, ST>>>(p, g, m, v, n, split, lr0, lr1, b1, b2, eps, bc1, bc2, wd);
     return check_launch("update_adam");
+}
+extern "C" int dvsr_update_peers(float* p, const float* const* grads_dev, int n_peers, long long grad_offset, float scale, float* m,
+                                 float* v, long long n, long long split, float lr0, float lr1, float b1, float b2, float eps,
+                                 float bc1, float bc2, float wd, int adam, void* stream) {
+    DVSR_REQUIRE(p && grads_dev && n_peers >= 1 && n > 0 && (n & 3) == 0, "update_peers: bad arguments (n must be a multiple of 4)");
+    DVSR_REQUIRE(!adam || (m && v), "update_peers: Adam needs the moment buffers");
+    DVSR_REQUIRE((((uintptr_t)p) & 15) == 0 && (grad_offset & 3) == 0, "update_peers: 16-byte alignment required");
+    if (adam) update_peers_kernel<true><<<blocks_for(n >> 2), 256, 0, ST>>>(p, grads_dev, n_peers, grad_offset, scale, m, v, n, split, lr0, lr1, b1, b2, eps, bc1, bc2, wd);
+    else update_peers_kernel<false><<<blocks_for(n >> 2), 256, 0, ST>>>(p, grads_dev, n_peers, grad_offset, scale, m, v, n, split, lr0, lr1, b1, b2, eps, bc1, bc2, wd);
+    return check_launch("update_peers");
 }
 extern "C" int dvsr_abs_sum(const float* x, float* out, long long npix, int pix_stride, int c0, int c1, void* stream) {
     DVSR_REQUIRE(x && out && npix > 0 && c1 > c0 && pix_stride >= c1, "abs_sum: bad arguments");

@@ -16,9 +16,13 @@ outer gradient; ``reference_quirk=True`` reproduces that accumulation (meta_grad
 grad L_q(theta)/B + grad L_e(theta)/(10B)]) for a numerical side-by-side on one GPU.
 
 B200-first structure: theta' (EDVR u MFDN) is one flat buffer, so "deepcopy" = one D2D copy, the inner update = one launch,
-``meta_grad += grad`` = one axpy over the flat gradient (kernels accumulate weight gradients straight into it), the
-exchange step = ONE NCCL all-reduce of 15 MB (EDVR-M) / 84 MB (EDVR-L) over NVLink instead of DDP's bucketed hooks
-firing inside the inner loop, and the outer update = one launch on the flat meta-weights.
+``meta_grad += grad`` = one axpy over the flat gradient (kernels accumulate weight gradients straight into it).  The
+exchange step and the outer update are ONE kernel (``dvsr_update_peers``): the flat meta-gradient lives in symmetric memory
+(torch.distributed._symmetric_memory), every rank reads all ranks' 15 MB (EDVR-M) / 84 MB (EDVR-L) over NVLink peer pointers,
+sums in rank order, averages and applies Adam to its meta-weights in the same pass -- instead of DDP's bucketed hooks firing
+inside the inner loop, a reduced-gradient round trip through HBM and a separate optimiser launch.  ``exchange='nccl'`` (or a
+process group without peer access, e.g. gloo in CPU tests) falls back to ONE NCCL all-reduce of the flat buffer + the fused
+update launch.
 """
 import ctypes
 
@@ -44,7 +48,7 @@ class MetaLearner(object):
 
     def __init__(self, netG, netE, inner_steps=1, lr_alpha=1e-5, lr_alpha_est=None, inner_optimizer='Adam',
                  inner_betas=(0.9, 0.99), criterion='cb', pixel_weight=1.0, est_loss='l1', outer_optimizer='Adam',
-                 lr_outer=1e-5, outer_betas=(0.9, 0.99), reference_quirk=False):
+                 lr_outer=1e-5, outer_betas=(0.9, 0.99), reference_quirk=False, exchange='peer'):
         if inner_optimizer not in ('SGD', 'Adam') or outer_optimizer not in ('SGD', 'Adam'):
             raise NotImplementedError()
         if criterion not in ('l1', 'l2', 'cb', 'huber'):
@@ -60,6 +64,21 @@ class MetaLearner(object):
         self.work = FlatParams([netG, netE], scope=self.scope)      # theta' (+ its gradient buffer)
         self.theta = self.work.meta                                  # theta: restored into theta' per task
         self.meta_grad = torch.zeros_like(self.theta)
+        self._peer = None
+        self.exchange = 'local'
+        if exchange != 'none' and torch.distributed.is_available() and torch.distributed.is_initialized() \
+                and torch.distributed.get_world_size() > 1:
+            self.exchange = 'nccl'
+            if exchange == 'peer' and torch.distributed.get_backend() == 'nccl':
+                try:        # flat meta-gradient in symmetric memory: peers read it directly (fused exchange + update)
+                    import torch.distributed._symmetric_memory as symm
+                    g = symm.empty(self.theta.numel(), dtype=torch.float32, device=self.theta.device)
+                    hdl = symm.rendezvous(g, torch.distributed.group.WORLD)
+                    g.zero_()
+                    self.meta_grad, self._peer, self.exchange = g, hdl, 'peer'
+                except Exception as e:      # no peer access / no symmetric-memory support in this build
+                    import warnings
+                    warnings.warn('MetaLearner: symmetric memory unavailable (%s); using NCCL all-reduce' % (e,))
         self.m = torch.zeros_like(self.theta) if outer_optimizer == 'Adam' else None
         self.v = torch.zeros_like(self.theta) if outer_optimizer == 'Adam' else None
         self.outer_steps = 0
@@ -132,13 +151,28 @@ class MetaLearner(object):
                 lq.append(a); le.append(b); inner.append(c)
             if self.reference_quirk:
                 self.meta_grad.copy_(fl.grad)
-            # ---- the single exchange step: mean of the flat meta-gradient over ranks (NCCL over NVLink)
-            ddist.allreduce_flat_gradient(self.meta_grad, average=True)
-            # ---- outer update on theta (:438), one launch
             lr = self.lr_outer if lr is None else lr
             self.outer_steps += 1
             n = self.theta.numel()
-            if self.outer_optimizer == 'SGD':
+            if self._peer is not None:
+                # ---- exchange + outer update in ONE kernel over NVLink peer memory
+                h = self._peer
+                world = torch.distributed.get_world_size()
+                b1, b2 = self.outer_betas
+                t = self.outer_steps
+                adam = self.outer_optimizer == 'Adam'
+                h.barrier(channel=0)               # every rank's meta-gradient is complete
+                call('dvsr_update_peers', _p(self.theta), ctypes.c_void_p(int(h.buffer_ptrs_dev)), world,
+                     int(getattr(h, 'offset', 0)) // 4, 1.0 / world, _p(self.m), _p(self.v), n, n, float(lr), float(lr), float(b1),
+                     float(b2), 1e-8, float(1 - b1 ** t) if adam else 1.0, float(1 - b2 ** t) if adam else 1.0, 0.0,
+                     1 if adam else 0, _stream())
+                h.barrier(channel=1)               # nobody overwrites its gradient while a peer still reads it
+            elif self.exchange == 'nccl':
+                # ---- fallback: ONE all-reduce (mean) of the flat meta-gradient, then the fused update launch
+                ddist.allreduce_flat_gradient(self.meta_grad, average=True)
+            if self._peer is not None:
+                pass
+            elif self.outer_optimizer == 'SGD':
                 call('dvsr_update_sgd', _p(self.theta), _p(self.meta_grad), n, n, float(lr), float(lr), 0.0, _stream())
             else:
                 b1, b2 = self.outer_betas

@@ -284,6 +284,13 @@ int dvsr_update_sgd(float* p, const float* g, long long n, long long split, floa
  * bias corrections bc1 = 1-b1^t, bc2 = 1-b2^t. */
 int dvsr_update_adam(float* p, const float* g, float* m, float* v, long long n, long long split, float lr0,
                      float lr1, float b1, float b2, float eps, float bc1, float bc2, float wd, void* stream);
+/* Meta-training exchange fused with the outer update (train_dynavsr.py:438): grads_dev is a DEVICE array of n_peers pointers to
+ * the ranks' flat meta-gradient buffers (peer-mapped symmetric memory, NVLink), grad_offset the element offset of the gradient
+ * inside each buffer.  p -= update(scale * sum_r grads[r][i]) with Adam (adam != 0; torch.optim.Adam semantics as
+ * dvsr_update_adam) or SGD.  The caller barriers all ranks before (gradients complete) and after (buffers reusable). */
+int dvsr_update_peers(float* p, const float* const* grads_dev, int n_peers, long long grad_offset, float scale, float* m, float* v,
+                      long long n, long long split, float lr0, float lr1, float b1, float b2, float eps, float bc1, float bc2,
+                      float wd, int adam, void* stream);
 /* sum |x| over channels [c0, c1) of an NHWC tensor -> out[0] (+=); the `offset_mean > 100` check of
  * deform_conv.py:285-287 without a host sync per call. */
 int dvsr_abs_sum(const float* x, float* out, long long npix, int pix_stride, int c0, int c1, void* stream);

@@ -26,25 +26,66 @@ def nets():
 gen = torch.Generator().manual_seed(9)
 tasks = [{'LQs': torch.rand(1, 5, 3, 32, 32, generator=gen).cuda(), 'GT': torch.rand(1, 3, 128, 128, generator=gen).cuda(),
           'SuperLQs': torch.rand(1, 5, 3, 8, 8, generator=gen).cuda()} for _ in range(world)]
-kw = dict(inner_steps=1, lr_alpha=1e-3, inner_optimizer='SGD', criterion='l2', outer_optimizer='SGD', lr_outer=1e-2)
-ml = MetaLearner(*nets(), **kw)
-ml.outer_step([tasks[rank]])                       # sharded: one task per rank, one all-reduce
-mine = ml.theta.clone()
-# reference on every rank without the collective: both tasks locally.  per-task scaling 1/B with B = 2, and no averaging,
-# equals (1/1 per rank) averaged over 2 ranks.
-dist.barrier()
-import dynavsr_b200.dist as dd  # noqa: E402
-orig = dd.allreduce_flat_gradient
-dd.allreduce_flat_gradient = lambda g, average=True: g
-ml2 = MetaLearner(*nets(), **kw)
-ml2.outer_step(tasks)
-dd.allreduce_flat_gradient = orig
-theta0 = MetaLearner(*nets(), **kw).theta
-err = float(((mine - theta0) - (ml2.theta - theta0)).norm() / (ml2.theta - theta0).norm())
-all_same = [torch.zeros_like(mine) for _ in range(world)]
-dist.all_gather(all_same, mine)
-drift = max(float((t - mine).abs().max()) for t in all_same)
-if rank == 0:
-    print('meta step, %d ranks: sharded+allreduce vs single-process update rel %.3e; rank drift %.3e' % (world, err, drift))
-    assert err < 5e-3 and drift == 0.0
+kw = dict(inner_steps=1, lr_alpha=1e-3, inner_optimizer='SGD', criterion='l2', lr_outer=1e-2)
+theta0 = MetaLearner(*nets(), exchange='none', **kw).theta.clone()
+for outer in ('SGD', 'Adam'):
+    # single-process truth: both tasks locally, no collective.  Per-task scaling 1/B with B = world equals B = 1 per rank averaged
+    # over the ranks.
+    ref = MetaLearner(*nets(), outer_optimizer=outer, exchange='none', **kw)
+    for _ in range(2):
+        ref.outer_step(tasks)
+    for exch in ('peer', 'nccl'):
+        ml = MetaLearner(*nets(), outer_optimizer=outer, exchange=exch, **kw)
+        for _ in range(2):
+            ml.outer_step([tasks[rank]])          # sharded: one task per rank, one exchange per outer step
+        torch.cuda.synchronize()
+        err = float(((ml.theta - theta0) - (ref.theta - theta0)).norm() / (ref.theta - theta0).norm())
+        gathered = [torch.zeros_like(ml.theta) for _ in range(world)]
+        dist.all_gather(gathered, ml.theta)
+        drift = max(float((t - ml.theta).abs().max()) for t in gathered)
+        if rank == 0:
+            print('meta step x2, %d ranks, outer %s, exchange requested %s -> used %s: update vs single-process rel %.3e; rank drift %.3e'
+                  % (world, outer, exch, ml.exchange, err, drift), flush=True)
+            assert err < (5e-3 if outer == 'SGD' else 5e-2) and drift == 0.0
+        dist.barrier()
+# timing of the exchange + update alone (EDVR-M + MFDN flat buffer), both paths
+ml_p = MetaLearner(*nets(), outer_optimizer='Adam', exchange='peer', **kw)
+ml_n = MetaLearner(*nets(), outer_optimizer='Adam', exchange='nccl', **kw)
+import ctypes  # noqa: E402
+from dynavsr_b200._lib import call  # noqa: E402
+from dynavsr_b200 import dist as dd  # noqa: E402
+
+
+def t_peer():
+    h = ml_p._peer
+    h.barrier(channel=0)
+    call('dvsr_update_peers', ctypes.c_void_p(ml_p.theta.data_ptr()), ctypes.c_void_p(int(h.buffer_ptrs_dev)), world, 0, 1.0 / world,
+         ctypes.c_void_p(ml_p.m.data_ptr()), ctypes.c_void_p(ml_p.v.data_ptr()), ml_p.theta.numel(), ml_p.theta.numel(), 1e-5, 1e-5, 0.9, 0.99,
+         1e-8, 0.1, 0.01, 0.0, 1, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    h.barrier(channel=1)
+
+
+def t_nccl():
+    dd.allreduce_flat_gradient(ml_n.meta_grad, average=True)
+    call('dvsr_update_adam', ctypes.c_void_p(ml_n.theta.data_ptr()), ctypes.c_void_p(ml_n.meta_grad.data_ptr()), ctypes.c_void_p(ml_n.m.data_ptr()),
+         ctypes.c_void_p(ml_n.v.data_ptr()), ml_n.theta.numel(), ml_n.theta.numel(), 1e-5, 1e-5, 0.9, 0.99, 1e-8, 0.1, 0.01, 0.0,
+         ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+
+
+for name, fn in (('peer-memory fused exchange+Adam', t_peer), ('NCCL all-reduce + Adam launch', t_nccl)):
+    if name.startswith('peer') and ml_p._peer is None:
+        continue
+    for _ in range(5):
+        fn()
+    dist.barrier(); torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(50):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    tt = torch.tensor([a.elapsed_time(b) / 50 * 1e3], device='cuda')
+    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        print('%-34s %7.1f us per outer exchange (%.1f MB flat gradient, max over ranks)' % (name, float(tt), ml_p.theta.numel() * 4 / 1e6), flush=True)
 dist.destroy_process_group()
