@@ -226,6 +226,18 @@ class InnerLoopAdapter(object):
             self.last_losses = st['losses']
             return st['hr']
 
+    def set_meta_weights(self, state_dict_G=None, state_dict_E=None, strict=True):
+        """Replace the meta-weights every frame restarts from (e.g. after a meta-training step or when another checkpoint is
+        loaded).  The working copy still holds the LAST frame's adapted weights, so it is first restored, then overwritten,
+        then snapshotted; captured CUDA graphs pick the new weights (and their packs) up on the next call."""
+        with ops.scope(self.scope):
+            self.flat.restore()
+            if state_dict_G is not None:
+                self.netG.load_state_dict(state_dict_G, strict=strict)
+            if state_dict_E is not None:
+                self.netE.load_state_dict(state_dict_E, strict=strict)
+            self.flat.snapshot()
+
     def adapt_and_infer(self, lr_clip):
         """lr_clip: [B, N, 3, H, W] (reference tensor layout, host or device) -> HR [B, 3, sH, sW]."""
         B, N, C, H, W = lr_clip.shape

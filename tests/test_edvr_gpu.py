@@ -310,3 +310,58 @@ def test_full_size_tc_vs_fp32_cuda_core_path(mods):
     assert rel(out, ref) < NS_TOL
     base = torch.nn.functional.interpolate(x[:, 2], scale_factor=4, mode='bicubic', align_corners=False)
     assert abs(psnr_uint8(out, base) - psnr_uint8(ref, base)) < 0.01
+
+
+def test_vid4_shaped_window_tc_vs_exact_path(mods):
+    """BASELINE config 3 shape (Vid4 'city' LR 176x144 -> SLR 44x36): the tensor-core adaptation path against this library's
+    exact-fp32 path on the same window (CUDA graphs on), north-star tolerance."""
+    adapt, ops = mods[2], mods[3]
+    g = torch.Generator().manual_seed(9)
+    clip = torch.rand(1, 5, 3, 176, 144, generator=g)
+
+    def run(tc):
+        ops.set_conv_backend(tc)
+        try:
+            netG, _ = _edvr(mods, 1234)
+            netE, _ = _mfdn(mods, 77)
+            netF, _ = _mfdn(mods, 78)
+            eng = adapt.InnerLoopAdapter(netG, netE, netF, steps=2, lr_alpha=1e-5, optimizer='SGD', criterion='l2', use_graphs=tc)
+            out = eng.adapt_and_infer(clip).cpu()
+            return out, eng.last_losses.cpu()
+        finally:
+            ops.set_conv_backend(False)
+    ref, lref = run(False)
+    out, lout = run(True)
+    assert out.shape == (1, 3, 704, 576)
+    assert rel(out, ref) < NS_TOL and abs(psnr_uint8(out, ref)) > 60
+    assert np.allclose(lout.numpy(), lref.numpy(), rtol=2e-3)
+
+
+def test_graph_engine_follows_new_meta_weights(mods):
+    """New meta-weights after the graphs were captured (e.g. after a meta-training step): the captured restore-copy must pick
+    up the refreshed pack snapshot -- outputs equal those of a fresh engine built on the new weights (up to the run-to-run
+    jitter of the atomically accumulated weight gradients, ~3e-5 here)."""
+    adapt, ops = mods[2], mods[3]
+    from oracle import params as P
+    g = torch.Generator().manual_seed(3)
+    clip = torch.rand(1, 5, 3, 32, 48, generator=g)
+    ops.set_conv_backend(True)
+    try:
+        netG, _ = _edvr(mods, 1)
+        netE, _ = _mfdn(mods, 2)
+        netF, _ = _mfdn(mods, 3)
+        eng = adapt.InnerLoopAdapter(netG, netE, netF, steps=1, lr_alpha=1e-4, optimizer='SGD', criterion='l2', use_graphs=True)
+        a = eng.adapt_and_infer(clip).clone()
+        new = P.make_params(P.edvr_param_shapes(), seed=99)
+        eng.set_meta_weights(state_dict_G=new)       # restore (drop the last frame's adaptation), load, snapshot
+        b = eng.adapt_and_infer(clip).clone()
+        b2 = eng.adapt_and_infer(clip).clone()       # and again: restart from the NEW meta-weights
+        netG2, _ = _edvr(mods, 99)
+        netE2, _ = _mfdn(mods, 2)
+        netF2, _ = _mfdn(mods, 3)
+        fresh = adapt.InnerLoopAdapter(netG2, netE2, netF2, steps=1, lr_alpha=1e-4, optimizer='SGD', criterion='l2', use_graphs=False)
+        c = fresh.adapt_and_infer(clip)
+    finally:
+        ops.set_conv_backend(False)
+    assert rel(b, c) < 1e-4 and rel(b2, c) < 1e-4
+    assert rel(a, c) > 1e-2
