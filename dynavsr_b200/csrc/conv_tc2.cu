@@ -2,22 +2,32 @@
 //
 // Persistent tcgen05 implicit-GEMM convolution with SHARED-MEMORY-RESIDENT weights and halo reuse -- the
 // workhorse for EDVR's 64-channel 3x3 layers (feature extraction, PCD offset/feature convs, TSA, the
-// reconstruction trunk, HRconv) and the 1x1 fusion convs.
+// reconstruction trunk, upconv / HRconv / conv_last), the 1x1 fusion convs and MFDN's stride-1 layers.
 //
 // conv_tc.cu (v1) re-fetches, for every 128-pixel tile, nine tap-shifted copies of the activations plus the
 // whole weight tensor from L2: 432 KB per tile, which pins it at the L2 bandwidth (~5 TB/s, ~110 TFLOP/s).
 // Here
 //   * each CTA (one per SM, persistent over tiles) loads the weights of its 64 output channels ONCE
-//     (<= 147 KB: 9 taps x 64 ci x 64 co fp32, pre-rounded to TF32) and keeps them in shared memory;
-//   * per tile and 32-channel chunk ONE halo tile ((16+KH-1) x (8+KW-1) pixels) is TMA-loaded and rounded to
-//     TF32 in place; the KH*KW tap operands are descriptors that start at different 128-byte rows of that
-//     tile (stride-byte-offset = halo row pitch; validated by tools/umma_probe.cu P1);
-//   => 46 KB of L2 traffic per tile instead of 432 KB.
-//   * two TMEM accumulators (2 x 64 columns) so the epilogue of tile i overlaps the MMAs of tile i+1.
-// Warp roles: 0 = TMA producer, 1 = MMA issuer / TMEM owner, 2-5 = TF32 rounding of the halo tile,
-// 6-9 = epilogue (bias, ReLU / LeakyReLU / sigmoid-split, residual, PixelShuffle(2), K-split accumulation).
-// Output channels are processed in groups of 64 (blockIdx.y); inputs whose weights do not fit are K-split
-// over several launches by the host wrapper (`accum_in`).
+//     (<= 144 KiB) and keeps them in shared memory;
+//   * per tile and 32-channel chunk ONE halo tile ((16+KH-1) x (8+KW-1) pixels) is TMA-loaded and converted in
+//     place; the KH*KW tap operands are descriptors that start at different 128-byte rows of that tile
+//     (stride-byte-offset = halo row pitch; validated by tools/umma_probe.cu P1)  => 46 KB of L2 traffic per tile;
+//   * two TMEM accumulators so the epilogue of tile i overlaps the MMAs of tile i+1.
+// Precision (dvsr_conv_tc2_set_precision):
+//   BF16x3 (default) -- the split warps rewrite every 128-byte pixel row (32 fp32 channels) as [32 x bf16 hi | 32 x bf16 lo]
+//     (packed cvt.rn.bf16x2); weights are packed (pack modes 9 / 10) as 16 KiB blocks per (64-channel pair, tap) whose rows
+//     0-63 hold the hi parts and rows 64-127 the lo parts of the 64 output channels.  Per tap and k-step the MMA warp issues
+//     x_hi . [w_hi | w_lo] as ONE N = 128 MMA (columns [0,64) and [64,128) of the accumulator) and x_lo . w_hi as an N = 64 MMA
+//     into columns [0,64); the epilogue adds the two halves.  fp32-class accuracy (4.6e-6 per layer) at the speed of the
+//     single-pass TF32 mode, because one read of the activation operand serves two products.
+//   TF32 -- operands rounded to nearest in shared memory / at pack time (modes 5 / 6), one product (2.9e-4 per layer).
+// The kernel is bounded by shared-memory bandwidth (both MMA operands come from shared memory: 321 KB per chunk-tile at
+// 128 B/clk, see profiles/r1_conv_tc2_timeline.txt).
+// Warp roles: 0 = TMA producer, 1 = MMA issuer / TMEM owner, 2-5 = operand conversion of the halo tile,
+// 6-9 = epilogue (bias, ReLU / LeakyReLU / sigmoid-split, residual, PixelShuffle(2), K-split accumulation; scalar path for
+// narrow / unaligned outputs such as conv_last 64 -> 3).  Output channels are processed in groups of 64 (blockIdx.y); inputs
+// whose weights do not fit are K-split over several launches by the host wrapper (`accum_in`).  Grid policy: cta_budget() CTAs
+// at most and >= min_tiles tiles per CTA (throughput mode of adapt.AdaptationPool).
 #include "tc_common.cuh"
 #include "pack_device.cuh"
 

@@ -12,6 +12,9 @@
 //     the weights that stay resident in shared memory for the whole kernel (persistent CTAs, one per SM);
 //   * 4 epilogue warps drain the double-buffered TMEM accumulator (bias, LeakyReLU, 256-bit stores).
 // Exact reference sampling semantics: zero outside (-1,H)x(-1,W), per-corner bounds (kernel.cu:466-496,617).
+// Two gather variants: mdcn_tc_kernel reads the corners straight from global memory (256-bit loads, next stage's offsets
+// prefetched; any geometry, small launches); mdcn_tcs_kernel (below) stages an input window per tile in shared memory with
+// TMA and is used for the 3x3 / stride-1 launches of EDVR with at least two tiles per SM.
 #include "tc_common.cuh"
 
 namespace dvsr {
