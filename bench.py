@@ -173,7 +173,8 @@ def run_reference(args, rank):
     line = {'impl': 'reference', 'metric': METRIC, 'value': base['value'], 'unit': UNIT, 'n_gpus': args.gpus,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1000.0 / base['value'],
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': 'adapt2_sgd_l2 REDS4-shaped 5x3x180x320 (cropped 176x320) -> 3x704x1280, CPU sample'},
+            'config': {'workload': 'adapt2_sgd_l2+final_forward EDVR-M 4x + MFDN, REDS4-shaped 5x3x180x320 window cropped to %dx%d -> 3x%dx%d' % (
+                LR_H, LR_W, SCALE * LR_H, SCALE * LR_W), 'inner': INNER, 'arm': 'reference algorithm (oracle port), host cores, bounded sample'},
             'cpu_baseline': base,
             'e2e': {'value': base['value'], 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
     print(json.dumps(line))
