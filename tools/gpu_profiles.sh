@@ -15,7 +15,7 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:conv
 cap() {  # name regex skip count
   timeout 600 ncu --set full --clock-control none --import-source on -k "regex:$2" -s $3 -c $4 -o gpurun_out/prof_$1 -f python tools/one_frame.py 1 > gpurun_out/ncu_$1.log 2>&1
 }
-cap mdcn_fwd '^mdcn_tc_kernel$' 14 1          # 16 launches per frame: #15 = L1 DCN of the final forward (5x176x320)
+cap mdcn_fwd '^mdcn_tcs_kernel$' 2 1          # staged kernel: only the full-resolution launches use it; #3 = L1 DCN of the final forward
 cap tsa '^tsa_temporal_kernel$' 2 1           # 3 per frame: the third is the final forward
 cap mdcn_bwd '^mdcn_bwd_data_kernel$' 3 1     # L1 DCN backward of step 1 (5x44x80)
 cap wgrad '^conv_wgrad_tc_kernel$' 0 1
