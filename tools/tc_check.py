@@ -106,41 +106,5 @@ def main():
     print('tc_check done')
 
 
-
-
-def edvr_level():
-    """Whole-network parity of the tcgen05 path against the golden vectors of the reference."""
-    import numpy as np
-    from oracle import params as P
-    from dynavsr_b200 import adapt
-    from dynavsr_b200.models.archs import EDVR_arch, LRimg_estimator
-    gold = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tests', 'golden')
-    g = np.load(os.path.join(gold, 'edvr_m_32.npz'))
-    net = EDVR_arch.EDVR()
-    net.load_state_dict(P.make_params(P.edvr_param_shapes(), seed=int(g['seed'])))
-    net = net.cuda()
-    x = torch.from_numpy(g['x']).cuda()
-    ref = torch.from_numpy(g['out']).cuda()
-    for tc in (False, True):
-        ops.set_conv_backend(tc)
-        with torch.no_grad():
-            out = net(x)
-        print('EDVR forward vs reference golden, tc=%s: rel %.3e  maxabs %.3e' % (tc, rel(out, ref), float((out - ref).abs().max())), flush=True)
-    for tag, optimizer, crit in (('sgd2_l2', 'SGD', 'l2'), ('adam1_cb', 'Adam', 'cb')):
-        g = np.load(os.path.join(gold, 'adapt_%s.npz' % tag))
-        for tc in (False, True):
-            ops.set_conv_backend(tc)
-            netG = EDVR_arch.EDVR(); netG.load_state_dict(P.make_params(P.edvr_param_shapes(), seed=int(g['seed_G'])))
-            netE = LRimg_estimator.DirectKernelEstimatorVideo(64, 3, 4); netE.load_state_dict(P.make_params(P.mfdn_param_shapes(), seed=int(g['seed_E'])))
-            netF = LRimg_estimator.DirectKernelEstimatorVideo(64, 3, 4); netF.load_state_dict(P.make_params(P.mfdn_param_shapes(), seed=int(g['seed_E_fixed'])))
-            eng = adapt.InnerLoopAdapter(netG.cuda(), netE.cuda(), netF.cuda(), steps=int(g['steps']), lr_alpha=float(g['lr_alpha']),
-                                         optimizer=optimizer, betas=(0.9, 0.99), criterion=crit, use_graphs=False)
-            hr = eng.adapt_and_infer(torch.from_numpy(g['lr']))
-            print('adapt %s tc=%s: rel %.3e  losses %s (ref %s)' % (tag, tc, rel(hr, torch.from_numpy(g['out']).cuda()),
-                                                                     eng.last_losses.cpu().numpy(), g['losses']), flush=True)
-    ops.set_conv_backend(False)
-
-
 if __name__ == '__main__':
-    main()
-    edvr_level()
+    main()      # network-level parity against the reference goldens lives in tests/test_edvr_gpu.py
