@@ -21,8 +21,10 @@ namespace dvsr {
 
 constexpr int MD_ASTAGES = 4;
 constexpr int MD_A_BYTES = 128 * 128;     // 128 pixel rows x 128 B
-constexpr int MD_GATHER = 256;            // gather threads
-constexpr int MD_THREADS = 448;           // 1 producer + 1 MMA + 8 gather + 4 epilogue warps
+constexpr int MD_GATHER = 512;            // gather threads: one (pixel, deformable group of the chunk) each -- 16 warps, because the
+                                          // gather is a long dependent instruction stream per thread and needs warps, not ILP, to hide it
+constexpr int MD_PPT = 512 / MD_GATHER;   // pixels per gather thread (128 pixels x 4 groups per stage)
+constexpr int MD_THREADS = 64 + MD_GATHER + 128;   // 1 producer + 1 MMA + 16 gather + 4 epilogue warps
 
 struct MdParams {
     const float* x; int C, pix_stride; long long img_stride;
@@ -70,8 +72,8 @@ mdcn_tc_kernel(const __grid_constant__ CUtensorMap wmap, const MdParams p) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(128) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    if (threadIdx.x >= 320 && threadIdx.x < 384) {
-        const int co = threadIdx.x - 320;
+    if (threadIdx.x >= 64 && threadIdx.x < 128) {
+        const int co = threadIdx.x - 64;
         bias_s[co] = (p.bias && co < p.Co) ? __ldg(p.bias + co) : 0.f;
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -114,17 +116,17 @@ mdcn_tc_kernel(const __grid_constant__ CUtensorMap wmap, const MdParams p) {
                 if (++stage == MD_ASTAGES) { stage = 0; phase ^= 1; }
             }
         }
-    } else if (warp < 10) {
+    } else if (warp < 2 + MD_GATHER / 32) {
         // ===================== gather: modulated bilinear samples -> swizzled bf16 hi|lo operand rows =====================
         const int t = threadIdx.x - 64;                 // 0..255
         const int gl = t & 3;                           // deformable group inside the 32-channel chunk (8 channels each)
         int stage = 0, phase = 0;
         for (int tile = blockIdx.x; tile < p.tiles_total; tile += gridDim.x) {
             // the two pixels this thread serves in every stage of this tile
-            long long mlin[2]; int n_[2], oy[2], ox[2]; bool ok[2];
+            long long mlin[MD_PPT]; int n_[MD_PPT], oy[MD_PPT], ox[MD_PPT]; bool ok[MD_PPT];
 #pragma unroll
-            for (int i = 0; i < 2; ++i) {
-                const int prow = (t >> 2) + 64 * i;
+            for (int i = 0; i < MD_PPT; ++i) {
+                const int prow = (t >> 2) + (MD_GATHER / 4) * i;
                 mlin[i] = (long long)tile * 128 + prow;
                 ok[i] = mlin[i] < M;
                 const long long mm = ok[i] ? mlin[i] : 0;
@@ -134,11 +136,11 @@ mdcn_tc_kernel(const __grid_constant__ CUtensorMap wmap, const MdParams p) {
             }
             // offsets / mask of stage it + 1 are fetched while stage it gathers: one dependent memory round trip per stage
             // (offset -> corner addresses) instead of two
-            float ody[2], odx[2], omk[2], ndy[2] = {0.f, 0.f}, ndx[2] = {0.f, 0.f}, nmk[2] = {0.f, 0.f};
-            auto load_off = [&](int c, int tap, float (&dy)[2], float (&dx)[2], float (&mk)[2]) {
+            float ody[MD_PPT], odx[MD_PPT], omk[MD_PPT], ndy[MD_PPT] = {}, ndx[MD_PPT] = {}, nmk[MD_PPT] = {};
+            auto load_off = [&](int c, int tap, float (&dy)[MD_PPT], float (&dx)[MD_PPT], float (&mk)[MD_PPT]) {
                 const int g = c * 4 + gl;
 #pragma unroll
-                for (int i = 0; i < 2; ++i) {
+                for (int i = 0; i < MD_PPT; ++i) {
                     dy[i] = dx[i] = mk[i] = 0.f;
                     if (ok[i]) {
                         const float* op = p.offset + mlin[i] * p.off_pix_stride + (g * KK + tap) * 2;
@@ -159,8 +161,8 @@ mdcn_tc_kernel(const __grid_constant__ CUtensorMap wmap, const MdParams p) {
                     mbar_wait(&a_empty[stage], phase ^ 1);
                     uint8_t* tile_a = smem_a + stage * MD_A_BYTES;
 #pragma unroll
-                    for (int i = 0; i < 2; ++i) {
-                        const int prow = (t >> 2) + 64 * i;
+                    for (int i = 0; i < MD_PPT; ++i) {
+                        const int prow = (t >> 2) + (MD_GATHER / 4) * i;
                         float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
                         if (ok[i]) {
                             const float dy = ody[i], dx = odx[i], mk = omk[i];
@@ -199,7 +201,7 @@ mdcn_tc_kernel(const __grid_constant__ CUtensorMap wmap, const MdParams p) {
                     mbar_arrive(&a_ready[stage]);
                     if (++stage == MD_ASTAGES) { stage = 0; phase ^= 1; }
 #pragma unroll
-                    for (int i = 0; i < 2; ++i) { ody[i] = ndy[i]; odx[i] = ndx[i]; omk[i] = nmk[i]; }
+                    for (int i = 0; i < MD_PPT; ++i) { ody[i] = ndy[i]; odx[i] = ndx[i]; omk[i] = nmk[i]; }
                 }
             }
         }
@@ -299,8 +301,8 @@ mdcn_tcs_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant_
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(128) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    if (threadIdx.x >= 320 && threadIdx.x < 384) {
-        const int co = threadIdx.x - 320;
+    if (threadIdx.x >= 64 && threadIdx.x < 128) {
+        const int co = threadIdx.x - 64;
         bias_s[co] = (p.bias && co < p.Co) ? __ldg(p.bias + co) : 0.f;
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -355,7 +357,7 @@ mdcn_tcs_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant_
                 if (++stage == MDS_ASTAGES) { stage = 0; phase ^= 1; }
             }
         }
-    } else if (warp < 10) {
+    } else if (warp < 2 + MD_GATHER / 32) {
         // ===================== gather from the staged window =====================
         const int t = threadIdx.x - 64;                 // 0..255
         const int gl = t & 3;                           // deformable group inside the 32-channel chunk
@@ -365,10 +367,10 @@ mdcn_tcs_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant_
             const int tn = tile / tiles_per_img, tr = tile - tn * tiles_per_img;
             const int oy0 = (tr / p.tiles_w) * 16, ox0 = (tr % p.tiles_w) * 8;
             const int wy0 = oy0 - 1 - p.margin, wx0 = ox0 - 1 - p.margin;       // image coordinates of window pixel (0, 0)
-            long long mlin[2]; int oy[2], ox[2]; bool ok[2];
+            long long mlin[MD_PPT]; int oy[MD_PPT], ox[MD_PPT]; bool ok[MD_PPT];
 #pragma unroll
-            for (int i = 0; i < 2; ++i) {
-                const int prow = (t >> 2) + 64 * i;
+            for (int i = 0; i < MD_PPT; ++i) {
+                const int prow = (t >> 2) + (MD_GATHER / 4) * i;
                 oy[i] = oy0 + (prow >> 3);
                 ox[i] = ox0 + (prow & 7);
                 ok[i] = oy[i] < p.Ho && ox[i] < p.Wo;
@@ -378,9 +380,9 @@ mdcn_tcs_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant_
             for (int c = 0; c < chunks; ++c) {
                 const int g = c * 4 + gl;
                 // all 9 taps' offsets / masks of this thread's two pixels: independent loads in flight while the window lands
-                float ody[2][9], odx[2][9], omk[2][9];
+                float ody[MD_PPT][9], odx[MD_PPT][9], omk[MD_PPT][9];
 #pragma unroll
-                for (int i = 0; i < 2; ++i) {
+                for (int i = 0; i < MD_PPT; ++i) {
                     const float* op = p.offset + mlin[i] * p.off_pix_stride + g * KK * 2;
                     const float* mp = p.mask + mlin[i] * p.mask_pix_stride + g * KK;
 #pragma unroll
@@ -400,8 +402,8 @@ mdcn_tcs_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant_
                     mbar_wait(&a_empty[stage], phase ^ 1);
                     uint8_t* tile_a = smem_a + stage * MD_A_BYTES;
 #pragma unroll
-                    for (int i = 0; i < 2; ++i) {
-                        const int prow = (t >> 2) + 64 * i;
+                    for (int i = 0; i < MD_PPT; ++i) {
+                        const int prow = (t >> 2) + (MD_GATHER / 4) * i;
                         float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
                         const float h = (float)(oy[i] - 1 + kh) + ody[i][tap];
                         const float w = (float)(ox[i] - 1 + kw) + odx[i][tap];
