@@ -257,7 +257,13 @@ mdcn_tc_kernel(const __grid_constant__ CUtensorMap wmap, const MdParams p) {
 // into shared memory, and the 9 taps x 4 corners x 128 pixels x 4 groups bilinear reads of that chunk are served from there
 // (swizzled LDS.128 pairs) instead of L1/L2 -- 48 KB of L2 traffic per chunk-tile instead of ~590 KB.  Corners that a large
 // offset pushes outside the window fall back to the global 256-bit load, so the result is exact for any offset.
-constexpr int MDS_ASTAGES = 2;
+// Weights are NOT resident here: the gather, not the GEMM, bounds this kernel, and a measurement with the gather switched off
+// showed the 2-stage operand ring that resident weights left room for to be latency-bound (MMA completion -> slot-free
+// round trip: 267 us of 417 us).  Each stage therefore carries its own 8 KiB weight block, streamed by TMA from L2 (317 MB per
+// full-resolution call), which buys a 4-stage ring and a double-buffered input window.
+constexpr int MDS_ASTAGES = 4;             // (A operand tile 16 KiB + streamed weight block 8 KiB) per stage
+constexpr int MDS_STAGE_BYTES = MD_A_BYTES + 8192;
+constexpr int MDS_WINBUFS = 2;             // input window double-buffered: the TMA of chunk c+1 flies while chunk c is gathered
 
 __device__ __forceinline__ void lds8(uint32_t addr0, uint32_t addr1, float4& a, float4& b) {
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w) : "r"(addr0));
@@ -268,19 +274,18 @@ __global__ void __launch_bounds__(MD_THREADS, 1)
 mdcn_tcs_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__ CUtensorMap xmap, const MdParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    uint8_t* smem_b = smem;                                    // [nblocks][64 x 128 B] resident weights
-    uint8_t* smem_w = smem + p.nblocks * 8192;                 // input window [win_h * win_w][128 B], 128B-swizzled by TMA
-    uint8_t* smem_a = smem_w + p.win_bytes;                    // [MDS_ASTAGES][16 KiB]
-    uint64_t* bars = (uint64_t*)(smem_a + MDS_ASTAGES * MD_A_BYTES);
-    uint64_t* b_full = bars;                       // [1]
-    uint64_t* a_ready = bars + 1;                  // [2] 256 gather arrivals
-    uint64_t* a_empty = bars + 3;                  // [2] MMA commit
-    uint64_t* acc_full = bars + 5;                 // [2]
-    uint64_t* acc_empty = bars + 7;                // [2]
-    uint64_t* win_full = bars + 9;                 // [1] TMA
-    uint64_t* win_empty = bars + 10;               // [1] 256 gather arrivals
-    uint32_t* tmem_slot = (uint32_t*)(bars + 12);
-    float* bias_s = (float*)(bars + 14);           // [64]
+    uint8_t* smem_w = smem;                                    // [MDS_WINBUFS] input windows [win_h * win_w][128 B], 128B-swizzled by TMA
+    uint8_t* smem_a = smem_w + MDS_WINBUFS * p.win_bytes;      // [MDS_ASTAGES][A tile 16 KiB | weight block 8 KiB]
+    uint64_t* bars = (uint64_t*)(smem_a + MDS_ASTAGES * MDS_STAGE_BYTES);
+    uint64_t* w_full = bars;                       // [4] TMA weight block landed
+    uint64_t* a_ready = bars + 4;                  // [4] 512 gather arrivals
+    uint64_t* a_empty = bars + 8;                  // [4] MMA commit
+    uint64_t* acc_full = bars + 12;                // [2]
+    uint64_t* acc_empty = bars + 14;               // [2]
+    uint64_t* win_full = bars + 16;                // [2] TMA
+    uint64_t* win_empty = bars + 18;               // [2] 512 gather arrivals
+    uint32_t* tmem_slot = (uint32_t*)(bars + 20);
+    float* bias_s = (float*)(bars + 22);           // [64]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int KK = 9;
@@ -290,11 +295,9 @@ mdcn_tcs_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant_
     if (warp == 0 && elect_one()) { prefetch_tmap(&wmap); prefetch_tmap(&xmap); }
     if (warp == 1) {
         if (elect_one()) {
-            mbar_init(b_full, 1);
-            for (int i = 0; i < MDS_ASTAGES; ++i) { mbar_init(&a_ready[i], MD_GATHER); mbar_init(&a_empty[i], 1); }
+            for (int i = 0; i < MDS_ASTAGES; ++i) { mbar_init(&w_full[i], 1); mbar_init(&a_ready[i], MD_GATHER); mbar_init(&a_empty[i], 1); }
             for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
-            mbar_init(win_full, 1);
-            mbar_init(win_empty, MD_GATHER);
+            for (int i = 0; i < MDS_WINBUFS; ++i) { mbar_init(&win_full[i], 1); mbar_init(&win_empty[i], MD_GATHER); }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
@@ -311,19 +314,29 @@ mdcn_tcs_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant_
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ===================== producer: weights once, then one input window per (tile, chunk) =====================
+        // ===================== producer: input window per (tile, chunk), one weight block per stage =====================
         if (elect_one()) {
-            mbar_expect_tx(b_full, (uint32_t)p.nblocks * 8192u);
-            for (int b = 0; b < p.nblocks; ++b) tma_load_2d(&wmap, b_full, smem_b + b * 8192, 0, b * 64);
-            int wphase = 0;
-            for (int tile = blockIdx.x; tile < p.tiles_total; tile += gridDim.x) {
+            auto load_window = [&](int tile, int c, int cc) {          // cc = running chunk count of this CTA
+                const int wb = cc & 1;
                 const int tn = tile / tiles_per_img, tr = tile - tn * tiles_per_img;
                 const int oy0 = (tr / p.tiles_w) * 16, ox0 = (tr % p.tiles_w) * 8;
-                for (int c = 0; c < chunks; ++c) {
-                    mbar_wait_relaxed(win_empty, wphase ^ 1);
-                    mbar_expect_tx(win_full, (uint32_t)p.win_bytes);
-                    tma_load_4d(&xmap, win_full, smem_w, c * 32, ox0 - 1 - p.margin, oy0 - 1 - p.margin, tn);
-                    wphase ^= 1;
+                mbar_wait_relaxed(&win_empty[wb], ((cc >> 1) & 1) ^ 1);
+                mbar_expect_tx(&win_full[wb], (uint32_t)p.win_bytes);
+                tma_load_4d(&xmap, &win_full[wb], smem_w + wb * p.win_bytes, c * 32, ox0 - 1 - p.margin, oy0 - 1 - p.margin, tn);
+            };
+            int stage = 0, phase = 0, cc = 0;
+            if ((int)blockIdx.x < p.tiles_total) load_window(blockIdx.x, 0, 0);
+            for (int tile = blockIdx.x; tile < p.tiles_total; tile += gridDim.x) {
+                for (int c = 0; c < chunks; ++c, ++cc) {
+                    // window of the NEXT chunk (its buffer was freed when chunk cc - 1 finished)
+                    if (c + 1 < chunks) load_window(tile, c + 1, cc + 1);
+                    else if (tile + (int)gridDim.x < p.tiles_total) load_window(tile + (int)gridDim.x, 0, cc + 1);
+                    for (int tap = 0; tap < KK; ++tap) {
+                        mbar_wait_relaxed(&a_empty[stage], phase ^ 1, 32);
+                        mbar_expect_tx(&w_full[stage], 8192u);
+                        tma_load_2d(&wmap, &w_full[stage], smem_a + stage * MDS_STAGE_BYTES + MD_A_BYTES, 0, (c * KK + tap) * 64);
+                        if (++stage == MDS_ASTAGES) { stage = 0; phase ^= 1; }
+                    }
                 }
             }
         }
@@ -331,7 +344,6 @@ mdcn_tcs_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant_
         // ===================== MMA issuer (BF16x3) =====================
         const uint32_t idesc = make_idesc_bf16(128, 64);
         const uint64_t d_const = make_desc(0, 16, 1024, 2);
-        mbar_wait(b_full, 0);
         int stage = 0, phase = 0, local = 0;
         for (int tile = blockIdx.x; tile < p.tiles_total; tile += gridDim.x, ++local) {
             const int acc = local & 1;
@@ -339,11 +351,12 @@ mdcn_tcs_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant_
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t dcol = tmem_base + acc * 64;
             for (int it = 0; it < chunks * KK; ++it) {        // block order = chunk-major, then tap (pack mode 7)
-                mbar_wait_relaxed(&a_ready[stage], phase, 64);
+                mbar_wait(&w_full[stage], phase);
+                mbar_wait(&a_ready[stage], phase);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (elect_one()) {
-                    const uint64_t ad = d_const + (uint64_t)(smem_u32(smem_a + stage * MD_A_BYTES) >> 4);
-                    const uint64_t bd = d_const + (uint64_t)(smem_u32(smem_b + it * 8192) >> 4);
+                    const uint64_t ad = d_const + (uint64_t)(smem_u32(smem_a + stage * MDS_STAGE_BYTES) >> 4);
+                    const uint64_t bd = d_const + (uint64_t)(smem_u32(smem_a + stage * MDS_STAGE_BYTES + MD_A_BYTES) >> 4);
                     mma_bf16(dcol, ad, bd, idesc, it > 0 ? 1u : 0u);          // x_hi . w_hi
                     mma_bf16(dcol, ad + 2, bd + 2, idesc, 1u);
                     mma_bf16(dcol, ad + 4, bd, idesc, 1u);                    // x_lo . w_hi
@@ -361,8 +374,7 @@ mdcn_tcs_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant_
         // ===================== gather from the staged window =====================
         const int t = threadIdx.x - 64;                 // 0..255
         const int gl = t & 3;                           // deformable group inside the 32-channel chunk
-        const uint32_t win_s = smem_u32(smem_w);
-        int stage = 0, phase = 0, wphase = 0;
+        int stage = 0, phase = 0, cc = 0;
         for (int tile = blockIdx.x; tile < p.tiles_total; tile += gridDim.x) {
             const int tn = tile / tiles_per_img, tr = tile - tn * tiles_per_img;
             const int oy0 = (tr / p.tiles_w) * 16, ox0 = (tr % p.tiles_w) * 8;
@@ -394,13 +406,14 @@ mdcn_tcs_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant_
                         omk[i][tap] = ok[i] ? __ldg(mp + tap) : 0.f;
                     }
                 }
-                mbar_wait(win_full, wphase);
-                wphase ^= 1;
+                const int wb = cc & 1;
+                const uint32_t win_s = smem_u32(smem_w + wb * p.win_bytes);
+                mbar_wait(&win_full[wb], (cc >> 1) & 1);
 #pragma unroll
                 for (int tap = 0; tap < 9; ++tap) {
                     const int kh = tap / 3, kw = tap - kh * 3;
                     mbar_wait(&a_empty[stage], phase ^ 1);
-                    uint8_t* tile_a = smem_a + stage * MD_A_BYTES;
+                    uint8_t* tile_a = smem_a + stage * MDS_STAGE_BYTES;
 #pragma unroll
                     for (int i = 0; i < MD_PPT; ++i) {
                         const int prow = (t >> 2) + (MD_GATHER / 4) * i;
@@ -453,7 +466,8 @@ mdcn_tcs_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant_
                     mbar_arrive(&a_ready[stage]);
                     if (++stage == MDS_ASTAGES) { stage = 0; phase ^= 1; }
                 }
-                mbar_arrive(win_empty);                 // this thread is done reading the window of (tile, chunk)
+                mbar_arrive(&win_empty[wb]);            // this thread is done reading the window of (tile, chunk)
+                ++cc;
             }
         }
     } else {
@@ -583,7 +597,7 @@ extern "C" int dvsr_mdcn_tc_fprop(const dvsr_conv_desc* d, const float* wp, void
         CUresult r = encode(&xmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)g.ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         DVSR_REQUIRE(r == CUDA_SUCCESS, "mdcn_tc_fprop: cuTensorMapEncodeTiled(input window) failed with %d", (int)r);
-        const size_t smem_s = 1024 + (size_t)p.nblocks * 8192 + (size_t)p.win_bytes + (size_t)MDS_ASTAGES * MD_A_BYTES + 512;
+        const size_t smem_s = 1024 + (size_t)MDS_WINBUFS * p.win_bytes + (size_t)MDS_ASTAGES * MDS_STAGE_BYTES + 512;
         if (smem_s <= 232448) {
             static size_t smem_set_s = 0;
             if (smem_s > smem_set_s) {
