@@ -42,3 +42,34 @@ def test_multistep_restart_weights():
     sch2 = MultiStepLR_Restart(_Opt([1.0]), [2, 7], restarts=[4], weights=[0.5], gamma=0.1)
     sch2.load_state_dict(sd)
     assert sch2.last_epoch == sch.last_epoch
+
+
+def test_flat_params_layout_and_views():
+    """adapt.FlatParams is plain tensor bookkeeping until a kernel is launched: parameters become views of ONE flat buffer
+    (256-byte aligned slots), gradient slots alias ONE flat gradient, the second group starts at `split`, state_dict values and
+    keys survive, restore() brings the working copy back to the snapshot."""
+    from dynavsr_b200.adapt import FlatParams
+    torch.manual_seed(0)
+    a, b = torch.nn.Conv2d(3, 5, 3), torch.nn.Conv2d(5, 2, 1)
+    before = {k: v.clone() for k, v in list(a.state_dict().items()) + [('b.' + k, v) for k, v in b.state_dict().items()]}
+    fp = FlatParams([a, b])
+    sizes = [p.numel() for p in list(a.parameters()) + list(b.parameters())]
+    assert fp.offsets == [0, 192, 256, 320] and fp.numel == 384 and fp.split == 256      # 135 -> 192, 5 -> 64, 10 -> 64, 2 -> 64
+    for p, o, n in zip(fp.params, fp.offsets, sizes):
+        assert p.data.data_ptr() == fp.flat.data_ptr() + 4 * o and p._dvsr_grad.data_ptr() == fp.grad.data_ptr() + 4 * o
+        assert p._dvsr_grad.shape == p.shape and p._dvsr_scope is fp.scope
+    assert all(torch.equal(a.state_dict()[k], before[k]) for k in a.state_dict())
+    assert all(torch.equal(b.state_dict()[k], before['b.' + k]) for k in b.state_dict())
+    with torch.no_grad():
+        a.weight.add_(1.0)                       # an "adaptation step" on the working copy
+    assert float((fp.flat - fp.meta).abs().max()) == 1.0
+    fp.restore()
+    assert torch.equal(fp.flat, fp.meta) and torch.equal(a.weight, before['weight'])
+    fp.grad.fill_(2.0)
+    fp.zero_grad()
+    assert float(fp.grad.abs().max()) == 0.0
+    # explicit optimiser groups (Video_base_model.py:57-126): group 0 first, then group 1
+    c = torch.nn.Conv2d(3, 4, 1)
+    g = FlatParams([[c.bias], [c.weight]])
+    assert g.split == 64 and g.params[0] is c.bias and c.weight.data.data_ptr() == g.flat.data_ptr() + 4 * 64
+
