@@ -9,58 +9,53 @@ import torch
 from . import networks
 from .. import ops
 from ..optim import FlatOptimizer
-from .base_model import BaseModel, DataParallel, DistributedDataParallel
+from .base_model import BaseModel, DataParallel, DistributedDataParallel, NetWrapperMixin
 from .lr_scheduler import MultiStepLR_Restart
 from .Video_base_model import _LogDict, _PixelCriterion
 
 logger = logging.getLogger('base')
 
 
-class LRimgestimator_Model(BaseModel):
+class LRimgestimator_Model(NetWrapperMixin, BaseModel):
     def name(self):
         return 'Estimator_Model'
 
     def __init__(self, opt):
         super(LRimgestimator_Model, self).__init__(opt)
+        net_opt, self.train_opt = opt['network_E'], opt['train']
         self.rank = torch.distributed.get_rank() if opt['dist'] else -1
-        train_opt = opt['train']
-        self.train_opt = train_opt
-        ds = (opt.get('datasets') or {}).get('train')
-        self.kernel_size = ds['kernel_size'] if ds else None
-        self.patch_size = ds['patch_size'] if ds else None
-        self.batch_size = ds['batch_size'] if ds else None
-        self.scale = opt['scale']
-        self.model_name = opt['network_E']['which_model_E']
-        self.mode = opt['network_E']['mode']
+        self.scale, self.model_name, self.mode = opt['scale'], net_opt['which_model_E'], net_opt['mode']
         if self.mode == 'image':
             raise NotImplementedError("network_E.mode 'image' (SFDN) is not on the DynaVSR-R hot path (MFDN = 'video')")
+        train_set = (opt.get('datasets') or {}).get('train') or {}
+        for key in ('kernel_size', 'patch_size', 'batch_size'):
+            setattr(self, key, train_set.get(key))
 
-        self.netE = networks.define_E(opt).to(self.device)
-        self.netE = DistributedDataParallel(self.netE) if opt['dist'] else DataParallel(self.netE)
+        wrap = DistributedDataParallel if opt['dist'] else DataParallel
+        self.netE = wrap(networks.define_E(opt).to(self.device))
         self.load()
-
-        if train_opt['loss_ftn'] in ('l1', 'l2'):
-            self.MyLoss = _PixelCriterion(train_opt['loss_ftn'])
-        else:
-            self.MyLoss = None
+        kind = self.train_opt['loss_ftn']
+        self.MyLoss = _PixelCriterion(kind) if kind in ('l1', 'l2') else None
         self.log_dict = _LogDict()
-
         if self.is_train:
-            self.netE.train()
-            wd_R = train_opt['weight_decay_R'] if train_opt['weight_decay_R'] else 0
-            optim_params = [v for _, v in self.netE.named_parameters() if v.requires_grad]
-            self.optimizer_E = FlatOptimizer(optim_params, kind='Adam', lr=train_opt['lr_C'], weight_decay=wd_R)
-            self.optimizers = [self.optimizer_E]
-            if train_opt['lr_scheme'] == 'MultiStepLR':
-                self.schedulers = [MultiStepLR_Restart(o, train_opt['lr_steps'],
-                                                       gamma=train_opt['lr_gamma'] if train_opt['lr_gamma'] is not None else 0.1)
-                                   for o in self.optimizers]
-            else:
-                raise NotImplementedError('MultiStepLR learning rate scheme is enough.')
+            self._setup_training()
+
+    def _setup_training(self):
+        """Adam over the estimator's flat parameter buffer + restartable multi-step schedule (LRestimator_model.py:61-97)."""
+        t = self.train_opt
+        if t['lr_scheme'] != 'MultiStepLR':
+            raise NotImplementedError('MultiStepLR learning rate scheme is enough.')
+        self.netE.train()
+        trainable = [p for p in self.netE.parameters() if p.requires_grad]
+        self.optimizer_E = FlatOptimizer(trainable, kind='Adam', lr=t['lr_C'], weight_decay=t['weight_decay_R'] or 0)
+        self.optimizers = [self.optimizer_E]
+        gamma = 0.1 if t['lr_gamma'] is None else t['lr_gamma']
+        self.schedulers = [MultiStepLR_Restart(o, t['lr_steps'], gamma=gamma) for o in self.optimizers]
 
     def feed_data(self, data):
-        self.real_H = data['LQs'].to(self.device, non_blocking=True)
-        self.real_L = None if 'SuperLQs' not in data.keys() else data['SuperLQs'].to(self.device, non_blocking=True)
+        put = lambda t: t.to(self.device, non_blocking=True)
+        self.real_H = put(data['LQs'])
+        self.real_L = put(data['SuperLQs']) if 'SuperLQs' in data else None
         self.var_H = self.real_H.transpose(1, 2)        # B C T H W (LRestimator_model.py:103)
 
     def _forward(self):
@@ -88,29 +83,23 @@ class LRimgestimator_Model(BaseModel):
             self.fake_L = self._forward()
         self.netE.train()
 
-    def get_current_log(self):
-        return self.log_dict
-
     def get_current_visuals(self, need_GT=True):
-        out_dict = OrderedDict()
-        T = self.fake_L.size(1)
-        out_dict['LQ'] = self.real_L.detach()[0, T // 2].float().cpu()
-        out_dict['rlt'] = self.fake_L.detach()[0, T // 2].float().cpu()
+        mid = self.fake_L.size(1) // 2                       # centre frame of the clip
+        pick = lambda t: t.detach()[0, mid].float().cpu()
+        out = OrderedDict(LQ=pick(self.real_L), rlt=pick(self.fake_L))
         if need_GT:
-            out_dict['GT'] = self.real_H.detach()[0, T // 2].float().cpu()
-        return out_dict
+            out['GT'] = pick(self.real_H)
+        return out
 
     def print_network(self):
-        s, n = self.get_network_description(self.netE)
-        logger.info('Network R structure: {} - {}, with parameters: {:,d}'.format(
-            self.netE.__class__.__name__, self.netE.module.__class__.__name__, n))
-        logger.info(s)
+        self._log_structure(logger, self.netE, 'R')
 
     def load(self):
-        load_path_E = self.opt['path']['pretrain_model_E']
-        if load_path_E is not None:
-            logger.info('Loading pretrained model for E [{:s}] ...'.format(load_path_E))
-            self.load_network(load_path_E, self.netE)
+        ckpt = self.opt['path']['pretrain_model_E']
+        if ckpt is None:
+            return
+        logger.info('Loading pretrained model for E [{:s}] ...'.format(ckpt))
+        self.load_network(ckpt, self.netE)
 
     def save(self, iter_step):
         self.save_network(self.netE, 'E', iter_step)

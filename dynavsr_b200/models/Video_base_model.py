@@ -21,7 +21,7 @@ import torch
 from . import lr_scheduler, networks
 from .. import ops
 from ..optim import FlatOptimizer
-from .base_model import BaseModel, DataParallel, DistributedDataParallel
+from .base_model import BaseModel, DataParallel, DistributedDataParallel, NetWrapperMixin
 
 logger = logging.getLogger('base')
 
@@ -55,7 +55,7 @@ class _LogDict(OrderedDict):
         return [(k, self[k]) for k in self.keys()]
 
 
-class VideoBaseModel(BaseModel):
+class VideoBaseModel(NetWrapperMixin, BaseModel):
     def __init__(self, opt):
         super(VideoBaseModel, self).__init__(opt)
         self.rank = torch.distributed.get_rank() if opt['dist'] else -1
@@ -150,24 +150,16 @@ class VideoBaseModel(BaseModel):
             self.fake_H = self.netG(self.var_L)
         self.netG.train()
 
-    # ------------------------------------------------------------------ logs / visuals
-    def get_current_log(self):
-        return self.log_dict
-
+    # ------------------------------------------------------------------ visuals (log: NetWrapperMixin)
     def get_current_visuals(self, need_GT=True):
-        out_dict = OrderedDict()
-        out_dict['LQ'] = self.var_L.detach()[0].float().cpu()
-        out_dict['rlt'] = self.fake_H.detach()[0].float().cpu()
+        out = OrderedDict(LQ=self._cpu_frame(self.var_L), rlt=self._cpu_frame(self.fake_H))
         if need_GT:
-            out_dict['GT'] = self.real_H.detach()[0].float().cpu()
-        return out_dict
+            out['GT'] = self._cpu_frame(self.real_H)
+        return out
 
     def print_network(self):
-        s, n = self.get_network_description(self.netG)
         if self.rank <= 0:
-            logger.info('Network G structure: {} - {}, with parameters: {:,d}'.format(
-                self.netG.__class__.__name__, self.netG.module.__class__.__name__, n))
-            logger.info(s)
+            self._log_structure(logger, self.netG, 'G')
 
     # ------------------------------------------------------------------ checkpoints
     def load(self, verbose=True):
