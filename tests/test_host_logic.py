@@ -73,3 +73,108 @@ def test_flat_params_layout_and_views():
     g = FlatParams([[c.bias], [c.weight]])
     assert g.split == 64 and g.params[0] is c.bias and c.weight.data.data_ptr() == g.flat.data_ptr() + 4 * 64
 
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# BaseModel plumbing (codes/models/base_model.py:8-121): file names, key prefixes, warm-up ramp, state resume.
+def _toy_model(tmp_path):
+    import torch.nn as nn
+    from dynavsr_b200.models.base_model import BaseModel, DataParallel, NetWrapperMixin
+    from dynavsr_b200.models.lr_scheduler import MultiStepLR_Restart
+
+    class Toy(NetWrapperMixin, BaseModel):
+        pass
+
+    for sub in ('models', 'training_state'):
+        (tmp_path / sub).mkdir(exist_ok=True)
+    opt = {'gpu_ids': [0], 'is_train': True,
+           'path': {'models': str(tmp_path / 'models'), 'training_state': str(tmp_path / 'training_state')}}
+    m = Toy(opt)
+    m.net = DataParallel(nn.Sequential(nn.Linear(3, 4), nn.Linear(4, 2)))
+    o = torch.optim.SGD(m.net.parameters(), lr=0.1, momentum=0.9)
+    m.optimizers = [o]
+    m.schedulers = [MultiStepLR_Restart(o, [2, 4], gamma=0.5)]
+    m.log_dict = {'l_pix': 1.0}
+    return m
+
+
+def test_base_model_requires_gpu_ids():
+    from dynavsr_b200.models.base_model import BaseModel
+    with pytest.raises(NotImplementedError):
+        BaseModel({'gpu_ids': None, 'is_train': False})
+
+
+def test_base_model_warmup_and_schedule(tmp_path):
+    m = _toy_model(tmp_path)
+    lrs = []
+    for it in range(1, 7):
+        m.update_learning_rate(it, warmup_iter=3)
+        lrs.append(m.get_current_learning_rate()[0])
+    # iterations 1, 2 ramp linearly to initial_lr (0.1); afterwards the multi-step schedule (milestones 2, 4) is in force
+    assert lrs[0] == pytest.approx(0.1 / 3) and lrs[1] == pytest.approx(0.2 / 3)
+    assert lrs[2:] == pytest.approx([0.05, 0.025, 0.025, 0.025])
+    assert m.get_current_log() is m.log_dict
+
+
+def test_base_model_network_files_and_prefix_stripping(tmp_path):
+    import torch.nn as nn
+    m = _toy_model(tmp_path)
+    m.save_network(m.net, 'G', 1234)
+    path = tmp_path / 'models' / '1234_G.pth'
+    assert path.exists()
+    saved = torch.load(str(path))
+    assert list(saved) == ['0.weight', '0.bias', '1.weight', '1.bias']          # wrapper prefix never reaches the file
+    assert all(v.device.type == 'cpu' for v in saved.values())
+    # a checkpoint written from a torch DataParallel model carries 'module.' keys: they load into a bare network
+    prefixed = tmp_path / 'models' / 'dp.pth'
+    torch.save({'module.' + k: v + 1 for k, v in saved.items()}, str(prefixed))
+    fresh = nn.Sequential(nn.Linear(3, 4), nn.Linear(4, 2))
+    storage = fresh[0].weight.data_ptr()
+    m.load_network(str(prefixed), fresh)
+    assert fresh[0].weight.data_ptr() == storage                                 # copied INTO the existing storage
+    for k, v in fresh.state_dict().items():
+        assert torch.equal(v, saved[k] + 1)
+    with pytest.raises(RuntimeError):
+        m.load_network(str(prefixed), nn.Sequential(nn.Linear(3, 4)), strict=True)
+    text, count = m.get_network_description(m.net)
+    assert count == 3 * 4 + 4 + 4 * 2 + 2 and 'Linear' in text
+
+
+def test_base_model_training_state_round_trip(tmp_path):
+    m = _toy_model(tmp_path)
+    loss = m.net(torch.ones(1, 3)).sum()
+    loss.backward()
+    m.optimizers[0].step()
+    for it in range(1, 4):
+        m.update_learning_rate(it)
+    m.save_training_state(7, 300)
+    m.save_training_state(7, 300, model_type='E')
+    d = tmp_path / 'training_state'
+    assert (d / '300.state').exists() and (d / '300_E.state').exists()
+    state = torch.load(str(d / '300.state'))
+    assert state['epoch'] == 7 and state['iter'] == 300
+    m2 = _toy_model(tmp_path)
+    m2.resume_training(state)
+    assert m2.get_current_learning_rate() == m.get_current_learning_rate()
+    assert m2.schedulers[0].last_epoch == m.schedulers[0].last_epoch
+    buf = lambda mm: [s['momentum_buffer'] for s in mm.optimizers[0].state_dict()['state'].values()]
+    assert all(torch.equal(a, b) for a, b in zip(buf(m), buf(m2)))
+    m2.optimizers.append(m2.optimizers[0])
+    with pytest.raises(AssertionError):
+        m2.resume_training(state)
+
+
+def test_net_wrapper_structure_log(tmp_path):
+    import logging
+    m = _toy_model(tmp_path)
+    records = []
+
+    class H(logging.Handler):
+        def emit(self, r):
+            records.append(r.getMessage())
+
+    lg = logging.getLogger('test_structure')
+    lg.setLevel(logging.INFO)
+    lg.addHandler(H())
+    m._log_structure(lg, m.net, 'G')
+    assert 'DataParallel - Sequential' in records[0] and 'parameters: 26' in records[0]
