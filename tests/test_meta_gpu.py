@@ -111,3 +111,45 @@ def test_edvr_L_width_forward_backward_vs_oracle():
         # path pins the gradients; the tensor-core path is held to the output tolerance and a sanity band.
         for k, a, b in zip(keys, gd, gr):
             assert rel(a, b) < (1e-1 if tc else 1e-4), (tc, k)
+
+
+def test_reference_quirk_step_vs_reference_training_loop_golden():
+    """Product vs the reference's OWN training driver: tests/golden/meta_loop_sgd.npz holds the weights the unmodified
+    train_dynavsr.py main() leaves after one outer SGD step (lr 1 => update = accumulated gradient) on a narrow EDVR
+    (nf 8, 3 frames, 2 deformable groups) + MFDN; ``MetaLearner(reference_quirk=True)`` must take the same step."""
+    if not torch.cuda.is_available():
+        pytest.skip('no CUDA device')
+    import numpy as np
+    from util import gold
+    from oracle import params as P
+    from dynavsr_b200.meta import MetaLearner
+    from dynavsr_b200.models.archs import EDVR_arch, LRimg_estimator
+    g, s = gold('meta_loop.npz'), gold('meta_loop_sgd.npz')
+    nf, nframes, groups, front, back, nf_e, scale, batch, iters, inner = [int(v) for v in g['cfg']]
+    cfg = dict(nf=nf, nframes=nframes, groups=groups, front_RBs=front, back_RBs=back, scale=scale)
+    shapes_G, shapes_E = P.edvr_param_shapes(**cfg), P.mfdn_param_shapes(nf=nf_e, scale=scale)
+
+    def unflat(vec, shapes):
+        out, o = {}, 0
+        for k, shp in shapes.items():
+            n = int(np.prod(shp))
+            out[k] = torch.from_numpy(vec[o:o + n].reshape(shp).copy())
+            o += n
+        return out
+
+    sdG, sdE = unflat(g['G0'], shapes_G), unflat(g['E0'], shapes_E)
+    refG, refE = unflat(s['G1'], shapes_G), unflat(s['E1'], shapes_E)
+    netG = EDVR_arch.EDVR(**cfg)
+    netG.load_state_dict(sdG, strict=True)
+    netE = LRimg_estimator.DirectKernelEstimatorVideo(nf_e, 3, scale)
+    netE.load_state_dict(sdE, strict=True)
+    tasks = [{'LQs': torch.from_numpy(g['it0_LQs'][b:b + 1]).cuda(), 'GT': torch.from_numpy(g['it0_GT'][b:b + 1]).cuda(),
+              'SuperLQs': torch.from_numpy(g['it0_SuperLQs'][b:b + 1]).cuda()} for b in range(batch)]
+    ml = MetaLearner(netG.cuda(), netE.cuda(), inner_steps=inner, lr_alpha=1e-3, lr_alpha_est=2e-3, inner_optimizer='Adam',
+                     criterion='cb', est_loss='l1', outer_optimizer='SGD', lr_outer=float(s['lr_G']), reference_quirk=True)
+    total = ml.outer_step(tasks)
+    assert float(total) == pytest.approx(float(s['train_loss'][0]), rel=1e-4)
+    newG, newE = ml.state_dicts()
+    cat = lambda new, old, keys: torch.cat([(new[k].cpu() - old[k]).reshape(-1) for k in keys])
+    assert rel(cat(newG, sdG, shapes_G), cat(refG, sdG, shapes_G)) < 2e-3
+    assert rel(cat(newE, sdE, shapes_E), cat(refE, sdE, shapes_E)) < 2e-3

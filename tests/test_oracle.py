@@ -115,3 +115,96 @@ def test_edvr_variant_oracle_matches_reference_golden(tag, kw):
     y = O.edvr_forward(sd, torch.from_numpy(g[tag + '_x']), front_RBs=1, back_RBs=1, predeblur_=kw['predeblur'],
                        HR_in=kw['HR_in'], w_TSA=kw['w_TSA'])
     assert torch.equal(y, torch.from_numpy(g[tag + '_out']))
+
+
+def _meta_loop_fixture():
+    g = gold('meta_loop.npz')
+    nf, nframes, groups, front, back, nf_e, scale, batch, iters, inner = [int(v) for v in g['cfg']]
+    shapes_G = P.edvr_param_shapes(nf=nf, nframes=nframes, groups=groups, front_RBs=front, back_RBs=back, scale=scale)
+    shapes_E = P.mfdn_param_shapes(nf=nf_e, scale=scale)
+    assert list(g['keys_G']) == list(shapes_G) and list(g['keys_E']) == list(shapes_E)
+
+    def unflat(vec, shapes):
+        out, o = {}, 0
+        for k, s in shapes.items():
+            n = int(np.prod(s))
+            out[k] = torch.from_numpy(vec[o:o + n].reshape(s).copy())
+            o += n
+        assert o == vec.size
+        return out
+
+    cfg = dict(nf=nf, nframes=nframes, groups=groups, front_RBs=front, back_RBs=back)
+    return g, shapes_G, shapes_E, unflat, cfg, scale, batch, iters, inner
+
+
+def test_meta_oracle_vs_reference_training_loop():
+    """The loop structure of the outer step, pinned: tests/golden/meta_loop.npz holds the weights the UNMODIFIED
+    train_dynavsr.py main() leaves after each of two outer iterations (oracle/make_golden_meta.py ran it on CPU);
+    meta_oracle's ``as_written`` mode must land on the same weights from the same start, tasks and hyper-parameters."""
+    from oracle.meta_oracle import meta_outer_step
+    g, shapes_G, shapes_E, unflat, cfg, scale, batch, iters, inner = _meta_loop_fixture()
+    sdG, sdE = unflat(g['G0'], shapes_G), unflat(g['E0'], shapes_E)
+    # the start weights are the seeded ones (make_golden_meta.py re-seeds the reference modules with seeds 21 / 22)
+    for k, v in P.make_params(shapes_G, 21).items():
+        assert torch.equal(v, sdG[k])
+    state = None
+    for it in range(iters):
+        tasks = [{'LQs': torch.from_numpy(g['it%d_LQs' % it][b:b + 1]), 'GT': torch.from_numpy(g['it%d_GT' % it][b:b + 1]),
+                  'SuperLQs': torch.from_numpy(g['it%d_SuperLQs' % it][b:b + 1])} for b in range(batch)]
+        sdG, sdE, info = meta_outer_step(sdG, sdE, tasks, inner_steps=inner, lr_alpha=1e-3, lr_alpha_est=2e-3,
+                                         inner_optimizer='Adam', inner_betas=(0.9, 0.99), criterion='cb', est_loss='l1',
+                                         outer='Adam', lr_outer=1e-3, outer_betas=(0.9, 0.99), outer_state=state,
+                                         mode='as_written', scale=scale, edvr_cfg=cfg)
+        state = info['outer_state']
+        # 'Train loss' scalar of train_dynavsr.py:432 = sum of loss_q / batch
+        assert abs(sum(info['loss_q']) / batch - float(g['train_loss'][it])) < 1e-5
+        refG, refE = unflat(g['G%d' % (it + 1)], shapes_G), unflat(g['E%d' % (it + 1)], shapes_E)
+        prevG, prevE = unflat(g['G%d' % it], shapes_G), unflat(g['E%d' % it], shapes_E)
+        # compare the UPDATES (Adam's first steps are ~lr * sign(g): the weights themselves would agree trivially)
+        dG = torch.cat([(sdG[k] - prevG[k]).reshape(-1) for k in shapes_G])
+        dE = torch.cat([(sdE[k] - prevE[k]).reshape(-1) for k in shapes_E])
+        rG = torch.cat([(refG[k] - prevG[k]).reshape(-1) for k in shapes_G])
+        rE = torch.cat([(refE[k] - prevE[k]).reshape(-1) for k in shapes_E])
+        assert rel(dG, rG) < 2e-3, (it, rel(dG, rG))
+        assert rel(dE, rE) < 2e-3, (it, rel(dE, rE))
+        sdG, sdE = refG, refE            # continue from the reference's own weights (no drift accumulation)
+
+
+def test_meta_loop_golden_is_not_first_order_maml():
+    """Documents WHY there are two modes: on the same inputs the ``fomaml`` mode gives a different outer update than the
+    reference's training loop -- the reference loop does not adapt its working copy."""
+    from oracle.meta_oracle import meta_outer_step
+    g, shapes_G, shapes_E, unflat, cfg, scale, batch, iters, inner = _meta_loop_fixture()
+    sdG, sdE = unflat(g['G0'], shapes_G), unflat(g['E0'], shapes_E)
+    tasks = [{'LQs': torch.from_numpy(g['it0_LQs'][b:b + 1]), 'GT': torch.from_numpy(g['it0_GT'][b:b + 1]),
+              'SuperLQs': torch.from_numpy(g['it0_SuperLQs'][b:b + 1])} for b in range(batch)]
+    _, _, info = meta_outer_step(sdG, sdE, tasks, inner_steps=inner, lr_alpha=1e-3, lr_alpha_est=2e-3, criterion='cb',
+                                 outer='Adam', lr_outer=1e-3, mode='fomaml', scale=scale, edvr_cfg=cfg)
+    assert abs(sum(info['loss_q']) / batch - float(g['train_loss'][0])) > 1e-4
+
+
+def test_meta_oracle_outer_gradient_vs_reference_training_loop():
+    """Outer SGD with lr 1 makes the reference's update equal to its accumulated outer gradient: compare it with
+    meta_oracle's ``as_written`` gradient tensor by tensor (the Adam pin above is insensitive to gradient magnitudes)."""
+    from oracle.meta_oracle import meta_outer_step
+    g, shapes_G, shapes_E, unflat, cfg, scale, batch, iters, inner = _meta_loop_fixture()
+    s = gold('meta_loop_sgd.npz')
+    sdG, sdE = unflat(g['G0'], shapes_G), unflat(g['E0'], shapes_E)
+    refG, refE = unflat(s['G1'], shapes_G), unflat(s['E1'], shapes_E)
+    tasks = [{'LQs': torch.from_numpy(g['it0_LQs'][b:b + 1]), 'GT': torch.from_numpy(g['it0_GT'][b:b + 1]),
+              'SuperLQs': torch.from_numpy(g['it0_SuperLQs'][b:b + 1])} for b in range(batch)]
+    nG, nE, info = meta_outer_step(sdG, sdE, tasks, inner_steps=inner, lr_alpha=1e-3, lr_alpha_est=2e-3,
+                                   inner_optimizer='Adam', inner_betas=(0.9, 0.99), criterion='cb', est_loss='l1',
+                                   outer='SGD', lr_outer=float(s['lr_G']), mode='as_written', scale=scale, edvr_cfg=cfg)
+    assert abs(sum(info['loss_q']) / batch - float(s['train_loss'][0])) < 1e-5
+    worst = 0.0
+    for sd, ref, grads in ((sdG, refG, info['gG']), (sdE, refE, info['gE'])):
+        for k in sd:
+            g_ref = (sd[k] - ref[k]) / float(s['lr_G'])
+            scale_k = float(g_ref.abs().max())
+            assert scale_k > 0, k                      # every tensor receives gradient in the reference loop
+            # absolute error relative to the tensor's largest gradient entry; the reference's w - lr*g is rounded to fp32
+            err = float((grads[k] - g_ref).abs().max()) / max(scale_k, 1e-4)
+            worst = max(worst, err)
+            assert err < 1e-4, (k, err, scale_k)
+    assert rel(torch.cat([v.reshape(-1) for v in nG.values()]), torch.cat([v.reshape(-1) for v in refG.values()])) < 1e-6
