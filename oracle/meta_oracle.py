@@ -6,10 +6,13 @@ base weights; what the reference's own validation loop :633-677 does), ``as_writ
 training loop (the inner optimiser is bound to the copy, the loss to the original, :322-399 -- nothing adapts and the
 inner gradients pile up unscaled in the outer gradient).  See SURVEY.md section 3.2.
 
-Parity pin: the training driver is one 1100-line ``main()`` that imports imageio / lmdb (absent here) and cannot be
-called as a function, so this file is pinned only through the functions it is built from (edvr_forward / mfdn_forward /
-pixel_loss, themselves pinned against the unmodified reference modules by make_golden.py) and torch.optim -- the loop
-structure itself is "parity unpinned" and says so in DESIGN.md.
+Parity pin: oracle/make_golden_meta.py runs the UNMODIFIED ``main()`` of train_dynavsr.py on CPU (stand-ins only for
+absent modules, the data loader, output paths and the hard-coded ``.to('cuda')``) and stores the weights it leaves after
+outer Adam (two iterations) and outer SGD (lr 1: update = accumulated gradient) steps in tests/golden/meta_loop*.npz;
+``as_written`` reproduces the reference's accumulated outer gradient to 8e-8 relative
+(tests/test_oracle.py::test_meta_oracle_*).  ``fomaml`` has no reference counterpart to pin against (the reference's
+training loop never runs it): it is built from the pinned pieces (edvr_forward / mfdn_forward / pixel_loss, torch.optim)
+and differs from ``as_written`` only in which weights the losses are evaluated at.
 """
 import torch
 import torch.nn.functional as F
