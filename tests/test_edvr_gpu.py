@@ -365,3 +365,47 @@ def test_graph_engine_follows_new_meta_weights(mods):
         ops.set_conv_backend(False)
     assert rel(b, c) < 1e-4 and rel(b2, c) < 1e-4
     assert rel(a, c) > 1e-2
+
+
+def _driver_engine(mods, g, **kw):
+    from oracle import params as P
+    adapt = mods[2]
+    gain = float(g['head_gain'])
+    nets = []
+    for seed in (int(g['seed_G']), int(g['seed_baseline_G'])):
+        net, sd = _edvr(mods, seed)
+        sd['conv_last.weight'] *= gain             # oracle/make_golden_driver.tame_head: outputs inside [0, 1]
+        sd['conv_last.bias'] *= gain
+        net.load_state_dict(sd, strict=True)
+        nets.append(net)
+    netE, _ = _mfdn(mods, int(g['seed_E']))
+    netF, _ = _mfdn(mods, int(g['seed_E_fixed']))
+    eng = adapt.InnerLoopAdapter(nets[0], netE, netF, steps=int(g['steps']), lr_alpha=float(g['lr_alpha']),
+                                 optimizer=str(g['optimizer']), betas=(0.9, 0.99), criterion=str(g['criterion']),
+                                 slr_weight=10.0, **kw)
+    return eng, nets[1]
+
+
+@pytest.mark.parametrize('backend', ['fp32', 'tensor-core'])
+@pytest.mark.parametrize('tag', ['adam1_cb', 'sgd2_l2'])
+def test_adaptation_vs_reference_test_driver(mods, tag, backend):
+    """The north-star criterion against the reference's OWN driver: tests/golden/driver_<tag>.npz holds the frame, the PNG
+    bytes and the PSNR numbers the unmodified test_dynavsr.py main() produced for one clip (oracle/make_golden_driver.py).
+    Product: frame within 1e-3 relative, PSNR within 0.01 dB of the driver's psnr_update.csv, for both kernel paths."""
+    ops = mods[3]
+    g = gold('driver_%s.npz' % tag)
+    lq, gt = torch.from_numpy(g['lq']), torch.from_numpy(g['gt'])
+    ops.set_conv_backend(backend == 'tensor-core')
+    try:
+        eng, baseline = _driver_engine(mods, g, use_graphs=(backend == 'tensor-core'))
+        for rep in range(2):
+            hr = eng.adapt_and_infer(lq)[0].float().cpu()
+            assert rel(hr.clamp(0, 1), torch.from_numpy(g['out'])) < NS_TOL, rep
+            assert abs(psnr_uint8(hr, gt) - float(g['psnr_adapted'])) < 0.01, rep
+            image = (hr.clamp(0, 1) * 255.0).round().permute(1, 2, 0).numpy().astype(np.int32)
+            assert int(np.abs(image - g['image'].astype(np.int32)).max()) <= 1       # PNG bytes: at most one level off
+        with torch.no_grad():
+            base = baseline(lq.cuda())[0].float().cpu()
+        assert abs(psnr_uint8(base, gt) - float(g['psnr_baseline'])) < 0.01
+    finally:
+        ops.set_conv_backend(False)

@@ -208,3 +208,41 @@ def test_meta_oracle_outer_gradient_vs_reference_training_loop():
             worst = max(worst, err)
             assert err < 1e-4, (k, err, scale_k)
     assert rel(torch.cat([v.reshape(-1) for v in nG.values()]), torch.cat([v.reshape(-1) for v in refG.values()])) < 1e-6
+
+
+def _driver_weights(g):
+    gain = float(g['head_gain'])
+
+    def edvr(seed):
+        sd = P.make_params(P.edvr_param_shapes(), seed=seed)
+        sd['conv_last.weight'] *= gain             # make_golden_driver.tame_head: outputs inside [0, 1]
+        sd['conv_last.bias'] *= gain
+        return sd
+
+    return (edvr(int(g['seed_G'])), P.make_params(P.mfdn_param_shapes(), seed=int(g['seed_E'])),
+            P.make_params(P.mfdn_param_shapes(), seed=int(g['seed_E_fixed'])), edvr(int(g['seed_baseline_G'])))
+
+
+@pytest.mark.parametrize('tag', ['adam1_cb', 'sgd2_l2'])
+def test_adapt_oracle_vs_reference_test_driver(tag):
+    """tests/golden/driver_<tag>.npz is what the UNMODIFIED test_dynavsr.py main() produced for one clip (baseline
+    inference, deepcopy, K inner steps, final inference, tensor2img, PSNR -- oracle/make_golden_driver.py): the oracle's
+    adapt_and_infer must give the same frame, the same PNG bytes and the same PSNR."""
+    from util import psnr_uint8
+    g = gold('driver_%s.npz' % tag)
+    sdG, sdE, sdF, sdB = _driver_weights(g)
+    lq, gt = torch.from_numpy(g['lq']), torch.from_numpy(g['gt'])
+    out, losses, pG, pE = O.adapt_and_infer(sdG, sdE, sdF, lq, steps=int(g['steps']), lr_alpha=float(g['lr_alpha']),
+                                            optimizer=str(g['optimizer']), criterion=str(g['criterion']),
+                                            return_losses=True)
+    out = out[0].clamp(0, 1)                      # the driver's tensor2img clamps in place on CPU (utils/util.py:118)
+    assert rel(out, torch.from_numpy(g['out'])) < 1e-6
+    image = (out * 255.0).round().permute(1, 2, 0).numpy().astype(np.uint8)
+    assert int((image != g['image']).sum()) <= 16            # rounding ties only (measured: 0-6 of 73 728 bytes)
+    assert abs(psnr_uint8(out, gt) - float(g['psnr_adapted'])) < 1e-3
+    assert rel(pG['conv_first.weight'] - sdG['conv_first.weight'], torch.from_numpy(g['d_conv_first'])) < 1e-4
+    assert rel(pE['conv6.weight'] - sdE['conv6.weight'], torch.from_numpy(g['d_conv6'])) < 1e-4
+    with torch.no_grad():
+        base = O.edvr_forward(sdB, lq)[0]
+    assert abs(psnr_uint8(base, gt) - float(g['psnr_baseline'])) < 1e-3
+    assert float(g['psnr_adapted']) > float(g['psnr_baseline'])
