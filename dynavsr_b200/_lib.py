@@ -105,6 +105,7 @@ SIGNATURES = {
     'dvsr_degrade': [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P],
     'dvsr_spatial_mean': [_P, _P, _I, _I, _I, _P],
     'dvsr_add_channel_bias': [_P, _P, _P, _I, _I, _I, _F, _P],
+    'dvsr_frame_to_u8': [_P, _P, _P, _P, _LL, _I, _I, _P],
     'dvsr_act_bwd': [_P, _P, _P, _P, _P, _LL, _I, _I, _F, _I, _I, _I, _I, _P],
     'dvsr_tsa_temporal': [_P, _P, _P, _P, _P, _I, _I, _LL, _I, _P],
     'dvsr_tsa_temporal_bwd': [_P] * 8 + [_I, _I, _LL, _I, _P],

@@ -444,6 +444,45 @@ __global__ void act_bwd_kernel(const float* __restrict__ gy, const float* __rest
     }
 }
 
+// ---------------------------------------------------------------- frame -> 8-bit image (+ squared error vs a reference image)
+// utils/util.py:112-142 (tensor2img: clamp to [0, 1], * 255, round half to even, uint8, HWC, RGB or BGR) fused with the
+// integer part of calculate_psnr (:262-269): sse += sum (img - ref)^2, exact in 64-bit integers.  One thread makes four
+// consecutive output bytes (one 32-bit store).
+__global__ void frame_to_u8_kernel(const float* __restrict__ x, unsigned char* __restrict__ out,
+                                   const unsigned char* __restrict__ ref, unsigned long long* __restrict__ sse,
+                                   long long total, int C, int reverse) {
+    unsigned int err = 0;           // <= 4 * 255^2 per iteration; a thread makes < 2^14 iterations for any sane frame
+    const long long quads = (total + 3) / 4;
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < quads; q += (long long)gridDim.x * blockDim.x) {
+        unsigned int word = 0;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const long long i = q * 4 + e;
+            if (i >= total) break;
+            const long long pix = i / C;
+            const int c = (int)(i - pix * C);
+            const float v = __ldg(x + pix * C + (reverse ? C - 1 - c : c));
+            const int b = __float2int_rn(fminf(fmaxf(v, 0.f), 1.f) * 255.f);
+            word |= (unsigned int)b << (8 * e);
+            if (ref) {
+                const int d = b - (int)__ldg(ref + i);
+                err += (unsigned int)(d * d);
+            }
+        }
+        if (q * 4 + 3 < total) {
+            *reinterpret_cast<unsigned int*>(out + q * 4) = word;
+        } else {
+            for (int e = 0; q * 4 + e < total; ++e) out[q * 4 + e] = (unsigned char)(word >> (8 * e));
+        }
+    }
+    if (sse) {
+        unsigned long long e64 = err;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) e64 += __shfl_xor_sync(0xffffffffu, e64, o);
+        if ((threadIdx.x & 31) == 0 && e64) atomicAdd(sse, e64);
+    }
+}
+
 template <typename F>
 static int launch_1d(long long total, F f) {
     int blocks = (int)((total + 255) / 256);
@@ -646,6 +685,16 @@ extern "C" int dvsr_add_channel_bias(const float* x, const float* m, float* y, i
     const long long total = (long long)N * HW * C;
     launch_1d(total, [&](int b) { add_channel_bias_kernel<<<b, 256, 0, ST>>>(x, m, y, total, (long long)HW * C, C, sign); });
     return check_launch("add_channel_bias");
+}
+
+extern "C" int dvsr_frame_to_u8(const float* x, unsigned char* out, const unsigned char* ref, unsigned long long* sse,
+                                long long npix, int C, int reverse, void* stream) {
+    DVSR_REQUIRE(x && out && npix > 0 && C > 0, "frame_to_u8: bad arguments");
+    DVSR_REQUIRE((((uintptr_t)out) & 3) == 0, "frame_to_u8: the image buffer must be 4-byte aligned");
+    DVSR_REQUIRE(!sse || ref, "frame_to_u8: a squared-error accumulator needs a reference image");
+    const long long total = npix * C;
+    launch_1d((total + 3) / 4, [&](int b) { frame_to_u8_kernel<<<b, 256, 0, ST>>>(x, out, ref, sse, total, C, reverse); });
+    return check_launch("frame_to_u8");
 }
 
 extern "C" int dvsr_act_bwd(const float* gy, const float* y, const float* res, float* gpre, float* gbias, long long npix,

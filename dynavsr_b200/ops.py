@@ -16,7 +16,7 @@ from ._lib import ACT_LRELU, ACT_NONE, ACT_RELU, ACT_SIGMOID_SPLIT, ConvDesc, WL
 
 __all__ = ['conv3d_rgb', 'PackScope', 'new_scope', 'scope', 'repack_all', 'snapshot_packs', 'restore_packs', 'invalidate_pack_snapshot', 'weights_updated', 'join_async', 'Seg', 'conv', 'conv3d_padded', 'mdcn', 'upsample', 'pool_maxavg', 'pad2d', 'pad3d_replicate',
            'tsa_temporal', 'tsa_combine', 'pixel_loss', 'to_nhwc', 'to_nchw', 'invalidate_weight_cache',
-           'ACT_NONE', 'ACT_RELU', 'ACT_LRELU', 'ACT_SIGMOID_SPLIT', 'set_conv_backend']
+           'ACT_NONE', 'ACT_RELU', 'ACT_LRELU', 'ACT_SIGMOID_SPLIT', 'set_conv_backend', 'frame_to_u8']
 
 
 def _stream():
@@ -1050,3 +1050,23 @@ def abs_sum(x, c0, c1, out):
     """out[0] += sum |x[..., c0:c1]| (device-side accumulation of the offset-magnitude check)."""
     N, H, W, C = x.shape
     call('dvsr_abs_sum', _ptr(x), _ptr(out), N * H * W, C, c0, c1, _stream())
+
+
+def frame_to_u8(frame, out=None, ref=None, sse=None, bgr=False):
+    """Result frame -> 8-bit HWC image on the device (utils/util.py:112-142 tensor2img: clamp, * 255, round half to even).
+    ``frame``: [..., H, W, C] channels-last float32; ``out`` / ``ref``: uint8 tensors of the same shape; with ``ref`` and
+    ``sse`` (a one-element int64 device tensor the caller zeroed) the exact sum of squared differences between the new image
+    and ``ref`` is ADDED to ``sse`` -- the integer part of calculate_psnr (:262-269).  ``bgr`` reverses the channel order
+    (tensor2img's default mode; cv2.imwrite wants it).  Not differentiable."""
+    _check_cuda(frame)
+    frame = frame.detach().contiguous()
+    C = frame.shape[-1]
+    if out is None:
+        out = torch.empty(frame.shape, dtype=torch.uint8, device=frame.device)
+    for t in (out, ref):
+        if t is not None and (t.dtype != torch.uint8 or not t.is_cuda or not t.is_contiguous() or t.numel() != frame.numel()):
+            raise RuntimeError('frame_to_u8: image buffers must be contiguous CUDA uint8 tensors with the shape of the frame')
+    if sse is not None and (sse.dtype != torch.int64 or not sse.is_cuda or sse.numel() != 1):
+        raise RuntimeError('frame_to_u8: sse must be a one-element int64 CUDA tensor')
+    call('dvsr_frame_to_u8', _ptr(frame), _ptr(out), _ptr(ref), _ptr(sse), frame.numel() // C, C, 1 if bgr else 0, _stream())
+    return out

@@ -247,6 +247,14 @@ int dvsr_degrade(const float* x, const float* k, float* y, int T, int H, int W, 
 int dvsr_spatial_mean(const float* x, float* m, int N, int HW, int C, void* stream);
 int dvsr_add_channel_bias(const float* x, const float* m, float* y, int N, int HW, int C, float sign, void* stream);
 
+/* Result frame -> 8-bit image, the device half of utils/util.py:112-142 (tensor2img) + :262-269 (calculate_psnr):
+ * out[i] = uint8(rint(clamp(x, 0, 1) * 255)) for an [npix][C] channels-last frame (= the HWC image the reference writes),
+ * channel order kept (reverse = 0, 'rgb') or reversed (reverse = 1, the 'bgr' default of tensor2img).  With ref (an image
+ * of the same layout) and sse: *sse += sum (out - ref)^2, exact (PSNR = 20 log10(255 / sqrt(sse / (npix * C)))).
+ * out must be 4-byte aligned; the caller zeroes *sse. */
+int dvsr_frame_to_u8(const float* x, unsigned char* out, const unsigned char* ref, unsigned long long* sse,
+                     long long npix, int C, int reverse, void* stream);
+
 /* gpre = gy * act'(y - res) [+ un-PixelShuffle]; gbias[c] += sum_pix gpre[pix][c] (if gbias).  In-place allowed
  * when shuffle == 0.  y is the saved forward OUTPUT (relu / lrelu / sigmoid-split derivatives are functions of
  * it); res (optional) is the residual that the forward epilogue added AFTER the activation. */
