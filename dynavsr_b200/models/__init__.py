@@ -1,27 +1,28 @@
-"""Mirror of codes/models/__init__.py:5-37: ``create_model(opt)`` with the reference's model names and the
-``'video_base+lrimgestimator'`` -> ``[VideoBaseModel, LRimgestimator_Model]`` list order that test_dynavsr.py:105-109 and
-train_dynavsr.py:161-165 unpack.  Only the two wrappers on the DynaVSR hot path exist here."""
+"""Model factory with the reference's names (codes/models/__init__.py:5-37): ``create_model(opt)`` returns one wrapper, or
+for ``'a+b'`` a list in that order -- ``'video_base+lrimgestimator'`` -> ``[VideoBaseModel, LRimgestimator_Model]``, which is
+what test_dynavsr.py:105-109 and train_dynavsr.py:161-165 unpack.  Only the two wrappers on the DynaVSR hot path exist here."""
+import importlib
 import logging
 
 logger = logging.getLogger('base')
 
+_WRAPPERS = {'video_base': ('Video_base_model', 'VideoBaseModel'),
+             'lrimgestimator': ('LRestimator_model', 'LRimgestimator_Model')}
+_OUTSIDE_HOT_PATH = ('sr', 'srgan', 'classifier', 'estimator')
+
+
+def _build(name, opt):
+    if name not in _WRAPPERS:
+        why = 'is outside the DynaVSR hot path (SURVEY.md section 2 rows 20-21).' if name in _OUTSIDE_HOT_PATH \
+            else 'not recognized.'
+        raise NotImplementedError('Model [{:s}] {}'.format(name, why))
+    module, cls = _WRAPPERS[name]
+    wrapper = getattr(importlib.import_module('.' + module, __name__), cls)(opt)
+    logger.info('Model [{:s}] is created.'.format(cls))
+    return wrapper
+
 
 def create_model(opt):
-    models = opt['model']
-
-    def _create(model):
-        if model == 'video_base':
-            from .Video_base_model import VideoBaseModel as M
-        elif model == 'lrimgestimator':
-            from .LRestimator_model import LRimgestimator_Model as M
-        elif model in ('sr', 'srgan', 'classifier', 'estimator'):
-            raise NotImplementedError('Model [{:s}] is outside the DynaVSR hot path (SURVEY.md section 2 rows 20-21).'.format(model))
-        else:
-            raise NotImplementedError('Model [{:s}] not recognized.'.format(model))
-        m = M(opt)
-        logger.info('Model [{:s}] is created.'.format(m.__class__.__name__))
-        return m
-
-    if '+' in models:
-        return [_create(name) for name in models.split('+')]
-    return _create(models)
+    spec = opt['model']
+    built = [_build(name, opt) for name in spec.split('+')]
+    return built if '+' in spec else built[0]

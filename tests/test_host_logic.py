@@ -178,3 +178,27 @@ def test_net_wrapper_structure_log(tmp_path):
     lg.addHandler(H())
     m._log_structure(lg, m.net, 'G')
     assert 'DataParallel - Sequential' in records[0] and 'parameters: 26' in records[0]
+
+
+def test_create_model_names_and_order(monkeypatch):
+    """codes/models/__init__.py:5-37: 'a+b' -> list in that order, single name -> the wrapper itself, unknown names raise."""
+    import dynavsr_b200.models as M
+    from dynavsr_b200.models import LRestimator_model, Video_base_model
+
+    class G(object):
+        def __init__(self, opt):
+            self.opt = opt
+
+    class E(G):
+        pass
+
+    monkeypatch.setattr(Video_base_model, 'VideoBaseModel', G)
+    monkeypatch.setattr(LRestimator_model, 'LRimgestimator_Model', E)
+    opt = {'model': 'video_base+lrimgestimator'}
+    both = M.create_model(opt)
+    assert [type(m) for m in both] == [G, E] and both[0].opt is opt
+    assert [type(m) for m in M.create_model({'model': 'lrimgestimator+video_base'})] == [E, G]
+    assert type(M.create_model({'model': 'video_base'})) is G
+    for name, text in (('srgan', 'outside the DynaVSR hot path'), ('nope', 'not recognized')):
+        with pytest.raises(NotImplementedError, match=text):
+            M.create_model({'model': name})
