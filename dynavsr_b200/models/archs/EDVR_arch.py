@@ -13,7 +13,6 @@ hand-written sm_100a kernels of libdvsr_b200.so on channels-last tensors:
 """
 import functools
 
-import torch
 import torch.nn as nn
 
 from . import arch_util

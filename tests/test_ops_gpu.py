@@ -1,6 +1,5 @@
 """GPU parity tests of every kernel family against a plain PyTorch reference computed on CPU in
 float64 (tolerances are written at each assert; the north-star bar is 1e-3 relative fp32)."""
-import numpy as np
 import pytest
 import torch
 import torch.nn.functional as F

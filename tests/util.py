@@ -3,7 +3,6 @@ layout kernels are among the things under test)."""
 import os
 
 import numpy as np
-import torch
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 
