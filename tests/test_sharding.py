@@ -51,6 +51,16 @@ def _worker(rank, world, port, n_frames):
     g = torch.full((1000,), float(rank + 1))
     D.allreduce_flat_gradient(g, average=True)
     assert torch.allclose(g, torch.full((1000,), (1 + 2) / 2.0))
+    # evaluation tables (dynavsr_b200/driver.py): every rank holds its own frames' rows, rank 0 ends up with all of them
+    from collections import OrderedDict
+    from dynavsr_b200 import driver
+    rows = OrderedDict(('clip/%08d' % i, [28.0 + i, 31.0 + i, float('nan'), 0.9]) for i in D.shard_indices(n_frames, rank, world))
+    merged = driver.gather_rows(rows, dst=0)
+    if rank == 0:
+        assert list(merged) == ['clip/%08d' % i for i in range(n_frames)]
+        assert all(merged['clip/%08d' % i][1] == 31.0 + i for i in range(n_frames))
+    else:
+        assert merged is None
     dist.destroy_process_group()
 
 
