@@ -127,3 +127,33 @@ def test_evaluate_reproduces_reference_driver_table(cuda, mode, tmp_path):
             _lib.lib().dvsr_set_cta_budget(148)
             _lib.lib().dvsr_conv_tc2_set_min_tiles_per_cta(1)
             _lib.lib().dvsr_conv_wgrad_tc_set_min_chunks_per_cta(4)
+
+
+def test_resident_clips_feed_the_evaluation_loop(cuda):
+    """clips.ResidentClips (device-resident clip, GPU degradation, window gather) -> driver.evaluate: every row must equal
+    what the plain per-window API gives for that window (adapt_and_infer + host-side tensor2img / PSNR)."""
+    import torch.nn.functional as F
+    from util import psnr_uint8
+    from dynavsr_b200 import adapt, clips, driver
+    from dynavsr_b200.degradation import Degradation
+    g = gold('driver_sgd2_l2.npz')
+    netG, netE, netF, _ = _nets(g)
+    gen = torch.Generator().manual_seed(5)
+    hr = F.interpolate(torch.rand(1, 3, 10, 14, generator=gen), size=(128 + 8, 192 + 8), mode='bicubic', align_corners=False).clamp(0, 1)
+    hr = torch.stack([hr[0, :, t:t + 128, t:t + 192] for t in range(6)])          # a 6-frame panning clip [6, 3, 128, 192]
+    store = clips.ResidentClips(n_frames=5, padding='new_info', scale=4, device='cuda')
+    store.add_degraded('pan', hr, Degradation(21, 4, sigma=[1.6, 1.6]))
+    assert len(store) == 6
+    it = store.item(0)
+    assert it['LQs'].is_cuda and it['LQs'].shape == (5, 3, 32, 48) and it['GT'].shape == (5, 3, 128, 192)
+    assert it['SuperLQs'].shape == (5, 3, 8, 12) and store.window_indices(0) == [4, 3, 0, 1, 2]
+    eng = adapt.InnerLoopAdapter(netG, netE, netF, steps=2, lr_alpha=1e-4, optimizer='SGD', criterion='l2', slr_weight=10.0,
+                                 use_graphs=False)
+    rows = driver.evaluate(eng, store, compute_ssim=False)
+    assert list(rows) == ['pan/%08d' % i for i in range(6)]
+    for i in (0, 3, 5):
+        d = store[i]
+        out = eng.adapt_and_infer(d['LQs'])[0]
+        want = psnr_uint8(out, d['GT'][0, 2])
+        assert abs(rows['pan/%08d' % i][1] - want) < 1e-3, (i, rows['pan/%08d' % i][1], want)
+    assert len({round(v[1], 3) for v in rows.values()}) > 1                       # the windows really differ
