@@ -107,8 +107,13 @@ class VideoBaseModel(NetWrapperMixin, BaseModel):
                         optimizer, train_opt['lr_steps'], restarts=train_opt['restarts'], weights=train_opt['restart_weights'],
                         gamma=train_opt['lr_gamma'] if train_opt['lr_gamma'] is not None else 0.1,
                         clear_state=train_opt['clear_state']))
+            elif train_opt['lr_scheme'] == 'CosineAnnealingLR_Restart':
+                for optimizer in self.optimizers:
+                    self.schedulers.append(lr_scheduler.CosineAnnealingLR_Restart(
+                        optimizer, train_opt['T_period'], eta_min=train_opt['eta_min'], restarts=train_opt['restarts'],
+                        weights=train_opt['restart_weights']))
             elif train_opt['lr_scheme'] is not None:
-                raise NotImplementedError('lr_scheme [{}]: only MultiStepLR is on the DynaVSR path'.format(train_opt['lr_scheme']))
+                raise NotImplementedError('lr_scheme [{}] is not a DynaVSR scheme'.format(train_opt['lr_scheme']))
 
     # ------------------------------------------------------------------ data
     def feed_data(self, data, need_GT=True):

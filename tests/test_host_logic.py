@@ -202,3 +202,28 @@ def test_create_model_names_and_order(monkeypatch):
     for name, text in (('srgan', 'outside the DynaVSR hot path'), ('nope', 'not recognized')):
         with pytest.raises(NotImplementedError, match=text):
             M.create_model({'model': name})
+
+
+@pytest.mark.parametrize('case', ['cosine_restarts', 'cosine_two_groups', 'multistep_restarts'])
+def test_lr_schedules_match_reference_traces(case):
+    """tests/golden/lr_schedules.json: per-iteration learning rates of the UNMODIFIED reference scheduler classes
+    (oracle/make_golden_lr.py), incl. weighted restarts, two parameter groups and running past the last cosine period."""
+    import json
+    import os
+    from util import GOLD
+    from dynavsr_b200.models import lr_scheduler as S
+    c = json.load(open(os.path.join(GOLD, 'lr_schedules.json')))[case]
+    params = [torch.nn.Parameter(torch.zeros(1)) for _ in c['lrs']]
+    opt = torch.optim.SGD([{'params': [p], 'lr': lr} for p, lr in zip(params, c['lrs'])], lr=c['lrs'][0])
+    cls = S.CosineAnnealingLR_Restart if c['kind'] == 'cosine' else S.MultiStepLR_Restart
+    sch = cls(opt, **c['kw'])
+    floor = 1e-12 * max(c['lrs'])              # the reference's recursion reaches the troughs with ~1e-20 of rounding residue
+    for t, want in enumerate(c['trace']):
+        sch.step()
+        got = [g['lr'] for g in opt.param_groups]
+        assert got == pytest.approx(want, rel=1e-9, abs=floor), (t, got, want)
+    # resuming from a state dict continues the same trace
+    sch2 = cls(torch.optim.SGD([{'params': [p], 'lr': lr} for p, lr in zip(params, c['lrs'])], lr=c['lrs'][0]), **c['kw'])
+    sch2.load_state_dict({'last_epoch': 9})
+    sch2.step()
+    assert [g['lr'] for g in sch2.optimizer.param_groups] == pytest.approx(c['trace'][9], rel=1e-9, abs=floor)
