@@ -28,6 +28,7 @@ import torch
 from . import ops
 
 COLUMNS = ['PSNR_Bicubic', 'PSNR_Ours', 'SSIM_Bicubic', 'SSIM_Ours']        # test_dynavsr.py:118
+_DEVICE = 'cuda'            # the loop's tensors live here (host-logic tests substitute stand-ins for the device pieces)
 
 
 def psnr_from_sse(sse, n):
@@ -119,7 +120,8 @@ class _PinnedRing(object):
     """Pinned host image buffers reused round-robin; a slot is handed out again only after its job has finished."""
 
     def __init__(self, shape, slots):
-        self.buffers = [torch.empty(shape, dtype=torch.uint8).pin_memory() for _ in range(slots)]
+        pin = (lambda t: t.pin_memory()) if torch.cuda.is_available() else (lambda t: t)
+        self.buffers = [pin(torch.empty(shape, dtype=torch.uint8)) for _ in range(slots)]
         self.free = queue.Queue()
         for i in range(slots):
             self.free.put(i)
@@ -151,7 +153,7 @@ class _SseTable(object):
     def cell(self, i):
         b, o = divmod(i, self.BLOCK)
         while b >= len(self.blocks):
-            self.blocks.append(torch.zeros(self.BLOCK, dtype=torch.int64, device='cuda'))
+            self.blocks.append(torch.zeros(self.BLOCK, dtype=torch.int64, device=_DEVICE))
         return self.blocks[b][o:o + 1]
 
     def tolist(self):
@@ -218,13 +220,18 @@ def evaluate(engine, loader, baseline_netG=None, with_GT=True, save_dir=None, co
             ring = rings[shape]
             i = len(records)
             records.append((name, h * scale * w * scale * C))
-            frames = ops.to_nhwc(lq.to('cuda', non_blocking=True).reshape(N, C, h, w))
+            frames = ops.to_nhwc(lq.to(_DEVICE, non_blocking=True).reshape(N, C, h, w))
             gt_u8, gt_img = None, [None]
             if with_GT:
                 gt = data['GT'][0, N // 2]                                              # :183
-                gt_u8 = ops.frame_to_u8(ops.to_nhwc(gt.unsqueeze(0).to('cuda', non_blocking=True))[0])
+                gt_u8 = ops.frame_to_u8(ops.to_nhwc(gt.unsqueeze(0).to(_DEVICE, non_blocking=True))[0])
+            gt_ready = None
+            if with_GT and compute_ssim and gt.is_cuda:
+                gt_ready = torch.cuda.Event()          # a device-resident clip: the writer thread reads ``gt`` on ITS stream,
+                gt_ready.record()                      # so it first waits until this stream has produced the frame
 
-            def ssim_job(kind, gt=gt if with_GT else None, gt_img=gt_img, name=name, folder=folder, idx_d=idx_d):
+            def ssim_job(kind, gt=gt if with_GT else None, gt_img=gt_img, name=name, folder=folder, idx_d=idx_d,
+                         gt_ready=gt_ready):
                 def job(img):
                     if kind == 1 and save_dir is not None:                              # :158-165, :283
                         d = os.path.join(save_dir, folder, 'DynaVSR')
@@ -232,6 +239,8 @@ def evaluate(engine, loader, baseline_netG=None, with_GT=True, save_dir=None, co
                         sink(os.path.join(d, '{:08d}.png'.format(idx_d)), img)
                     if compute_ssim and gt is not None:
                         if gt_img[0] is None:       # jobs run one at a time on the writer thread
+                            if gt_ready is not None:
+                                gt_ready.synchronize()
                             gt_img[0] = _host_image(gt)
                         v = ssim_u8(img, gt_img[0])
                         with lock:
