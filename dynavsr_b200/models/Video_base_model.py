@@ -7,7 +7,7 @@ B200-first differences behind the same API:
   * the pixel loss value AND its gradient come from one kernel (``ops.pixel_loss``: l1 / l2 / cb / huber,
     Video_base_model.py:39-50, loss.py:5-30);
   * parameters live in one flat buffer; ``optimizer_G`` is a ``FlatOptimizer`` (one launch per step, same
-    ``param_groups`` interface, the ``ft_tsa_only`` / ``small_offset_lr`` groupings of :57-126 kept);
+    ``param_groups`` interface, the reference's effective ``ft_tsa_only`` / ``small_offset_lr`` groupings: ``param_group_spec``);
   * ``log_dict['l_pix']`` is a device scalar, converted to float when the log is read (the reference's ``.item()`` per
     step, :178,:189,:194, is a host sync on the critical path);
   * one process drives one GPU: the DataParallel / DDP wrappers are a ``.module`` pass-through (base_model.py here).
@@ -55,6 +55,27 @@ class _LogDict(OrderedDict):
         return [(k, self[k]) for k in self.keys()]
 
 
+def param_group_spec(names, train_opt):
+    """Optimiser groups ``[(lr, [parameter names]), ...]`` exactly as the reference ends up with them
+    (Video_base_model.py:57-130), which is not what its options suggest: the two groups built for ``ft_tsa_only`` (:57-78)
+    are overwritten by the ``freeze_front`` / ``small_offset_lr`` / else chain that follows (:79-130).  So
+
+      * ``small_offset_lr``: [others at lr_G, {pcd_align, fea_L*, feature_extraction, conv_first} at 0.1 * lr_G], with or
+        without ``ft_tsa_only``;
+      * otherwise ONE group with every parameter -- also for ``ft_tsa_only`` alone, where ``set_params_lr_zero`` (:161-163)
+        then zeroes the rate of everything for the first ``ft_tsa_only`` iterations (and the chained schedule keeps it at
+        zero until a restart: models/lr_scheduler.py here).
+
+    Checked against the unmodified reference class (tests/golden/wrapper_train.json)."""
+    lr = train_opt['lr_G']
+    if train_opt['freeze_front']:
+        raise NotImplementedError('freeze_front targets DUF layer names (Video_base_model.py:79-97); EDVR only here')
+    if train_opt['small_offset_lr']:
+        slow = lambda k: any(t in k for t in ('pcd_align', 'fea_L', 'feature_extraction', 'conv_first'))
+        return [(lr, [k for k in names if not slow(k)]), (lr * 0.1, [k for k in names if slow(k)])]   # "normal params first"
+    return [(lr, list(names))]
+
+
 class VideoBaseModel(NetWrapperMixin, BaseModel):
     def __init__(self, opt):
         super(VideoBaseModel, self).__init__(opt)
@@ -80,21 +101,12 @@ class VideoBaseModel(NetWrapperMixin, BaseModel):
                 if not v.requires_grad and self.rank <= 0:
                     logger.warning('Params [{:s}] will not optimize.'.format(k))
             named = [(k, v) for k, v in named if v.requires_grad]
-            if train_opt['freeze_front']:
-                raise NotImplementedError('freeze_front targets DUF layer names (Video_base_model.py:79-97); EDVR only here')
-            if train_opt['ft_tsa_only']:
-                sel = lambda k: 'tsa_fusion' in k
-                lrs = (train_opt['lr_G'], train_opt['lr_G'])
-            elif train_opt['small_offset_lr']:
-                sel = lambda k: any(t in k for t in ('pcd_align', 'fea_L', 'feature_extraction', 'conv_first'))
-                lrs = (train_opt['lr_G'], train_opt['lr_G'] * 0.1)
+            spec = param_group_spec([k for k, _ in named], train_opt)
+            by_name = dict(named)
+            if len(spec) == 1:
+                optim_params = [by_name[k] for k in spec[0][1]]
             else:
-                sel, lrs = None, None
-            if sel is None:
-                optim_params = [v for _, v in named]
-            else:       # "normal params first" (:64-73,:113-122)
-                optim_params = [{'params': [v for k, v in named if not sel(k)], 'lr': lrs[0]},
-                                {'params': [v for k, v in named if sel(k)], 'lr': lrs[1]}]
+                optim_params = [{'params': [by_name[k] for k in names], 'lr': lr} for lr, names in spec]
             kind = 'SGD' if train_opt['optim'] == 'SGD' else 'Adam'
             betas = (train_opt['beta1'] if train_opt['beta1'] is not None else 0.9,
                      train_opt['beta2'] if train_opt['beta2'] is not None else 0.999)

@@ -110,9 +110,10 @@ def test_base_model_warmup_and_schedule(tmp_path):
     for it in range(1, 7):
         m.update_learning_rate(it, warmup_iter=3)
         lrs.append(m.get_current_learning_rate()[0])
-    # iterations 1, 2 ramp linearly to initial_lr (0.1); afterwards the multi-step schedule (milestones 2, 4) is in force
-    assert lrs[0] == pytest.approx(0.1 / 3) and lrs[1] == pytest.approx(0.2 / 3)
-    assert lrs[2:] == pytest.approx([0.05, 0.025, 0.025, 0.025])
+    # iterations 1, 2: the warm-up writes initial_lr * it / 3 over whatever the schedule computed (milestone 2 included); from
+    # iteration 3 on the CHAINED schedule carries the last warm-up value (0.2 / 3) forward and halves it at milestone 4 --
+    # the reference's behaviour (torch chained schedulers; trace 'multistep_warmup' in tests/golden/lr_schedules.json)
+    assert lrs == pytest.approx([0.1 / 3, 0.2 / 3, 0.2 / 3, 0.1 / 3, 0.1 / 3, 0.1 / 3])
     assert m.get_current_log() is m.log_dict
 
 
@@ -204,26 +205,73 @@ def test_create_model_names_and_order(monkeypatch):
             M.create_model({'model': name})
 
 
-@pytest.mark.parametrize('case', ['cosine_restarts', 'cosine_two_groups', 'multistep_restarts'])
-def test_lr_schedules_match_reference_traces(case):
+@pytest.mark.parametrize('case', ['cosine_restarts', 'cosine_two_groups', 'multistep_restarts', 'multistep_warmup',
+                                  'multistep_zero_group0', 'cosine_warmup'])
+def test_lr_schedules_match_reference_traces(case, tmp_path):
     """tests/golden/lr_schedules.json: per-iteration learning rates of the UNMODIFIED reference scheduler classes
-    (oracle/make_golden_lr.py), incl. weighted restarts, two parameter groups and running past the last cosine period."""
+    (oracle/make_golden_lr.py), incl. weighted restarts, two parameter groups, running past the last cosine period, and --
+    driven through ``BaseModel.update_learning_rate`` -- rates written from outside (warm-up, a group frozen at zero), which
+    the reference's chained schedulers carry forward."""
     import json
     import os
     from util import GOLD
     from dynavsr_b200.models import lr_scheduler as S
     c = json.load(open(os.path.join(GOLD, 'lr_schedules.json')))[case]
-    params = [torch.nn.Parameter(torch.zeros(1)) for _ in c['lrs']]
-    opt = torch.optim.SGD([{'params': [p], 'lr': lr} for p, lr in zip(params, c['lrs'])], lr=c['lrs'][0])
-    cls = S.CosineAnnealingLR_Restart if c['kind'] == 'cosine' else S.MultiStepLR_Restart
-    sch = cls(opt, **c['kw'])
+
+    def build():
+        params = [torch.nn.Parameter(torch.zeros(1)) for _ in c['lrs']]
+        opt = torch.optim.SGD([{'params': [p], 'lr': lr} for p, lr in zip(params, c['lrs'])], lr=c['lrs'][0])
+        cls = S.CosineAnnealingLR_Restart if c['kind'] == 'cosine' else S.MultiStepLR_Restart
+        return opt, cls(opt, **c['kw'])
+
+    opt, sch = build()
     floor = 1e-12 * max(c['lrs'])              # the reference's recursion reaches the troughs with ~1e-20 of rounding residue
+    outside = c.get('warmup_iter') is not None or c.get('zero_group0_before') is not None
+    if outside:
+        m = _toy_model(tmp_path)
+        m.optimizers, m.schedulers = [opt], [sch]
     for t, want in enumerate(c['trace']):
-        sch.step()
+        if outside:
+            m.update_learning_rate(t + 1, warmup_iter=c.get('warmup_iter') or -1)
+            if t + 1 < (c.get('zero_group0_before') or 0):
+                opt.param_groups[0]['lr'] = 0
+        else:
+            sch.step()
         got = [g['lr'] for g in opt.param_groups]
         assert got == pytest.approx(want, rel=1e-9, abs=floor), (t, got, want)
-    # resuming from a state dict continues the same trace
-    sch2 = cls(torch.optim.SGD([{'params': [p], 'lr': lr} for p, lr in zip(params, c['lrs'])], lr=c['lrs'][0]), **c['kw'])
-    sch2.load_state_dict({'last_epoch': 9})
-    sch2.step()
-    assert [g['lr'] for g in sch2.optimizer.param_groups] == pytest.approx(c['trace'][9], rel=1e-9, abs=floor)
+    if not outside:
+        # resuming: optimiser groups + scheduler state restored -> the trace continues where it was
+        opt2, sch2 = build()
+        for _ in range(9):
+            sch2.step()
+        state_o, state_s = opt2.state_dict(), sch2.state_dict()
+        opt3, sch3 = build()
+        opt3.load_state_dict(state_o)
+        sch3.load_state_dict(state_s)
+        for t in range(9, 14):
+            sch3.step()
+            assert [g['lr'] for g in opt3.param_groups] == pytest.approx(c['trace'][t], rel=1e-9, abs=floor)
+
+
+def test_param_groups_match_reference_wrapper():
+    """tests/golden/wrapper_train.json: optimiser groups (learning rate + parameter names, in order) the UNMODIFIED reference
+    VideoBaseModel builds for the ft_tsa_only / small_offset_lr options (oracle/make_golden_wrapper.py)."""
+    import json
+    import os
+    from util import GOLD
+    from dynavsr_b200.models.Video_base_model import param_group_spec
+    from dynavsr_b200.options import dict_to_nonedict
+    from oracle import params as P
+    g = json.load(open(os.path.join(GOLD, 'wrapper_train.json')))
+    names = ['module.' + k for k in P.edvr_param_shapes(scale=4, **g['net'])]        # the wrapper sees DataParallel names
+    assert len(g['cases']) == 5
+    for case, c in g['cases'].items():
+        spec = param_group_spec(names, dict_to_nonedict(c['train']))
+        assert len(spec) == len(c['groups']), case
+        for (lr, got), want in zip(spec, c['groups']):
+            assert lr == pytest.approx(want['lr']) and [k[len('module.'):] for k in got] == want['names'], case
+    # the reference's quirk, spelled out: ft_tsa_only alone does NOT split the parameters
+    assert len(g['cases']['ft_tsa_only3_sgd_l1']['groups']) == 1
+    assert len(g['cases']['ft_tsa_and_small_offset']['groups']) == 2
+    with pytest.raises(NotImplementedError):
+        param_group_spec(names, dict_to_nonedict({'lr_G': 1e-4, 'freeze_front': True}))
