@@ -147,6 +147,21 @@ def adapt_study():
             out = O.adapt_and_infer(sdG, sdE, sdF, lr_clip, **kw)
             what = 'exact' if final is None else ('x3' if final is not mixed else 'x3, trunk + offset/mask convs x1')
             print('| %s / %s ; final forward %s | %.2e |' % (fwd, bwd, what, rel(out, ref)))
+        # the deformable convolutions' own products too: bf16 features and weights while gradients are enabled (the cast's
+        # backward rounds the gradients to bf16 as well); offsets and masks stay fp32 as on the GPU
+        real_mdcn = O.mdcn_torch
+        bf = lambda t: t.to(torch.bfloat16).to(torch.float32)
+
+        def mdcn(x, offset, mask, w, b, *a):
+            if torch.is_grad_enabled():
+                return real_mdcn(bf(x), offset, mask, bf(w), b, *a)
+            return real_mdcn(x, offset, mask, w, b, *a)
+        O.mdcn_torch = mdcn
+        try:
+            out = O.adapt_and_infer(sdG, sdE, sdF, lr_clip, **kw)
+        finally:
+            O.mdcn_torch = real_mdcn
+        print('| x1 / x1 incl. the deformable convolutions\' products ; final forward %s | %.2e |' % (what, rel(out, ref)))
     finally:
         O._conv = orig
 
