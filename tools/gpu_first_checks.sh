@@ -1,0 +1,30 @@
+#!/bin/bash
+# First GPU call of a new round: the checks that were written after the previous round's GPU minutes ran out
+# ("First on a GPU next round").  Usage: gpurun --timeout 600 -- 'bash tools/gpu_first_checks.sh'
+mkdir -p gpurun_out
+DVSR_RUN_UNVERIFIED=1 timeout 300 python -m pytest tests/test_models_gpu.py -x -q -m gpu -k wrapper_golden -p no:cacheprovider \
+    > gpurun_out/first_wrapper_golden.log 2>&1; echo "wrapper golden rc=$?"; tail -3 gpurun_out/first_wrapper_golden.log
+# device-resident clip + SSIM (the gt_ready event path of driver.evaluate)
+timeout 300 python - > gpurun_out/first_resident_ssim.log 2>&1 <<'PY'
+import sys, torch
+sys.path.insert(0, '.'); sys.path.insert(0, 'tests')
+import torch.nn.functional as F
+from util import gold
+import test_driver_gpu as T
+from dynavsr_b200 import adapt, clips, driver
+from dynavsr_b200.degradation import Degradation
+g = gold('driver_sgd2_l2.npz')
+netG, netE, netF, base = T._nets(g)
+gen = torch.Generator().manual_seed(5)
+hr = F.interpolate(torch.rand(1, 3, 10, 14, generator=gen), size=(136, 200), mode='bicubic', align_corners=False).clamp(0, 1)
+hr = torch.stack([hr[0, :, t:t + 128, t:t + 192] for t in range(6)])
+store = clips.ResidentClips(5, 'new_info', 4, 'cuda').add_degraded('pan', hr, Degradation(21, 4, sigma=[1.6, 1.6]))
+eng = adapt.InnerLoopAdapter(netG, netE, netF, steps=2, lr_alpha=1e-4, optimizer='SGD', criterion='l2', slr_weight=10.0, use_graphs=False)
+with torch.cuda.stream(torch.cuda.Stream()):
+    rows = driver.evaluate(eng, store, baseline_netG=base, compute_ssim=True)
+for k, v in rows.items():
+    print(k, ['%.4f' % x for x in v])
+    assert all(x == x for x in v)
+print('resident + ssim ok')
+PY
+echo "resident ssim rc=$?"; tail -3 gpurun_out/first_resident_ssim.log
