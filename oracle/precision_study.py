@@ -12,7 +12,7 @@ output frame against the exact-fp32 oracle (north-star tolerance: 1e-3):
     x1      x_hi.w_hi                     -- plain bf16                                             (1 product)
     tf32    tf32(x).tf32(w) round-to-nearest (one product at half the bf16 rate)
 
-    python -m oracle.precision_study [H W]      # default 32 x 32 LR, seeded weights of the goldens
+    python -m oracle.precision_study [H W [seed]]   # default 32 x 32 LR, weight seed 1234 (the goldens')
     python -m oracle.precision_study adapt      # second table: precision of the INNER adaptation steps (forward and
                                                 # backward of the 2 SGD steps) vs the adapted frame; final forward exact
 """
@@ -170,8 +170,9 @@ def main():
     if len(sys.argv) > 1 and sys.argv[1] == 'adapt':
         return adapt_study()
     H, W = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (32, 32)
+    seed = int(sys.argv[3]) if len(sys.argv) > 3 else 1234
     torch.manual_seed(0)
-    sd = P.make_params(P.edvr_param_shapes(), seed=1234)
+    sd = P.make_params(P.edvr_param_shapes(), seed=seed)
     x = torch.rand(1, 5, 3, H, W, generator=torch.Generator().manual_seed(7))
     ref = run(sd, x, {})
     names = [g for g, _ in GROUPS]
