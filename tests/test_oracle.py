@@ -246,3 +246,24 @@ def test_adapt_oracle_vs_reference_test_driver(tag):
         base = O.edvr_forward(sdB, lq)[0]
     assert abs(psnr_uint8(base, gt) - float(g['psnr_baseline'])) < 1e-3
     assert float(g['psnr_adapted']) > float(g['psnr_baseline'])
+
+
+def test_precision_study_operand_emulation():
+    """The operand roundings oracle/precision_study.py emulates (its conclusions feed DESIGN.md section 7): TF32 = round to
+    nearest even on 10 explicit mantissa bits, bf16 split = hi + lo reconstructs 16 mantissa bits; the three-product scheme
+    of the kernels equals the exact product up to the dropped lo.lo term."""
+    from oracle import precision_study as S
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(4096, generator=g) * torch.logspace(-6, 6, 4096)
+    t = S._tf32(x)
+    assert int((t.view(torch.int32) & 0x1FFF).abs().max()) == 0                       # 13 low mantissa bits cleared
+    assert float(((t - x).abs() / x.abs()).max()) <= 2.0 ** -11 * (1 + 1e-6)
+    tie = torch.tensor([1.0 + 2.0 ** -11, 1.0 + 3 * 2.0 ** -11])                      # exactly half way between neighbours
+    assert S._tf32(tie).tolist() == [1.0, 1.0 + 2.0 ** -9]                            # ties go to the even mantissa
+    hi, lo = S._bf16_split(x)
+    assert float(((hi + lo - x).abs() / x.abs()).max()) <= 2.0 ** -16
+    a, w = torch.randn(2, 8, 9, 9, generator=g), torch.randn(4, 8, 3, 3, generator=g) * 0.1
+    exact = torch.nn.functional.conv2d(a.double(), w.double(), None, padding=1)
+    err = lambda scheme: rel(S.emulated_conv(scheme, a, w, None, 1, 1), exact)
+    assert err('x3') < 3e-5 < err('tf32') < 2e-3 and err('tf32') < err('x2w') < 2 * err('x1') and err('x1') < 1e-2
+    assert S.group_of('recon_trunk.3.conv1') == 'trunk' and S.group_of('pcd_align.L1_dcnpack.conv_offset_mask') == 'dcn_offset_mask'
