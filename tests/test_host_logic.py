@@ -275,3 +275,57 @@ def test_param_groups_match_reference_wrapper():
     assert len(g['cases']['ft_tsa_and_small_offset']['groups']) == 2
     with pytest.raises(NotImplementedError):
         param_group_spec(names, dict_to_nonedict({'lr_G': 1e-4, 'freeze_front': True}))
+
+
+def test_wrappers_construct_with_reference_option_dicts(monkeypatch):
+    """Factory -> wrappers -> optimiser groups -> schedules with the device redirected to the CPU (construction is host logic;
+    the steps themselves need the CUDA library and are covered by tests/test_models_gpu.py)."""
+    import dynavsr_b200.models.base_model as BM
+    from dynavsr_b200.models import create_model
+    from dynavsr_b200.options import dict_to_nonedict
+    real_device = torch.device
+
+    class CpuTorch(object):
+        def __getattr__(self, k):
+            return getattr(torch, k)
+
+        @staticmethod
+        def device(*a, **k):
+            return real_device('cpu')
+
+    monkeypatch.setattr(BM, 'torch', CpuTorch())
+
+    def opt(model, is_train=True, **train):
+        t = dict(pixel_criterion='cb', pixel_weight=1.0, optim='Adam', lr_G=1e-4, beta1=0.9, beta2=0.99, lr_scheme='MultiStepLR',
+                 lr_steps=[2, 4], lr_gamma=0.5, loss_ftn='l1', lr_C=1e-4)
+        t.update(train)
+        return dict_to_nonedict({
+            'model': model, 'scale': 4, 'gpu_ids': [0], 'dist': False, 'is_train': is_train,
+            'network_G': {'which_model_G': 'EDVR', 'nf': 16, 'nframes': 3, 'groups': 2, 'front_RBs': 1, 'back_RBs': 1,
+                          'predeblur': False, 'HR_in': False, 'w_TSA': True},
+            'network_E': {'which_model_E': 'MFDN', 'mode': 'video', 'nf': 16, 'in_nc': 3},
+            'path': {'strict_load': True}, 'train': t})
+
+    g, e = create_model(opt('video_base+lrimgestimator', is_train=False))              # the test-time drivers' call
+    assert type(g).__name__ == 'VideoBaseModel' and type(e).__name__ == 'LRimgestimator_Model' and not g.optimizers
+    g, e = create_model(opt('video_base+lrimgestimator', ft_tsa_only=5))
+    assert [len(grp['params']) for grp in g.optimizer_G.param_groups] == [len(list(g.netG.parameters()))]   # ONE group (quirk)
+    assert len(e.optimizer_E.param_groups) == 1 and len(e.optimizer_E.param_groups[0]['params']) == 14
+    g.update_learning_rate(1)
+    g.update_learning_rate(2)
+    assert g.get_current_learning_rate() == [pytest.approx(5e-5)]                       # milestone at 2
+    g.set_params_lr_zero()
+    g.update_learning_rate(3)
+    g.update_learning_rate(4)
+    assert g.get_current_learning_rate() == [0]                                         # chained schedule: stays frozen
+    c = create_model(opt('video_base', small_offset_lr=True, lr_scheme='CosineAnnealingLR_Restart', T_period=[10, 10],
+                         restarts=[10], restart_weights=[1], eta_min=1e-7))
+    lrs = [grp['lr'] for grp in c.optimizer_G.param_groups]
+    assert lrs == [pytest.approx(1e-4), pytest.approx(1e-5)] and type(c.schedulers[0]).__name__ == 'CosineAnnealingLR_Restart'
+    for it in range(1, 11):
+        c.update_learning_rate(it)
+    assert c.get_current_learning_rate() == [pytest.approx(1e-7), pytest.approx(1e-7)]   # the trough after one period
+    with pytest.raises(NotImplementedError):
+        create_model(opt('video_base', lr_scheme='StepLR'))
+    with pytest.raises(NotImplementedError):
+        create_model(opt('lrimgestimator', lr_scheme='CosineAnnealingLR_Restart'))       # the estimator only knows MultiStepLR
