@@ -310,7 +310,7 @@ def _packed_parity(weight, wl, seg, KH, KW, a, b):
 def _packed_tc2(weight, wl, mode, seg_lo, seg_hi):
     """Resident-weight layout of conv_tc2.cu (mode 5 forward over segments [seg_lo, seg_hi), mode 6 data gradient).
     BF16x3 precision uses modes 9 / 10: 16 KiB blocks per (64-channel pair, tap) with the hi and lo parts stacked along N."""
-    bf = _backend['precision'] == 'bf16x3'
+    bf = _backend['precision'] in ('bf16x3', 'bf16')          # 'bf16' reads the same packs (their hi rows only)
     kdiv = 64 if bf else 32
     if mode == 5:
         nblocks = sum(wl.taps * ((wl.seg_C[s] + kdiv - 1) // kdiv) for s in range(seg_lo, seg_hi))
@@ -354,15 +354,20 @@ def _dgrad_stride2_tc(gpre, weight, wl, seg, shape, spec):
 _backend = {'tc': False, 'precision': 'bf16x3'}
 
 
+_PRECISION_CODE = {'tf32': 0, 'bf16x3': 1, 'bf16': 2}
+
+
 def set_conv_backend(tensor_cores, precision=None):
     """Select the tcgen05 implicit-GEMM path for eligible layers.  ``precision`` of the resident-weight kernel:
-    'bf16x3' (default; split operands, 3 products, fp32-class accuracy) or 'tf32' (single pass, ~3e-4 per layer)."""
+    'bf16x3' (default; split operands, 3 products, fp32-class accuracy), 'tf32' (single pass, ~3e-4 per layer) or 'bf16'
+    (the bf16x3 layouts with only the hi.hi product issued: ~3e-3 per layer, a third of the tensor-core work)."""
     _backend['tc'] = bool(tensor_cores)
     if precision is not None:
-        assert precision in ('bf16x3', 'tf32')
+        assert precision in _PRECISION_CODE
         _backend['precision'] = precision
-    if _lib.lib().dvsr_conv_tc2_get_precision() != (1 if _backend['precision'] == 'bf16x3' else 0):
-        _lib.lib().dvsr_conv_tc2_set_precision(1 if _backend['precision'] == 'bf16x3' else 0)
+    code = _PRECISION_CODE[_backend['precision']]
+    if _lib.lib().dvsr_conv_tc2_get_precision() != code:
+        _lib.lib().dvsr_conv_tc2_set_precision(code)
 
 
 # Weight gradients are leaves of the backward pass: when they accumulate into the flat gradient buffer nobody reads

@@ -599,3 +599,27 @@ def test_packed_weight_cache_never_aliases_freed_weights(ops):
         ref = F.conv2d(x.permute(0, 3, 1, 2).double().cpu(), w.double().cpu(), padding=1)
         assert rel(nchw(outs[-1]), ref) < TOL
         del w
+
+
+@pytest.mark.skipif(not __import__('os').environ.get('DVSR_RUN_UNVERIFIED'),
+                    reason='written after the round-1 GPU budget was spent: not yet run on a GPU; enable with DVSR_RUN_UNVERIFIED=1')
+@pytest.mark.parametrize('shape', [(5, 44, 80, 64, 64), (1, 33, 40, 128, 64), (2, 16, 24, 64, 216)],
+                         ids=['slr_trunk', 'two_segments_worth_of_K', 'offset_mask_conv'])
+def test_conv_tc2_single_product_mode(ops, shape):
+    """``set_conv_backend(True, 'bf16')``: the resident-weight kernel issues only x_hi . w_hi on the BF16x3 layouts.  Expected:
+    the result of bf16-rounded operands with fp32 accumulation (so ~1e-6 against a reference computed from rounded operands,
+    ~3e-3 against fp32), and the default mode unchanged afterwards."""
+    N, H, W, Ci, Co = shape
+    x, w, b = _rand(N, Ci, H, W, seed=11), _rand(Co, Ci, 3, 3, seed=12, scale=0.05), _rand(Co, seed=13, scale=0.1)
+    exact = F.conv2d(x.double(), w.double(), b.double(), padding=1)
+    rounded = F.conv2d(x.bfloat16().double(), w.bfloat16().double(), b.double(), padding=1)
+    try:
+        ops.set_conv_backend(True, 'bf16')
+        y1 = nchw(ops.conv(nhwc(_dev(x)), _dev(w), _dev(b), stride=1, pad=1))
+        ops.set_conv_backend(True, 'bf16x3')
+        y3 = nchw(ops.conv(nhwc(_dev(x)), _dev(w), _dev(b), stride=1, pad=1))
+    finally:
+        ops.set_conv_backend(False, 'bf16x3')
+    assert rel(y1, rounded) < 2e-5                       # exactly the single product (fp32 accumulation order aside)
+    assert 5e-4 < rel(y1, exact) < 1e-2                  # bf16-level error against fp32
+    assert rel(y3, exact) < 5e-5                         # the default mode is untouched

@@ -4,6 +4,8 @@
 mkdir -p gpurun_out
 DVSR_RUN_UNVERIFIED=1 timeout 300 python -m pytest tests/test_models_gpu.py -x -q -m gpu -k wrapper_golden -p no:cacheprovider \
     > gpurun_out/first_wrapper_golden.log 2>&1; echo "wrapper golden rc=$?"; tail -3 gpurun_out/first_wrapper_golden.log
+DVSR_RUN_UNVERIFIED=1 timeout 300 python -m pytest tests/test_ops_gpu.py -x -q -m gpu -k single_product -p no:cacheprovider \
+    > gpurun_out/first_single_product.log 2>&1; echo "single-product conv rc=$?"; tail -3 gpurun_out/first_single_product.log
 # device-resident clip + SSIM (the gt_ready event path of driver.evaluate)
 timeout 300 python - > gpurun_out/first_resident_ssim.log 2>&1 <<'PY'
 import sys, torch
