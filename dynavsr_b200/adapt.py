@@ -119,7 +119,7 @@ class InnerLoopAdapter(object):
     """
 
     def __init__(self, netG, netE, netE_fixed, steps=2, lr_alpha=1e-5, lr_alpha_est=None, optimizer='SGD',
-                 betas=(0.9, 0.99), criterion='l2', slr_weight=10.0, pixel_weight=1.0, use_graphs=True):
+                 betas=(0.9, 0.99), criterion='l2', slr_weight=10.0, pixel_weight=1.0, use_graphs=True, inner_precision=None):
         if optimizer not in ('SGD', 'Adam'):
             raise NotImplementedError(optimizer)
         if criterion not in ('l1', 'l2', 'cb'):
@@ -130,6 +130,10 @@ class InnerLoopAdapter(object):
         self.lr_alpha_est = lr_alpha if lr_alpha_est is None else lr_alpha_est
         self.slr_weight, self.pixel_weight = slr_weight, pixel_weight
         self.use_graphs = use_graphs
+        # operand precision of the tensor-core convolutions DURING the adaptation steps (None = the backend's setting; 'bf16' =
+        # single product: the steps' errors reach the frame attenuated by how little the adaptation moves it,
+        # profiles/r1_precision_study.md); the final forward always runs at the backend's precision
+        self.inner_precision = inner_precision
         self.scope = ops.new_scope()        # this engine's weight packs / pack table / weight-gradient side stream
         self.flat = FlatParams([netG, netE], scope=self.scope)
         for p in netE_fixed.parameters():
@@ -170,7 +174,8 @@ class InnerLoopAdapter(object):
         gt = frames.view(B, self.N, H, W, 3)[:, self.center].contiguous()
         with torch.no_grad():
             slr_fixed = self.netE_fixed.forward_nhwc(frames, B, self.N)
-        losses = [self._inner_step(frames, gt, slr_fixed, B, i) for i in range(self.steps)]
+        with ops.conv_precision(self.inner_precision):
+            losses = [self._inner_step(frames, gt, slr_fixed, B, i) for i in range(self.steps)]
         with torch.no_grad():
             hr = self.netG.forward_nhwc(frames, B, self.N)
         return hr, losses

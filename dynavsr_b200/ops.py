@@ -16,7 +16,7 @@ from ._lib import ACT_LRELU, ACT_NONE, ACT_RELU, ACT_SIGMOID_SPLIT, ConvDesc, WL
 
 __all__ = ['conv3d_rgb', 'PackScope', 'new_scope', 'scope', 'repack_all', 'snapshot_packs', 'restore_packs', 'invalidate_pack_snapshot', 'weights_updated', 'join_async', 'Seg', 'conv', 'conv3d_padded', 'mdcn', 'upsample', 'pool_maxavg', 'pad2d', 'pad3d_replicate',
            'tsa_temporal', 'tsa_combine', 'pixel_loss', 'to_nhwc', 'to_nchw', 'invalidate_weight_cache',
-           'ACT_NONE', 'ACT_RELU', 'ACT_LRELU', 'ACT_SIGMOID_SPLIT', 'set_conv_backend', 'frame_to_u8']
+           'ACT_NONE', 'ACT_RELU', 'ACT_LRELU', 'ACT_SIGMOID_SPLIT', 'set_conv_backend', 'conv_precision', 'frame_to_u8']
 
 
 def _stream():
@@ -368,6 +368,27 @@ def set_conv_backend(tensor_cores, precision=None):
     code = _PRECISION_CODE[_backend['precision']]
     if _lib.lib().dvsr_conv_tc2_get_precision() != code:
         _lib.lib().dvsr_conv_tc2_set_precision(code)
+
+
+class conv_precision(object):
+    """``with ops.conv_precision('bf16'):`` -- operand precision of the resident-weight tensor-core convolution for the
+    launches issued (or captured into a CUDA graph) inside the block; restored on exit.  ``None`` and the exact-fp32 backend
+    make it a no-op.  The setting is process-global in the library: one host thread drives the launches of a process."""
+
+    def __init__(self, precision):
+        self.precision, self.previous = precision, None
+
+    def __enter__(self):
+        if self.precision is not None and _backend['tc'] and self.precision != _backend['precision']:
+            self.previous = _backend['precision']
+            set_conv_backend(True, self.precision)
+        return self
+
+    def __exit__(self, *exc):
+        if self.previous is not None:
+            set_conv_backend(_backend['tc'], self.previous)
+            self.previous = None
+        return False
 
 
 # Weight gradients are leaves of the backward pass: when they accumulate into the flat gradient buffer nobody reads

@@ -329,3 +329,40 @@ def test_wrappers_construct_with_reference_option_dicts(monkeypatch):
         create_model(opt('video_base', lr_scheme='StepLR'))
     with pytest.raises(NotImplementedError):
         create_model(opt('lrimgestimator', lr_scheme='CosineAnnealingLR_Restart'))       # the estimator only knows MultiStepLR
+
+
+def test_conv_precision_context(monkeypatch):
+    """ops.conv_precision: temporary operand precision of the resident-weight conv (library call stubbed): nests, restores,
+    is a no-op for None and under the exact-fp32 backend."""
+    from dynavsr_b200 import ops
+    calls = []
+
+    class Lib(object):
+        def dvsr_conv_tc2_get_precision(self):
+            return calls[-1] if calls else 1
+
+        def dvsr_conv_tc2_set_precision(self, code):
+            calls.append(code)
+
+    monkeypatch.setattr(ops._lib, 'lib', lambda: Lib())
+    monkeypatch.setitem(ops._backend, 'tc', True)
+    monkeypatch.setitem(ops._backend, 'precision', 'bf16x3')
+    with ops.conv_precision('bf16'):
+        assert ops._backend['precision'] == 'bf16' and calls == [2]
+        with ops.conv_precision(None):
+            assert ops._backend['precision'] == 'bf16'
+        with ops.conv_precision('tf32'):
+            assert calls == [2, 0]
+        assert ops._backend['precision'] == 'bf16' and calls == [2, 0, 2]
+    assert ops._backend['precision'] == 'bf16x3' and calls == [2, 0, 2, 1]
+    with pytest.raises(RuntimeError):
+        with ops.conv_precision('bf16'):
+            raise RuntimeError('launch failed')
+    assert ops._backend['precision'] == 'bf16x3'                       # restored on the error path too
+    monkeypatch.setitem(ops._backend, 'tc', False)
+    n = len(calls)
+    with ops.conv_precision('bf16'):
+        assert ops._backend['precision'] == 'bf16x3'
+    assert len(calls) == n
+    with pytest.raises(AssertionError):
+        ops.set_conv_backend(True, 'fp8')

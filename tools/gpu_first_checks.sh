@@ -30,3 +30,9 @@ for k, v in rows.items():
 print('resident + ssim ok')
 PY
 echo "resident ssim rc=$?"; tail -3 gpurun_out/first_resident_ssim.log
+# the precision policy end to end: default vs single-product inner steps (value, e2e, parity.rel_l2 must stay <= 1e-3)
+for prec in bf16x3 bf16; do
+  timeout 300 python bench.py --no-cpu-baseline --inner-precision $prec 2>gpurun_out/first_bench_$prec.err | tail -1 > gpurun_out/first_bench_$prec.json
+  python -c "
+import json; d=json.loads(open('gpurun_out/first_bench_$prec.json').read()); print('$prec', 'value %.2f e2e %.2f parity %.2e' % (d['value'], d['e2e']['value'], d['parity']['rel_l2']))"
+done
