@@ -21,9 +21,6 @@
 //     into columns [0,64); the epilogue adds the two halves.  fp32-class accuracy (4.6e-6 per layer) at the speed of the
 //     single-pass TF32 mode, because one read of the activation operand serves two products.
 //   TF32 -- operands rounded to nearest in shared memory / at pack time (modes 5 / 6), one product (2.9e-4 per layer).
-//   BF16 (mode 2) -- the BF16x3 layouts and packs unchanged, but only x_hi . w_hi is issued (N = n_mma, rows 0-63 of a weight
-//     block): plain bf16 operands with fp32 accumulation, ~3e-3 per layer.  Meant for the inner adaptation steps, whose errors
-//     reach the output frame attenuated by how little the adaptation moves it (profiles/r1_precision_study.md).
 // The kernel is bounded by shared-memory bandwidth (both MMA operands come from shared memory: 321 KB per chunk-tile at
 // 128 B/clk, see profiles/r1_conv_tc2_timeline.txt).
 // Warp roles: 0 = TMA producer, 1 = MMA issuer / TMEM owner, 2-5 = operand conversion of the halo tile,
@@ -63,8 +60,7 @@ struct T2Params {
     int shuffle;
     float* y; int y_pix_stride;
     int y_vec8;                           // y rows are 32-byte aligned: 256-bit stores
-    int bf16x3;                           // 1: operands split into bf16 hi + lo, 3 products (fp32-class accuracy);
-                                          // 2: same layouts, only x_hi . w_hi is issued (plain bf16 operands, fp32 accumulate)
+    int bf16x3;                           // 1: operands split into bf16 hi + lo, 3 products (fp32-class accuracy)
     int n_mma;                            // MMA N (16..64): output channels of this launch's widest group, rounded up to 16
     int scalar_out;                       // narrow / unaligned outputs (conv_last 64 -> 3): scalar epilogue, Co <= 32
     long long* trace;                     // optional per-event clock64 trace of CTA (0,0): [event][chunk]
@@ -173,8 +169,7 @@ conv_tc2_kernel(const __grid_constant__ T2Maps maps, const T2Params p) {
         // ===================== MMA issuer =====================
         const uint32_t idesc = p.bf16x3 ? make_idesc_bf16(128, p.n_mma) : make_idesc_tf32(128, p.n_mma);
         const uint32_t idesc_wide = make_idesc_bf16(128, 2 * T2_NG);      // [w_hi | w_lo] stacked along N (BF16x3, full groups)
-        const bool wide = p.bf16x3 == 1 && p.n_mma == T2_NG;
-        const bool single = p.bf16x3 == 2;
+        const bool wide = p.bf16x3 && p.n_mma == T2_NG;
         // descriptor templates: only the 14-bit (address >> 4) field changes per tap / k-step
         const uint64_t ad_const = make_desc(0, 16, (uint32_t)p.halo_w * 128u, 2);
         const uint64_t bd_const = make_desc(0, 16, 1024, 2);
@@ -206,9 +201,6 @@ conv_tc2_kernel(const __grid_constant__ T2Maps maps, const T2Params p) {
                                 mma_tf32(dcol, ad + 2, bd + 2, idesc, 1u);
                                 mma_tf32(dcol, ad + 4, bd + 4, idesc, 1u);
                                 mma_tf32(dcol, ad + 6, bd + 6, idesc, 1u);
-                            } else if (single) {
-                                mma_bf16(dcol, ad, bd, idesc, first);                 // x_hi . w_hi only
-                                mma_bf16(dcol, ad + 2, bd + 2, idesc, 1u);
                             } else if (wide) {
                                 // activation row = [hi(32 bf16) | lo(32 bf16)]; weight rows 0-63 = hi, 64-127 = lo; K = 16 = +2
                                 mma_bf16(dcol, ad, bd, idesc_wide, first);            // x_hi . [w_hi | w_lo] -> columns [0,64) | [64,128)
@@ -301,7 +293,7 @@ conv_tc2_kernel(const __grid_constant__ T2Maps maps, const T2Params p) {
             if (threadIdx.x == 192) T2_TRACE(5, local);
             float v0[32], v1[32];
             const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 2 * T2_NG);
-            const bool wide = p.bf16x3 == 1 && p.n_mma == T2_NG;     // columns [64,128) hold the x_hi . w_lo partial sums
+            const bool wide = p.bf16x3 && p.n_mma == T2_NG;     // columns [64,128) hold the x_hi . w_lo partial sums
             tmem_ld32(tacc, v0);
             if (p.scalar_out) {
                 // narrow output (Co <= 32, any alignment): one 32-column read, per-channel loads / stores
@@ -462,7 +454,7 @@ extern "C" int dvsr_pack_weights_tc2(const float* w, float* wp, const dvsr_wlayo
 }
 
 // 1 (default): BF16x3 split operands (3 products, ~1e-5 per layer); 0: single-pass TF32 with round-to-nearest (~3e-4)
-extern "C" int dvsr_conv_tc2_set_precision(int bf16x3) { g_t2_bf16x3 = bf16x3 == 2 ? 2 : (bf16x3 ? 1 : 0); return 0; }
+extern "C" int dvsr_conv_tc2_set_precision(int bf16x3) { g_t2_bf16x3 = bf16x3 ? 1 : 0; return 0; }
 extern "C" int dvsr_conv_tc2_get_precision(void) { return g_t2_bf16x3; }
 
 extern "C" int dvsr_conv_tc2_fprop(const dvsr_conv_desc* d, const float* wp, const float* accum_in, int accum_pix_stride, void* stream) {

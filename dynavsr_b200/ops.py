@@ -360,7 +360,8 @@ _PRECISION_CODE = {'tf32': 0, 'bf16x3': 1, 'bf16': 2}
 def set_conv_backend(tensor_cores, precision=None):
     """Select the tcgen05 implicit-GEMM path for eligible layers.  ``precision`` of the resident-weight kernel:
     'bf16x3' (default; split operands, 3 products, fp32-class accuracy), 'tf32' (single pass, ~3e-4 per layer) or 'bf16'
-    (the bf16x3 layouts with only the hi.hi product issued: ~3e-3 per layer, a third of the tensor-core work)."""
+    (the bf16x3 layouts with only the hi.hi product issued: ~3e-3 per layer, a third of the tensor-core work; needs a library
+    built with tools/patches/conv_tc2_single_product.diff -- raises NotImplementedError otherwise)."""
     _backend['tc'] = bool(tensor_cores)
     if precision is not None:
         assert precision in _PRECISION_CODE
@@ -368,6 +369,11 @@ def set_conv_backend(tensor_cores, precision=None):
     code = _PRECISION_CODE[_backend['precision']]
     if _lib.lib().dvsr_conv_tc2_get_precision() != code:
         _lib.lib().dvsr_conv_tc2_set_precision(code)
+        if _lib.lib().dvsr_conv_tc2_get_precision() != code:        # a library built without that mode: fail loudly
+            _backend['precision'] = 'bf16x3'
+            _lib.lib().dvsr_conv_tc2_set_precision(1)
+            raise NotImplementedError('this build of libdvsr_b200.so has no conv precision %r '
+                                      '(single-product mode: tools/patches/conv_tc2_single_product.diff)' % precision)
 
 
 class conv_precision(object):

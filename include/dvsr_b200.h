@@ -165,9 +165,7 @@ int dvsr_pack_weights_tc2(const float* w, float* wp, const dvsr_wlayout* wl, int
 int dvsr_conv_tc2_fprop(const dvsr_conv_desc* d, const float* wp, const float* accum_in, int accum_pix_stride, void* stream);
 /* Operand precision of conv_tc2: 1 (default) = BF16x3 -- activations and weights are split into bf16 hi + lo parts and
  * the three significant products are accumulated in fp32 (per-layer error ~1e-5, weights packed with mode 9 / 10);
- * 0 = single-pass TF32 with operands rounded to nearest (~3e-4 per layer, weights packed with mode 5 / 6);
- * 2 = plain bf16: the layouts and packs of mode 1, only the x_hi.w_hi product is issued (~3e-3 per layer; one third of the
- * tensor-core work -- for the inner adaptation steps, see profiles/r1_precision_study.md). */
+ * 0 = single-pass TF32 with operands rounded to nearest (~3e-4 per layer, weights packed with mode 5 / 6). */
 int dvsr_conv_tc2_set_precision(int bf16x3);
 int dvsr_conv_tc2_get_precision(void);
 /* Grid policy of conv_tc2: at least n tiles (128 output pixels each) per persistent CTA.  1 (default) spreads a small

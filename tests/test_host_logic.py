@@ -366,3 +366,13 @@ def test_conv_precision_context(monkeypatch):
     assert len(calls) == n
     with pytest.raises(AssertionError):
         ops.set_conv_backend(True, 'fp8')
+
+    class OldLib(Lib):                                                  # a build without the single-product mode stores 1 for 2
+        def dvsr_conv_tc2_set_precision(self, code):
+            calls.append(1 if code else 0)
+
+    monkeypatch.setattr(ops._lib, 'lib', lambda: OldLib())
+    monkeypatch.setitem(ops._backend, 'tc', True)
+    with pytest.raises(NotImplementedError):
+        ops.set_conv_backend(True, 'bf16')
+    assert ops._backend['precision'] == 'bf16x3' and calls[-1] == 1     # nothing silently different

@@ -602,7 +602,8 @@ def test_packed_weight_cache_never_aliases_freed_weights(ops):
 
 
 @pytest.mark.skipif(not __import__('os').environ.get('DVSR_RUN_UNVERIFIED'),
-                    reason='written after the round-1 GPU budget was spent: not yet run on a GPU; enable with DVSR_RUN_UNVERIFIED=1')
+                    reason='needs a library built with tools/patches/conv_tc2_single_product.diff (written after the round-1 GPU budget was spent, '
+                           'not yet run on a GPU); enable with DVSR_RUN_UNVERIFIED=1')
 @pytest.mark.parametrize('shape', [(5, 44, 80, 64, 64), (1, 33, 40, 128, 64), (2, 16, 24, 64, 216)],
                          ids=['slr_trunk', 'two_segments_worth_of_K', 'offset_mask_conv'])
 def test_conv_tc2_single_product_mode(ops, shape):

@@ -1,6 +1,8 @@
 #!/bin/bash
 # First GPU call of a new round: the checks that were written after the previous round's GPU minutes ran out
-# ("First on a GPU next round").  Usage: gpurun --timeout 600 -- 'bash tools/gpu_first_checks.sh'
+# ("First on a GPU next round").  BEFORE the call, in the build container:
+#     git apply tools/patches/conv_tc2_single_product.diff && make -C dynavsr_b200/csrc
+# Usage: gpurun --timeout 900 -- 'bash tools/gpu_first_checks.sh'
 mkdir -p gpurun_out
 DVSR_RUN_UNVERIFIED=1 timeout 300 python -m pytest tests/test_models_gpu.py -x -q -m gpu -k wrapper_golden -p no:cacheprovider \
     > gpurun_out/first_wrapper_golden.log 2>&1; echo "wrapper golden rc=$?"; tail -3 gpurun_out/first_wrapper_golden.log
