@@ -44,6 +44,8 @@ def parse():
     ap.add_argument('--no-tc', action='store_true', help='exact-fp32 CUDA-core convolutions only')
     ap.add_argument('--inner-precision', default=None, choices=['bf16x3', 'bf16', 'tf32'],
                     help='operand precision of the tensor-core convs during the inner steps (default: same as the final forward, bf16x3)')
+    ap.add_argument('--inner-backward-precision', default=None, choices=['bf16x3', 'bf16', 'tf32'],
+                    help='... of their backward passes only (default: --inner-precision)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--height', type=int, default=LR_H)
     ap.add_argument('--width', type=int, default=LR_W)
@@ -216,7 +218,7 @@ def main():
     # frames in flight: 6 for the adaptation workload (latency-bound inner steps), 2 for plain inference (GPU-filling kernels)
     P = max(1, args.pipelines if args.pipelines is not None else (6 if args.workload == 'adapt' else 2))
     pool = adapt.AdaptationPool(*build(1234), pipelines=P, cta_budget=args.cta_budget, min_tiles_per_cta=args.min_tiles,
-                                use_graphs=not args.no_graphs, inner_precision=args.inner_precision, **INNER)
+                                use_graphs=not args.no_graphs, inner_precision=(args.inner_precision, args.inner_backward_precision or args.inner_precision), **INNER)
     min_tiles, budget = pool.min_tiles_per_cta, pool.cta_budget
     if args.wg_chunks is not None:
         _lib.lib().dvsr_conv_wgrad_tc_set_min_chunks_per_cta(args.wg_chunks)
@@ -360,7 +362,8 @@ def main():
                 'data': 'synthetic',
                 'config': {'workload': ('adapt2_sgd_l2+final_forward' if args.workload == 'adapt' else 'inference_only') +
                            ' EDVR-M 4x + MFDN, REDS4-shaped 5x3x180x320 window cropped to %dx%d -> 3x%dx%d' % (H, W, SCALE * H, SCALE * W),
-                           'inner': INNER, 'inner_conv_precision': args.inner_precision or 'bf16x3', 'clips_per_rank': n_clips,
+                           'inner': INNER, 'inner_conv_precision': {'forward': args.inner_precision or 'bf16x3',
+                                                    'backward': args.inner_backward_precision or args.inner_precision or 'bf16x3'}, 'clips_per_rank': n_clips,
                            'cuda_graphs': not args.no_graphs,
                            'frames_in_flight_per_gpu': P, 'conv_min_tiles_per_cta': min_tiles, 'cta_budget_per_launch': budget,
                            'l2': 'per-step working set (activations ~GBs) exceeds the 126 MB L2; inputs rotate over %d clips' % n_clips,

@@ -130,9 +130,10 @@ class InnerLoopAdapter(object):
         self.lr_alpha_est = lr_alpha if lr_alpha_est is None else lr_alpha_est
         self.slr_weight, self.pixel_weight = slr_weight, pixel_weight
         self.use_graphs = use_graphs
-        # operand precision of the tensor-core convolutions DURING the adaptation steps (None = the backend's setting; 'bf16' =
-        # single product: the steps' errors reach the frame attenuated by how little the adaptation moves it,
-        # profiles/r1_precision_study.md); the final forward always runs at the backend's precision
+        # operand precision of the tensor-core convolutions DURING the adaptation steps: None = the backend's setting, a name
+        # ('bf16' = single product) or a (forward, backward) pair.  The steps' errors reach the frame attenuated by how little
+        # the adaptation moves it (profiles/r1_precision_study.md: SGD tolerates 'bf16' throughout; Adam's normalised step does
+        # not -- keep its forward at 'bf16x3', i.e. (None, 'bf16')).  The final forward always runs at the backend's precision.
         self.inner_precision = inner_precision
         self.scope = ops.new_scope()        # this engine's weight packs / pack table / weight-gradient side stream
         self.flat = FlatParams([netG, netE], scope=self.scope)
@@ -149,11 +150,14 @@ class InnerLoopAdapter(object):
     def _inner_step(self, frames, gt, slr_fixed, B, step_idx):
         """One adaptation step on channels-last tensors; returns the (device) loss scalar."""
         self.flat.zero_grad()
-        slr = self.netE.forward_nhwc(frames, B, self.N)
-        sr = self.netG.forward_nhwc(slr, B, self.N)
-        loss = ops.pixel_loss(sr, gt, self.criterion, self.pixel_weight) + \
-            ops.pixel_loss(slr, slr_fixed, 'l1', self.slr_weight)
-        loss.backward()
+        p_fwd, p_bwd = self.inner_precision if isinstance(self.inner_precision, (tuple, list)) else (self.inner_precision,) * 2
+        with ops.conv_precision(p_fwd):
+            slr = self.netE.forward_nhwc(frames, B, self.N)
+            sr = self.netG.forward_nhwc(slr, B, self.N)
+            loss = ops.pixel_loss(sr, gt, self.criterion, self.pixel_weight) + \
+                ops.pixel_loss(slr, slr_fixed, 'l1', self.slr_weight)
+        with ops.conv_precision(p_bwd):
+            loss.backward()
         if self.optimizer == 'SGD':
             self.flat.sgd_step(self.lr_alpha, self.lr_alpha_est)
         else:
@@ -174,8 +178,7 @@ class InnerLoopAdapter(object):
         gt = frames.view(B, self.N, H, W, 3)[:, self.center].contiguous()
         with torch.no_grad():
             slr_fixed = self.netE_fixed.forward_nhwc(frames, B, self.N)
-        with ops.conv_precision(self.inner_precision):
-            losses = [self._inner_step(frames, gt, slr_fixed, B, i) for i in range(self.steps)]
+        losses = [self._inner_step(frames, gt, slr_fixed, B, i) for i in range(self.steps)]
         with torch.no_grad():
             hr = self.netG.forward_nhwc(frames, B, self.N)
         return hr, losses

@@ -13,7 +13,7 @@ output frame against the exact-fp32 oracle (north-star tolerance: 1e-3):
     tf32    tf32(x).tf32(w) round-to-nearest (one product at half the bf16 rate)
 
     python -m oracle.precision_study [H W [seed]]   # default 32 x 32 LR, weight seed 1234 (the goldens')
-    python -m oracle.precision_study adapt      # second table: precision of the INNER adaptation steps (forward and
+    python -m oracle.precision_study adapt [adam]   # second table: precision of the INNER adaptation steps (forward and
                                                 # backward of the 2 SGD steps) vs the adapted frame; final forward exact
 """
 import sys
@@ -123,7 +123,11 @@ def adapt_study():
     sdG = P.make_params(P.edvr_param_shapes(), seed=1234)
     sdE = P.make_params(P.mfdn_param_shapes(), seed=77)
     sdF = P.make_params(P.mfdn_param_shapes(), seed=78)
-    kw = dict(steps=2, lr_alpha=1e-4, optimizer='SGD', criterion='l2')
+    if len(sys.argv) > 2 and sys.argv[2] == 'adam':              # the shipped test YMLs: one Adam step, Charbonnier, lr 1e-5
+        kw = dict(steps=1, lr_alpha=1e-5, optimizer='Adam', criterion='cb')
+    else:
+        kw = dict(steps=2, lr_alpha=1e-4, optimizer='SGD', criterion='l2')
+    print('inner loop:', kw)
     ref = O.adapt_and_infer(sdG, sdE, sdF, lr_clip, **kw)
     with torch.no_grad():
         unadapted = O.edvr_forward(sdG, lr_clip)
