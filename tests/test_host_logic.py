@@ -1,4 +1,4 @@
-"""CPU-side host logic: option dict, LR schedule with restarts (closed form vs torch's chained scheduler)."""
+"""CPU-side host logic: option dict, LR schedules (against torch and against traces of the reference classes), model-wrapper plumbing."""
 import pytest
 import torch
 
@@ -14,7 +14,7 @@ class _Opt(object):
         self.param_groups = [{'lr': lr} for lr in lrs]
 
 
-def test_multistep_restart_closed_form_matches_torch_multistep():
+def test_multistep_restart_matches_torch_multistep():
     from dynavsr_b200.models.lr_scheduler import MultiStepLR_Restart
     ours = _Opt([1e-3, 1e-4])
     sch = MultiStepLR_Restart(ours, [3, 5, 9], gamma=0.5)
