@@ -38,3 +38,7 @@ for prec in bf16x3 bf16; do
   python -c "
 import json; d=json.loads(open('gpurun_out/first_bench_$prec.json').read()); print('$prec', 'value %.2f e2e %.2f parity %.2e' % (d['value'], d['e2e']['value'], d['parity']['rel_l2']))"
 done
+# launch list of bench.py itself (the profiles/ list of round 1 came from tools/one_frame.py, the same kernels launched eagerly)
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 4000 -c 2000 --csv --log-file gpurun_out/first_bench_launches.csv \
+    python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/first_bench_under_ncu.log 2>&1
+python tools/ncu_summary.py gpurun_out/first_bench_launches.csv > gpurun_out/first_bench_launches_summary.md 2>/dev/null; head -12 gpurun_out/first_bench_launches_summary.md
