@@ -267,3 +267,49 @@ def test_precision_study_operand_emulation():
     err = lambda scheme: rel(S.emulated_conv(scheme, a, w, None, 1, 1), exact)
     assert err('x3') < 3e-5 < err('tf32') < 2e-3 and err('tf32') < err('x2w') < 2 * err('x1') and err('x1') < 1e-2
     assert S.group_of('recon_trunk.3.conv1') == 'trunk' and S.group_of('pcd_align.L1_dcnpack.conv_offset_mask') == 'dcn_offset_mask'
+
+
+@pytest.mark.parametrize('case', ['plain_adam_cb', 'small_offset_sgd_l2', 'ft_tsa_only3_sgd_l1', 'ft_tsa_and_small_offset',
+                                  'weight_decay_sgd'])
+def test_training_iterations_vs_reference_wrapper_golden(case):
+    """The host logic of the training path put together on CPU -- ``param_group_spec`` + the chained schedules +
+    ``update_learning_rate`` ordering + the ft_tsa_only freeze -- around the oracle's forward / loss and torch.optim, against
+    what the UNMODIFIED reference VideoBaseModel did (tests/golden/wrapper_train.*): losses, learning rates, probe deltas."""
+    import json
+    import os
+    from util import GOLD
+    from dynavsr_b200.models.Video_base_model import param_group_spec
+    from dynavsr_b200.models.lr_scheduler import MultiStepLR_Restart
+    from dynavsr_b200.options import dict_to_nonedict
+    g = json.load(open(os.path.join(GOLD, 'wrapper_train.json')))
+    arr = np.load(os.path.join(GOLD, 'wrapper_train.npz'))
+    c = g['cases'][case]
+    t = dict_to_nonedict(dict(c['train'], lr_steps=[2], lr_gamma=0.5))
+    sd0 = P.make_params(P.edvr_param_shapes(scale=4, **g['net']), seed=int(g['seed']))
+    w = {k: v.clone().requires_grad_(True) for k, v in sd0.items()}
+    groups = [{'params': [w[k] for k in names], 'lr': lr} for lr, names in param_group_spec(list(w), t)]
+    wd = t['weight_decay_G'] or 0
+    opt = torch.optim.SGD(groups, lr=t['lr_G'], weight_decay=wd) if t['optim'] == 'SGD' else \
+        torch.optim.Adam(groups, lr=t['lr_G'], weight_decay=wd, betas=(0.9, 0.99))
+    sch = MultiStepLR_Restart(opt, t['lr_steps'], gamma=t['lr_gamma'])
+    x, gt = torch.from_numpy(arr['LQs']), torch.from_numpy(arr['GT'])
+    losses, lrs = [], []
+    for step in range(1, int(g['steps']) + 1):
+        sch.step()                                                    # update_learning_rate (no warm-up)
+        if t['ft_tsa_only'] and step < t['ft_tsa_only']:
+            opt.param_groups[0]['lr'] = 0                             # set_params_lr_zero
+        opt.zero_grad()
+        loss = O.pixel_loss(t['pixel_criterion'], O.edvr_forward(w, x, **g['net']), gt)
+        loss.backward()
+        opt.step()
+        losses.append(float(loss.detach()))
+        lrs.append([grp['lr'] for grp in opt.param_groups])
+    assert lrs == [pytest.approx(v) for v in c['lrs_after_step']]
+    assert losses == pytest.approx(c['losses'], rel=1e-5)
+    for k in g['probes']:
+        want = torch.from_numpy(arr['%s/%s' % (case, k)])
+        got = w[k].detach() - sd0[k]
+        if float(want.abs().max()) == 0.0:
+            assert float(got.abs().max()) == 0.0, k
+        else:
+            assert rel(got, want) < 1e-3, k
