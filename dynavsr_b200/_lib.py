@@ -21,6 +21,15 @@ class ConvSeg(ctypes.Structure):
                 ('dt', ctypes.c_int), ('t_fixed', ctypes.c_int)]
 
 
+class Policy(ctypes.Structure):
+    """dvsr_policy: launch policy of one call (all zero = library defaults)."""
+    _fields_ = [('cta_budget', ctypes.c_int), ('min_tiles', ctypes.c_int), ('min_chunks', ctypes.c_int),
+                ('precision', ctypes.c_int), ('mdcn_staged', ctypes.c_int)]
+
+
+PREC_BF16X3, PREC_TF32, PREC_BF16 = 0, 1, 2
+
+
 class ConvDesc(ctypes.Structure):
     _fields_ = [('N', ctypes.c_int), ('H', ctypes.c_int), ('W', ctypes.c_int),
                 ('Ho', ctypes.c_int), ('Wo', ctypes.c_int),
@@ -35,7 +44,7 @@ class ConvDesc(ctypes.Structure):
                 ('shuffle', ctypes.c_int), ('accumulate', ctypes.c_int),
                 ('y', ctypes.c_void_p), ('y_pix_stride', ctypes.c_int),
                 ('out_step', ctypes.c_int), ('out_off_y', ctypes.c_int), ('out_off_x', ctypes.c_int),
-                ('out_H', ctypes.c_int), ('out_W', ctypes.c_int)]
+                ('out_H', ctypes.c_int), ('out_W', ctypes.c_int), ('policy', Policy)]
 
 
 class WLayout(ctypes.Structure):
@@ -78,16 +87,11 @@ SIGNATURES = {
     'dvsr_pack_weights_tc2': [_P, _P, _WP, _I, _I, _I, _P],
     'dvsr_conv_tc2_fprop': [_DP, _P, _P, _I, _P],
     'dvsr_conv_tc2_set_trace': [_P],
-    'dvsr_conv_tc2_set_precision': [_I],
-    'dvsr_conv_tc2_get_precision': [],
-    'dvsr_conv_tc2_set_min_tiles_per_cta': [_I],
     'dvsr_conv_wgrad_tc_supported': [_DP, _I],
-    'dvsr_conv_wgrad_tc_set_min_chunks_per_cta': [_I],
     'dvsr_conv_wgrad_tc': [_DP, _I, _P, _I, _P, _WP, _P],
     'dvsr_mdcn_bwd_data': [_DP, _P, _I, _P, _P, _I, _P, _I, _P, _I, _P],
     'dvsr_mdcn_tc_supported': [_DP],
     'dvsr_mdcn_tc_fprop': [_DP, _P, _P],
-    'dvsr_mdcn_tc_set_staged': [_I],
     'dvsr_mdcn_workspace_bytes': [_I] * 12,
     'dvsr_mdcn_forward_nchw': [_P] * 6 + [_I] * 12 + [_P, _LL, _P],
     'dvsr_mdcn_backward_nchw': [_P] * 10 + [_I] * 12 + [_P, _LL, _P],
@@ -117,8 +121,7 @@ SIGNATURES = {
     'dvsr_update_adam': [_P, _P, _P, _P, _LL, _LL, _F, _F, _F, _F, _F, _F, _F, _F, _P],
     'dvsr_update_peers': [_P, _P, _I, _LL, _F, _P, _P, _LL, _LL, _F, _F, _F, _F, _F, _F, _F, _F, _I, _P],
     'dvsr_abs_sum': [_P, _P, _LL, _I, _I, _I, _P],
-    'dvsr_set_cta_budget': [_I],
-    'dvsr_get_cta_budget': [],
+    'dvsr_sm_count': [],
     'dvsr_last_error': [],
     'dvsr_version': [],
 }

@@ -16,6 +16,7 @@ step (forward, backward, update) and the final forward are captured in CUDA grap
 """
 import copy
 import ctypes
+import weakref
 
 import torch
 
@@ -56,6 +57,14 @@ class FlatParams(object):
                 n += (p.numel() + self.ALIGN - 1) // self.ALIGN * self.ALIGN
         if self.split is None:
             self.split = n
+        for p in params:
+            owner = getattr(p, '_dvsr_flat', None)
+            owner = owner() if owner is not None else None
+            if owner is not None and owner is not self:
+                # a parameter lives in exactly one flat buffer: re-homing it again would orphan the first owner's buffers
+                # (its optimiser would then step a buffer no parameter points to).  Release the previous owner explicitly.
+                raise RuntimeError('parameter already belongs to another FlatParams (e.g. the FlatOptimizer create_model built '
+                                   'for is_train); call its .release() first, or hand that FlatParams to the new engine')
         device = device or params[0].device
         self.numel = n
         self.flat = torch.zeros(n, device=device, dtype=torch.float32)
@@ -69,17 +78,37 @@ class FlatParams(object):
                 p.grad = None
                 p._dvsr_grad = self.grad[o:o + p.numel()].view(p.shape)   # kernels accumulate here directly
                 p._dvsr_scope = self.scope
+                p._dvsr_flat = weakref.ref(self)
+        self.released = False
         self.meta = self.flat.clone()       # the meta-weights every frame restarts from
         self.m = self.v = None
         self.step_count = 0
         ops.invalidate_weight_cache(self.scope)
 
+    def release(self):
+        """Give the parameters back: each gets its own storage again (current values), the flat-gradient slots and the scope
+        tag are removed, and every later use of this object raises.  After this another FlatParams / engine may adopt them."""
+        with torch.no_grad():
+            for p in self.params:
+                p.data = p.data.clone()
+                for a in ('_dvsr_grad', '_dvsr_scope', '_dvsr_flat'):
+                    if hasattr(p, a):
+                        delattr(p, a)
+        self.released = True
+        ops.invalidate_weight_cache(self.scope)
+
+    def _alive(self):
+        if self.released:
+            raise RuntimeError('this FlatParams was released: its parameters now live elsewhere')
+
     def snapshot(self):
+        self._alive()
         self.meta.copy_(self.flat)
         ops.invalidate_pack_snapshot(self.scope)
 
     def restore(self):
         """test_dynavsr.py:208 -- one D2D copy instead of two module deep-copies."""
+        self._alive()
         self.flat.copy_(self.meta)
         self.step_count = 0
         if self.m is not None:
@@ -90,24 +119,36 @@ class FlatParams(object):
     def zero_grad(self):
         self.grad.zero_()
 
+    def fold_autograd_grads(self):
+        """Gradients that reached a parameter through ``p.grad`` (ops that are not this library's: a torch loss on the weights,
+        a regulariser) are added to the flat gradient and cleared, so the fused update never silently ignores them."""
+        for p in self.params:
+            if p.grad is not None:
+                p._dvsr_grad.add_(p.grad)
+                p.grad = None
+
     def sgd_step(self, lr0, lr1, weight_decay=0.0):
-        ops.join_async()        # weight-gradient kernels run on a side stream
+        self._alive()
+        self.fold_autograd_grads()
+        ops.join_async(self.scope)        # weight-gradient kernels run on this scope's side stream
         call('dvsr_update_sgd', _p(self.flat), _p(self.grad), self.numel, self.split, float(lr0), float(lr1),
              float(weight_decay), _stream())
-        ops.weights_updated()
+        ops.weights_updated(self.scope)
 
     def adam_step(self, lr0, lr1, betas=(0.9, 0.999), eps=1e-8, step=None, weight_decay=0.0):
+        self._alive()
+        self.fold_autograd_grads()
         if self.m is None:
             self.m = torch.zeros_like(self.flat)
             self.v = torch.zeros_like(self.flat)
-        ops.join_async()
+        ops.join_async(self.scope)
         self.step_count = self.step_count + 1 if step is None else step
         t = self.step_count
         bc1, bc2 = 1.0 - betas[0] ** t, 1.0 - betas[1] ** t
         call('dvsr_update_adam', _p(self.flat), _p(self.grad), _p(self.m), _p(self.v), self.numel, self.split,
              float(lr0), float(lr1), float(betas[0]), float(betas[1]), float(eps), float(bc1), float(bc2),
              float(weight_decay), _stream())
-        ops.weights_updated()
+        ops.weights_updated(self.scope)
 
 
 class InnerLoopAdapter(object):
@@ -119,7 +160,7 @@ class InnerLoopAdapter(object):
     """
 
     def __init__(self, netG, netE, netE_fixed, steps=2, lr_alpha=1e-5, lr_alpha_est=None, optimizer='SGD',
-                 betas=(0.9, 0.99), criterion='l2', slr_weight=10.0, pixel_weight=1.0, use_graphs=True, inner_precision=None):
+                 betas=(0.9, 0.99), criterion='l2', slr_weight=10.0, pixel_weight=1.0, use_graphs=True, inner_precision=None, policy=None):
         if optimizer not in ('SGD', 'Adam'):
             raise NotImplementedError(optimizer)
         if criterion not in ('l1', 'l2', 'cb'):
@@ -135,7 +176,8 @@ class InnerLoopAdapter(object):
         # the adaptation moves it (profiles/r1_precision_study.md: SGD tolerates 'bf16' throughout; Adam's normalised step does
         # not -- keep its forward at 'bf16x3', i.e. (None, 'bf16')).  The final forward always runs at the backend's precision.
         self.inner_precision = inner_precision
-        self.scope = ops.new_scope()        # this engine's weight packs / pack table / weight-gradient side stream
+        # this engine's weight packs / pack table / weight-gradient side stream / launch policy of the persistent kernels
+        self.scope = ops.new_scope(policy)
         self.flat = FlatParams([netG, netE], scope=self.scope)
         for p in netE_fixed.parameters():
             p.requires_grad_(False)
@@ -273,20 +315,22 @@ class AdaptationPool(object):
     CUDA graphs and streams; nothing is shared but the (read-only) meta-weights they were cloned from.
     """
 
-    def __init__(self, netG, netE, netE_fixed, pipelines=6, cta_budget=None, min_tiles_per_cta=None, **kw):
+    def __init__(self, netG, netE, netE_fixed, pipelines=6, cta_budget=None, min_tiles_per_cta=None, min_chunks_per_cta=None, **kw):
         assert pipelines >= 1
         # Launch policy of the persistent kernels while several frames share the GPU (measured on B200, bench.py sweep):
         # a launch is held to ~1/4 of the SMs and every conv CTA takes >= 2 tiles, so the pipelines' launches run side by
         # side instead of queueing behind each other's 148-CTA grids.  One pipeline keeps the whole GPU per launch.
-        self.cta_budget = cta_budget if cta_budget is not None else (148 if pipelines == 1 else (74 if pipelines < 4 else 37))
+        # The policy lives in each engine's PackScope and travels inside every descriptor (dvsr_policy): two pools with
+        # different policies in one process do not interact.
+        sms = _lib.lib().dvsr_sm_count() if torch.cuda.is_available() else 148
+        self.cta_budget = cta_budget if cta_budget is not None else (sms if pipelines == 1 else (sms // 2 if pipelines < 4 else sms // 4))
         self.min_tiles_per_cta = min_tiles_per_cta if min_tiles_per_cta is not None else (1 if pipelines == 1 else 2)
-        _lib.lib().dvsr_set_cta_budget(self.cta_budget)
-        _lib.lib().dvsr_conv_tc2_set_min_tiles_per_cta(self.min_tiles_per_cta)
-        _lib.lib().dvsr_conv_wgrad_tc_set_min_chunks_per_cta(4 if pipelines == 1 else 24)   # fewer split-K partial sums
+        self.min_chunks_per_cta = min_chunks_per_cta if min_chunks_per_cta is not None else (4 if pipelines == 1 else 24)   # fewer split-K partial sums
         nets = [(netG, netE, netE_fixed)]
         for _ in range(pipelines - 1):          # clone BEFORE any engine re-homes the parameters
             nets.append((copy.deepcopy(netG), copy.deepcopy(netE), copy.deepcopy(netE_fixed)))
-        self.engines = [InnerLoopAdapter(g, e, f, **kw) for g, e, f in nets]
+        self.engines = [InnerLoopAdapter(g, e, f, policy=ops.LaunchPolicy(self.cta_budget, self.min_tiles_per_cta, self.min_chunks_per_cta),
+                                         **kw) for g, e, f in nets]
         self.streams = [torch.cuda.Stream() for _ in self.engines]
         self._next = 0
         self.scale = netG.scale

@@ -26,15 +26,26 @@ int check_launch(const char* what) {
     return DVSR_OK;
 }
 
-static int g_cta_budget = 148;
-int cta_budget() { return g_cta_budget; }
+// SMs of the current device, queried once per device (nothing assumes 148)
+int sm_count() {
+    static int cached[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+    if (cached[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n < 1) n = 148;
+        cached[dev] = n;
+    }
+    return cached[dev];
+}
+// CTAs one launch of a persistent kernel may use: the call's policy, clamped to the device (0 = every SM)
+int cta_budget(const dvsr_policy& pol) {
+    const int n = sm_count();
+    return (pol.cta_budget < 1 || pol.cta_budget > n) ? n : pol.cta_budget;
+}
 
 }  // namespace dvsr
 
-// SM budget of ONE launch of the persistent kernels (conv_tc2, conv_wgrad_tc, mdcn_tc): with P frames in flight on P
-// streams (adapt.AdaptationPool) every launch is held to ~148 / P CTAs, so the pipelines run side by side instead of a
-// 148-CTA launch of one frame holding up the 30-CTA launches of the others.  148 (default) = the whole GPU.
-extern "C" int dvsr_set_cta_budget(int n) { dvsr::g_cta_budget = n < 1 ? 1 : (n > 148 ? 148 : n); return 0; }
-extern "C" int dvsr_get_cta_budget(void) { return dvsr::g_cta_budget; }
+extern "C" int dvsr_sm_count(void) { return dvsr::sm_count(); }
 extern "C" const char* dvsr_last_error(void) { return dvsr::g_err; }
 extern "C" int dvsr_version(void) { return 100; }

@@ -11,7 +11,8 @@ namespace dvsr {
 // ---- error plumbing: every extern "C" entry returns 0 or a negative code; message via dvsr_last_error()
 void set_error(const char* fmt, ...);
 int check_launch(const char* what);   // cudaGetLastError() -> code
-int cta_budget();                     // CTAs one launch of a persistent kernel may use (dvsr_set_cta_budget)
+int sm_count();                       // SMs of the current device (cached query)
+int cta_budget(const dvsr_policy& pol);   // CTAs one launch of a persistent kernel may use (policy, clamped to the device)
 
 #define DVSR_REQUIRE(cond, ...)                 \
     do {                                        \

@@ -700,8 +700,8 @@ extern "C" int dvsr_conv_wgrad(const dvsr_conv_desc* d, const float* gy, int gy_
     for (int s = 0; s < d->nseg; ++s) chunks += dense ? (KK * d->seg[s].C + BK - 1) / BK : ((d->seg[s].C + BK - 1) / BK) * KK;
     const long long M = (long long)d->N * d->Ho * d->Wo;
     const int gx = cdiv(chunks, WK / BK), gyd = cdiv(d->Co, BN);
-    // enough pixel splits for ~4 waves of 148 SMs x 2 CTAs, at least 256 pixels per split
-    long long splits = (4LL * 296 + (long long)gx * gyd - 1) / ((long long)gx * gyd);
+    // enough pixel splits for ~4 waves of 2 CTAs per SM, at least 256 pixels per split
+    long long splits = (8LL * sm_count() + (long long)gx * gyd - 1) / ((long long)gx * gyd);
     long long max_splits = (M + 255) / 256;
     if (splits > max_splits) splits = max_splits;
     if (splits < 1) splits = 1;
@@ -733,7 +733,7 @@ extern "C" int dvsr_conv_small_co(const dvsr_conv_desc* d, const float* wp, void
     DVSR_REQUIRE(smem <= 48 * 1024, "conv_small_co: weights do not fit in shared memory");
     if (d->seg[0].C % 16 == 0) {
         int blocks = cdiv(M * 4, 256);
-        if (blocks > 148 * 8) blocks = 148 * 8;
+        if (blocks > sm_count() * 8) blocks = sm_count() * 8;
         conv_small_co4_kernel<<<blocks, 256, smem, (cudaStream_t)stream>>>(*d, wp);
     }
     else conv_small_co_kernel<<<cdiv(M, 128), 128, smem, (cudaStream_t)stream>>>(*d, wp);

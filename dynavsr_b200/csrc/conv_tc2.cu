@@ -21,6 +21,9 @@
 //     into columns [0,64); the epilogue adds the two halves.  fp32-class accuracy (4.6e-6 per layer) at the speed of the
 //     single-pass TF32 mode, because one read of the activation operand serves two products.
 //   TF32 -- operands rounded to nearest in shared memory / at pack time (modes 5 / 6), one product (2.9e-4 per layer).
+//   BF16 (mode 2) -- the BF16x3 layouts and packs unchanged, but only x_hi . w_hi is issued (N = n_mma, rows 0-63 of a weight
+//     block): plain bf16 operands with fp32 accumulation, ~3e-3 per layer.  Meant for the inner adaptation steps, whose errors
+//     reach the output frame attenuated by how little the adaptation moves it (profiles/r1_precision_study.md).
 // The kernel is bounded by shared-memory bandwidth (both MMA operands come from shared memory: 321 KB per chunk-tile at
 // 128 B/clk, see profiles/r1_conv_tc2_timeline.txt).
 // Warp roles: 0 = TMA producer, 1 = MMA issuer / TMEM owner, 2-5 = operand conversion of the halo tile,
@@ -60,7 +63,8 @@ struct T2Params {
     int shuffle;
     float* y; int y_pix_stride;
     int y_vec8;                           // y rows are 32-byte aligned: 256-bit stores
-    int bf16x3;                           // 1: operands split into bf16 hi + lo, 3 products (fp32-class accuracy)
+    int bf16x3;                           // 1: operands split into bf16 hi + lo, 3 products (fp32-class accuracy);
+                                          // 2: same layouts, only x_hi . w_hi is issued (plain bf16 operands, fp32 accumulate)
     int n_mma;                            // MMA N (16..64): output channels of this launch's widest group, rounded up to 16
     int scalar_out;                       // narrow / unaligned outputs (conv_last 64 -> 3): scalar epilogue, Co <= 32
     long long* trace;                     // optional per-event clock64 trace of CTA (0,0): [event][chunk]
@@ -169,7 +173,8 @@ conv_tc2_kernel(const __grid_constant__ T2Maps maps, const T2Params p) {
         // ===================== MMA issuer =====================
         const uint32_t idesc = p.bf16x3 ? make_idesc_bf16(128, p.n_mma) : make_idesc_tf32(128, p.n_mma);
         const uint32_t idesc_wide = make_idesc_bf16(128, 2 * T2_NG);      // [w_hi | w_lo] stacked along N (BF16x3, full groups)
-        const bool wide = p.bf16x3 && p.n_mma == T2_NG;
+        const bool wide = p.bf16x3 == 1 && p.n_mma == T2_NG;
+        const bool single = p.bf16x3 == 2;
         // descriptor templates: only the 14-bit (address >> 4) field changes per tap / k-step
         const uint64_t ad_const = make_desc(0, 16, (uint32_t)p.halo_w * 128u, 2);
         const uint64_t bd_const = make_desc(0, 16, 1024, 2);
@@ -201,6 +206,9 @@ conv_tc2_kernel(const __grid_constant__ T2Maps maps, const T2Params p) {
                                 mma_tf32(dcol, ad + 2, bd + 2, idesc, 1u);
                                 mma_tf32(dcol, ad + 4, bd + 4, idesc, 1u);
                                 mma_tf32(dcol, ad + 6, bd + 6, idesc, 1u);
+                            } else if (single) {
+                                mma_bf16(dcol, ad, bd, idesc, first);                 // x_hi . w_hi only
+                                mma_bf16(dcol, ad + 2, bd + 2, idesc, 1u);
                             } else if (wide) {
                                 // activation row = [hi(32 bf16) | lo(32 bf16)]; weight rows 0-63 = hi, 64-127 = lo; K = 16 = +2
                                 mma_bf16(dcol, ad, bd, idesc_wide, first);            // x_hi . [w_hi | w_lo] -> columns [0,64) | [64,128)
@@ -293,7 +301,7 @@ conv_tc2_kernel(const __grid_constant__ T2Maps maps, const T2Params p) {
             if (threadIdx.x == 192) T2_TRACE(5, local);
             float v0[32], v1[32];
             const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 2 * T2_NG);
-            const bool wide = p.bf16x3 && p.n_mma == T2_NG;     // columns [64,128) hold the x_hi . w_lo partial sums
+            const bool wide = p.bf16x3 == 1 && p.n_mma == T2_NG;     // columns [64,128) hold the x_hi . w_lo partial sums
             tmem_ld32(tacc, v0);
             if (p.scalar_out) {
                 // narrow output (Co <= 32, any alignment): one 32-column read, per-channel loads / stores
@@ -377,20 +385,21 @@ conv_tc2_kernel(const __grid_constant__ T2Maps maps, const T2Params p) {
 using namespace dvsr;
 
 static long long* g_t2_trace = nullptr;
-static int g_t2_min_tiles = 1;
-// Grid policy: 1 (default) = one tile per CTA until the GPU is full (lowest latency of a single launch); n > 1 = at least n
-// tiles per CTA (fewer, longer-lived CTAs: less SM-time per launch when several streams share the GPU).
-extern "C" int dvsr_conv_tc2_set_min_tiles_per_cta(int n) { g_t2_min_tiles = n < 1 ? 1 : n; return 0; }
+// Grid policy (d->policy.min_tiles): 1 (default) = one tile per CTA until the GPU is full (lowest latency of a single launch);
+// n > 1 = at least n tiles per CTA (fewer, longer-lived CTAs: less SM-time per launch when several streams share the GPU).
 // debugging aid: device buffer of 8 x 64 clock64 stamps written by CTA (0,0) of the next launches (nullptr = off)
 extern "C" int dvsr_conv_tc2_set_trace(long long* dev_buffer) { g_t2_trace = dev_buffer; return 0; }
 
-static int g_t2_bf16x3 = 1;
+// kernel-side precision code (T2Params.bf16x3): 0 = TF32, 1 = BF16x3, 2 = plain bf16 on the BF16x3 layouts
+static int t2_prec_code(const dvsr_conv_desc* d) {
+    return d->policy.precision == DVSR_PREC_TF32 ? 0 : (d->policy.precision == DVSR_PREC_BF16 ? 2 : 1);
+}
 // resident weight footprint in 8 KiB units: TF32 -- one 64-row block per (32-channel chunk, tap); BF16x3 -- one 128-row
 // (16 KiB) block per (64-channel pair, tap)
 static int t2_blocks(const dvsr_conv_desc* d) {
     int n = 0;
     for (int s = 0; s < (d->wshare ? 1 : d->nseg); ++s)
-        n += g_t2_bf16x3 ? 2 * ((d->seg[s].C + 63) / 64) : (d->seg[s].C + 31) / 32;
+        n += t2_prec_code(d) ? 2 * ((d->seg[s].C + 63) / 64) : (d->seg[s].C + 31) / 32;
     return n * d->KH * d->KW;
 }
 
@@ -453,10 +462,6 @@ extern "C" int dvsr_pack_weights_tc2(const float* w, float* wp, const dvsr_wlayo
     return dvsr_pack_job_run(&j, stream);      // the kernel lives in pack_table.cu (no cross-TU device linking)
 }
 
-// 1 (default): BF16x3 split operands (3 products, ~1e-5 per layer); 0: single-pass TF32 with round-to-nearest (~3e-4)
-extern "C" int dvsr_conv_tc2_set_precision(int bf16x3) { g_t2_bf16x3 = bf16x3 ? 1 : 0; return 0; }
-extern "C" int dvsr_conv_tc2_get_precision(void) { return g_t2_bf16x3; }
-
 extern "C" int dvsr_conv_tc2_fprop(const dvsr_conv_desc* d, const float* wp, const float* accum_in, int accum_pix_stride, void* stream) {
     DVSR_REQUIRE(d && wp && d->y, "conv_tc2_fprop: null pointer");
     DVSR_REQUIRE(dvsr_conv_tc2_supported(d), "conv_tc2_fprop: unsupported shape");
@@ -472,7 +477,7 @@ extern "C" int dvsr_conv_tc2_fprop(const dvsr_conv_desc* d, const float* wp, con
     p.Co = d->Co;
     p.halo_h = T2_TH + d->KH - 1; p.halo_w = T2_TW + d->KW - 1;
     p.a_bytes = (p.halo_h * p.halo_w * 128 + 1023) / 1024 * 1024;
-    p.bf16x3 = g_t2_bf16x3;
+    p.bf16x3 = t2_prec_code(d);
     p.wblk_rows = p.bf16x3 ? 128 : T2_NG;
     p.wblk_bytes = p.wblk_rows * 128;
     {
@@ -531,11 +536,12 @@ extern "C" int dvsr_conv_tc2_fprop(const dvsr_conv_desc* d, const float* wp, con
             return check_launch("conv_tc2_fprop: cudaFuncSetAttribute");
         smem_set = smem;
     }
-    int ctas_x = cta_budget() / ngroups;
+    int ctas_x = cta_budget(d->policy) / ngroups;
     if (ctas_x < 1) ctas_x = 1;
-    // throughput mode: at least g_t2_min_tiles tiles per CTA, so that the per-CTA fixed cost (147 KB of weights, pipeline
+    // throughput mode: at least min_tiles tiles per CTA, so that the per-CTA fixed cost (147 KB of weights, pipeline
     // fill) is amortised and the SMs left free serve the other frames in flight (adapt.AdaptationPool)
-    const int want = (p.tiles_total + g_t2_min_tiles - 1) / g_t2_min_tiles;
+    const int min_tiles = d->policy.min_tiles < 1 ? 1 : d->policy.min_tiles;
+    const int want = (p.tiles_total + min_tiles - 1) / min_tiles;
     if (ctas_x > want) ctas_x = want;
     if (ctas_x > p.tiles_total) ctas_x = p.tiles_total;
     dim3 grid(ctas_x, ngroups);

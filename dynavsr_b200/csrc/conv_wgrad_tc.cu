@@ -182,10 +182,8 @@ static int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
 using namespace dvsr;
 
-static int g_wg_min_chunks = 4;
-// Split-K policy: at least n pixel chunks (8 x CH pixels each) per CTA.  4 (default) favours the latency of one launch;
-// larger values mean fewer CTAs and fewer red.global.add partial sums per launch -- less SM-time when streams share the GPU.
-extern "C" int dvsr_conv_wgrad_tc_set_min_chunks_per_cta(int n) { g_wg_min_chunks = n < 1 ? 1 : n; return 0; }
+// Split-K policy (d->policy.min_chunks): at least n pixel chunks (8 x CH pixels each) per CTA.  4 (default) favours the latency
+// of one launch; larger values mean fewer CTAs and fewer partial sums per launch -- less SM-time when streams share the GPU.
 
 // Is segment `seg` of forward descriptor `d` eligible for the tensor-core weight gradient?
 extern "C" int dvsr_conv_wgrad_tc_supported(const dvsr_conv_desc* d, int seg) {
@@ -245,10 +243,11 @@ extern "C" int dvsr_conv_wgrad_tc(const dvsr_conv_desc* d, int seg, const float*
     p.chunks_total = d->N * tiles_w * tiles_h;
     const int ztiles = (g.C + 127) / 128;
     // enough pixel splits to fill the GPU once (1 CTA per SM), at least 4 chunks per CTA
-    int splits = cta_budget() / (groups * ztiles);
+    int splits = cta_budget(d->policy) / (groups * ztiles);
     if (splits < 1) splits = 1;
     int per = (p.chunks_total + splits - 1) / splits;
-    if (per < g_wg_min_chunks) per = g_wg_min_chunks;
+    const int min_chunks = d->policy.min_chunks < 1 ? 4 : d->policy.min_chunks;
+    if (per < min_chunks) per = min_chunks;
     p.chunks_per_cta = per;
     splits = (p.chunks_total + per - 1) / per;
     p.co_stride = wl->co_stride; p.ci_stride = wl->ci_stride; p.seg_base = wl->seg_base[seg];

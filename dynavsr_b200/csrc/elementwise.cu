@@ -486,7 +486,7 @@ __global__ void frame_to_u8_kernel(const float* __restrict__ x, unsigned char* _
 template <typename F>
 static int launch_1d(long long total, F f) {
     int blocks = (int)((total + 255) / 256);
-    if (blocks > 148 * 16) blocks = 148 * 16;  // grid-stride; 16 CTAs of 256 threads per SM
+    if (blocks > sm_count() * 16) blocks = sm_count() * 16;  // grid-stride; 16 CTAs of 256 threads per SM
     if (blocks < 1) blocks = 1;
     f(blocks);
     return 0;
@@ -655,7 +655,7 @@ extern "C" int dvsr_tcat_pad3(const float* x, float* y, int B, int T, int H, int
     DVSR_REQUIRE(A16(y), "tcat_pad3: output must be 16-byte aligned");
     const long long total = (long long)B * T * (H + 2) * (W + 2);
     long long blocks = (total + 255) / 256;
-    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks > sm_count() * 16) blocks = sm_count() * 16;
     tcat_pad3_kernel<<<(int)blocks, 256, 0, ST>>>(x, y, B, T, H, W, C);
     return check_launch("tcat_pad3");
 }
@@ -709,7 +709,7 @@ extern "C" int dvsr_act_bwd(const float* gy, const float* y, const float* res, f
     DVSR_REQUIRE(threads <= 1024, "act_bwd: C=%d too wide", C);
     const int rows = threads / cw;
     long long blocks = (npix + (long long)rows * 8 - 1) / ((long long)rows * 8);
-    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks > sm_count() * 8) blocks = sm_count() * 8;
     if (blocks < 1) blocks = 1;
     long long per = (npix + blocks - 1) / blocks;
     per = (per + rows - 1) / rows * rows;

@@ -534,10 +534,8 @@ extern "C" int dvsr_mdcn_tc_supported(const dvsr_conv_desc* d) {
     return 1;
 }
 
-static int g_mdcn_staged = 1;
-// 1 (default): large 3x3 / stride 1 launches use the staged-window kernel; 0: always the direct-gather kernel; 2: staged at
-// every size (A/B measurements, tests)
-extern "C" int dvsr_mdcn_tc_set_staged(int on) { g_mdcn_staged = on < 0 ? 0 : on; return 0; }
+// d->policy.mdcn_staged -- 0 (default): large 3x3 / stride 1 launches use the staged-window kernel; 1: always the direct-gather
+// kernel; 2: staged at every size (A/B measurements, tests)
 
 // wp: dvsr_pack_weights_tc2 mode 7 (BF16x3 rows) over the single segment
 extern "C" int dvsr_mdcn_tc_fprop(const dvsr_conv_desc* d, const float* wp, void* stream) {
@@ -579,8 +577,9 @@ extern "C" int dvsr_mdcn_tc_fprop(const dvsr_conv_desc* d, const float* wp, void
     }
     // staged-window variant for the EDVR geometry (3x3, stride 1, pad 1, dilation 1); launches with fewer than ~2 tiles per SM
     // keep the direct kernel: one window load per CTA would not be amortised
-    if (g_mdcn_staged && d->KH == 3 && d->KW == 3 && d->stride == 1 && d->dil == 1 && d->pad == 1 && d->Ho == d->H && d->Wo == d->W &&
-        (g_mdcn_staged > 1 || (long long)d->N * ((d->Wo + 7) / 8) * ((d->Ho + 15) / 16) >= 296) &&
+    const int staged_mode = d->policy.mdcn_staged;
+    if (staged_mode != 1 && d->KH == 3 && d->KW == 3 && d->stride == 1 && d->dil == 1 && d->pad == 1 && d->Ho == d->H && d->Wo == d->W &&
+        (staged_mode == 2 || (long long)d->N * ((d->Wo + 7) / 8) * ((d->Ho + 15) / 16) >= 2 * sm_count()) &&
         (((uintptr_t)d->offset & 7) == 0) && ((d->off_pix_stride & 1) == 0)) {
         p.margin = 3;
         p.win_h = 16 + 2 + 2 * p.margin;
@@ -605,14 +604,14 @@ extern "C" int dvsr_mdcn_tc_fprop(const dvsr_conv_desc* d, const float* wp, void
                     return check_launch("mdcn_tc_fprop: cudaFuncSetAttribute");
                 smem_set_s = smem_s;
             }
-            const int ctas_s = p.tiles_total < cta_budget() ? p.tiles_total : cta_budget();
+            const int ctas_s = p.tiles_total < cta_budget(d->policy) ? p.tiles_total : cta_budget(d->policy);
             mdcn_tcs_kernel<<<ctas_s, MD_THREADS, smem_s, (cudaStream_t)stream>>>(wmap, xmap, p);
             return check_launch("mdcn_tc_fprop (staged)");
         }
         const long long M2 = (long long)d->N * d->Ho * d->Wo;
         p.tiles_total = (int)((M2 + 127) / 128);
     }
-    int ctas = p.tiles_total < cta_budget() ? p.tiles_total : cta_budget();
+    int ctas = p.tiles_total < cta_budget(d->policy) ? p.tiles_total : cta_budget(d->policy);
     mdcn_tc_kernel<<<ctas, MD_THREADS, smem, (cudaStream_t)stream>>>(wmap, p);
     return check_launch("mdcn_tc_fprop");
 }

@@ -98,7 +98,7 @@ __global__ void tsa_combine_bwd_kernel(const float* __restrict__ fea, const floa
 
 static int grid_for(long long work_items, int per_block) {
     long long b = (work_items + per_block - 1) / per_block;
-    if (b > 148 * 16) b = 148 * 16;
+    if (b > sm_count() * 16) b = sm_count() * 16;
     if (b < 1) b = 1;
     return (int)b;
 }

@@ -133,7 +133,7 @@ __global__ void abs_sum_kernel(const float* __restrict__ x, float* __restrict__ 
 
 static int blocks_for(long long n) {
     long long b = (n + 255) / 256;
-    if (b > 148 * 8) b = 148 * 8;
+    if (b > sm_count() * 8) b = sm_count() * 8;
     if (b < 1) b = 1;
     return (int)b;
 }

@@ -16,7 +16,7 @@ from ._lib import ACT_LRELU, ACT_NONE, ACT_RELU, ACT_SIGMOID_SPLIT, ConvDesc, WL
 
 __all__ = ['conv3d_rgb', 'PackScope', 'new_scope', 'scope', 'repack_all', 'snapshot_packs', 'restore_packs', 'invalidate_pack_snapshot', 'weights_updated', 'join_async', 'Seg', 'conv', 'conv3d_padded', 'mdcn', 'upsample', 'pool_maxavg', 'pad2d', 'pad3d_replicate',
            'tsa_temporal', 'tsa_combine', 'pixel_loss', 'to_nhwc', 'to_nchw', 'invalidate_weight_cache',
-           'ACT_NONE', 'ACT_RELU', 'ACT_LRELU', 'ACT_SIGMOID_SPLIT', 'set_conv_backend', 'conv_precision', 'frame_to_u8']
+           'ACT_NONE', 'ACT_RELU', 'ACT_LRELU', 'ACT_SIGMOID_SPLIT', 'LaunchPolicy', 'set_conv_backend', 'conv_precision', 'frame_to_u8']
 
 
 def _stream():
@@ -99,6 +99,19 @@ class _WeightCache(object):
 _wcache = _WeightCache()
 
 
+class LaunchPolicy(object):
+    """Launch policy of the persistent kernels for the calls of ONE engine (dvsr_policy in include/dvsr_b200.h; 0 = library
+    default).  It travels inside every descriptor: nothing about a launch is process-global state, so engines / pools with
+    different policies can share a process."""
+    __slots__ = ('cta_budget', 'min_tiles', 'min_chunks', 'mdcn_staged')
+
+    def __init__(self, cta_budget=0, min_tiles=0, min_chunks=0, mdcn_staged=0):
+        self.cta_budget, self.min_tiles, self.min_chunks, self.mdcn_staged = cta_budget, min_tiles, min_chunks, mdcn_staged
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k in self.__slots__}
+
+
 class PackScope(object):
     """Bookkeeping of ONE adaptation engine: its registered weight packs + device-side pack table, the epoch that marks
     packs stale after an out-of-band parameter write, and the side stream its weight-gradient kernels run on.
@@ -106,7 +119,8 @@ class PackScope(object):
     engine's single-launch re-pack never touches another engine's buffers.  Weights are bound to a scope with the
     ``_dvsr_scope`` attribute (adapt.FlatParams); untagged weights live in the process-wide default scope."""
 
-    def __init__(self):
+    def __init__(self, policy=None):
+        self.policy = policy or LaunchPolicy()
         self.registry = {}      # (id(weight), key) -> entry dict; entries die with their weight (weakref callback)
         self.table = {'dev': None, 'n': 0, 'blocks': 0, 'dirty': True}
         self.epoch = 0
@@ -120,8 +134,8 @@ _default_scope = PackScope()
 _current_scope = [_default_scope]
 
 
-def new_scope():
-    return PackScope()
+def new_scope(policy=None):
+    return PackScope(policy)
 
 
 class scope(object):
@@ -144,16 +158,28 @@ def _scope_of(weight):
     return getattr(weight, '_dvsr_scope', None) or _default_scope
 
 
+def _new_desc(weight=None):
+    """A zeroed dvsr_conv_desc carrying the launch policy of the engine that owns ``weight`` (its ``_dvsr_scope`` tag; the
+    current scope for untagged weights) and the operand precision in force (set_conv_backend / conv_precision)."""
+    d = ConvDesc()
+    pol = (getattr(weight, '_dvsr_scope', None) or _current_scope[0]).policy
+    d.policy.cta_budget, d.policy.min_tiles, d.policy.min_chunks, d.policy.mdcn_staged = \
+        pol.cta_budget, pol.min_tiles, pol.min_chunks, pol.mdcn_staged
+    d.policy.precision = _PRECISION_CODE[_backend['precision']]
+    return d
+
+
 def invalidate_weight_cache(s=None):
     """Call after parameters were modified through raw pointers; packs are refreshed lazily (one launch each)."""
     (s or _current_scope[0]).epoch += 1
 
 
-def weights_updated():
+def weights_updated(sc=None):
     """Call after a fused parameter update / restore: bumps the epoch and refreshes every registered pack with one
     table-driven launch (replaces ~370 per-layer pack launches per adaptation step)."""
-    _current_scope[0].epoch += 1
-    repack_all()
+    sc = sc or _current_scope[0]
+    sc.epoch += 1
+    repack_all(sc)
 
 
 def _layout(weight, seg_C, temporal):
@@ -220,10 +246,10 @@ def _drop_pack(scope_ref, rkey):
         sc.table['dirty'] = True
 
 
-def repack_all():
-    """Re-pack every weight layout registered in the current scope in ONE launch (dvsr_pack_table) and mark the packs
-    fresh."""
-    sc = _current_scope[0]
+def repack_all(sc=None):
+    """Re-pack every weight layout registered in scope ``sc`` (default: the current scope) in ONE launch (dvsr_pack_table)
+    and mark the packs fresh."""
+    sc = sc or _current_scope[0]
     _pack_table = sc.table
     ents = [e for e in sc.registry.values() if e['ref']() is not None]
     if not ents:
@@ -335,7 +361,7 @@ def _dgrad_stride2_tc(gpre, weight, wl, seg, shape, spec):
             Hi, Wi = (H - 1 - off_y) // 2 + 1, (W - 1 - off_x) // 2 + 1
             if KHs == 0 or KWs == 0:
                 continue
-            d = ConvDesc()
+            d = _new_desc(weight)
             d.N, d.H, d.W, d.Ho, d.Wo = N, spec.Ho, spec.Wo, Hi, Wi
             d.KH, d.KW, d.stride, d.pad, d.dil, d.transposed = KHs, KWs, 1, 0, 1, 1
             d.nseg = 1
@@ -351,41 +377,41 @@ def _dgrad_stride2_tc(gpre, weight, wl, seg, shape, spec):
 
 # --------------------------------------------------------------------------------------------------
 # convolution
-_backend = {'tc': False, 'precision': 'bf16x3'}
+_backend = {'tc': None, 'precision': 'bf16x3'}     # 'tc': None = auto (tcgen05 when the library exports it), True / False = forced
 
 
-_PRECISION_CODE = {'tf32': 0, 'bf16x3': 1, 'bf16': 2}
+_PRECISION_CODE = {'bf16x3': _lib.PREC_BF16X3, 'tf32': _lib.PREC_TF32, 'bf16': _lib.PREC_BF16}
+
+
+def _tc():
+    """Is the tcgen05 implicit-GEMM path selected?  It is the DEFAULT whenever the library has the entry points; the
+    exact-fp32 CUDA-core path is an explicit choice (``set_conv_backend(False)``: parity studies, op-level tests)."""
+    if _backend['tc'] is None:
+        _backend['tc'] = hasattr(_lib.lib(), 'dvsr_conv_tc2_fprop')
+    return _backend['tc']
 
 
 def set_conv_backend(tensor_cores, precision=None):
-    """Select the tcgen05 implicit-GEMM path for eligible layers.  ``precision`` of the resident-weight kernel:
-    'bf16x3' (default; split operands, 3 products, fp32-class accuracy), 'tf32' (single pass, ~3e-4 per layer) or 'bf16'
-    (the bf16x3 layouts with only the hi.hi product issued: ~3e-3 per layer, a third of the tensor-core work; needs a library
-    built with tools/patches/conv_tc2_single_product.diff -- raises NotImplementedError otherwise)."""
-    _backend['tc'] = bool(tensor_cores)
+    """Select the tcgen05 implicit-GEMM path (True, the default), the exact-fp32 CUDA-core path (False) or the library default
+    (None).  ``precision`` of the resident-weight kernel: 'bf16x3' (default; split operands, 3 products, fp32-class accuracy),
+    'tf32' (single pass, ~3e-4 per layer) or 'bf16' (the bf16x3 layouts with only the hi.hi product issued: ~3e-3 per layer, a
+    third of the tensor-core work).  The choice travels in every descriptor (dvsr_policy.precision), not in library state."""
+    _backend['tc'] = None if tensor_cores is None else bool(tensor_cores)
     if precision is not None:
         assert precision in _PRECISION_CODE
         _backend['precision'] = precision
-    code = _PRECISION_CODE[_backend['precision']]
-    if _lib.lib().dvsr_conv_tc2_get_precision() != code:
-        _lib.lib().dvsr_conv_tc2_set_precision(code)
-        if _lib.lib().dvsr_conv_tc2_get_precision() != code:        # a library built without that mode: fail loudly
-            _backend['precision'] = 'bf16x3'
-            _lib.lib().dvsr_conv_tc2_set_precision(1)
-            raise NotImplementedError('this build of libdvsr_b200.so has no conv precision %r '
-                                      '(single-product mode: tools/patches/conv_tc2_single_product.diff)' % precision)
 
 
 class conv_precision(object):
     """``with ops.conv_precision('bf16'):`` -- operand precision of the resident-weight tensor-core convolution for the
     launches issued (or captured into a CUDA graph) inside the block; restored on exit.  ``None`` and the exact-fp32 backend
-    make it a no-op.  The setting is process-global in the library: one host thread drives the launches of a process."""
+    make it a no-op.  The precision is stamped into each descriptor when the launch is issued."""
 
     def __init__(self, precision):
         self.precision, self.previous = precision, None
 
     def __enter__(self):
-        if self.precision is not None and _backend['tc'] and self.precision != _backend['precision']:
+        if self.precision is not None and _tc() and self.precision != _backend['precision']:
             self.previous = _backend['precision']
             set_conv_backend(True, self.precision)
         return self
@@ -403,36 +429,40 @@ class conv_precision(object):
 _async = {'on': True}
 
 
-def _side_stream():
-    sc = _current_scope[0]
+def _side_stream(sc=None):
+    sc = sc or _current_scope[0]
     if sc.side is None:
         sc.side = torch.cuda.Stream()
     return sc.side
 
 
-def join_async():
-    """Make the current stream wait for every weight-gradient kernel issued on the (current scope's) side stream."""
-    sc = _current_scope[0]
+def join_async(sc=None):
+    """Make the current stream wait for every weight-gradient kernel issued on the side stream of scope ``sc`` (default: the
+    current scope).  FlatParams joins its OWN scope, which is also the scope the kernels were queued under (the weight's
+    ``_dvsr_scope`` tag), so a backward pass run outside ``with ops.scope(...)`` is still ordered before the update."""
+    sc = sc or _current_scope[0]
     if sc.pending:
-        torch.cuda.current_stream().wait_stream(_side_stream())
+        torch.cuda.current_stream().wait_stream(_side_stream(sc))
         sc.pending.clear()
 
 
-def _run_wgrad(d, gpre, Co, gw, wl, keep=None, force_tc=False):
+def _run_wgrad(d, gpre, Co, gw, wl, keep=None, force_tc=False, weight=None):
     """gw += A^T gy with the tensor-core kernel when every segment qualifies, else the CUDA-core kernel.
-    ``keep`` (tensors the kernel reads) switches on side-stream execution; they stay referenced until join_async()."""
+    ``keep`` (tensors the kernel reads) switches on side-stream execution on the stream of the scope that owns ``weight``;
+    they stay referenced until that scope's join_async()."""
     if keep is not None and _async['on'] and not _lib.PROFILE['on']:
-        side = _side_stream()
+        sc = getattr(weight, '_dvsr_scope', None) or _current_scope[0]
+        side = _side_stream(sc)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             _run_wgrad(d, gpre, Co, gw, wl, force_tc=force_tc)
-        _current_scope[0].pending.append(keep)
+        sc.pending.append(keep)
         return
     L = _lib.lib()
     if _lib.PROFILE['on']:
         _lib.PROFILE['tag'] = 'wgrad %dx%dx%d C%s->%d k%d s%d%s' % (d.N, d.Ho, d.Wo, '+'.join(str(d.seg[i].C) for i in range(d.nseg)),
                                                                  d.Co, d.KH, d.stride, ' dcn' if d.deform else '')
-    if (_backend['tc'] or force_tc) and all(L.dvsr_conv_wgrad_tc_supported(ctypes.byref(d), s) == 1 for s in range(d.nseg)):
+    if (_tc() or force_tc) and all(L.dvsr_conv_wgrad_tc_supported(ctypes.byref(d), s) == 1 for s in range(d.nseg)):
         for s in range(d.nseg):
             call('dvsr_conv_wgrad_tc', ctypes.byref(d), s, _ptr(gpre), Co, _ptr(gw), ctypes.byref(wl), _stream())
     else:
@@ -486,7 +516,7 @@ def _try_tc2(d, weight, wl, data_grad, segs):
 
 
 def _use_tc(d):
-    return _backend['tc'] and _lib.lib().dvsr_conv_tc_supported(ctypes.byref(d)) == 1
+    return _tc() and _lib.lib().dvsr_conv_tc_supported(ctypes.byref(d)) == 1
 
 
 def _run_conv(d, weight, wl, data_grad=False, segs=(0,)):
@@ -497,7 +527,7 @@ def _run_conv(d, weight, wl, data_grad=False, segs=(0,)):
     if _lib.PROFILE['on']:
         _lib.PROFILE['tag'] = '%s %dx%dx%d C%s->%d k%d s%d' % ('dgrad' if data_grad else 'fprop', d.N, d.Ho, d.Wo,
                                                             '+'.join(str(d.seg[i].C) for i in range(d.nseg)), d.Co, d.KH, d.stride)
-    if _backend['tc'] and _backend.get('tc2', True) and _try_tc2(d, weight, wl, data_grad, segs):
+    if _tc() and _backend.get('tc2', True) and _try_tc2(d, weight, wl, data_grad, segs):
         return
     if data_grad:
         mode = 3 if tc else 1
@@ -514,8 +544,8 @@ def _run_conv(d, weight, wl, data_grad=False, segs=(0,)):
         call('dvsr_conv_fprop', ctypes.byref(d), _ptr(wp), _stream())
 
 
-def _fwd_desc(spec, tensors):
-    d = ConvDesc()
+def _fwd_desc(spec, tensors, weight=None):
+    d = _new_desc(weight)
     d.N, d.H, d.W, d.Ho, d.Wo = spec.N, spec.H, spec.W, spec.Ho, spec.Wo
     d.KH, d.KW, d.stride, d.pad, d.dil = spec.KH, spec.KW, spec.stride, spec.pad, 1
     d.nseg = len(tensors)
@@ -530,7 +560,7 @@ class _ConvFn(Function):
         _check_cuda(weight, bias, res, *tensors)
         Co = weight.shape[0]
         wl = _layout(weight, [t.shape[3] for t in tensors], spec.temporal)
-        d = _fwd_desc(spec, tensors)
+        d = _fwd_desc(spec, tensors, weight)
         d.Co = Co
         d.bias = bias.data_ptr() if bias is not None else None
         d.act, d.slope, d.sig_split, d.shuffle = spec.act, spec.slope, spec.sig_split, spec.shuffle
@@ -579,9 +609,9 @@ class _ConvFn(Function):
         gw = None
         if need_w:
             gw = ctx.wslot if ctx.wslot is not None else torch.zeros_like(weight)
-            d = _fwd_desc(spec, tensors)
+            d = _fwd_desc(spec, tensors, weight)
             d.Co = Co
-            _run_wgrad(d, gpre, Co, gw, wl, keep=(gpre, gy, tensors) if ctx.wslot is not None else None)
+            _run_wgrad(d, gpre, Co, gw, wl, keep=(gpre, gy, tensors) if ctx.wslot is not None else None, weight=weight)
         if ctx.wslot is not None:
             gw = None
         if ctx.bslot is not None:
@@ -594,7 +624,7 @@ class _ConvFn(Function):
                 t, m0 = tensors[0], spec.metas[0]
                 KT = len(tensors)
                 gx = torch.empty_like(t)
-                d = ConvDesc()
+                d = _new_desc(weight)
                 d.N, d.H, d.W, d.Ho, d.Wo = t.shape[0], spec.Ho, spec.Wo, spec.H, spec.W
                 d.KH, d.KW, d.stride, d.pad, d.dil, d.transposed = spec.KH, spec.KW, spec.stride, spec.pad, 1, 1
                 d.nseg = KT
@@ -608,12 +638,12 @@ class _ConvFn(Function):
             for i, (t, m) in enumerate(zip(tensors, spec.metas)):
                 if not ctx.needs_input_grad[4 + i]:
                     continue
-                if spec.stride == 2 and _backend['tc'] and m.T == 1 and m.Tsrc == 1 and Co % 4 == 0 and Co >= 16 \
+                if spec.stride == 2 and _tc() and m.T == 1 and m.Tsrc == 1 and Co % 4 == 0 and Co >= 16 \
                         and 16 <= t.shape[3] <= 256 and t.shape[3] % 4 == 0:
                     gts[i] = _dgrad_stride2_tc(gpre, weight, wl, i, tuple(t.shape), spec)
                     continue
                 gx = torch.empty(t.shape, device=gy.device, dtype=torch.float32)
-                d = ConvDesc()
+                d = _new_desc(weight)
                 d.N, d.H, d.W, d.Ho, d.Wo = t.shape[0], spec.Ho, spec.Wo, spec.H, spec.W
                 d.KH, d.KW, d.stride, d.pad, d.dil, d.transposed = spec.KH, spec.KW, spec.stride, spec.pad, 1, 1
                 if m.T == 1 and m.Tsrc == 1:
@@ -697,7 +727,7 @@ class _Conv3dRgbFn(Function):
         wl.ci_bits, wl.ci_lo_valid = 2, C
         wl.seg_base[0], wl.seg_C[0] = 0, 12
         wl.nseg, wl.taps, wl.Co = 1, 9, Co
-        d = ConvDesc()
+        d = _new_desc(weight)
         d.N, d.H, d.W, d.Ho, d.Wo = BT, H + 2, W + 2, H, W
         d.KH, d.KW, d.stride, d.pad, d.dil = 3, 3, 1, 0, 1
         d.nseg = 1
@@ -737,7 +767,7 @@ class _Conv3dRgbFn(Function):
         gw = None
         if ctx.needs_input_grad[1]:
             gw = ctx.wslot if ctx.wslot is not None else torch.zeros_like(weight)
-            d = ConvDesc()
+            d = _new_desc(weight)
             d.N, d.H, d.W, d.Ho, d.Wo = BT, H + 2, W + 2, H, W
             d.KH, d.KW, d.stride, d.pad, d.dil = 3, 3, 1, 0, 1
             d.nseg = 1
@@ -745,7 +775,7 @@ class _Conv3dRgbFn(Function):
             d.Co = Co
             if _lib.lib().dvsr_conv_wgrad_tc_supported(ctypes.byref(d), 0) != 1:
                 raise RuntimeError('conv3d_rgb: weight gradient shape not supported')
-            _run_wgrad(d, gpre, Co, gw, ctx.wl, keep=(gpre, gy, xc) if ctx.wslot is not None else None, force_tc=True)
+            _run_wgrad(d, gpre, Co, gw, ctx.wl, keep=(gpre, gy, xc) if ctx.wslot is not None else None, force_tc=True, weight=weight)
         return None, (None if ctx.wslot is not None else gw), (None if ctx.bslot is not None else gb), None, None, None
 
 
@@ -767,7 +797,7 @@ class _MdcnFn(Function):
         Wo = (W + 2 * pad - (dil * (KW - 1) + 1)) // stride + 1
         assert om.shape == (N, Ho, Wo, 3 * dg * KK) and om.is_contiguous() and x.is_contiguous()
         wl = _layout(weight, [C], False)
-        d = _MdcnFn._desc(x, om, dg, KH, KW, stride, pad, dil, Ho, Wo)
+        d = _MdcnFn._desc(x, om, dg, KH, KW, stride, pad, dil, Ho, Wo, weight)
         d.Co = Co
         d.bias = bias.data_ptr() if bias is not None else None
         d.act, d.slope = act, slope
@@ -775,7 +805,7 @@ class _MdcnFn(Function):
         d.y, d.y_pix_stride = y.data_ptr(), Co
         if _lib.PROFILE['on']:
             _lib.PROFILE['tag'] = 'mdcn fwd %dx%dx%d C%d->%d' % (N, Ho, Wo, C, Co)
-        if _backend['tc'] and _lib.lib().dvsr_mdcn_tc_supported(ctypes.byref(d)) == 1:
+        if _tc() and _lib.lib().dvsr_mdcn_tc_supported(ctypes.byref(d)) == 1:
             nblocks = KK * ((C + 31) // 32)
             wp = _get_pack(weight, wl, 7, 0, 1, a=(nblocks, 0, 0, 0),
                            total=_lib.lib().dvsr_conv_tc2_packed_floats(ctypes.byref(wl), 7, 0, 1))
@@ -789,10 +819,10 @@ class _MdcnFn(Function):
         return y
 
     @staticmethod
-    def _desc(x, om, dg, KH, KW, stride, pad, dil, Ho, Wo):
+    def _desc(x, om, dg, KH, KW, stride, pad, dil, Ho, Wo, weight=None):
         N, H, W, C = x.shape
         KK = KH * KW
-        d = ConvDesc()
+        d = _new_desc(weight)
         d.N, d.H, d.W, d.Ho, d.Wo = N, H, W, Ho, Wo
         d.KH, d.KW, d.stride, d.pad, d.dil = KH, KW, stride, pad, dil
         d.nseg = 1
@@ -822,7 +852,7 @@ class _MdcnFn(Function):
             gpre = gy
             if need_b:
                 call('dvsr_act_bwd', _ptr(gy), None, None, None, _ptr(gb), npix, Co, ACT_NONE, 0.0, 0, 0, Ho, Wo, _stream())
-        d = _MdcnFn._desc(x, om, dg, KH, KW, stride, pad, dil, Ho, Wo)
+        d = _MdcnFn._desc(x, om, dg, KH, KW, stride, pad, dil, Ho, Wo, weight)
         d.Co = Co
         gx = gom = gw = None
         if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
@@ -834,7 +864,7 @@ class _MdcnFn(Function):
                  _ptr(gx), C, ctypes.c_void_p(goff_p), om.shape[3], ctypes.c_void_p(gmask_p), om.shape[3], _stream())
         if ctx.needs_input_grad[2]:
             gw = ctx.wslot if ctx.wslot is not None else torch.zeros_like(weight)
-            _run_wgrad(d, gpre, Co, gw, wl, keep=(gpre, gy, x, om) if ctx.wslot is not None else None)
+            _run_wgrad(d, gpre, Co, gw, wl, keep=(gpre, gy, x, om) if ctx.wslot is not None else None, weight=weight)
         if ctx.wslot is not None:
             gw = None
         if ctx.bslot is not None:

@@ -56,9 +56,31 @@ class FlatOptimizer(torch.optim.Optimizer):
         return sd
 
     def load_state_dict(self, sd):
+        """Accepts only what ``state_dict()`` of a FlatOptimizer over the SAME parameter set wrote: the moments are flat
+        buffers that the update kernel indexes with this optimiser's element count, so a state of another network
+        configuration (EDVR-M vs L, a different ``requires_grad`` set) or a torch-format state (per-tensor ``state`` dict,
+        ``param_groups`` with ``params`` index lists) is refused instead of being read out of bounds / half-applied."""
+        if 'state' in sd or 'kind' not in sd:
+            raise ValueError('FlatOptimizer.load_state_dict: this is a torch.optim-format state (per-tensor moments); the flat '
+                             'optimiser resumes only from its own state_dict() -- restart the moments or convert them')
+        if sd['kind'] != self.kind:
+            raise ValueError('FlatOptimizer.load_state_dict: saved optimiser kind %r, this one is %r' % (sd['kind'], self.kind))
+        saved_groups = sd.get('param_groups', [])
+        if len(saved_groups) != len(self.param_groups):
+            raise ValueError('FlatOptimizer.load_state_dict: %d saved param groups, %d here' % (len(saved_groups), len(self.param_groups)))
+        m, v = sd.get('exp_avg'), sd.get('exp_avg_sq')
+        if (m is None) != (v is None):
+            raise ValueError('FlatOptimizer.load_state_dict: exp_avg and exp_avg_sq must come together')
+        if m is not None:
+            for name, t in (('exp_avg', m), ('exp_avg_sq', v)):
+                if not torch.is_tensor(t) or t.dtype != torch.float32 or t.dim() != 1 or t.numel() != self.flat.numel:
+                    raise ValueError('FlatOptimizer.load_state_dict: %s must be a float32 vector of %d elements (this parameter '
+                                     'set), got %s' % (name, self.flat.numel, tuple(t.shape) if torch.is_tensor(t) else type(t)))
         self._step = int(sd.get('step', 0))
-        for g, saved in zip(self.param_groups, sd.get('param_groups', [])):
-            g.update(saved)
-        if 'exp_avg' in sd:
-            self.flat.m = sd['exp_avg'].to(self.flat.flat.device).clone()
-            self.flat.v = sd['exp_avg_sq'].to(self.flat.flat.device).clone()
+        for g, saved in zip(self.param_groups, saved_groups):
+            g.update({k: val for k, val in saved.items() if k != 'params'})
+        if m is not None:
+            self.flat.m = m.to(self.flat.flat.device).clone()
+            self.flat.v = v.to(self.flat.flat.device).clone()
+        else:
+            self.flat.m = self.flat.v = None

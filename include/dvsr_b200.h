@@ -45,6 +45,32 @@ extern "C" {
 
 #define DVSR_MAX_SEG 5
 
+/* Operand precision of the resident-weight tensor-core convolution (conv_tc2.cu), per launch (dvsr_policy.precision):
+ *   DVSR_PREC_BF16X3 (0, default) activations and weights split into bf16 hi + lo parts, the three significant products
+ *                    accumulated in fp32 (~5e-6 per layer; weights packed with mode 9 / 10);
+ *   DVSR_PREC_TF32   single-pass TF32 with operands rounded to nearest (~3e-4 per layer; pack mode 5 / 6);
+ *   DVSR_PREC_BF16   the BF16X3 layouts and packs, only the x_hi.w_hi product issued: plain bf16 operands, fp32
+ *                    accumulation (~3e-3 per layer, a third of the tensor-core work) -- for the inner adaptation steps,
+ *                    whose errors reach the frame attenuated (profiles/r1_precision_study.md). */
+#define DVSR_PREC_BF16X3 0
+#define DVSR_PREC_TF32 1
+#define DVSR_PREC_BF16 2
+
+/* Launch policy of ONE call.  Zero-initialised = library defaults; nothing about a launch lives in process-global state, so
+ * several engines (adapt.AdaptationPool pipelines, two pools with different settings) can share a process.
+ *   cta_budget  CTAs one launch of a persistent kernel (conv_tc2, conv_wgrad_tc, mdcn_tc) may use; 0 = every SM of the
+ *               current device (queried, not assumed).  With P frames in flight on P streams ~SMs / P lets their launches run
+ *               side by side.
+ *   min_tiles   conv_tc2: at least this many 128-pixel tiles per persistent CTA (0 = 1: lowest single-launch latency; larger
+ *               amortises the resident weights and leaves SMs to the other frames in flight).
+ *   min_chunks  conv_wgrad_tc split-K: at least this many pixel chunks per CTA (0 = 4).
+ *   precision   DVSR_PREC_* of conv_tc2.
+ *   mdcn_staged DCN forward gather: 0 = staged shared-memory window when the launch has >= 2 tiles per SM, 1 = always the
+ *               direct-gather kernel, 2 = always the staged kernel (A/B measurements, tests). */
+typedef struct dvsr_policy {
+    int cta_budget, min_tiles, min_chunks, precision, mdcn_staged;
+} dvsr_policy;
+
 /* One input "segment" of a convolution's K dimension: a group of C input channels read from one
  * NHWC tensor.  torch.cat([a, b], 1) feeding a conv is two segments; the 5-frame 1x1 fusion convs
  * of TSA are five; a Conv3d is one segment per temporal tap.  Output image n reads source image
@@ -83,6 +109,7 @@ typedef struct dvsr_conv_desc {
      * (oy*out_step + out_off_y, ox*out_step + out_off_x) of an out_H x out_W image and skipped when that falls
      * outside -- one parity class of the data gradient of a stride-2 convolution. */
     int out_step, out_off_y, out_off_x, out_H, out_W;
+    dvsr_policy policy;  /* launch policy of this call (all zero = defaults) */
 } dvsr_conv_desc;
 
 /* Where element (co, seg s, ci, tap) of a PyTorch-layout weight lives:
@@ -119,10 +146,8 @@ typedef struct dvsr_pack_job {
 
 const char* dvsr_last_error(void);
 int dvsr_version(void);
-/* SM budget of one launch of the persistent kernels (conv_tc2, conv_wgrad_tc, mdcn_tc), 1..148 (default 148 = whole GPU).
- * With P independent frames in flight on P streams, ~148 / P lets their launches run side by side. */
-int dvsr_set_cta_budget(int n);
-int dvsr_get_cta_budget(void);
+/* number of SMs of the current device (what cta_budget = 0 resolves to) */
+int dvsr_sm_count(void);
 
 /* ---- convolution family (conv_simt.cu; tensor-core fast path in conv_tc.cu) ---------------------- */
 /* Packed layouts.  mode 0 (forward):  wp[k][co],  k = kofs(s) + tap*C_s + ci.
@@ -158,28 +183,17 @@ int dvsr_conv_tc_fprop(const dvsr_conv_desc* d, const float* wp, void* stream);
  * Weights: dvsr_pack_weights_tc2 mode 5 / 9 (forward, segments [seg_lo, seg_hi)), mode 6 / 10 (data gradient of seg_lo);
  * 5 / 6 = TF32 rows (8 KiB blocks per (32-channel chunk, tap)); 9 / 10 = BF16x3 (16 KiB blocks per (64-channel pair, tap):
  * rows 0-63 hold the bf16 hi parts of 64 output channels, rows 64-127 the lo parts, so ONE N = 128 MMA gives x_hi.w_hi and
- * x_hi.w_lo); modes 7 / 8 are the [hi | lo]-per-row variant read by dvsr_mdcn_tc_fprop (see dvsr_conv_tc2_set_precision). */
+ * x_hi.w_lo); modes 7 / 8 are the [hi | lo]-per-row variant read by dvsr_mdcn_tc_fprop.  d->policy.precision selects the
+ * operand precision and must match the pack mode. */
 int dvsr_conv_tc2_supported(const dvsr_conv_desc* d);
 long long dvsr_conv_tc2_packed_floats(const dvsr_wlayout* wl, int mode, int seg_lo, int seg_hi);
 int dvsr_pack_weights_tc2(const float* w, float* wp, const dvsr_wlayout* wl, int mode, int seg_lo, int seg_hi, void* stream);
 int dvsr_conv_tc2_fprop(const dvsr_conv_desc* d, const float* wp, const float* accum_in, int accum_pix_stride, void* stream);
-/* Operand precision of conv_tc2: 1 (default) = BF16x3 -- activations and weights are split into bf16 hi + lo parts and
- * the three significant products are accumulated in fp32 (per-layer error ~1e-5, weights packed with mode 9 / 10);
- * 0 = single-pass TF32 with operands rounded to nearest (~3e-4 per layer, weights packed with mode 5 / 6). */
-int dvsr_conv_tc2_set_precision(int bf16x3);
-int dvsr_conv_tc2_get_precision(void);
-/* Grid policy of conv_tc2: at least n tiles (128 output pixels each) per persistent CTA.  1 (default) spreads a small
- * launch over as many SMs as it has tiles (lowest single-launch latency); n > 1 amortises the per-CTA cost (resident
- * weights, pipeline fill) and leaves SMs to the other frames in flight -- less SM-time per launch, higher throughput. */
-int dvsr_conv_tc2_set_min_tiles_per_cta(int n);
 /* debugging aid: 8 x 64 clock64 stamps of CTA (0,0) (producer / rounding / MMA / epilogue events); NULL = off */
 int dvsr_conv_tc2_set_trace(long long* dev_buffer);
 /* Tensor-core weight gradient of segment `seg` of a stride-1 convolution (conv_wgrad_tc.cu): both operands are
  * consumed MN-major straight from the NHWC tensors, x through one halo tile per pixel chunk. */
 int dvsr_conv_wgrad_tc_supported(const dvsr_conv_desc* d, int seg);
-/* Split-K policy of the tensor-core weight gradient: at least n pixel chunks per CTA (default 4; larger = fewer CTAs and
- * fewer atomically added partial sums per launch: less SM-time per launch when several streams share the GPU). */
-int dvsr_conv_wgrad_tc_set_min_chunks_per_cta(int n);
 int dvsr_conv_wgrad_tc(const dvsr_conv_desc* d, int seg, const float* gy, int gy_pix_stride, float* gw,
                        const dvsr_wlayout* wl, void* stream);
 /* Small-Cout direct convolution (conv_last, 64 -> 3): one thread per output pixel. */
@@ -199,9 +213,7 @@ int dvsr_mdcn_tc_supported(const dvsr_conv_desc* d);
 int dvsr_mdcn_tc_fprop(const dvsr_conv_desc* d, const float* wp, void* stream);
 /* 3x3 / stride-1 / pad-1 launches (every DCN of EDVR) stage a 24 x 16-pixel input window per 16 x 8 output tile and 32-channel
  * chunk in shared memory with one TMA box and gather the 36 corners per pixel from there (global fallback for corners a large
- * offset pushes outside the window) when the launch has at least two tiles per SM.  on = 0 forces the direct-gather kernel,
- * on = 2 the staged one at every size (A/B measurements, tests). */
-int dvsr_mdcn_tc_set_staged(int on);
+ * offset pushes outside the window) when the launch has at least two tiles per SM (d->policy.mdcn_staged overrides). */
 
 /* Reference operator boundary, NCHW fp32 (deform_conv_cuda.cpp:486-492, :566-573).  groups must be 1
  * (no YML of the reference uses groups != 1).  Workspace: dvsr_mdcn_workspace_bytes() bytes. */

@@ -20,6 +20,12 @@ def _fresh_weight_cache():
         ops._wcache.clear()
         ops._default_scope.registry.clear()
         ops._default_scope.table.update(dev=None, n=0, blocks=0, dirty=True)
+        # The PRODUCT default is the tcgen05 path (ops._backend['tc'] = None -> auto).  The op-level parity tests pin the
+        # exact-fp32 CUDA-core path against the oracle at 1e-5-class tolerances and switch the tensor-core path on explicitly
+        # where they test it, so every test starts from the exact path, default precision and default launch policy.
+        ops._backend['tc'] = False
+        ops._backend['precision'] = 'bf16x3'
+        ops._default_scope.policy = ops.LaunchPolicy()
     except Exception:
         pass
     yield

@@ -37,14 +37,16 @@ def test_descriptor_struct_sizes_match_header():
     import subprocess
     import tempfile
     from dynavsr_b200 import _lib
-    prog = '#include <stdio.h>\n#include <stddef.h>\n#include "dvsr_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu\\n",' \
-           'sizeof(dvsr_conv_seg),sizeof(dvsr_conv_desc),sizeof(dvsr_wlayout),offsetof(dvsr_conv_desc,Co),offsetof(dvsr_conv_desc,y));return 0;}'
+    prog = '#include <stdio.h>\n#include <stddef.h>\n#include "dvsr_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu\\n",' \
+           'sizeof(dvsr_conv_seg),sizeof(dvsr_conv_desc),sizeof(dvsr_wlayout),offsetof(dvsr_conv_desc,Co),offsetof(dvsr_conv_desc,y),' \
+           'offsetof(dvsr_conv_desc,policy),sizeof(dvsr_policy));return 0;}'
     with tempfile.TemporaryDirectory() as d:
         open(os.path.join(d, 't.c'), 'w').write(prog)
         subprocess.check_call(['gcc', '-I', os.path.join(ROOT, 'include'), os.path.join(d, 't.c'), '-o', os.path.join(d, 't')])
         out = subprocess.check_output([os.path.join(d, 't')]).decode().split()
     assert [int(v) for v in out] == [ctypes.sizeof(_lib.ConvSeg), ctypes.sizeof(_lib.ConvDesc), ctypes.sizeof(_lib.WLayout),
-                                     _lib.ConvDesc.Co.offset, _lib.ConvDesc.y.offset]
+                                     _lib.ConvDesc.Co.offset, _lib.ConvDesc.y.offset, _lib.ConvDesc.policy.offset,
+                                     ctypes.sizeof(_lib.Policy)]
 
 
 def test_missing_library_fails_loudly(monkeypatch):

@@ -121,12 +121,7 @@ def test_evaluate_reproduces_reference_driver_table(cuda, mode, tmp_path):
                                save_dir=str(tmp_path / 'demo'))
         assert all(np.isnan(v).all() for v in demo.values()) and os.path.exists(str(tmp_path / 'demo' / 'clip' / 'DynaVSR' / '00000001.png'))
     finally:
-        ops.set_conv_backend(False)
-        if tc:
-            from dynavsr_b200 import _lib
-            _lib.lib().dvsr_set_cta_budget(148)
-            _lib.lib().dvsr_conv_tc2_set_min_tiles_per_cta(1)
-            _lib.lib().dvsr_conv_wgrad_tc_set_min_chunks_per_cta(4)
+        ops.set_conv_backend(False)       # (the pool's launch policy lives in its engines' scopes: nothing global to undo)
 
 
 def test_resident_clips_feed_the_evaluation_loop(cuda):

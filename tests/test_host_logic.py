@@ -332,47 +332,99 @@ def test_wrappers_construct_with_reference_option_dicts(monkeypatch):
 
 
 def test_conv_precision_context(monkeypatch):
-    """ops.conv_precision: temporary operand precision of the resident-weight conv (library call stubbed): nests, restores,
-    is a no-op for None and under the exact-fp32 backend."""
-    from dynavsr_b200 import ops
-    calls = []
-
-    class Lib(object):
-        def dvsr_conv_tc2_get_precision(self):
-            return calls[-1] if calls else 1
-
-        def dvsr_conv_tc2_set_precision(self, code):
-            calls.append(code)
-
-    monkeypatch.setattr(ops._lib, 'lib', lambda: Lib())
+    """ops.conv_precision: temporary operand precision of the resident-weight conv: nests, restores (also on the error path), is a
+    no-op for None and under the exact-fp32 backend.  The precision is stamped into each descriptor (dvsr_policy.precision)
+    together with the launch policy of the scope that owns the weight -- there is no library-global state to set."""
+    from dynavsr_b200 import _lib, ops
     monkeypatch.setitem(ops._backend, 'tc', True)
     monkeypatch.setitem(ops._backend, 'precision', 'bf16x3')
+    assert ops._new_desc().policy.precision == _lib.PREC_BF16X3 == 0            # zero-initialised descriptor = default
     with ops.conv_precision('bf16'):
-        assert ops._backend['precision'] == 'bf16' and calls == [2]
+        assert ops._backend['precision'] == 'bf16' and ops._new_desc().policy.precision == _lib.PREC_BF16
         with ops.conv_precision(None):
             assert ops._backend['precision'] == 'bf16'
         with ops.conv_precision('tf32'):
-            assert calls == [2, 0]
-        assert ops._backend['precision'] == 'bf16' and calls == [2, 0, 2]
-    assert ops._backend['precision'] == 'bf16x3' and calls == [2, 0, 2, 1]
+            assert ops._new_desc().policy.precision == _lib.PREC_TF32
+        assert ops._backend['precision'] == 'bf16'
+    assert ops._backend['precision'] == 'bf16x3'
     with pytest.raises(RuntimeError):
         with ops.conv_precision('bf16'):
             raise RuntimeError('launch failed')
     assert ops._backend['precision'] == 'bf16x3'                       # restored on the error path too
     monkeypatch.setitem(ops._backend, 'tc', False)
-    n = len(calls)
     with ops.conv_precision('bf16'):
         assert ops._backend['precision'] == 'bf16x3'
-    assert len(calls) == n
     with pytest.raises(AssertionError):
         ops.set_conv_backend(True, 'fp8')
+    # launch policy: per scope, picked up from the weight's owner, independent of the current scope
+    a, b = ops.new_scope(ops.LaunchPolicy(37, 2, 24)), ops.new_scope(ops.LaunchPolicy(cta_budget=74, mdcn_staged=2))
+    w = torch.zeros(1)
+    w._dvsr_scope = a
+    with ops.scope(b):
+        d_cur, d_own = ops._new_desc(), ops._new_desc(w)
+    assert (d_cur.policy.cta_budget, d_cur.policy.min_tiles, d_cur.policy.min_chunks, d_cur.policy.mdcn_staged) == (74, 0, 0, 2)
+    assert (d_own.policy.cta_budget, d_own.policy.min_tiles, d_own.policy.min_chunks, d_own.policy.mdcn_staged) == (37, 2, 24, 0)
+    p0 = ops._new_desc().policy
+    assert (p0.cta_budget, p0.min_tiles, p0.min_chunks, p0.mdcn_staged) == (0, 0, 0, 0)
 
-    class OldLib(Lib):                                                  # a build without the single-product mode stores 1 for 2
-        def dvsr_conv_tc2_set_precision(self, code):
-            calls.append(1 if code else 0)
 
-    monkeypatch.setattr(ops._lib, 'lib', lambda: OldLib())
-    monkeypatch.setitem(ops._backend, 'tc', True)
-    with pytest.raises(NotImplementedError):
-        ops.set_conv_backend(True, 'bf16')
-    assert ops._backend['precision'] == 'bf16x3' and calls[-1] == 1     # nothing silently different
+def test_flat_params_single_owner_and_release():
+    """A parameter lives in exactly ONE flat buffer: re-homing it into a second FlatParams must fail loudly instead of
+    orphaning the first owner's buffers; release() hands the parameters back, after which the old owner refuses to be used."""
+    from dynavsr_b200.adapt import FlatParams
+    net = torch.nn.Sequential(torch.nn.Conv2d(3, 4, 3), torch.nn.Conv2d(4, 2, 1))
+    want = [p.detach().clone() for p in net.parameters()]
+    a = FlatParams([net])
+    assert all(p._dvsr_flat() is a and p.data.data_ptr() >= a.flat.data_ptr() for p in net.parameters())
+    with pytest.raises(RuntimeError, match='already belongs'):
+        FlatParams([net])
+    a.release()
+    assert all(not hasattr(p, '_dvsr_grad') and not hasattr(p, '_dvsr_flat') for p in net.parameters())
+    assert all(torch.equal(p.detach(), w) for p, w in zip(net.parameters(), want))
+    with pytest.raises(RuntimeError, match='released'):
+        a.restore()
+    b = FlatParams([net])                                        # adoptable again
+    assert all(p._dvsr_flat() is b for p in net.parameters())
+    # gradients that arrive through p.grad are folded into the flat gradient, not ignored
+    p0 = next(net.parameters())
+    p0.grad = torch.ones_like(p0)
+    b.fold_autograd_grads()
+    assert p0.grad is None and float(b.grad[:p0.numel()].sum()) == p0.numel()
+
+
+def test_flat_optimizer_state_round_trip_and_validation():
+    """FlatOptimizer.state_dict / load_state_dict: resume restores step, group settings and the flat moments; a state
+    of another parameter set, of another optimiser kind, or in torch.optim's per-tensor format is refused (the update kernel would
+    index the moments out of bounds / silently drop them)."""
+    from dynavsr_b200.optim import FlatOptimizer
+    mk = lambda co: torch.nn.Sequential(torch.nn.Conv2d(3, co, 3), torch.nn.Conv2d(co, 2, 1))
+    net = mk(4)
+    opt = FlatOptimizer([{'params': list(net[0].parameters())}, {'params': list(net[1].parameters()), 'lr': 5e-4}], kind='Adam', lr=1e-3)
+    opt.flat.m = torch.arange(opt.flat.numel, dtype=torch.float32)
+    opt.flat.v = torch.arange(opt.flat.numel, dtype=torch.float32) * 2
+    opt._step = 7
+    opt.param_groups[1]['lr'] = 2.5e-4
+    sd = opt.state_dict()
+    assert all('params' not in g for g in sd['param_groups'])
+    net2 = mk(4)
+    opt2 = FlatOptimizer([{'params': list(net2[0].parameters())}, {'params': list(net2[1].parameters()), 'lr': 5e-4}], kind='Adam', lr=1e-3)
+    opt2.load_state_dict(sd)
+    assert opt2._step == 7 and opt2.param_groups[1]['lr'] == 2.5e-4 and opt2.param_groups[0]['lr'] == 1e-3
+    assert torch.equal(opt2.flat.m, opt.flat.m) and torch.equal(opt2.flat.v, opt.flat.v)
+    assert all(isinstance(p, torch.nn.Parameter) for g in opt2.param_groups for p in g['params'])      # not clobbered by indices
+    net3 = mk(8)                                                                                          # another parameter set
+    opt3 = FlatOptimizer([{'params': list(net3[0].parameters())}, {'params': list(net3[1].parameters())}], kind='Adam')
+    with pytest.raises(ValueError, match='elements'):
+        opt3.load_state_dict(sd)
+    assert opt3.flat.m is None
+    net4 = mk(4)
+    with pytest.raises(ValueError, match='kind'):
+        FlatOptimizer([{'params': list(net4[0].parameters())}, {'params': list(net4[1].parameters())}], kind='SGD').load_state_dict(sd)
+    net5 = mk(4)
+    topt = torch.optim.Adam(net5.parameters())
+    with pytest.raises(ValueError, match='torch.optim-format'):
+        opt2.load_state_dict(topt.state_dict())
+    bad = dict(sd)
+    bad.pop('exp_avg_sq')
+    with pytest.raises(ValueError, match='together'):
+        opt2.load_state_dict(bad)

@@ -128,8 +128,6 @@ def test_lrimgestimator_model_vs_oracle(P):
     assert rel(est.netE.module.conv6.weight.detach().cpu() - sd['conv6.weight'], d_ref) < 3e-2
 
 
-@pytest.mark.skipif(not __import__('os').environ.get('DVSR_RUN_UNVERIFIED'),
-                    reason='written after the round-1 GPU budget was spent: not yet run on a GPU; enable with DVSR_RUN_UNVERIFIED=1')
 @pytest.mark.parametrize('case', ['plain_adam_cb', 'small_offset_sgd_l2', 'ft_tsa_only3_sgd_l1', 'ft_tsa_and_small_offset',
                                   'weight_decay_sgd'])
 def test_video_base_model_training_loop_vs_reference_wrapper_golden(P, case):

@@ -169,7 +169,7 @@ def test_mdcn_nhwc(ops, cfg):
     _mdcn_case(ops, N, C, H, W, Co, dg, s, act, seed=7)
 
 
-@pytest.mark.parametrize('staged', [2, 0], ids=['staged_window', 'direct_gather'])
+@pytest.mark.parametrize('staged', [2, 1], ids=['staged_window', 'direct_gather'])
 @pytest.mark.parametrize('shape,off_scale', [((2, 19, 21), 1.0), ((1, 33, 40), 3.0), ((1, 16, 8), 12.0), ((5, 44, 80), 2.0)],
                          ids=['small_offsets', 'edge_of_window', 'mostly_outside_window', 'slr_size'])
 def test_mdcn_tensor_core_forward(ops, staged, shape, off_scale):
@@ -184,11 +184,10 @@ def test_mdcn_tensor_core_forward(ops, staged, shape, off_scale):
     y = F.leaky_relu(mdcn_torch(x, off, m, w, b, 1, 1, 1, 1, 8), 0.1)
     om = torch.cat([nhwc(_dev(off)), nhwc(_dev(m))], 3).contiguous()
     ops.set_conv_backend(True)
-    ops._lib.lib().dvsr_mdcn_tc_set_staged(staged)
     try:
-        yd = ops.mdcn(nhwc(_dev(x)), om, _dev(w), _dev(b), 8, 1, 1, 1, ops.ACT_LRELU)
+        with ops.scope(ops.new_scope(ops.LaunchPolicy(mdcn_staged=staged))):       # dvsr_policy.mdcn_staged: 2 = staged, 1 = direct
+            yd = ops.mdcn(nhwc(_dev(x)), om, _dev(w), _dev(b), 8, 1, 1, 1, ops.ACT_LRELU)
     finally:
-        ops._lib.lib().dvsr_mdcn_tc_set_staged(1)
         ops.set_conv_backend(False)
     assert rel(nchw(yd), y) < 1e-4          # BF16x3: fp32-class
 
@@ -601,9 +600,6 @@ def test_packed_weight_cache_never_aliases_freed_weights(ops):
         del w
 
 
-@pytest.mark.skipif(not __import__('os').environ.get('DVSR_RUN_UNVERIFIED'),
-                    reason='needs a library built with tools/patches/conv_tc2_single_product.diff (written after the round-1 GPU budget was spent, '
-                           'not yet run on a GPU); enable with DVSR_RUN_UNVERIFIED=1')
 @pytest.mark.parametrize('shape', [(5, 44, 80, 64, 64), (1, 33, 40, 128, 64), (2, 16, 24, 64, 216)],
                          ids=['slr_trunk', 'two_segments_worth_of_K', 'offset_mask_conv'])
 def test_conv_tc2_single_product_mode(ops, shape):
