@@ -75,6 +75,8 @@ def parse():
     ap.add_argument('--nf', type=int, default=128)
     ap.add_argument('--back-rbs', type=int, default=40)
     ap.add_argument('--exchange', default='peer', choices=['peer', 'nccl'])
+    ap.add_argument('--meta-precision', default='bf16', choices=['bf16', 'bf16x3'],
+                    help="meta workload: conv operand precision; bf16 = BASELINE config 4's bf16 compute over fp32 masters")
     return ap.parse_args()
 
 
@@ -352,7 +354,8 @@ def run_meta(args, rank, world, local):
     netG = seed_parameters(EDVR_arch.EDVR(nf=args.nf, nframes=5, groups=8, front_RBs=5, back_RBs=args.back_rbs, scale=4), 1).cuda()
     netE = seed_parameters(LRimg_estimator.DirectKernelEstimatorVideo(64, 3, 4), 2).cuda()
     ml = MetaLearner(netG, netE, inner_steps=1, lr_alpha=1e-5, inner_optimizer='Adam', criterion='cb', outer_optimizer='Adam',
-                     lr_outer=1e-5, exchange=args.exchange, use_graphs=not args.no_graphs)
+                     lr_outer=1e-5, exchange=args.exchange, use_graphs=not args.no_graphs,
+                     precision=None if args.meta_precision == 'bf16x3' else args.meta_precision)
     g = torch.Generator().manual_seed(10 + rank)
     T = args.tasks_per_rank
     host = [{'LQs': torch.rand(1, 5, 3, 64, 64, generator=g).pin_memory(), 'GT': torch.rand(1, 3, 256, 256, generator=g).pin_memory(),

@@ -92,9 +92,9 @@ SIGNATURES = {
     'dvsr_mdcn_bwd_data': [_DP, _P, _I, _P, _P, _I, _P, _I, _P, _I, _P],
     'dvsr_mdcn_tc_supported': [_DP],
     'dvsr_mdcn_tc_fprop': [_DP, _P, _P],
-    'dvsr_mdcn_workspace_bytes': [_I] * 12,
-    'dvsr_mdcn_forward_nchw': [_P] * 6 + [_I] * 12 + [_P, _LL, _P],
-    'dvsr_mdcn_backward_nchw': [_P] * 10 + [_I] * 12 + [_P, _LL, _P],
+    'dvsr_mdcn_workspace_bytes': [_I] * 15,
+    'dvsr_mdcn_forward_nchw': [_P] * 6 + [_I] * 15 + [_P, _LL, _P],
+    'dvsr_mdcn_backward_nchw': [_P] * 10 + [_I] * 15 + [_P, _LL, _P],
     'dvsr_nchw_to_nhwc': [_P, _P, _I, _I, _I, _I, _P],
     'dvsr_nhwc_to_nchw': [_P, _P, _I, _I, _I, _I, _P],
     'dvsr_upsample_bilinear': [_P, _P, _I, _I, _I, _I, _I, _F, _I, _P],

@@ -160,7 +160,8 @@ class InnerLoopAdapter(object):
     """
 
     def __init__(self, netG, netE, netE_fixed, steps=2, lr_alpha=1e-5, lr_alpha_est=None, optimizer='SGD',
-                 betas=(0.9, 0.99), criterion='l2', slr_weight=10.0, pixel_weight=1.0, use_graphs=True, inner_precision=None, policy=None):
+                 betas=(0.9, 0.99), criterion='l2', slr_weight=10.0, pixel_weight=1.0, use_graphs=True, inner_precision=None, policy=None,
+                 use_real=False, use_patch=False, num_patch=1, patch_size=128):
         if optimizer not in ('SGD', 'Adam'):
             raise NotImplementedError(optimizer)
         if criterion not in ('l1', 'l2', 'cb'):
@@ -170,7 +171,11 @@ class InnerLoopAdapter(object):
         self.lr_alpha = lr_alpha
         self.lr_alpha_est = lr_alpha if lr_alpha_est is None else lr_alpha_est
         self.slr_weight, self.pixel_weight = slr_weight, pixel_weight
-        self.use_graphs = use_graphs
+        # the two optional branches of the reference loop: train.use_real (the dataset's pre-generated super-LR clip replaces
+        # MFDN(LR) and only EDVR adapts, test_dynavsr.py:218-221,243-244) and train.maml.use_patch (the pixel loss is taken on
+        # num_patch random crops, :118-145,255-260).  Crop positions are drawn per frame, so use_patch runs eagerly (no graph).
+        self.use_real, self.use_patch, self.num_patch, self.patch_size = bool(use_real), bool(use_patch), int(num_patch), int(patch_size)
+        self.use_graphs = use_graphs and not self.use_patch
         # operand precision of the tensor-core convolutions DURING the adaptation steps: None = the backend's setting, a name
         # ('bf16' = single product) or a (forward, backward) pair.  The steps' errors reach the frame attenuated by how little
         # the adaptation moves it (profiles/r1_precision_study.md: SGD tolerates 'bf16' throughout; Adam's normalised step does
@@ -189,14 +194,32 @@ class InnerLoopAdapter(object):
         self.launches_per_step = None
 
     # ------------------------------------------------------------------ eager building blocks
-    def _inner_step(self, frames, gt, slr_fixed, B, step_idx):
+    def _draw_patches(self, h, w):
+        """Crop positions of one inner step, drawn exactly as the reference does (preprocessing.common_crop :76-77 through
+        test_dynavsr.crop :138-141: per patch ``py`` then ``px`` from Python's ``random``), in SLR pixels."""
+        import random
+        q = self.patch_size // 2
+        if q > h or q > w:
+            raise RuntimeError('use_patch: patch_size // 2 = %d exceeds the super-LR frame %dx%d' % (q, h, w))
+        return [(random.randrange(0, h - q + 1), random.randrange(0, w - q + 1)) for _ in range(self.num_patch)]
+
+    def _inner_step(self, frames, gt, slr_fixed, B, step_idx, slr_given=None, positions=None):
         """One adaptation step on channels-last tensors; returns the (device) loss scalar."""
         self.flat.zero_grad()
         p_fwd, p_bwd = self.inner_precision if isinstance(self.inner_precision, (tuple, list)) else (self.inner_precision,) * 2
         with ops.conv_precision(p_fwd):
-            slr = self.netE.forward_nhwc(frames, B, self.N)
-            sr = self.netG.forward_nhwc(slr, B, self.N)
-            loss = ops.pixel_loss(sr, gt, self.criterion, self.pixel_weight) + \
+            slr = slr_given if self.use_real else self.netE.forward_nhwc(frames, B, self.N)
+            if self.use_patch:
+                if B != 1:
+                    raise RuntimeError('use_patch crops one clip into a batch of patches: B must be 1 (test_dynavsr.py:134)')
+                q, s = self.patch_size // 2, self.netG.scale
+                pos = positions if positions is not None else self._draw_patches(slr.shape[1], slr.shape[2])
+                s_in = torch.cat([slr[:, py:py + q, px:px + q, :] for py, px in pos], 0).contiguous()            # [P*N, q, q, 3]
+                s_gt = torch.cat([gt[:, s * py:s * (py + q), s * px:s * (px + q), :] for py, px in pos], 0).contiguous()
+                sr, target = self.netG.forward_nhwc(s_in, len(pos), self.N), s_gt
+            else:
+                sr, target = self.netG.forward_nhwc(slr, B, self.N), gt
+            loss = ops.pixel_loss(sr, target, self.criterion, self.pixel_weight) + \
                 ops.pixel_loss(slr, slr_fixed, 'l1', self.slr_weight)
         with ops.conv_precision(p_bwd):
             loss.backward()
@@ -214,27 +237,28 @@ class InnerLoopAdapter(object):
             if not torch.cuda.is_current_stream_capturing():
                 ops.snapshot_packs()
 
-    def _run_eager(self, frames, B):
+    def _run_eager(self, frames, B, slr_given=None, positions=None):
         H, W = frames.shape[1], frames.shape[2]
         self._restore_packs()
         gt = frames.view(B, self.N, H, W, 3)[:, self.center].contiguous()
         with torch.no_grad():
             slr_fixed = self.netE_fixed.forward_nhwc(frames, B, self.N)
-        losses = [self._inner_step(frames, gt, slr_fixed, B, i) for i in range(self.steps)]
+        losses = [self._inner_step(frames, gt, slr_fixed, B, i, slr_given, positions[i] if positions is not None else None)
+                  for i in range(self.steps)]
         with torch.no_grad():
             hr = self.netG.forward_nhwc(frames, B, self.N)
         return hr, losses
 
     # ------------------------------------------------------------------ CUDA-graph path
-    def _build_graphs(self, frames, B):
+    def _build_graphs(self, frames, B, slr=None):
         key = (tuple(frames.shape), B)
-        st = {'in': frames.clone()}
+        st = {'in': frames.clone(), 'slr': slr.clone() if slr is not None else None}
         # warm-up on a side stream (allocator + autograd warm-up, as PyTorch's capture recipe requires)
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             self.flat.restore()
-            self._run_eager(st['in'], B)
+            self._run_eager(st['in'], B, st['slr'])
             self.flat.restore()
         torch.cuda.current_stream().wait_stream(side)
         ops.repack_all()            # (re)build the device-side pack table now: it must not change during capture
@@ -242,7 +266,7 @@ class InnerLoopAdapter(object):
         g = torch.cuda.CUDAGraph()
         n0 = _lib.COUNTER[0]
         with torch.cuda.graph(g):
-            hr, losses = self._run_eager(st['in'], B)
+            hr, losses = self._run_eager(st['in'], B, st['slr'])
             st['hr'], st['losses'] = hr, torch.stack(losses) if losses else None
         self.launches_per_step = _lib.COUNTER[0] - n0      # kernels of libdvsr_b200.so inside one replay
         st['graph'] = g
@@ -250,20 +274,26 @@ class InnerLoopAdapter(object):
         return st
 
     # ------------------------------------------------------------------ public API
-    def adapt_and_infer_nhwc(self, frames, B=1):
-        """frames: [B*N, H, W, 3] device tensor (LR window, channels-last) -> HR [B, sH, sW, 3]."""
+    def adapt_and_infer_nhwc(self, frames, B=1, slr=None, patch_positions=None):
+        """frames: [B*N, H, W, 3] device tensor (LR window, channels-last) -> HR [B, sH, sW, 3].
+        ``slr`` ([B*N, H/s, W/s, 3]) is the pre-generated super-LR clip of the ``use_real`` branch; ``patch_positions`` (per inner
+        step a list of (py, px) in SLR pixels) overrides the random crops of the ``use_patch`` branch."""
         H, W = frames.shape[1], frames.shape[2]
         s = self.netG.scale
+        if self.use_real and slr is None:
+            raise RuntimeError("use_real: pass the dataset's super-LR clip (val_data['SuperLQs'], test_dynavsr.py:243-244) as slr=")
+        if not self.use_real:
+            slr = None
         if H % (4 * s) or W % (4 * s):
             raise RuntimeError('adaptation runs EDVR on LR/scale: H and W must be multiples of %d, got %dx%d '
                                '(the reference dataset crops for this: video_test_dataset_int.py:185-189)' % (4 * s, H, W))
         with ops.scope(self.scope):
             if not self.use_graphs:
                 self.flat.restore()
-                hr, losses = self._run_eager(frames, B)
+                hr, losses = self._run_eager(frames, B, slr, patch_positions)
                 self.last_losses = torch.stack(losses) if losses else None
                 return hr
-            st = self._graphs.get((tuple(frames.shape), B)) or self._build_graphs(frames, B)
+            st = self._graphs.get((tuple(frames.shape), B)) or self._build_graphs(frames, B, slr)
             if not self.scope.arena_valid:
                 # the meta-weights changed since the graphs were captured (FlatParams.snapshot): refresh the pack
                 # snapshot the captured restore-copy reads, in place
@@ -271,6 +301,8 @@ class InnerLoopAdapter(object):
                 ops.repack_all()
                 ops.snapshot_packs()
             st['in'].copy_(frames, non_blocking=True)
+            if slr is not None:
+                st['slr'].copy_(slr, non_blocking=True)
             self.flat.restore()
             st['graph'].replay()
             self.last_losses = st['losses']
@@ -288,12 +320,16 @@ class InnerLoopAdapter(object):
                 self.netE.load_state_dict(state_dict_E, strict=strict)
             self.flat.snapshot()
 
-    def adapt_and_infer(self, lr_clip):
-        """lr_clip: [B, N, 3, H, W] (reference tensor layout, host or device) -> HR [B, 3, sH, sW]."""
+    def adapt_and_infer(self, lr_clip, slr_clip=None, patch_positions=None):
+        """lr_clip: [B, N, 3, H, W] (reference tensor layout, host or device) -> HR [B, 3, sH, sW]; slr_clip: [B, N, 3, H/s, W/s]
+        (``val_data['SuperLQs']``) for the use_real branch."""
         B, N, C, H, W = lr_clip.shape
         x = lr_clip.to('cuda', non_blocking=True).reshape(B * N, C, H, W)
         frames = ops.to_nhwc(x)
-        return ops.to_nchw(self.adapt_and_infer_nhwc(frames, B))
+        slr = None
+        if slr_clip is not None:
+            slr = ops.to_nhwc(slr_clip.to('cuda', non_blocking=True).reshape(B * N, C, slr_clip.shape[-2], slr_clip.shape[-1]))
+        return ops.to_nchw(self.adapt_and_infer_nhwc(frames, B, slr, patch_positions))
 
     def infer_nhwc(self, frames, B=1):
         """Plain EDVR forward with the meta-weights (no adaptation)."""

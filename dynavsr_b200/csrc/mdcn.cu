@@ -249,8 +249,21 @@ Ws plan(int B, int C, int H, int W, int Co, int kh, int kw, int stride, int pad,
 }
 }  // namespace
 
-extern "C" long long dvsr_mdcn_workspace_bytes(int B, int C, int H, int W, int Co, int kh, int kw, int stride,
-                                               int pad, int dil, int dg, int backward) {
+// The reference entry points take (h, w) pairs for stride / padding / dilation (deform_conv_cuda.cpp:486-492); every kernel of
+// this library is isotropic (as is every call the reference's Python layer makes: deform_conv.py:104-106 passes the same value
+// twice), so an anisotropic request is reported as unsupported instead of being silently squared.
+static int iso(const char* who, int sh, int sw, int ph, int pw, int dh, int dw) {
+    if (sh != sw || ph != pw || dh != dw) {
+        set_error("%s: anisotropic stride/pad/dilation (%d,%d)/(%d,%d)/(%d,%d) is not supported", who, sh, sw, ph, pw, dh, dw);
+        return DVSR_ERR_UNSUPPORTED;
+    }
+    return 0;
+}
+
+extern "C" long long dvsr_mdcn_workspace_bytes(int B, int C, int H, int W, int Co, int kh, int kw, int stride_h, int stride_w,
+                                               int pad_h, int pad_w, int dil_h, int dil_w, int dg, int backward) {
+    if (iso("mdcn_workspace_bytes", stride_h, stride_w, pad_h, pad_w, dil_h, dil_w)) return DVSR_ERR_UNSUPPORTED;
+    const int stride = stride_h, pad = pad_h, dil = dil_h;
     return plan(B, C, H, W, Co, kh, kw, stride, pad, dil, dg, backward, nullptr, nullptr).total * (long long)sizeof(float);
 }
 
@@ -281,9 +294,11 @@ static dvsr_wlayout conv2d_layout(int Co, int C, int kh, int kw) {
 
 extern "C" int dvsr_mdcn_forward_nchw(const float* x, const float* offset, const float* mask, const float* weight,
                                       const float* bias, float* y, int B, int C, int H, int W, int Co, int kh, int kw,
-                                      int stride, int pad, int dil, int groups, int dg, void* workspace,
-                                      long long workspace_bytes, void* stream) {
+                                      int stride_h, int stride_w, int pad_h, int pad_w, int dil_h, int dil_w, int groups, int dg,
+                                      void* workspace, long long workspace_bytes, void* stream) {
     DVSR_REQUIRE(x && offset && mask && weight && y && workspace, "mdcn_forward_nchw: null pointer");
+    if (int rc0 = iso("mdcn_forward_nchw", stride_h, stride_w, pad_h, pad_w, dil_h, dil_w)) return rc0;
+    const int stride = stride_h, pad = pad_h, dil = dil_h;
     if (groups != 1) { set_error("mdcn_forward_nchw: groups=%d is not supported (the reference never uses groups != 1)", groups); return DVSR_ERR_UNSUPPORTED; }
     DVSR_REQUIRE(dg > 0 && C % dg == 0, "mdcn_forward_nchw: channels %d not divisible by deformable groups %d", C, dg);
     int Ho, Wo;
@@ -309,10 +324,12 @@ extern "C" int dvsr_mdcn_forward_nchw(const float* x, const float* offset, const
 
 extern "C" int dvsr_mdcn_backward_nchw(const float* x, const float* offset, const float* mask, const float* weight,
                                        const float* gy, float* gx, float* goffset, float* gmask, float* gweight,
-                                       float* gbias, int B, int C, int H, int W, int Co, int kh, int kw, int stride,
-                                       int pad, int dil, int groups, int dg, void* workspace,
-                                       long long workspace_bytes, void* stream) {
+                                       float* gbias, int B, int C, int H, int W, int Co, int kh, int kw, int stride_h,
+                                       int stride_w, int pad_h, int pad_w, int dil_h, int dil_w, int groups, int dg,
+                                       void* workspace, long long workspace_bytes, void* stream) {
     DVSR_REQUIRE(x && offset && mask && weight && gy && workspace, "mdcn_backward_nchw: null pointer");
+    if (int rc0 = iso("mdcn_backward_nchw", stride_h, stride_w, pad_h, pad_w, dil_h, dil_w)) return rc0;
+    const int stride = stride_h, pad = pad_h, dil = dil_h;
     DVSR_REQUIRE(gx && goffset && gmask && gweight, "mdcn_backward_nchw: null gradient buffer");
     if (groups != 1) { set_error("mdcn_backward_nchw: groups=%d is not supported", groups); return DVSR_ERR_UNSUPPORTED; }
     DVSR_REQUIRE(dg > 0 && C % dg == 0, "mdcn_backward_nchw: channels %d not divisible by deformable groups %d", C, dg);

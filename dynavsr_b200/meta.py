@@ -48,7 +48,8 @@ class MetaLearner(object):
 
     def __init__(self, netG, netE, inner_steps=1, lr_alpha=1e-5, lr_alpha_est=None, inner_optimizer='Adam',
                  inner_betas=(0.9, 0.99), criterion='cb', pixel_weight=1.0, est_loss='l1', outer_optimizer='Adam',
-                 lr_outer=1e-5, outer_betas=(0.9, 0.99), reference_quirk=False, exchange='peer'):
+                 lr_outer=1e-5, outer_betas=(0.9, 0.99), reference_quirk=False, exchange='peer', use_graphs=False,
+                 precision=None, policy=None):
         if inner_optimizer not in ('SGD', 'Adam') or outer_optimizer not in ('SGD', 'Adam'):
             raise NotImplementedError()
         if criterion not in ('l1', 'l2', 'cb', 'huber'):
@@ -60,7 +61,16 @@ class MetaLearner(object):
         self.criterion, self.pixel_weight, self.est_loss = criterion, pixel_weight, est_loss
         self.outer_optimizer, self.lr_outer, self.outer_betas = outer_optimizer, lr_outer, outer_betas
         self.reference_quirk = reference_quirk
-        self.scope = ops.new_scope()
+        # One CUDA graph per (task shape, tasks per step): the outer step of EDVR-L is ~4 000 launches of small-patch kernels and
+        # was launch-bound when issued eagerly (47.9 ms, profiles/r1_meta_bench.txt).  The as-written reference mode keeps the
+        # eager path (it exists for numerical side-by-sides only).
+        self.use_graphs = bool(use_graphs) and not reference_quirk
+        # operand precision of the tensor-core convolutions of a task: None = the backend's (bf16x3, fp32-class), 'bf16' = plain
+        # bf16 operands with fp32 accumulation over the fp32 master weights -- BASELINE config 4's "bf16 compute, fp32 masters"
+        self.precision = precision
+        self._graphs = {}
+        self.exchange_events = []
+        self.scope = ops.new_scope(policy)
         self.work = FlatParams([netG, netE], scope=self.scope)      # theta' (+ its gradient buffer)
         self.theta = self.work.meta                                  # theta: restored into theta' per task
         self.meta_grad = torch.zeros_like(self.theta)
@@ -90,6 +100,43 @@ class MetaLearner(object):
 
     # ------------------------------------------------------------------ one task
     def _task(self, task, n_tasks):
+        if not self.use_graphs:
+            with ops.conv_precision(self.precision):
+                return self._task_eager(task, n_tasks)
+        key = tuple(tuple(task[k].shape) for k in ('LQs', 'GT', 'SuperLQs')) + (n_tasks,)
+        st = self._graphs.get(key) or self._capture_task(key, task, n_tasks)
+        for k in ('LQs', 'GT', 'SuperLQs'):
+            st['in'][k].copy_(task[k], non_blocking=True)
+        st['graph'].replay()
+        lq, le, inner = st['out']                   # static tensors of the graph: copy out before the next replay overwrites them
+        return lq.clone(), le.clone(), [t.clone() for t in inner]
+
+    def _capture_task(self, key, task, n_tasks):
+        """Warm up and capture one task (theta' <- theta, K inner steps, meta-test backward, meta_grad += grad) as a CUDA graph
+        over static input buffers.  The packs of theta are restored from the scope's snapshot arena inside the graph; outer_step
+        refreshes that snapshot after every meta-update."""
+        fl = self.work
+        st = {'in': {k: task[k].clone() for k in ('LQs', 'GT', 'SuperLQs')}}
+        keep = self.meta_grad.clone()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side), ops.conv_precision(self.precision):
+            for _ in range(2):                      # allocator / autograd / pack-registry warm-up
+                self._task_eager(st['in'], n_tasks)
+        torch.cuda.current_stream().wait_stream(side)
+        self.meta_grad.copy_(keep)
+        fl.restore()
+        ops.repack_all()
+        ops.snapshot_packs()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g), ops.conv_precision(self.precision):
+            st['out'] = self._task_eager(st['in'], n_tasks, from_snapshot=True)
+        st['graph'] = g
+        self._graphs[key] = st
+        self.meta_grad.copy_(keep)                  # capture does not execute, but keep the invariant explicit
+        return st
+
+    def _task_eager(self, task, n_tasks, from_snapshot=False):
         """task: dict of device tensors  LQs [1, N, 3, h, w], GT [1, N, 3, sh, sw] or [1, 3, sh, sw], SuperLQs [1, N, 3, h/s, w/s]."""
         LQs, GT, SLQ = task['LQs'], task['GT'], task['SuperLQs']
         B, N, C, h, w = LQs.shape
@@ -101,7 +148,11 @@ class MetaLearner(object):
         fl = self.work
         if not self.reference_quirk:
             fl.restore()                                                            # theta' <- theta (:322)
-            ops.repack_all()
+            if from_snapshot:
+                if not ops.restore_packs():                                         # one copy launch from the snapshot arena
+                    raise RuntimeError('MetaLearner: weight-pack snapshot invalid during CUDA-graph capture')
+            else:
+                ops.repack_all()
         inner = []
         for k in range(self.K):
             if not self.reference_quirk:
@@ -126,7 +177,7 @@ class MetaLearner(object):
         slr = self.netE.forward_nhwc(frames, B, N)
         loss_e = ops.pixel_loss(slr, slr_true, self.est_loss, 1.0)
         (loss_e / (n_tasks * 10)).backward()
-        ops.join_async()
+        ops.join_async(self.scope)
         if not self.reference_quirk:
             self.meta_grad.add_(fl.grad)
         return loss_q.detach(), loss_e.detach(), inner
@@ -154,6 +205,8 @@ class MetaLearner(object):
             lr = self.lr_outer if lr is None else lr
             self.outer_steps += 1
             n = self.theta.numel()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
             if self._peer is not None:
                 # ---- exchange + outer update in ONE kernel over NVLink peer memory
                 h = self._peer
@@ -179,11 +232,41 @@ class MetaLearner(object):
                 t = self.outer_steps
                 call('dvsr_update_adam', _p(self.theta), _p(self.meta_grad), _p(self.m), _p(self.v), n, n, float(lr), float(lr),
                      float(b1), float(b2), 1e-8, float(1 - b1 ** t), float(1 - b2 ** t), 0.0, _stream())
+            ev1.record()
+            if len(self.exchange_events) < 256:
+                self.exchange_events.append((ev0, ev1))
             ops.invalidate_pack_snapshot(self.scope)
             fl.restore()                           # the modules now hold the updated meta-weights
             ops.repack_all()
+            if self.use_graphs:
+                ops.snapshot_packs()               # the captured tasks restore theta's packs from this arena
         self.last = {'loss_q': torch.stack(lq), 'loss_e': torch.stack(le), 'inner': inner}
         return torch.stack(lq).sum() / len(tasks)
+
+    def exchange_timing(self, reset=True):
+        """Device time of the exchange + outer-update section of the recorded outer steps (CUDA events on the launching stream;
+        includes the two symmetric-memory barriers of the fused path) and the NVLink read rate it implies for the fused kernel:
+        every rank reads (world - 1) peers' flat gradients."""
+        if not self.exchange_events:
+            return None
+        torch.cuda.synchronize()
+        ms = sorted(a.elapsed_time(b) for a, b in self.exchange_events)
+        if reset:
+            self.exchange_events = []
+        world = torch.distributed.get_world_size() if (torch.distributed.is_available() and torch.distributed.is_initialized()) else 1
+        med = ms[len(ms) // 2]
+        nbytes = self.theta.numel() * 4
+        return {'path': self.exchange, 'median_us': med * 1e3, 'min_us': ms[0] * 1e3, 'flat_gradient_bytes': nbytes,
+                'peer_bytes_read_per_rank': (world - 1) * nbytes,
+                'nvlink_GBps_per_rank': ((world - 1) * nbytes / (med * 1e-3) / 1e9) if world > 1 else None,
+                'local_hbm_GBps': ((3 if self.outer_optimizer == 'SGD' else 7) * nbytes / (med * 1e-3) / 1e9)}
+
+    def dtype_string(self):
+        if not ops._tc():
+            return 'f32 (exact CUDA-core path)'
+        if self.precision == 'bf16':
+            return 'bf16 tensor-core operands (tcgen05), fp32 accumulate, fp32 master weights / gradients / optimiser state'
+        return 'f32 storage; tcgen05 %s operands, fp32 accumulate' % (self.precision or ops._backend['precision'])
 
     def state_dicts(self):
         """(EDVR state_dict, MFDN state_dict) of the meta-weights, reference key names (checkpoint contract)."""

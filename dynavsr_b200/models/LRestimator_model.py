@@ -1,4 +1,4 @@
-"""Mirror of codes/models/LRestimator_model.py:28-171 -- ``LRimgestimator_Model``: owns ``netE`` (MFDN), maps an LR clip
+"""Mirror of codes/models/LRestimator_model.py:28-171 -- ``LRimgestimator_Model``: owns ``netE`` (MFDN or SFDN), maps an LR clip
 ``data['LQs']`` [B, T, C, H, W] to its super-LR estimate ``fake_L`` [B, T, C, H/s, W/s] (``forward_without_optim`` with
 gradients for the inner adaptation step, ``test`` without), and can pre-train the estimator (``optimize_parameters``)."""
 import logging
@@ -25,8 +25,8 @@ class LRimgestimator_Model(NetWrapperMixin, BaseModel):
         net_opt, self.train_opt = opt['network_E'], opt['train']
         self.rank = torch.distributed.get_rank() if opt['dist'] else -1
         self.scale, self.model_name, self.mode = opt['scale'], net_opt['which_model_E'], net_opt['mode']
-        if self.mode == 'image':
-            raise NotImplementedError("network_E.mode 'image' (SFDN) is not on the DynaVSR-R hot path (MFDN = 'video')")
+        if self.mode not in ('image', 'video'):
+            raise NotImplementedError("network_E.mode must be 'image' (SFDN) or 'video' (MFDN), got %r" % (self.mode,))
         train_set = (opt.get('datasets') or {}).get('train') or {}
         for key in ('kernel_size', 'patch_size', 'batch_size'):
             setattr(self, key, train_set.get(key))
@@ -59,7 +59,8 @@ class LRimgestimator_Model(NetWrapperMixin, BaseModel):
         self.var_H = self.real_H.transpose(1, 2)        # B C T H W (LRestimator_model.py:103)
 
     def _forward(self):
-        # MFDN's native layout is frames-major channels-last: skip the two transposes of the reference round trip
+        # both estimators run frames-major channels-last: 'image' mode (SFDN, LRestimator_model.py:101-102,110-113) treats the
+        # B*T frames independently, 'video' mode (MFDN, :103-104,115) convolves over T -- no transposes either way
         B, T, C, H, W = self.real_H.shape
         net = self.netE.module
         frames = ops.to_nhwc(self.real_H.reshape(B * T, C, H, W))

@@ -66,11 +66,11 @@ class ModulatedDeformConvFunction(Function):
                 mask.shape != (B, deformable_groups * kh * kw, Ho, Wo):
             raise RuntimeError('offset/mask shapes %s %s do not match the output size' % (tuple(offset.shape), tuple(mask.shape)))
         output = input.new_empty((B, Co, Ho, Wo))
-        nbytes = ops._lib.lib().dvsr_mdcn_workspace_bytes(B, C, H, W, Co, kh, kw, stride, padding, dilation,
-                                                          deformable_groups, 0)
+        nbytes = ops._lib.lib().dvsr_mdcn_workspace_bytes(B, C, H, W, Co, kh, kw, stride, stride, padding, padding, dilation,
+                                                          dilation, deformable_groups, 0)
         ws = _workspace(nbytes, input.device)
         call('dvsr_mdcn_forward_nchw', _p(input), _p(offset), _p(mask), _p(weight), _p(bias), _p(output),
-             B, C, H, W, Co, kh, kw, stride, padding, dilation, groups, deformable_groups, _p(ws), ws.numel(),
+             B, C, H, W, Co, kh, kw, stride, stride, padding, padding, dilation, dilation, groups, deformable_groups, _p(ws), ws.numel(),
              _stream())
         if weight.requires_grad or mask.requires_grad or offset.requires_grad or input.requires_grad:
             ctx.save_for_backward(input, offset, mask, weight)
@@ -89,11 +89,11 @@ class ModulatedDeformConvFunction(Function):
         grad_input, grad_offset, grad_mask = torch.empty_like(input), torch.empty_like(offset), torch.empty_like(mask)
         grad_weight = torch.empty_like(weight)
         grad_bias = input.new_empty(Co) if ctx.with_bias else None
-        nbytes = ops._lib.lib().dvsr_mdcn_workspace_bytes(B, C, H, W, Co, kh, kw, stride, padding, dilation, dg, 1)
+        nbytes = ops._lib.lib().dvsr_mdcn_workspace_bytes(B, C, H, W, Co, kh, kw, stride, stride, padding, padding, dilation, dilation, dg, 1)
         ws = _workspace(nbytes, input.device)
         call('dvsr_mdcn_backward_nchw', _p(input), _p(offset), _p(mask), _p(weight), _p(grad_output),
              _p(grad_input), _p(grad_offset), _p(grad_mask), _p(grad_weight), _p(grad_bias),
-             B, C, H, W, Co, kh, kw, stride, padding, dilation, groups, dg, _p(ws), ws.numel(), _stream())
+             B, C, H, W, Co, kh, kw, stride, stride, padding, padding, dilation, dilation, groups, dg, _p(ws), ws.numel(), _stream())
         return (grad_input, grad_offset, grad_mask, grad_weight, grad_bias, None, None, None, None, None)
 
 
@@ -147,11 +147,11 @@ class DeformConvFunction(Function):
         input, offset, weight, grad_output = (t.contiguous() for t in (input, offset, weight, grad_output))
         grad_input, grad_offset, grad_mask = torch.empty_like(input), torch.empty_like(offset), torch.empty_like(mask)
         grad_weight = torch.empty_like(weight)
-        nbytes = ops._lib.lib().dvsr_mdcn_workspace_bytes(B, C, H, W, Co, kh, kw, stride, padding, dilation, dg, 1)
+        nbytes = ops._lib.lib().dvsr_mdcn_workspace_bytes(B, C, H, W, Co, kh, kw, stride, stride, padding, padding, dilation, dilation, dg, 1)
         ws = _workspace(nbytes, input.device)
         call('dvsr_mdcn_backward_nchw', _p(input), _p(offset), _p(mask), _p(weight), _p(grad_output),
              _p(grad_input), _p(grad_offset), _p(grad_mask), _p(grad_weight), None,
-             B, C, H, W, Co, kh, kw, stride, padding, dilation, groups, dg, _p(ws), ws.numel(), _stream())
+             B, C, H, W, Co, kh, kw, stride, stride, padding, padding, dilation, dilation, groups, dg, _p(ws), ws.numel(), _stream())
         return (grad_input, grad_offset, grad_weight, None, None, None, None, None, None)
 
 

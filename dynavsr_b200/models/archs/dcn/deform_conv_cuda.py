@@ -64,9 +64,9 @@ def _fwd(input, weight, bias, offset, mask, output, kh, kw, stride, pad, dil, gr
     Wo = (W + 2 * pad - (dil * (kw - 1) + 1)) // stride + 1
     if tuple(output.shape) != (B, Co, Ho, Wo):
         output.resize_(B, Co, Ho, Wo)                     # the reference views / resizes the caller's tensor (.cpp:525)
-    ws = _workspace(_lib.lib().dvsr_mdcn_workspace_bytes(B, C, H, W, Co, kh, kw, stride, pad, dil, dg, 0), input.device)
+    ws = _workspace(_lib.lib().dvsr_mdcn_workspace_bytes(B, C, H, W, Co, kh, kw, stride, stride, pad, pad, dil, dil, dg, 0), input.device)
     call('dvsr_mdcn_forward_nchw', _p(input), _p(offset), _p(mask), _p(weight), _p(bias), _p(output), B, C, H, W, Co, kh, kw,
-         stride, pad, dil, group, dg, _p(ws), ws.numel(), _stream())
+         stride, stride, pad, pad, dil, dil, group, dg, _p(ws), ws.numel(), _stream())
     return Ho, Wo
 
 
@@ -76,9 +76,9 @@ def _bwd(input, weight, offset, mask, grad_output, kh, kw, stride, pad, dil, gro
     gi, go, gm = torch.empty_like(input), torch.empty_like(offset), torch.empty_like(mask)
     gw = torch.empty_like(weight)
     gb = input.new_empty(Co) if want_bias else None
-    ws = _workspace(_lib.lib().dvsr_mdcn_workspace_bytes(B, C, H, W, Co, kh, kw, stride, pad, dil, dg, 1), input.device)
+    ws = _workspace(_lib.lib().dvsr_mdcn_workspace_bytes(B, C, H, W, Co, kh, kw, stride, stride, pad, pad, dil, dil, dg, 1), input.device)
     call('dvsr_mdcn_backward_nchw', _p(input), _p(offset), _p(mask), _p(weight), _p(grad_output), _p(gi), _p(go), _p(gm),
-         _p(gw), _p(gb), B, C, H, W, Co, kh, kw, stride, pad, dil, group, dg, _p(ws), ws.numel(), _stream())
+         _p(gw), _p(gb), B, C, H, W, Co, kh, kw, stride, stride, pad, pad, dil, dil, group, dg, _p(ws), ws.numel(), _stream())
     return gi, go, gm, gw, gb
 
 

@@ -21,5 +21,5 @@ def define_E(opt):
     if which_model == 'MFDN':
         return LRimg_estimator.DirectKernelEstimatorVideo(in_nc=opt_net['in_nc'], nf=opt_net['nf'], scale=opt['scale'])
     if which_model == 'SFDN':
-        raise NotImplementedError('Estimator model [SFDN] is not on the DynaVSR-R hot path (MFDN only).')
+        return LRimg_estimator.DirectKernelEstimator_CMS(nf=opt_net['nf'])
     raise NotImplementedError('Estimator model [{:s}] not recognized'.format(which_model))

@@ -215,19 +215,21 @@ int dvsr_mdcn_tc_fprop(const dvsr_conv_desc* d, const float* wp, void* stream);
  * chunk in shared memory with one TMA box and gather the 36 corners per pixel from there (global fallback for corners a large
  * offset pushes outside the window) when the launch has at least two tiles per SM (d->policy.mdcn_staged overrides). */
 
-/* Reference operator boundary, NCHW fp32 (deform_conv_cuda.cpp:486-492, :566-573).  groups must be 1
- * (no YML of the reference uses groups != 1).  Workspace: dvsr_mdcn_workspace_bytes() bytes. */
-long long dvsr_mdcn_workspace_bytes(int B, int C, int H, int W, int Co, int kh, int kw, int stride,
-                                    int pad, int dil, int dg, int backward);
+/* Reference operator boundary, NCHW fp32: the tensors and the (h, w) geometry pairs of modulated_deform_conv_cuda_forward /
+ * _backward (deform_conv_cuda.cpp:486-492, :566-573).  groups must be 1 and each pair isotropic (stride_h == stride_w, ...):
+ * no YML / Python call site of the reference uses anything else (deform_conv.py:104-106 passes each value twice);
+ * other requests return DVSR_ERR_UNSUPPORTED.  Workspace: dvsr_mdcn_workspace_bytes() bytes (negative = error code). */
+long long dvsr_mdcn_workspace_bytes(int B, int C, int H, int W, int Co, int kh, int kw, int stride_h, int stride_w,
+                                    int pad_h, int pad_w, int dil_h, int dil_w, int dg, int backward);
 int dvsr_mdcn_forward_nchw(const float* x, const float* offset, const float* mask, const float* weight,
                            const float* bias, float* y, int B, int C, int H, int W, int Co, int kh,
-                           int kw, int stride, int pad, int dil, int groups, int dg, void* workspace,
-                           long long workspace_bytes, void* stream);
+                           int kw, int stride_h, int stride_w, int pad_h, int pad_w, int dil_h, int dil_w, int groups,
+                           int dg, void* workspace, long long workspace_bytes, void* stream);
 int dvsr_mdcn_backward_nchw(const float* x, const float* offset, const float* mask, const float* weight,
                             const float* gy, float* gx, float* goffset, float* gmask, float* gweight,
-                            float* gbias, int B, int C, int H, int W, int Co, int kh, int kw, int stride,
-                            int pad, int dil, int groups, int dg, void* workspace,
-                            long long workspace_bytes, void* stream);
+                            float* gbias, int B, int C, int H, int W, int Co, int kh, int kw, int stride_h,
+                            int stride_w, int pad_h, int pad_w, int dil_h, int dil_w, int groups, int dg,
+                            void* workspace, long long workspace_bytes, void* stream);
 
 /* ---- layout, resampling, pooling, padding (elementwise.cu) --------------------------------------- */
 int dvsr_nchw_to_nhwc(const float* x, float* y, int N, int C, int H, int W, void* stream);

@@ -192,6 +192,16 @@ def mfdn_forward(sd, x, scale=4):
     return fea + m
 
 
+def sfdn_forward(sd, x):
+    """SFDN, LRimg_estimator.py:38-67 (DirectKernelEstimator_CMS).  x: [N, 3, H, W] -> [N, 3, H/2, W/2]."""
+    m = x.mean(2, keepdim=True).mean(3, keepdim=True)
+    rp = lambda t: F.pad(t, (1, 1, 1, 1), mode='reflect')
+    fea = x - m
+    for i in range(6):
+        fea = _lrelu(F.conv2d(rp(fea), sd['conv%d.weight' % i], sd['conv%d.bias' % i], stride=2 if i == 3 else 1))
+    return F.conv2d(fea, sd['conv6.weight'], sd['conv6.bias']) + m
+
+
 def pixel_loss(kind, a, b):
     """Video_base_model.py:39-50, loss.py:5-30."""
     if kind == 'l1':
@@ -210,8 +220,13 @@ def pixel_loss(kind, a, b):
 
 def adapt_and_infer(sd_G, sd_E, sd_E_fixed, lr_clip, steps=2, lr_alpha=1e-5, optimizer='SGD',
                     betas=(0.9, 0.99), criterion='l2', slr_weight=10.0, scale=4, edvr_cfg=None,
-                    return_losses=False):
+                    return_losses=False, slr_given=None, patches=None, patch_size=None):
     """test_dynavsr.py:208-283 for one output frame.
+
+    slr_given ([1, N, 3, H/s, W/s]): the ``train.use_real`` branch (:218-221,243-244) -- the dataset's pre-generated super-LR
+    clip replaces MFDN(LR) and only EDVR is optimised (the frozen-MFDN L1 term stays in the loss value, :267-274).
+    patches (per step, a list of (py, px) in SLR pixels) + patch_size: the ``maml.use_patch`` branch (:118-145,255-260) -- the
+    pixel loss is taken on SLR crops of (patch_size // 2)^2 and the matching LR crops (preprocessing.common_crop :57-85).
 
     lr_clip: [1, N, 3, H, W] LR window.  Returns the adapted HR estimate [1, 3, sH, sW]
     (and the per-step losses).  sd_* are not modified (the reference deep-copies, :208).
@@ -219,7 +234,7 @@ def adapt_and_infer(sd_G, sd_E, sd_E_fixed, lr_clip, steps=2, lr_alpha=1e-5, opt
     cfg = dict(edvr_cfg or {})
     pG = {k: v.detach().clone().requires_grad_(True) for k, v in sd_G.items()}
     pE = {k: v.detach().clone().requires_grad_(True) for k, v in sd_E.items()}
-    params = list(pG.values()) + list(pE.values())
+    params = list(pG.values()) + (list(pE.values()) if slr_given is None else [])       # :213-221
     if optimizer == 'SGD':
         opt = torch.optim.SGD(params, lr=lr_alpha)
     elif optimizer == 'Adam':
@@ -232,11 +247,18 @@ def adapt_and_infer(sd_G, sd_E, sd_E_fixed, lr_clip, steps=2, lr_alpha=1e-5, opt
     with torch.no_grad():
         slr_fixed = mfdn_forward(sd_E_fixed, xin, scale).transpose(1, 2)   # :267-270 (constant over steps)
     losses = []
-    for _ in range(steps):
-        slr = mfdn_forward(pE, xin, scale).transpose(1, 2)                 # :238-241
+    for k in range(steps):
+        slr = mfdn_forward(pE, xin, scale).transpose(1, 2) if slr_given is None else slr_given      # :238-244
         opt.zero_grad()
-        sr = edvr_forward(pG, slr, scale=scale, **cfg)                     # :262-264
-        loss = pixel_loss(criterion, sr, gt) + slr_weight * F.l1_loss(slr, slr_fixed)   # :274
+        if patches is not None:                                            # :255-260 crop() -> common_crop
+            q = patch_size // 2
+            s_in = torch.stack([slr[0, :, :, py:py + q, px:px + q] for py, px in patches[k]])
+            s_gt = torch.stack([gt[0, :, scale * py:scale * (py + q), scale * px:scale * (px + q)] for py, px in patches[k]])
+            loss = pixel_loss(criterion, edvr_forward(pG, s_in, scale=scale, **cfg), s_gt)
+        else:
+            sr = edvr_forward(pG, slr, scale=scale, **cfg)                 # :262-264
+            loss = pixel_loss(criterion, sr, gt)
+        loss = loss + slr_weight * F.l1_loss(slr, slr_fixed)               # :274
         loss.backward()                                                    # :276
         opt.step()                                                         # :277
         losses.append(float(loss.detach()))

@@ -16,7 +16,7 @@ absent ``imageio`` / ``lmdb``; the DCN op routed to ``torchvision.ops.deform_con
 checkpoint files the YML names (written to a scratch directory in this repo from oracle/params.py seeds); the working
 directory set inside the scratch directory (the script writes ``../test_results``); ``Tensor.to('cuda')`` answered on CPU.
 
-    python -m oracle.make_golden_driver        # both configurations
+    python -m oracle.make_golden_driver [tag ...]       # all configurations, or the named ones
 """
 import os
 import shutil
@@ -37,7 +37,13 @@ SCRATCH = os.path.join(HERE, '_ref', 'driver_scratch')
 SEED_G, SEED_E, SEED_E_FIXED, SEED_BASELINE_G, SEED_CLIP = 1234, 77, 78, 1235, 4321
 NFRAMES, SCALE, H, W = 5, 4, 32, 48
 CONFIGS = {'adam1_cb': dict(optimizer='Adam', steps=1, criterion='cb', lr_alpha='1e-5'),      # the shipped test YMLs
-           'sgd2_l2': dict(optimizer='SGD', steps=2, criterion='l2', lr_alpha='1e-4')}        # BASELINE.json's 2-step case
+           'sgd2_l2': dict(optimizer='SGD', steps=2, criterion='l2', lr_alpha='1e-4'),        # BASELINE.json's 2-step case
+           # the two optional branches of the inner loop (test_dynavsr.py:118-145,218-221,237-260)
+           'sgd2_l2_patch': dict(optimizer='SGD', steps=2, criterion='l2', lr_alpha='1e-4', use_patch='true', num_patch=2,
+                                 patch_size=16),          # SLR crops of 8x8 (patch_size // 2) out of 8x12, LR crops of 32x32
+           'adam1_cb_real': dict(optimizer='Adam', steps=1, criterion='cb', lr_alpha='1e-5', use_real='true')}
+DEFAULTS = dict(use_patch='false', num_patch=1, patch_size=64, use_real='false')
+PATCH_SEED = 2024          # random.seed() right before main(): the driver draws its crop positions from `random` (preprocessing.py:76-77)
 
 YML = """
 name: driver_pin
@@ -92,11 +98,11 @@ train:
   lr_steps: [1000]
   lr_gamma: 0.2
   loss_ftn: l1
-  use_real: false
+  use_real: {use_real}
   maml:
-    use_patch: false
-    num_patch: 1
-    patch_size: 64
+    use_patch: {use_patch}
+    num_patch: {num_patch}
+    patch_size: {patch_size}
     optimizer: {optimizer}
     lr_alpha: !!float {lr_alpha}
     beta1: 0.9
@@ -137,16 +143,28 @@ def synthetic_clip():
 def run(tag, cfg, T, P, state):
     yml = os.path.join(SCRATCH, 'driver_%s.yml' % tag)
     with open(yml, 'w') as f:
-        f.write(YML.format(scale=SCALE, nframes=NFRAMES, dir=SCRATCH, **cfg))
+        f.write(YML.format(scale=SCALE, nframes=NFRAMES, dir=SCRATCH, **dict(DEFAULTS, **cfg)))
     lq, hr = synthetic_clip()
-    state.update(models=[], written=[])
+    # use_real: the dataset supplies the pre-generated super-LR clip (video_test_dataset_int.py 'SuperLQs'); here a bicubic
+    # 4x reduction of the LR clip
+    slq = F.interpolate(lq[0], scale_factor=1.0 / SCALE, mode='bicubic', align_corners=False).clamp(0, 1).unsqueeze(0).contiguous()
+    state.update(models=[], written=[], crops=[])
+    import random
+    random.seed(PATCH_SEED)
+    real_randrange = random.randrange
+
+    def logged_randrange(*a, **k):
+        v = real_randrange(*a, **k)
+        state['crops'].append(v)
+        return v
+    random.randrange = logged_randrange
 
     class Loader(object):
         def __len__(self):
             return 1
 
         def __iter__(self):
-            yield {'LQs': lq.clone(), 'GT': hr.clone(), 'folder': ['clip'], 'idx': ['0/1']}
+            yield {'LQs': lq.clone(), 'GT': hr.clone(), 'SuperLQs': slq.clone(), 'folder': ['clip'], 'idx': ['0/1']}
 
     T.create_dataset = lambda dataset_opt, **kw: [0]
     T.create_dataloader = lambda dataset, dataset_opt, opt=None, sampler=None: Loader()
@@ -156,6 +174,7 @@ def run(tag, cfg, T, P, state):
         T.main()
     finally:
         sys.argv = argv
+        random.randrange = real_randrange
     assert len(state['written']) == 1
     image, out, dG, dE = state['written'][0]
     import pandas as pd
@@ -167,10 +186,12 @@ def run(tag, cfg, T, P, state):
                         ssim_baseline=float(row['SSIM_Bicubic']), ssim_adapted=float(row['SSIM_Ours']),
                         seed_G=SEED_G, seed_E=SEED_E, seed_E_fixed=SEED_E_FIXED, seed_baseline_G=SEED_BASELINE_G,
                         steps=cfg['steps'], lr_alpha=float(cfg['lr_alpha']), optimizer=cfg['optimizer'],
-                        criterion=cfg['criterion'], head_gain=HEAD_GAIN)
+                        criterion=cfg['criterion'], head_gain=HEAD_GAIN, slq=slq.numpy(), crops=np.array(state['crops'], dtype=np.int64),
+                        patch_seed=PATCH_SEED, use_patch=cfg.get('use_patch', 'false') == 'true', num_patch=int(cfg.get('num_patch', 1)),
+                        patch_size=int(cfg.get('patch_size', 64)), use_real=cfg.get('use_real', 'false') == 'true')
     print('[%s] driver PSNR baseline %.4f adapted %.4f ; SSIM %.4f / %.4f' % (
         tag, row['PSNR_Bicubic'], row['PSNR_Ours'], row['SSIM_Bicubic'], row['SSIM_Ours']))
-    return lq, hr, out
+    return lq, hr, out, slq, list(state['crops'])
 
 
 def main():
@@ -233,10 +254,19 @@ def main():
 
     torch.Tensor.to = to
     try:
-        for tag, cfg in CONFIGS.items():
-            lq, hr, out = run(tag, cfg, T, P, state)
+        tags = [a for a in sys.argv[1:] if a in CONFIGS] or list(CONFIGS)
+        for tag in tags:
+            cfg = CONFIGS[tag]
+            lq, hr, out, slq, crops = run(tag, cfg, T, P, state)
+            extra = {}
+            if cfg.get('use_real') == 'true':
+                extra['slr_given'] = slq
+            if cfg.get('use_patch') == 'true':
+                n = int(cfg['num_patch'])
+                pos = [(crops[2 * i], crops[2 * i + 1]) for i in range(len(crops) // 2)]
+                extra.update(patches=[pos[k * n:(k + 1) * n] for k in range(cfg['steps'])], patch_size=int(cfg['patch_size']))
             o_hr = O.adapt_and_infer(sdG, sdE, sdF, lq, steps=cfg['steps'], lr_alpha=float(cfg['lr_alpha']),
-                                     optimizer=cfg['optimizer'], criterion=cfg['criterion'])
+                                     optimizer=cfg['optimizer'], criterion=cfg['criterion'], **extra)
             o_hr = o_hr[0] if isinstance(o_hr, tuple) else o_hr
             print('[%s] oracle vs driver: rel %.3e ; fraction clamped %.4f' % (
                 tag, float((o_hr[0].clamp(0, 1) - out).norm() / out.norm()), float(((o_hr < 0) | (o_hr > 1)).float().mean())))

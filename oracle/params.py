@@ -113,6 +113,19 @@ def mfdn_param_shapes(nf=64, in_nc=3, scale=4):
     return d
 
 
+def sfdn_param_shapes(nf=64):
+    """DirectKernelEstimator_CMS, LRimg_estimator.py:39-50."""
+    d = OrderedDict()
+    _conv(d, 'conv0', nf, 3, 3)
+    _conv(d, 'conv1', nf, nf, 3)
+    _conv(d, 'conv2', nf, nf, 3)
+    _conv(d, 'conv3', nf * 2, nf, 4)
+    _conv(d, 'conv4', nf * 2, nf * 2, 3)
+    _conv(d, 'conv5', nf, nf * 2, 3)
+    _conv(d, 'conv6', 3, nf, 1)
+    return d
+
+
 def make_params(shapes, seed, residual_scale=0.1, offset_std=0.02, dtype=torch.float32):
     """Deterministic weights: kaiming-like N(0, 2/fan_in) (x``residual_scale`` for residual-block
     convs, as arch_util.py:7-24 does), small random biases, and NON-zero ``conv_offset_mask``

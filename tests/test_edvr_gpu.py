@@ -128,6 +128,31 @@ def test_mfdn_matches_reference_golden(mods):
     assert rel(slr, torch.from_numpy(g['slr'])) < NS_TOL
 
 
+@pytest.mark.parametrize('tc', [False, True], ids=['exact_fp32', 'tcgen05'])
+def test_sfdn_matches_reference_golden(mods, tc):
+    """SFDN (DirectKernelEstimator_CMS, LRimg_estimator.py:38-67; networks.define_E 'SFDN') vs the golden of the unmodified
+    reference module: output, input gradient (mean kept in the graph) and weight / bias gradients."""
+    from oracle import params as P
+    L, ops = mods[1], mods[3]
+    g = gold('sfdn_32x48.npz')
+    net = L.DirectKernelEstimator_CMS(nf=64)
+    net.load_state_dict(P.make_params(P.sfdn_param_shapes(64), seed=int(g['seed'])), strict=True)
+    net = net.cuda()
+    x = torch.from_numpy(g['x']).cuda().requires_grad_(True)
+    ops.set_conv_backend(tc)
+    try:
+        out = net(x)
+        (out * torch.from_numpy(g['probe']).cuda()).sum().backward()
+    finally:
+        ops.set_conv_backend(False)
+    tol = 1e-3 if tc else 2e-5
+    assert out.shape == (3, 3, 16, 24) and rel(out, torch.from_numpy(g['out'])) < tol
+    assert rel(x.grad, torch.from_numpy(g['gx'])) < 5 * tol
+    assert rel(net.conv0.weight.grad, torch.from_numpy(g['g_conv0_w'])) < 5 * tol
+    assert rel(net.conv3.weight.grad, torch.from_numpy(g['g_conv3_w'])) < 5 * tol
+    assert rel(net.conv6.bias.grad, torch.from_numpy(g['g_conv6_b'])) < 5 * tol
+
+
 def test_mfdn_gradients_vs_oracle(mods):
     from oracle import edvr_oracle as O
     net, sd = _mfdn(mods, 5)
@@ -407,5 +432,45 @@ def test_adaptation_vs_reference_test_driver(mods, tag, backend):
         with torch.no_grad():
             base = baseline(lq.cuda())[0].float().cpu()
         assert abs(psnr_uint8(base, gt) - float(g['psnr_baseline'])) < 0.01
+    finally:
+        ops.set_conv_backend(False)
+
+
+@pytest.mark.parametrize('backend', ['fp32', 'tensor-core'])
+@pytest.mark.parametrize('tag', ['sgd2_l2_patch', 'adam1_cb_real'])
+def test_optional_inner_loop_branches_vs_reference_test_driver(mods, tag, backend):
+    """``maml.use_patch`` (B = num_patch random crops, test_dynavsr.py:118-145,255-260) and ``train.use_real`` (EDVR-only
+    adaptation on the dataset's super-LR clip, :218-221,243-244) against what the UNMODIFIED driver produced.  use_patch is
+    checked twice: with the logged crop positions passed in, and with Python's ``random`` seeded like the harness did -- the
+    engine must then draw the very same positions (py before px, per patch, per step)."""
+    import random
+    ops = mods[3]
+    g = gold('driver_%s.npz' % tag)
+    lq, gt = torch.from_numpy(g['lq']), torch.from_numpy(g['gt'])
+    kw, call_kw = {}, [{}]
+    if bool(g['use_real']):
+        kw.update(use_real=True)
+        call_kw = [dict(slr_clip=torch.from_numpy(g['slq']))]
+    if bool(g['use_patch']):
+        n, c = int(g['num_patch']), g['crops'].tolist()
+        pos = [(c[2 * i], c[2 * i + 1]) for i in range(len(c) // 2)]
+        kw.update(use_patch=True, num_patch=n, patch_size=int(g['patch_size']))
+        call_kw = [dict(patch_positions=[pos[k * n:(k + 1) * n] for k in range(int(g['steps']))]), {}]
+    ops.set_conv_backend(backend == 'tensor-core')
+    try:
+        eng, _ = _driver_engine(mods, g, use_graphs=(backend == 'tensor-core'), **kw)
+        e0 = {k: v.detach().clone() for k, v in eng.netE.state_dict().items()}
+        for ck in call_kw:
+            random.seed(int(g['patch_seed']))
+            hr = eng.adapt_and_infer(lq, **ck)[0].float().cpu()
+            assert rel(hr.clamp(0, 1), torch.from_numpy(g['out'])) < NS_TOL
+            assert abs(psnr_uint8(hr, gt) - float(g['psnr_adapted'])) < 0.01
+            if bool(g['use_real']):       # MFDN receives no gradient: bit-identical after the update
+                assert all(torch.equal(v, e0[k]) for k, v in eng.netE.state_dict().items())
+        with pytest.raises(RuntimeError):
+            if bool(g['use_real']):
+                eng.adapt_and_infer(lq)                      # use_real without the super-LR clip
+            else:
+                raise RuntimeError('n/a')
     finally:
         ops.set_conv_backend(False)

@@ -153,3 +153,67 @@ def test_reference_quirk_step_vs_reference_training_loop_golden():
     cat = lambda new, old, keys: torch.cat([(new[k].cpu() - old[k]).reshape(-1) for k in keys])
     assert rel(cat(newG, sdG, shapes_G), cat(refG, sdG, shapes_G)) < 2e-3
     assert rel(cat(newE, sdE, shapes_E), cat(refE, sdE, shapes_E)) < 2e-3
+
+
+def test_meta_graph_path_matches_eager_path():
+    """``MetaLearner(use_graphs=True)``: every task replays one CUDA graph (theta' <- theta, packs from the snapshot arena,
+    K inner steps, meta-test backward, meta_grad += grad) over static input buffers; two outer steps (the second one sees the
+    UPDATED meta-weights through the refreshed snapshot) must give what the eager path gives, losses included."""
+    from dynavsr_b200 import ops
+    from dynavsr_b200.meta import MetaLearner
+    kw = dict(inner_steps=2, lr_alpha=1e-3, lr_alpha_est=5e-4, inner_optimizer='Adam', criterion='cb', est_loss='l1', lr_outer=1e-2,
+              outer_optimizer='SGD')
+    ops.set_conv_backend(True)
+    try:
+        res = []
+        for graphs in (False, True):
+            sdG, sdE, netG, netE, tasks = _setup(51)
+            ml = MetaLearner(netG, netE, use_graphs=graphs, **kw)
+            tot = [float(ml.outer_step(_dev(tasks))) for _ in range(2)]
+            assert ml.use_graphs == graphs and (len(ml._graphs) == 1) == graphs
+            res.append((tot, ml.last['loss_e'].cpu(), [torch.stack(i).cpu() for i in ml.last['inner']], ml.theta.clone(),
+                        ml.exchange_timing()))
+        (t0, e0, i0, th0, x0), (t1, e1, i1, th1, x1) = res
+        theta_init = MetaLearner(*_setup(51)[2:4], **kw).theta
+    finally:
+        ops.set_conv_backend(False)
+    assert t1 == pytest.approx(t0, rel=1e-4) and t0[1] != pytest.approx(t0[0], rel=1e-6)      # the second step moved on
+    assert torch.allclose(e1, e0, rtol=1e-4) and all(torch.allclose(a, b, rtol=1e-4) for a, b in zip(i0, i1))
+    assert rel(th1 - theta_init, th0 - theta_init) < 1e-3                                      # split-K atomics jitter only
+    assert x0['path'] == x1['path'] == 'local' and x1['median_us'] > 0
+
+
+def test_outer_adam_sensitivity_is_confined_to_near_zero_gradients():
+    """a 2-rank outer ADAM step differed from the single-process run by 2.4e-2 (SGD: 4e-5).  Cause: the first
+    Adam steps move every element by ~lr * g / |g| -- magnitude-free -- so the summation-order / split-K-atomics noise of the
+    meta-gradient (1e-5-class, harmless for SGD) flips or rescales exactly those elements whose gradient is itself noise-sized.
+    Emulated on one GPU by swapping the task order (what a 2-rank exchange changes is the summation order): SGD agrees to
+    1e-4; under Adam the disagreeing elements are a small fraction and all of them have near-zero gradients."""
+    from dynavsr_b200 import ops
+    from dynavsr_b200.meta import MetaLearner
+    kw = dict(inner_steps=1, lr_alpha=1e-5, inner_optimizer='Adam', criterion='cb', est_loss='l1')
+    lr = 1e-4
+    ops.set_conv_backend(True)
+    try:
+        out = {}
+        for outer in ('SGD', 'Adam'):
+            for order in (0, 1):
+                sdG, sdE, netG, netE, tasks = _setup(61)
+                ml = MetaLearner(netG, netE, outer_optimizer=outer, lr_outer=lr, **kw)
+                th0 = ml.theta.clone()
+                ml.outer_step(_dev(tasks[::-1] if order else tasks))
+                out[(outer, order)] = (ml.theta - th0, ml.meta_grad.clone())
+    finally:
+        ops.set_conv_backend(False)
+    dS0, dS1 = out[('SGD', 0)][0], out[('SGD', 1)][0]
+    assert rel(dS1, dS0) < 1e-4
+    dA0, dA1, g = out[('Adam', 0)][0], out[('Adam', 1)][0], out[('Adam', 0)][1]
+    live = g != 0                                                   # (alignment padding of the flat buffer has no gradient)
+    bad = ((dA0 - dA1).abs() > 0.01 * lr) & live
+    frac = float(bad.sum()) / float(live.sum())
+    assert frac < 1e-2, frac
+    rms = float(g[live].pow(2).mean().sqrt())
+    if int(bad.sum()):
+        assert float(g[bad].abs().median()) < 0.05 * rms            # the disagreement lives where the gradient is ~0
+    good = live & ~bad
+    assert rel(dA1[good], dA0[good]) < 1e-2

@@ -444,6 +444,7 @@ def test_fused_updates_match_torch_optim(ops):
         for (p, q) in zip(list(m1.parameters()) + list(m2.parameters()), list(r1.parameters()) + list(r2.parameters())):
             assert rel(p, q) < 1e-5, opt_name
         flat.restore()
+        flat.release()                      # hand the parameters back before the next FlatParams adopts them (single owner)
         r1.load_state_dict(m1.state_dict()); r2.load_state_dict(m2.state_dict())
 
 
@@ -610,11 +611,14 @@ def test_conv_tc2_single_product_mode(ops, shape):
     x, w, b = _rand(N, Ci, H, W, seed=11), _rand(Co, Ci, 3, 3, seed=12, scale=0.05), _rand(Co, seed=13, scale=0.1)
     exact = F.conv2d(x.double(), w.double(), b.double(), padding=1)
     rounded = F.conv2d(x.bfloat16().double(), w.bfloat16().double(), b.double(), padding=1)
+    # 128 input channels reach the resident-weight kernel as two 64-channel K-segments (torch.cat feeding a conv, as in PCD):
+    # the host K-splits them over two launches; a single 128-channel tensor would go to the streaming TF32 kernel instead
+    segs = lambda t: [nhwc(_dev(t[:, i:i + 64])) for i in range(0, Ci, 64)] if Ci > 64 else nhwc(_dev(t))
     try:
         ops.set_conv_backend(True, 'bf16')
-        y1 = nchw(ops.conv(nhwc(_dev(x)), _dev(w), _dev(b), stride=1, pad=1))
+        y1 = nchw(ops.conv(segs(x), _dev(w), _dev(b), stride=1, pad=1))
         ops.set_conv_backend(True, 'bf16x3')
-        y3 = nchw(ops.conv(nhwc(_dev(x)), _dev(w), _dev(b), stride=1, pad=1))
+        y3 = nchw(ops.conv(segs(x), _dev(w), _dev(b), stride=1, pad=1))
     finally:
         ops.set_conv_backend(False, 'bf16x3')
     assert rel(y1, rounded) < 2e-5                       # exactly the single product (fp32 accumulation order aside)

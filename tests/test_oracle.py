@@ -72,6 +72,18 @@ def test_edvr_oracle_matches_reference_golden():
     assert rel(inter['tsa'], torch.from_numpy(g['tsa'])) < 1e-6
 
 
+def test_sfdn_oracle_matches_reference_golden():
+    """SFDN restatement (LRimg_estimator.py:38-67) vs the unmodified reference module (oracle/make_golden_sfdn.py), forward
+    and the input gradient (the spatial mean stays in the graph)."""
+    g = gold('sfdn_32x48.npz')
+    sd = P.make_params(P.sfdn_param_shapes(64), seed=int(g['seed']))
+    x = torch.from_numpy(g['x']).requires_grad_(True)
+    out = O.sfdn_forward(sd, x)
+    assert rel(out, torch.from_numpy(g['out'])) < 1e-6
+    (out * torch.from_numpy(g['probe'])).sum().backward()
+    assert rel(x.grad, torch.from_numpy(g['gx'])) < 1e-5
+
+
 def test_mfdn_oracle_matches_reference_golden():
     g = gold('mfdn_32x48.npz')
     sd = P.make_params(P.mfdn_param_shapes(), seed=int(g['seed']))
@@ -246,6 +258,36 @@ def test_adapt_oracle_vs_reference_test_driver(tag):
         base = O.edvr_forward(sdB, lq)[0]
     assert abs(psnr_uint8(base, gt) - float(g['psnr_baseline'])) < 1e-3
     assert float(g['psnr_adapted']) > float(g['psnr_baseline'])
+
+
+@pytest.mark.parametrize('tag', ['sgd2_l2_patch', 'adam1_cb_real'])
+def test_adapt_oracle_optional_branches_vs_reference_test_driver(tag):
+    """The ``maml.use_patch`` (test_dynavsr.py:118-145,255-260) and ``train.use_real`` (:218-221,243-244) branches of the inner
+    loop, pinned the same way: the unmodified driver ran them (crop positions = what its ``random.randrange`` calls returned,
+    logged by the harness; 'SuperLQs' supplied by the loader) and the oracle reproduces frame, PSNR and parameter deltas --
+    with use_real MFDN must not move at all."""
+    from util import psnr_uint8
+    g = gold('driver_%s.npz' % tag)
+    sdG, sdE, sdF, _ = _driver_weights(g)
+    lq, gt = torch.from_numpy(g['lq']), torch.from_numpy(g['gt'])
+    extra = {}
+    if bool(g['use_real']):
+        extra['slr_given'] = torch.from_numpy(g['slq'])
+    if bool(g['use_patch']):
+        n, c = int(g['num_patch']), g['crops'].tolist()
+        pos = [(c[2 * i], c[2 * i + 1]) for i in range(len(c) // 2)]
+        assert len(pos) == n * int(g['steps'])
+        extra.update(patches=[pos[k * n:(k + 1) * n] for k in range(int(g['steps']))], patch_size=int(g['patch_size']))
+    out, losses, pG, pE = O.adapt_and_infer(sdG, sdE, sdF, lq, steps=int(g['steps']), lr_alpha=float(g['lr_alpha']),
+                                            optimizer=str(g['optimizer']), criterion=str(g['criterion']), return_losses=True, **extra)
+    out = out[0].clamp(0, 1)
+    assert rel(out, torch.from_numpy(g['out'])) < 1e-6
+    assert abs(psnr_uint8(out, gt) - float(g['psnr_adapted'])) < 1e-3
+    assert rel(pG['conv_first.weight'] - sdG['conv_first.weight'], torch.from_numpy(g['d_conv_first'])) < 1e-4
+    if bool(g['use_real']):
+        assert float(np.abs(g['d_conv6']).max()) == 0.0 and torch.equal(pE['conv6.weight'], sdE['conv6.weight'])
+    else:
+        assert rel(pE['conv6.weight'] - sdE['conv6.weight'], torch.from_numpy(g['d_conv6'])) < 1e-4
 
 
 def test_precision_study_operand_emulation():
