@@ -69,6 +69,7 @@ class MetaLearner(object):
         # bf16 operands with fp32 accumulation over the fp32 master weights -- BASELINE config 4's "bf16 compute, fp32 masters"
         self.precision = precision
         self._graphs = {}
+        self.replayed_launches = 0      # library kernels launched through graph replays (bench.py's gpu_launches)
         self.exchange_events = []
         self.scope = ops.new_scope(policy)
         self.work = FlatParams([netG, netE], scope=self.scope)      # theta' (+ its gradient buffer)
@@ -108,6 +109,7 @@ class MetaLearner(object):
         for k in ('LQs', 'GT', 'SuperLQs'):
             st['in'][k].copy_(task[k], non_blocking=True)
         st['graph'].replay()
+        self.replayed_launches += st['launches']
         lq, le, inner = st['out']                   # static tensors of the graph: copy out before the next replay overwrites them
         return lq.clone(), le.clone(), [t.clone() for t in inner]
 
@@ -129,8 +131,11 @@ class MetaLearner(object):
         ops.repack_all()
         ops.snapshot_packs()
         g = torch.cuda.CUDAGraph()
+        from . import _lib
+        n0 = _lib.COUNTER[0]
         with torch.cuda.graph(g), ops.conv_precision(self.precision):
             st['out'] = self._task_eager(st['in'], n_tasks, from_snapshot=True)
+        st['launches'] = _lib.COUNTER[0] - n0        # library kernels inside one replay of this graph
         st['graph'] = g
         self._graphs[key] = st
         self.meta_grad.copy_(keep)                  # capture does not execute, but keep the invariant explicit
@@ -264,9 +269,13 @@ class MetaLearner(object):
     def dtype_string(self):
         if not ops._tc():
             return 'f32 (exact CUDA-core path)'
-        if self.precision == 'bf16':
-            return 'bf16 tensor-core operands (tcgen05), fp32 accumulate, fp32 master weights / gradients / optimiser state'
-        return 'f32 storage; tcgen05 %s operands, fp32 accumulate' % (self.precision or ops._backend['precision'])
+        prec = self.precision or ops._backend['precision']
+        if getattr(self.netG, 'nf', 64) > 64:
+            # 128-channel layers exceed the resident-weight kernel's shared-memory budget and run on the streaming tcgen05 kernel
+            # (TF32 operands rounded to nearest); only the <= 64-channel layers (MFDN, head) follow `precision`
+            return ('f32 storage, fp32 master weights / gradients / optimiser state; tcgen05 TF32 operands (streaming kernel, nf = %d '
+                    'layers) and %s operands (<= 64-channel layers), fp32 accumulate' % (self.netG.nf, prec))
+        return 'f32 storage, fp32 master weights / gradients / optimiser state; tcgen05 %s operands, fp32 accumulate' % prec
 
     def state_dicts(self):
         """(EDVR state_dict, MFDN state_dict) of the meta-weights, reference key names (checkpoint contract)."""

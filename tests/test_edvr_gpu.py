@@ -147,10 +147,14 @@ def test_sfdn_matches_reference_golden(mods, tc):
         ops.set_conv_backend(False)
     tol = 1e-3 if tc else 2e-5
     assert out.shape == (3, 3, 16, 24) and rel(out, torch.from_numpy(g['out'])) < tol
-    assert rel(x.grad, torch.from_numpy(g['gx'])) < 5 * tol
-    assert rel(net.conv0.weight.grad, torch.from_numpy(g['g_conv0_w'])) < 5 * tol
-    assert rel(net.conv3.weight.grad, torch.from_numpy(g['g_conv3_w'])) < 5 * tol
-    assert rel(net.conv6.bias.grad, torch.from_numpy(g['g_conv6_b'])) < 5 * tol
+    # gradients of the reduced-precision path against an fp32 reference have an inherent floor: a pre-activation within the
+    # rounding error of zero flips its LeakyReLU mask (DESIGN.md "Numerics"), six layers deep here -- wide band for the
+    # tensor-core path, the exact path pins the gradient formulas (incl. the mean term: measured 2e-2 vs 1e-6)
+    gtol = 5e-2 if tc else 1e-4
+    assert rel(x.grad, torch.from_numpy(g['gx'])) < gtol
+    assert rel(net.conv0.weight.grad, torch.from_numpy(g['g_conv0_w'])) < gtol
+    assert rel(net.conv3.weight.grad, torch.from_numpy(g['g_conv3_w'])) < gtol
+    assert rel(net.conv6.bias.grad, torch.from_numpy(g['g_conv6_b'])) < gtol
 
 
 def test_mfdn_gradients_vs_oracle(mods):
