@@ -90,6 +90,8 @@ SIGNATURES = {
     'dvsr_conv_wgrad_tc_supported': [_DP, _I],
     'dvsr_conv_wgrad_tc': [_DP, _I, _P, _I, _P, _WP, _P],
     'dvsr_mdcn_bwd_data': [_DP, _P, _I, _P, _P, _I, _P, _I, _P, _I, _P],
+    'dvsr_mdcn_bwd_tc_supported': [_DP],
+    'dvsr_mdcn_bwd_tc': [_DP, _P, _I, _P, _P, _I, _P, _I, _P, _I, _P, _WP, _P],
     'dvsr_mdcn_tc_supported': [_DP],
     'dvsr_mdcn_tc_fprop': [_DP, _P, _P],
     'dvsr_mdcn_workspace_bytes': [_I] * 15,

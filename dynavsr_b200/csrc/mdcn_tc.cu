@@ -278,7 +278,7 @@ mdcn_tcs_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant_
     uint8_t* smem_a = smem_w + MDS_WINBUFS * p.win_bytes;      // [MDS_ASTAGES][A tile 16 KiB | weight block 8 KiB]
     uint64_t* bars = (uint64_t*)(smem_a + MDS_ASTAGES * MDS_STAGE_BYTES);
     uint64_t* w_full = bars;                       // [4] TMA weight block landed
-    uint64_t* a_ready = bars + 4;                  // [4] 512 gather arrivals
+    uint64_t* a_ready = bars + 4;                  // [4] 16 arrivals (one per gather warp)
     uint64_t* a_empty = bars + 8;                  // [4] MMA commit
     uint64_t* acc_full = bars + 12;                // [2]
     uint64_t* acc_empty = bars + 14;               // [2]
@@ -295,9 +295,9 @@ mdcn_tcs_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant_
     if (warp == 0 && elect_one()) { prefetch_tmap(&wmap); prefetch_tmap(&xmap); }
     if (warp == 1) {
         if (elect_one()) {
-            for (int i = 0; i < MDS_ASTAGES; ++i) { mbar_init(&w_full[i], 1); mbar_init(&a_ready[i], MD_GATHER); mbar_init(&a_empty[i], 1); }
+            for (int i = 0; i < MDS_ASTAGES; ++i) { mbar_init(&w_full[i], 1); mbar_init(&a_ready[i], MD_GATHER / 32); mbar_init(&a_empty[i], 1); }
             for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
-            for (int i = 0; i < MDS_WINBUFS; ++i) { mbar_init(&win_full[i], 1); mbar_init(&win_empty[i], MD_GATHER); }
+            for (int i = 0; i < MDS_WINBUFS; ++i) { mbar_init(&win_full[i], 1); mbar_init(&win_empty[i], MD_GATHER / 32); }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
@@ -372,79 +372,115 @@ mdcn_tcs_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant_
         }
     } else if (warp < 2 + MD_GATHER / 32) {
         // ===================== gather from the staged window =====================
-        const int t = threadIdx.x - 64;                 // 0..255
+        // One thread per (pixel, deformable group of the chunk), 9 taps unrolled.  Restructured after the round-1 ncu capture
+        // (141 SASS instructions per item, a third of them bounds branches and generic-address math; 18 offset loads stalling
+        // every chunk start; 512-thread mbarrier polls):
+        //   * the TMA window is zero-filled outside the image, so a sample whose 2 x 2 corner block lies inside the window needs NO
+        //     bounds test at all -- out-of-image corners read zeros, which is exactly the reference rule (kernel.cu:466-496); one
+        //     window-containment test per item selects this branch-free path (4 swizzled LDS.128 pairs at immediate offsets);
+        //     anything else (offsets beyond the 3-pixel margin) takes the exact per-corner path with global 256-bit loads;
+        //   * (dy, dx, mask) travel in a 3-deep rolling prefetch queue (9 registers instead of 27, latency hidden behind 3 stages);
+        //   * blend and hi|lo split in packed fp32x2 math (FFMA2), mask folded into the four bilinear weights;
+        //   * explicit shared-memory stores at per-thread constant offsets; one lane per warp polls / arrives on the mbarriers.
+        const int t = threadIdx.x - 64;                 // 0..511
         const int gl = t & 3;                           // deformable group inside the 32-channel chunk
-        int stage = 0, phase = 0, cc = 0;
-        for (int tile = blockIdx.x; tile < p.tiles_total; tile += gridDim.x) {
-            const int tn = tile / tiles_per_img, tr = tile - tn * tiles_per_img;
+        const int prow = t >> 2;                        // pixel row of the 128-pixel tile
+        const uint32_t ph = (uint32_t)(prow & 7);
+        const uint32_t st_hi = (uint32_t)prow * 128u + ((((uint32_t)gl) ^ ph) << 4);
+        const uint32_t st_lo = (uint32_t)prow * 128u + ((((uint32_t)(4 + gl)) ^ ph) << 4);
+        const uint32_t sa0 = smem_u32(smem_a);
+        const uint32_t g2 = (uint32_t)(gl * 2);
+        struct Geo { long long mlin; int oy, ox, tn, wy0, wx0; bool ok; };
+        auto geo_of = [&](int tile) {
+            Geo gq;
+            gq.tn = tile / tiles_per_img;
+            const int tr = tile - gq.tn * tiles_per_img;
             const int oy0 = (tr / p.tiles_w) * 16, ox0 = (tr % p.tiles_w) * 8;
-            const int wy0 = oy0 - 1 - p.margin, wx0 = ox0 - 1 - p.margin;       // image coordinates of window pixel (0, 0)
-            long long mlin[MD_PPT]; int oy[MD_PPT], ox[MD_PPT]; bool ok[MD_PPT];
-#pragma unroll
-            for (int i = 0; i < MD_PPT; ++i) {
-                const int prow = (t >> 2) + (MD_GATHER / 4) * i;
-                oy[i] = oy0 + (prow >> 3);
-                ox[i] = ox0 + (prow & 7);
-                ok[i] = oy[i] < p.Ho && ox[i] < p.Wo;
-                mlin[i] = ((long long)tn * p.Ho + (ok[i] ? oy[i] : 0)) * p.Wo + (ok[i] ? ox[i] : 0);
+            gq.wy0 = oy0 - 1 - p.margin; gq.wx0 = ox0 - 1 - p.margin;
+            gq.oy = oy0 + (prow >> 3); gq.ox = ox0 + (prow & 7);
+            gq.ok = gq.oy < p.Ho && gq.ox < p.Wo;
+            gq.mlin = ((long long)gq.tn * p.Ho + (gq.ok ? gq.oy : 0)) * p.Wo + (gq.ok ? gq.ox : 0);
+            return gq;
+        };
+        float qdy[3], qdx[3], qmk[3];
+        auto load_q = [&](int slot, const Geo& gq, int c, int tap) {
+            qdy[slot] = qdx[slot] = qmk[slot] = 0.f;
+            if (gq.ok) {
+                const int g = c * 4 + gl;
+                // (dy, dx) pairs are 8-byte aligned ([dg][k][2] layout, even pixel stride): one 64-bit request per tap
+                const float2 o2 = __ldg(reinterpret_cast<const float2*>(p.offset + gq.mlin * p.off_pix_stride + (g * 9 + tap) * 2));
+                qdy[slot] = o2.x; qdx[slot] = o2.y;
+                qmk[slot] = __ldg(p.mask + gq.mlin * p.mask_pix_stride + g * 9 + tap);
             }
-            const float* img0 = p.x + (long long)tn * p.img_stride;
+        };
+        int stage = 0, phase = 0, cc = 0;
+        Geo cur = geo_of(blockIdx.x < (unsigned)p.tiles_total ? (int)blockIdx.x : 0);
+        if ((int)blockIdx.x < p.tiles_total) {
+#pragma unroll
+            for (int i = 0; i < 3; ++i) load_q(i, cur, 0, i);
+        }
+        for (int tile = blockIdx.x; tile < p.tiles_total; tile += gridDim.x) {
+            const bool has_next = tile + (int)gridDim.x < p.tiles_total;
+            const Geo nxt = geo_of(has_next ? tile + (int)gridDim.x : tile);
+            const float* img0 = p.x + (long long)cur.tn * p.img_stride;
+            const float fy = (float)(cur.oy - 1), fx = (float)(cur.ox - 1);
             for (int c = 0; c < chunks; ++c) {
                 const int g = c * 4 + gl;
-                // all 9 taps' offsets / masks of this thread's two pixels: independent loads in flight while the window lands
-                float ody[MD_PPT][9], odx[MD_PPT][9], omk[MD_PPT][9];
-#pragma unroll
-                for (int i = 0; i < MD_PPT; ++i) {
-                    const float* op = p.offset + mlin[i] * p.off_pix_stride + g * KK * 2;
-                    const float* mp = p.mask + mlin[i] * p.mask_pix_stride + g * KK;
-#pragma unroll
-                    for (int tap = 0; tap < 9; ++tap) {
-                        // (dy, dx) pairs are 8-byte aligned ([dg][k][2] layout, even pixel stride): one 64-bit request per tap
-                        const float2 o2 = ok[i] ? __ldg(reinterpret_cast<const float2*>(op) + tap) : make_float2(0.f, 0.f);
-                        ody[i][tap] = o2.x;
-                        odx[i][tap] = o2.y;
-                        omk[i][tap] = ok[i] ? __ldg(mp + tap) : 0.f;
-                    }
-                }
                 const int wb = cc & 1;
                 const uint32_t win_s = smem_u32(smem_w + wb * p.win_bytes);
-                mbar_wait(&win_full[wb], (cc >> 1) & 1);
+                if (lane == 0) mbar_wait(&win_full[wb], (cc >> 1) & 1);
+                __syncwarp();
 #pragma unroll
                 for (int tap = 0; tap < 9; ++tap) {
                     const int kh = tap / 3, kw = tap - kh * 3;
-                    mbar_wait(&a_empty[stage], phase ^ 1);
-                    uint8_t* tile_a = smem_a + stage * MDS_STAGE_BYTES;
-#pragma unroll
-                    for (int i = 0; i < MD_PPT; ++i) {
-                        const int prow = (t >> 2) + (MD_GATHER / 4) * i;
+                    const int slot = tap % 3;
+                    const float dy = qdy[slot], dx = qdx[slot], mk = qmk[slot];
+                    // refill the slot with the stage three ahead (same chunk, next chunk, or chunk 0 of this CTA's next tile)
+                    if (tap + 3 < 9) load_q(slot, cur, c, tap + 3);
+                    else if (c + 1 < chunks) load_q(slot, cur, c + 1, tap + 3 - 9);
+                    else if (has_next) load_q(slot, nxt, 0, tap + 3 - 9);
+                    const float h = fy + (float)kh + dy, w = fx + (float)kw + dx;
+                    const float hf = floorf(h), wf = floorf(w);
+                    const int h0 = (int)hf, w0 = (int)wf;
+                    const float lh = h - hf, lw = w - wf, hh = 1.f - lh, hw = 1.f - lw;
+                    const int wy = h0 - cur.wy0, wx = w0 - cur.wx0;
+                    float2 v01, v23, v45, v67;
+                    if ((unsigned)wy < (unsigned)(p.win_h - 1) && (unsigned)wx < (unsigned)(p.win_w - 1)) {
+                        // ---- fast path: the whole 2 x 2 block is inside the (zero-filled) window
+                        const uint32_t row = (uint32_t)(wy * p.win_w + wx);
+                        const uint32_t r0 = win_s + row * 128u;
+                        const uint32_t a00 = r0 + ((g2 ^ (row & 7u)) << 4);
+                        const uint32_t a01 = r0 + 128u + ((g2 ^ ((row + 1u) & 7u)) << 4);
+                        const uint32_t dn = (uint32_t)p.win_w * 128u;          // next window row (win_w is a multiple of 8: same swizzle phase)
+                        float4 A0, A1, B0, B1, E0, E1, F0, F1;
+                        lds8(a00, a00 ^ 16u, A0, A1);
+                        lds8(a01, a01 ^ 16u, B0, B1);
+                        lds8(a00 + dn, (a00 ^ 16u) + dn, E0, E1);
+                        lds8(a01 + dn, (a01 ^ 16u) + dn, F0, F1);
+                        const float mh = hh * mk, ml = lh * mk;
+                        const float m00 = mh * hw, m01 = mh * lw, m10 = ml * hw, m11 = ml * lw;
+                        const float2 w00 = make_float2(m00, m00), w01 = make_float2(m01, m01), w10 = make_float2(m10, m10), w11 = make_float2(m11, m11);
+#define DVSR_BLEND2(lo_, hi_, A, B, E, F) __ffma2_rn(make_float2(F.lo_, F.hi_), w11, __ffma2_rn(make_float2(E.lo_, E.hi_), w10, \
+                            __ffma2_rn(make_float2(B.lo_, B.hi_), w01, __fmul2_rn(make_float2(A.lo_, A.hi_), w00))))
+                        v01 = DVSR_BLEND2(x, y, A0, B0, E0, F0);
+                        v23 = DVSR_BLEND2(z, w, A0, B0, E0, F0);
+                        v45 = DVSR_BLEND2(x, y, A1, B1, E1, F1);
+                        v67 = DVSR_BLEND2(z, w, A1, B1, E1, F1);
+#undef DVSR_BLEND2
+                    } else {
+                        // ---- exact path for samples whose corner block leaves the window (or the image by more than the margin)
                         float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                        const float h = (float)(oy[i] - 1 + kh) + ody[i][tap];
-                        const float w = (float)(ox[i] - 1 + kw) + odx[i][tap];
-                        if (ok[i] && h > -1.f && w > -1.f && h < (float)p.H && w < (float)p.W) {
-                            const float hf = floorf(h), wf = floorf(w);
-                            const int h0 = (int)hf, w0 = (int)wf;
-                            const float lh = h - hf, lw = w - wf, hh = 1.f - lh, hw = 1.f - lw;
-                            const float mk = omk[i][tap];
+                        if (cur.ok && h > -1.f && w > -1.f && h < (float)p.H && w < (float)p.W) {
                             const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
                             float4 q0[4], q1[4];
 #pragma unroll
                             for (int cr = 0; cr < 4; ++cr) {
                                 const int hc = h0 + (cr >> 1), wc = w0 + (cr & 1);
                                 q0[cr] = z; q1[cr] = z;
-                                if (hc >= 0 && hc <= p.H - 1 && wc >= 0 && wc <= p.W - 1) {      // kernel.cu:478-490 corner rule
-                                    const int wy = hc - wy0, wx = wc - wx0;
-                                    if (wy >= 0 && wy < p.win_h && wx >= 0 && wx < p.win_w) {
-                                        const int row = wy * p.win_w + wx;
-                                        const uint32_t ra = win_s + (uint32_t)row * 128u;
-                                        const uint32_t sw = (uint32_t)(row & 7);
-                                        lds8(ra + (((uint32_t)(gl * 2) ^ sw) << 4), ra + (((uint32_t)(gl * 2 + 1) ^ sw) << 4), q0[cr], q1[cr]);
-                                    } else {
-                                        ldg8(img0 + ((long long)hc * p.W + wc) * p.pix_stride + g * 8, q0[cr], q1[cr]);
-                                    }
-                                }
+                                if (hc >= 0 && hc <= p.H - 1 && wc >= 0 && wc <= p.W - 1)      // kernel.cu:478-490 corner rule
+                                    ldg8(img0 + ((long long)hc * p.W + wc) * p.pix_stride + g * 8, q0[cr], q1[cr]);
                             }
                             const float w00 = hh * hw, w01 = hh * lw, w10 = lh * hw, w11 = lh * lw;
-                            // same association as the reference: (w1*v1 + w2*v2 + w3*v3 + w4*v4) * mask
                             v[0] = (w00 * q0[0].x + w01 * q0[1].x + w10 * q0[2].x + w11 * q0[3].x) * mk;
                             v[1] = (w00 * q0[0].y + w01 * q0[1].y + w10 * q0[2].y + w11 * q0[3].y) * mk;
                             v[2] = (w00 * q0[0].z + w01 * q0[1].z + w10 * q0[2].z + w11 * q0[3].z) * mk;
@@ -454,21 +490,29 @@ mdcn_tcs_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant_
                             v[6] = (w00 * q1[0].z + w01 * q1[1].z + w10 * q1[2].z + w11 * q1[3].z) * mk;
                             v[7] = (w00 * q1[0].w + w01 * q1[1].w + w10 * q1[2].w + w11 * q1[3].w) * mk;
                         }
-                        uint32_t hi[4], lo[4];
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) split_bf16x2(v[2 * q], v[2 * q + 1], hi[q], lo[q]);
-                        uint4* row = reinterpret_cast<uint4*>(tile_a + prow * 128);
-                        const int ph = prow & 7;
-                        row[gl ^ ph] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                        row[(4 + gl) ^ ph] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                        v01 = make_float2(v[0], v[1]); v23 = make_float2(v[2], v[3]);
+                        v45 = make_float2(v[4], v[5]); v67 = make_float2(v[6], v[7]);
                     }
+                    uint32_t hi[4], lo[4];
+                    split_bf16x2_packed(v01, hi[0], lo[0]);
+                    split_bf16x2_packed(v23, hi[1], lo[1]);
+                    split_bf16x2_packed(v45, hi[2], lo[2]);
+                    split_bf16x2_packed(v67, hi[3], lo[3]);
+                    if (lane == 0) mbar_wait(&a_empty[stage], phase ^ 1);
+                    __syncwarp();
+                    const uint32_t sa = sa0 + (uint32_t)stage * MDS_STAGE_BYTES;
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sa + st_hi), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]) : "memory");
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sa + st_lo), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]) : "memory");
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    mbar_arrive(&a_ready[stage]);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&a_ready[stage]);
                     if (++stage == MDS_ASTAGES) { stage = 0; phase ^= 1; }
                 }
-                mbar_arrive(&win_empty[wb]);            // this thread is done reading the window of (tile, chunk)
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&win_empty[wb]);            // this warp is done reading the window of (tile, chunk)
                 ++cc;
             }
+            cur = nxt;
         }
     } else {
         // ===================== epilogue =====================

@@ -117,6 +117,15 @@ __device__ __forceinline__ void split_bf16x2(float x0, float x1, uint32_t& hi, u
     const __nv_bfloat162 l = __floats2bfloat162_rn(r0, r1);
     lo = *reinterpret_cast<const uint32_t*>(&l);
 }
+// the same split on a float2 with packed fp32x2 math (sm_100 FFMA2): the residual of both lanes in one instruction
+__device__ __forceinline__ void split_bf16x2_packed(float2 x, uint32_t& hi, uint32_t& lo) {
+    const __nv_bfloat162 h = __float22bfloat162_rn(x);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    const float2 hf = make_float2(__uint_as_float(hi << 16), __uint_as_float(hi & 0xffff0000u));
+    const float2 r = __ffma2_rn(hf, make_float2(-1.f, -1.f), x);
+    const __nv_bfloat162 l = __float22bfloat162_rn(r);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+}
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }

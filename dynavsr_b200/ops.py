@@ -855,16 +855,33 @@ class _MdcnFn(Function):
         d = _MdcnFn._desc(x, om, dg, KH, KW, stride, pad, dil, Ho, Wo, weight)
         d.Co = Co
         gx = gom = gw = None
-        if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
+        need_data = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        if _tc() and _backend.get('mdcn_bwd_tc', True) and _lib.lib().dvsr_mdcn_bwd_tc_supported(ctypes.byref(d)) == 1:
+            # ONE tcgen05 kernel: grad_col = gy . W^T in TMEM, offset / mask / input gradients, and the weight gradient from the
+            # modulated samples it rebuilds on the way (no `columns` buffer, no second gather pass)
             gx = torch.zeros_like(x) if ctx.needs_input_grad[0] else None
-            gom = torch.empty_like(om)
-            goff_p = gom.data_ptr()
-            gmask_p = gom.data_ptr() + 4 * 2 * dg * KK
-            call('dvsr_mdcn_bwd_data', ctypes.byref(d), _ptr(gpre), Co, _ptr(_packed(weight, wl, 1, 0)),
-                 _ptr(gx), C, ctypes.c_void_p(goff_p), om.shape[3], ctypes.c_void_p(gmask_p), om.shape[3], _stream())
-        if ctx.needs_input_grad[2]:
-            gw = ctx.wslot if ctx.wslot is not None else torch.zeros_like(weight)
-            _run_wgrad(d, gpre, Co, gw, wl, keep=(gpre, gy, x, om) if ctx.wslot is not None else None, weight=weight)
+            gom = torch.empty_like(om) if need_data else None
+            if ctx.needs_input_grad[2]:
+                gw = ctx.wslot if ctx.wslot is not None else torch.zeros_like(weight)
+            wp = _get_pack(weight, wl, 10, 0, 1, a=(KK * ((Co + 63) // 64), 0, 0, 0),
+                           total=_lib.lib().dvsr_conv_tc2_packed_floats(ctypes.byref(wl), 10, 0, 1))
+            if _lib.PROFILE['on']:
+                _lib.PROFILE['tag'] = 'mdcn bwd (tc) %dx%dx%d C%d->%d' % (N, Ho, Wo, C, Co)
+            call('dvsr_mdcn_bwd_tc', ctypes.byref(d), _ptr(gpre), Co, _ptr(wp), _ptr(gx), C,
+                 ctypes.c_void_p(gom.data_ptr()) if gom is not None else None, om.shape[3],
+                 ctypes.c_void_p(gom.data_ptr() + 4 * 2 * dg * KK) if gom is not None else None, om.shape[3],
+                 _ptr(gw), ctypes.byref(wl), _stream())
+        else:
+            if need_data:
+                gx = torch.zeros_like(x) if ctx.needs_input_grad[0] else None
+                gom = torch.empty_like(om)
+                goff_p = gom.data_ptr()
+                gmask_p = gom.data_ptr() + 4 * 2 * dg * KK
+                call('dvsr_mdcn_bwd_data', ctypes.byref(d), _ptr(gpre), Co, _ptr(_packed(weight, wl, 1, 0)),
+                     _ptr(gx), C, ctypes.c_void_p(goff_p), om.shape[3], ctypes.c_void_p(gmask_p), om.shape[3], _stream())
+            if ctx.needs_input_grad[2]:
+                gw = ctx.wslot if ctx.wslot is not None else torch.zeros_like(weight)
+                _run_wgrad(d, gpre, Co, gw, wl, keep=(gpre, gy, x, om) if ctx.wslot is not None else None, weight=weight)
         if ctx.wslot is not None:
             gw = None
         if ctx.bslot is not None:

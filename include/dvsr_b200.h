@@ -207,6 +207,18 @@ int dvsr_mdcn_bwd_data(const dvsr_conv_desc* d, const float* gy, int gy_pix_stri
                        float* gx, int gx_pix_stride, float* goff, int goff_pix_stride,
                        float* gmask, int gmask_pix_stride, void* stream);
 
+/* Tensor-core backward (mdcn_bwd_tc.cu) -- replaces modulated_deform_conv_cuda_backward's GEMMs + col2im / col2im_coord kernels
+ * (deform_conv_cuda.cpp:617-666, deform_conv_cuda_kernel.cu:634-766) with ONE kernel: grad_col = gy . W^T as tcgen05 MMAs into
+ * TMEM, consumed in place by the gather warps (grad_offset / grad_mask stores, grad_input red.global.add.v4), which also build the
+ * modulated samples transposed in shared memory for the weight-gradient MMAs (accumulators resident in TMEM, added to gw at the
+ * end).  EDVR geometry: 64 -> 64 channels, 8 deformable groups, <= 9 taps.  wp10 = dvsr_pack_weights_tc2 mode 10 of the weight.
+ * gx (may be NULL) must be zero-filled or hold a gradient to accumulate into; goff / gmask (may be NULL) are overwritten;
+ * gw (may be NULL; PyTorch layout through wl) is accumulated into. */
+int dvsr_mdcn_bwd_tc_supported(const dvsr_conv_desc* d);
+int dvsr_mdcn_bwd_tc(const dvsr_conv_desc* d, const float* gy, int gy_pix_stride, const float* wp10, float* gx,
+                     int gx_pix_stride, float* goff, int goff_pix_stride, float* gmask, int gmask_pix_stride, float* gw,
+                     const dvsr_wlayout* wl, void* stream);
+
 /* Tensor-core forward (mdcn_tc.cu): gather warps build the modulated bilinear samples as BF16x3 operand rows in shared
  * memory, resident weights (pack mode 7), persistent CTAs.  8 channels per deformable group, C*KH*KW <= 576, Co <= 64. */
 int dvsr_mdcn_tc_supported(const dvsr_conv_desc* d);

@@ -169,6 +169,52 @@ def test_mdcn_nhwc(ops, cfg):
     _mdcn_case(ops, N, C, H, W, Co, dg, s, act, seed=7)
 
 
+@pytest.mark.parametrize('shape,off_scale,kw', [((2, 19, 21), 1.0, {}), ((1, 33, 40), 3.0, {}), ((1, 16, 8), 12.0, {}),
+                                                ((5, 44, 80), 2.0, {}), ((2, 24, 20), 1.5, dict(stride=2)),
+                                                ((1, 20, 28), 1.5, dict(dil=2, pad=2))],
+                         ids=['small_offsets', 'ragged_last_tile', 'mostly_outside_image', 'slr_size', 'stride2', 'dilated'])
+def test_mdcn_tensor_core_backward(ops, shape, off_scale, kw):
+    """dvsr_mdcn_bwd_tc (mdcn_bwd_tc.cu): grad_col = gy . W^T as tcgen05 MMAs into TMEM, consumed in-kernel for the input / offset /
+    mask gradients, and the weight gradient from the modulated samples rebuilt on the way -- all five gradients against the
+    float64 oracle (deform_conv_cuda.cpp:566-679 semantics), BF16x3 = fp32-class.  Also: gx accumulates into what it holds, and
+    the launch-policy CTA budget does not change the numbers beyond the atomics' summation order."""
+    from oracle.torch_ops import mdcn_torch
+    N, H, W = shape
+    stride, pad, dil = kw.get('stride', 1), kw.get('pad', 1), kw.get('dil', 1)
+    x = _rand(N, 64, H, W, seed=1)
+    Ho, Wo = (H + 2 * pad - (dil * 2 + 1)) // stride + 1, (W + 2 * pad - (dil * 2 + 1)) // stride + 1
+    off = _rand(N, 144, Ho, Wo, seed=2, scale=off_scale)
+    m = torch.sigmoid(_rand(N, 72, Ho, Wo, seed=3))
+    w, b = _rand(64, 64, 3, 3, seed=4, scale=0.1), _rand(64, seed=5, scale=0.1)
+    leaves = [t.clone().requires_grad_(True) for t in (x, off, m, w, b)]
+    y = mdcn_torch(leaves[0], leaves[1], leaves[2], leaves[3], leaves[4], stride, pad, dil, 1, 8)
+    gy = _rand(*y.shape, seed=6)
+    gref = torch.autograd.grad(y, leaves, gy)
+    ops.set_conv_backend(True)
+    try:
+        outs = []
+        for budget in (0, 3):
+            with ops.scope(ops.new_scope(ops.LaunchPolicy(cta_budget=budget))):
+                xs = nhwc(_dev(x)).requires_grad_(True)
+                om = torch.cat([nhwc(_dev(off)), nhwc(_dev(m))], 3).contiguous().requires_grad_(True)
+                ws, bs = _dev(w).requires_grad_(True), _dev(b).requires_grad_(True)
+                yd = ops.mdcn(xs, om, ws, bs, 8, stride, pad, dil)
+                assert ops._lib.lib().dvsr_mdcn_bwd_tc_supported is not None
+                outs.append(torch.autograd.grad(yd, [xs, om, ws, bs], nhwc(_dev(gy))))
+    finally:
+        ops.set_conv_backend(False)
+    from util import rel_robust
+    for gx, gom, gw, gb in outs:
+        assert rel(nchw(gx), gref[0]) < 2e-4
+        # the offset gradient is discontinuous where a sampling coordinate crosses an integer: ignore the 1e-4 worst elements
+        # (fp32 vs fp64 floor of the same coordinate; measured 1.1e-3 plain relative L2 at 2.5 M elements, all from such flips)
+        assert rel_robust(nchw(gom[..., :144]), gref[1]) < 2e-4 and rel(nchw(gom[..., :144]), gref[1]) < 5e-3
+        assert rel(nchw(gom[..., 144:]), gref[2]) < 2e-4
+        assert rel(gw, gref[3]) < 2e-4
+        assert rel(gb, gref[4]) < 2e-5
+    assert rel(outs[1][0], outs[0][0]) < 1e-5 and rel(outs[1][2], outs[0][2]) < 1e-5
+
+
 @pytest.mark.parametrize('staged', [2, 1], ids=['staged_window', 'direct_gather'])
 @pytest.mark.parametrize('shape,off_scale', [((2, 19, 21), 1.0), ((1, 33, 40), 3.0), ((1, 16, 8), 12.0), ((5, 44, 80), 2.0)],
                          ids=['small_offsets', 'edge_of_window', 'mostly_outside_window', 'slr_size'])
