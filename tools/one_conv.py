@@ -9,7 +9,8 @@ from dynavsr_b200 import ops  # noqa: E402
 
 a = [int(v) for v in sys.argv[1:7]] if len(sys.argv) >= 7 else [5, 176, 320, 64, 64, 3]
 N, H, W, Ci, Co, k = a
-ops.set_conv_backend(True)
+PREC = sys.argv[sys.argv.index('--precision') + 1] if '--precision' in sys.argv else 'bf16x3'
+ops.set_conv_backend(True, PREC)
 x = torch.randn(N, H, W, Ci, device='cuda')
 w = torch.randn(Co, Ci, k, k, device='cuda') * 0.05
 b = torch.zeros(Co, device='cuda')
@@ -23,7 +24,7 @@ with torch.no_grad():
         y = ops.conv(x, w, b, pad=k // 2, act=ops.ACT_LRELU)
     e1.record()
     torch.cuda.synchronize()
-print('avg us', e0.elapsed_time(e1) / 20 * 1e3)
+print(PREC, 'avg us', e0.elapsed_time(e1) / 20 * 1e3)
 
 if '--trace' in sys.argv:
     import ctypes
@@ -38,7 +39,7 @@ if '--trace' in sys.argv:
     t0 = int(t[0, 0])
     names = ['prod:slot free', 'round:tile landed', 'round:done', 'mma:ready seen', 'mma:issued', 'epi:acc full', 'epi:done', 'epi:tmem read']
     for ev in range(8):
-        print('%-18s' % names[ev], ' '.join('%6d' % (int(v) - t0) for v in t[ev, :14]))
+        print('%-18s' % names[ev], ' '.join('%6d' % (int(v) - t0) for v in t[ev, :(30 if ev < 5 else 15)]))
 if '--both' in sys.argv:
     for prec in ('tf32', 'bf16x3'):
         ops.set_conv_backend(True, prec)
