@@ -184,7 +184,19 @@ conv_tc_kernel(const __grid_constant__ TcMaps maps, const TcParams p) {
         for (int c0 = 0; c0 < p.Co_pad; c0 += 32) {
             float v[32];
             tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);   // warp-collective: no divergence before it
-            if (!valid || c0 >= p.Co) continue;
+            if (c0 >= p.Co) continue;                  // (warp-uniform)
+            if (p.shuffle != 2 && p.out_step == 1 && p.out_off_y == 0 && p.out_off_x == 0) {
+                // dense output: quad transpose, then every quad writes full 128-byte lines (tc_common.cuh)
+                quad_transpose32(v, lane);
+                const int rb = row & ~3, i4 = lane & 3;
+                const int oyb = oy0 + rb / TC_TW, oxb = ox0 + rb % TC_TW;
+                const int nok = (oyb < p.Ho && oyb < p.out_H) ? max(0, min(4, min(p.Wo, p.out_W) - oxb)) : 0;
+                const long long pixb = ((long long)n_img * p.out_H + oyb) * p.out_W + oxb;
+                epilogue_store_t(v, p.bias ? p.bias + c0 + 8 * i4 : nullptr, c0 + 8 * i4, p.Co, pixb, nok, nullptr, 0, p.res, p.res_pix_stride,
+                                 p.y, p.y_pix_stride, false, p.act, p.slope, p.sig_split);
+                continue;
+            }
+            if (!valid) continue;
             epilogue_chunk(v, c0, p.Co, p.bias ? p.bias + c0 : nullptr, nullptr,
                            p.res ? p.res + pix * p.res_pix_stride + c0 : nullptr, p.act, p.slope, p.sig_split);
             if (p.shuffle == 2) {

@@ -216,29 +216,26 @@ mdcn_tc_kernel(const __grid_constant__ CUtensorMap wmap, const MdParams p) {
             const bool valid = pix < M;
             mbar_wait_relaxed(&acc_full[acc], (local >> 1) & 1, 256);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            float v0[32], v1[32];
-            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 64), v0);
-            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 64 + 32), v1);
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            mbar_arrive(&acc_empty[acc]);
-            if (valid) {
-#pragma unroll
+            {
+                // coalesced stores: quad transpose, then each quad writes one full 128-byte line per instruction (tc_common.cuh)
+                const long long pixb = (long long)tile * 128 + (row & ~3);
+                const int nok = (int)min(4LL, max(0LL, M - pixb));
+                const int i4 = lane & 3;
+#pragma unroll 1
                 for (int h = 0; h < 2; ++h) {
-                    float (&v)[32] = h == 0 ? v0 : v1;
+                    // one 32-column half at a time (register budget: 80 per thread in this 22-warp CTA); the accumulator is
+                    // handed back to the MMA warp as soon as its second half is in registers
+                    float v[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 64 + h * 32), v);
+                    if (h == 1) {
+                        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                        mbar_arrive(&acc_empty[acc]);
+                    }
                     const int c0 = h * 32;
                     if (c0 >= p.Co) continue;
-                    epilogue_chunk(v, c0, p.Co, bias_s + c0, nullptr, nullptr, p.act, p.slope, 0);
-                    float* yo = p.y + pix * p.y_pix_stride + c0;
-                    const int nvalid = min(32, p.Co - c0);
-                    if (p.y_vec8) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 8)
-                            if (j < nvalid) st_global_v8(yo + j, v[j], v[j + 1], v[j + 2], v[j + 3], v[j + 4], v[j + 5], v[j + 6], v[j + 7]);
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4)
-                            if (j < nvalid) *reinterpret_cast<float4*>(yo + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                    }
+                    quad_transpose32(v, lane);
+                    epilogue_store_t(v, bias_s + c0 + 8 * i4, c0 + 8 * i4, p.Co, pixb, nok, nullptr, 0, nullptr, 0, p.y, p.y_pix_stride,
+                                     p.y_vec8 != 0, p.act, p.slope, 0);
                 }
             }
         }
@@ -263,6 +260,8 @@ mdcn_tc_kernel(const __grid_constant__ CUtensorMap wmap, const MdParams p) {
 // full-resolution call), which buys a 4-stage ring and a double-buffered input window.
 constexpr int MDS_ASTAGES = 4;             // (A operand tile 16 KiB + streamed weight block 8 KiB) per stage
 constexpr int MDS_STAGE_BYTES = MD_A_BYTES + 8192;
+constexpr int MDS_MARGIN = 3;              // window margin for the learned offsets, pixels
+constexpr int MDS_WIN_H = 16 + 2 + 2 * MDS_MARGIN, MDS_WIN_W = 8 + 2 + 2 * MDS_MARGIN;     // 24 x 16 pixels
 constexpr int MDS_WINBUFS = 2;             // input window double-buffered: the TMA of chunk c+1 flies while chunk c is gathered
 
 __device__ __forceinline__ void lds8(uint32_t addr0, uint32_t addr1, float4& a, float4& b) {
@@ -274,7 +273,7 @@ __global__ void __launch_bounds__(MD_THREADS, 1)
 mdcn_tcs_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__ CUtensorMap xmap, const MdParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    uint8_t* smem_w = smem;                                    // [MDS_WINBUFS] input windows [win_h * win_w][128 B], 128B-swizzled by TMA
+    uint8_t* smem_w = smem;                                    // [MDS_WINBUFS] input windows [win_h * win_w][128 B], NOT swizzled
     uint8_t* smem_a = smem_w + MDS_WINBUFS * p.win_bytes;      // [MDS_ASTAGES][A tile 16 KiB | weight block 8 KiB]
     uint64_t* bars = (uint64_t*)(smem_a + MDS_ASTAGES * MDS_STAGE_BYTES);
     uint64_t* w_full = bars;                       // [4] TMA weight block landed
@@ -386,10 +385,20 @@ mdcn_tcs_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant_
         const int gl = t & 3;                           // deformable group inside the 32-channel chunk
         const int prow = t >> 2;                        // pixel row of the 128-pixel tile
         const uint32_t ph = (uint32_t)(prow & 7);
+        // Bank-conflict-free shared-memory traffic (the round-2 ncu capture showed 35.5 M of 65.1 M shared wavefronts of this
+        // kernel to be conflicts, L1TEX at 85 %): a 128-bit access is served per quarter-warp = 2 pixels x 4 groups here.
+        //   * window reads: the window is NOT swizzled, so the 16-byte chunk a lane reads is (2 * group + half) whatever pixel
+        //     its sample falls on; lanes of odd pixels read the upper half of their group's 32 bytes first, lanes of even pixels
+        //     the lower half -> the 8 lanes always cover 8 distinct chunks;
+        //   * operand-row stores (K-major 128B swizzle, required by the MMA): even pixels store hi then lo, odd pixels lo then hi
+        //     -> chunks {0..3}^s and {4..7}^(s^1) are disjoint.
+        // The price is 8 register selects per item (the two halves change places in odd lanes).
+        const bool par = (prow & 1) != 0;
         const uint32_t st_hi = (uint32_t)prow * 128u + ((((uint32_t)gl) ^ ph) << 4);
         const uint32_t st_lo = (uint32_t)prow * 128u + ((((uint32_t)(4 + gl)) ^ ph) << 4);
+        const uint32_t st_first = par ? st_lo : st_hi, st_second = par ? st_hi : st_lo;
         const uint32_t sa0 = smem_u32(smem_a);
-        const uint32_t g2 = (uint32_t)(gl * 2);
+        const uint32_t lane_off = (uint32_t)(gl * 32 + (par ? 16 : 0));
         struct Geo { long long mlin; int oy, ox, tn, wy0, wx0; bool ok; };
         auto geo_of = [&](int tile) {
             Geo gq;
@@ -444,28 +453,27 @@ mdcn_tcs_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant_
                     const int h0 = (int)hf, w0 = (int)wf;
                     const float lh = h - hf, lw = w - wf, hh = 1.f - lh, hw = 1.f - lw;
                     const int wy = h0 - cur.wy0, wx = w0 - cur.wx0;
-                    float2 v01, v23, v45, v67;
-                    if ((unsigned)wy < (unsigned)(p.win_h - 1) && (unsigned)wx < (unsigned)(p.win_w - 1)) {
+                    // vF* = the 4 channels of the half this lane reads first (lower half in even-pixel lanes, upper in odd), vS* = the other
+                    float2 vF01, vF23, vS01, vS23;
+                    if ((unsigned)wy < (unsigned)(MDS_WIN_H - 1) && (unsigned)wx < (unsigned)(MDS_WIN_W - 1)) {
                         // ---- fast path: the whole 2 x 2 block is inside the (zero-filled) window
-                        const uint32_t row = (uint32_t)(wy * p.win_w + wx);
-                        const uint32_t r0 = win_s + row * 128u;
-                        const uint32_t a00 = r0 + ((g2 ^ (row & 7u)) << 4);
-                        const uint32_t a01 = r0 + 128u + ((g2 ^ ((row + 1u) & 7u)) << 4);
-                        const uint32_t dn = (uint32_t)p.win_w * 128u;          // next window row (win_w is a multiple of 8: same swizzle phase)
+                        const uint32_t b0 = win_s + (uint32_t)(wy * MDS_WIN_W + wx) * 128u + lane_off;
+                        const uint32_t b1 = b0 ^ 16u;
+                        constexpr uint32_t dn = MDS_WIN_W * 128u;              // next window row
                         float4 A0, A1, B0, B1, E0, E1, F0, F1;
-                        lds8(a00, a00 ^ 16u, A0, A1);
-                        lds8(a01, a01 ^ 16u, B0, B1);
-                        lds8(a00 + dn, (a00 ^ 16u) + dn, E0, E1);
-                        lds8(a01 + dn, (a01 ^ 16u) + dn, F0, F1);
+                        lds8(b0, b1, A0, A1);
+                        lds8(b0 + 128u, b1 + 128u, B0, B1);
+                        lds8(b0 + dn, b1 + dn, E0, E1);
+                        lds8(b0 + dn + 128u, b1 + dn + 128u, F0, F1);
                         const float mh = hh * mk, ml = lh * mk;
                         const float m00 = mh * hw, m01 = mh * lw, m10 = ml * hw, m11 = ml * lw;
                         const float2 w00 = make_float2(m00, m00), w01 = make_float2(m01, m01), w10 = make_float2(m10, m10), w11 = make_float2(m11, m11);
 #define DVSR_BLEND2(lo_, hi_, A, B, E, F) __ffma2_rn(make_float2(F.lo_, F.hi_), w11, __ffma2_rn(make_float2(E.lo_, E.hi_), w10, \
                             __ffma2_rn(make_float2(B.lo_, B.hi_), w01, __fmul2_rn(make_float2(A.lo_, A.hi_), w00))))
-                        v01 = DVSR_BLEND2(x, y, A0, B0, E0, F0);
-                        v23 = DVSR_BLEND2(z, w, A0, B0, E0, F0);
-                        v45 = DVSR_BLEND2(x, y, A1, B1, E1, F1);
-                        v67 = DVSR_BLEND2(z, w, A1, B1, E1, F1);
+                        vF01 = DVSR_BLEND2(x, y, A0, B0, E0, F0);
+                        vF23 = DVSR_BLEND2(z, w, A0, B0, E0, F0);
+                        vS01 = DVSR_BLEND2(x, y, A1, B1, E1, F1);
+                        vS23 = DVSR_BLEND2(z, w, A1, B1, E1, F1);
 #undef DVSR_BLEND2
                     } else {
                         // ---- exact path for samples whose corner block leaves the window (or the image by more than the margin)
@@ -490,19 +498,24 @@ mdcn_tcs_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant_
                             v[6] = (w00 * q1[0].z + w01 * q1[1].z + w10 * q1[2].z + w11 * q1[3].z) * mk;
                             v[7] = (w00 * q1[0].w + w01 * q1[1].w + w10 * q1[2].w + w11 * q1[3].w) * mk;
                         }
-                        v01 = make_float2(v[0], v[1]); v23 = make_float2(v[2], v[3]);
-                        v45 = make_float2(v[4], v[5]); v67 = make_float2(v[6], v[7]);
+                        vF01 = par ? make_float2(v[4], v[5]) : make_float2(v[0], v[1]);
+                        vF23 = par ? make_float2(v[6], v[7]) : make_float2(v[2], v[3]);
+                        vS01 = par ? make_float2(v[0], v[1]) : make_float2(v[4], v[5]);
+                        vS23 = par ? make_float2(v[2], v[3]) : make_float2(v[6], v[7]);
                     }
-                    uint32_t hi[4], lo[4];
-                    split_bf16x2_packed(v01, hi[0], lo[0]);
-                    split_bf16x2_packed(v23, hi[1], lo[1]);
-                    split_bf16x2_packed(v45, hi[2], lo[2]);
-                    split_bf16x2_packed(v67, hi[3], lo[3]);
+                    uint32_t hiF[2], loF[2], hiS[2], loS[2];
+                    split_bf16x2_packed(vF01, hiF[0], loF[0]);
+                    split_bf16x2_packed(vF23, hiF[1], loF[1]);
+                    split_bf16x2_packed(vS01, hiS[0], loS[0]);
+                    split_bf16x2_packed(vS23, hiS[1], loS[1]);
+                    // even pixel: first store = hi chunk (F, S), second = lo chunk (F, S); odd pixel: first = lo chunk (S, F), second = hi chunk (S, F)
+                    const uint32_t s1a = par ? loS[0] : hiF[0], s1b = par ? loS[1] : hiF[1], s1c = par ? loF[0] : hiS[0], s1d = par ? loF[1] : hiS[1];
+                    const uint32_t s2a = par ? hiS[0] : loF[0], s2b = par ? hiS[1] : loF[1], s2c = par ? hiF[0] : loS[0], s2d = par ? hiF[1] : loS[1];
                     if (lane == 0) mbar_wait(&a_empty[stage], phase ^ 1);
                     __syncwarp();
                     const uint32_t sa = sa0 + (uint32_t)stage * MDS_STAGE_BYTES;
-                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sa + st_hi), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]), "r"(hi[3]) : "memory");
-                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sa + st_lo), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3]) : "memory");
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sa + st_first), "r"(s1a), "r"(s1b), "r"(s1c), "r"(s1d) : "memory");
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(sa + st_second), "r"(s2a), "r"(s2b), "r"(s2c), "r"(s2d) : "memory");
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&a_ready[stage]);
@@ -527,29 +540,28 @@ mdcn_tcs_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant_
             const long long pix = ((long long)tn * p.Ho + eoy) * p.Wo + eox;
             mbar_wait_relaxed(&acc_full[acc], (local >> 1) & 1, 256);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            float v0[32], v1[32];
-            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 64), v0);
-            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 64 + 32), v1);
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            mbar_arrive(&acc_empty[acc]);
-            if (valid) {
-#pragma unroll
+            {
+                // coalesced stores: quad transpose, then each quad writes one full 128-byte line per instruction (tc_common.cuh)
+                const int rb = row & ~3;
+                const int oyb = (tr / p.tiles_w) * 16 + (rb >> 3), oxb = (tr % p.tiles_w) * 8 + (rb & 7);
+                const int nok = oyb < p.Ho ? min(4, p.Wo - oxb) : 0;
+                const long long pixb = ((long long)tn * p.Ho + oyb) * p.Wo + oxb;
+                const int i4 = lane & 3;
+#pragma unroll 1
                 for (int h = 0; h < 2; ++h) {
-                    float (&v)[32] = h == 0 ? v0 : v1;
+                    // one 32-column half at a time (register budget: 80 per thread in this 22-warp CTA); the accumulator is
+                    // handed back to the MMA warp as soon as its second half is in registers
+                    float v[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 64 + h * 32), v);
+                    if (h == 1) {
+                        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                        mbar_arrive(&acc_empty[acc]);
+                    }
                     const int c0 = h * 32;
                     if (c0 >= p.Co) continue;
-                    epilogue_chunk(v, c0, p.Co, bias_s + c0, nullptr, nullptr, p.act, p.slope, 0);
-                    float* yo = p.y + pix * p.y_pix_stride + c0;
-                    const int nvalid = min(32, p.Co - c0);
-                    if (p.y_vec8) {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 8)
-                            if (j < nvalid) st_global_v8(yo + j, v[j], v[j + 1], v[j + 2], v[j + 3], v[j + 4], v[j + 5], v[j + 6], v[j + 7]);
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4)
-                            if (j < nvalid) *reinterpret_cast<float4*>(yo + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                    }
+                    quad_transpose32(v, lane);
+                    epilogue_store_t(v, bias_s + c0 + 8 * i4, c0 + 8 * i4, p.Co, pixb, nok, nullptr, 0, nullptr, 0, p.y, p.y_pix_stride,
+                                     p.y_vec8 != 0, p.act, p.slope, 0);
                 }
             }
         }
@@ -625,9 +637,9 @@ extern "C" int dvsr_mdcn_tc_fprop(const dvsr_conv_desc* d, const float* wp, void
     if (staged_mode != 1 && d->KH == 3 && d->KW == 3 && d->stride == 1 && d->dil == 1 && d->pad == 1 && d->Ho == d->H && d->Wo == d->W &&
         (staged_mode == 2 || (long long)d->N * ((d->Wo + 7) / 8) * ((d->Ho + 15) / 16) >= 2 * sm_count()) &&
         (((uintptr_t)d->offset & 7) == 0) && ((d->off_pix_stride & 1) == 0)) {
-        p.margin = 3;
-        p.win_h = 16 + 2 + 2 * p.margin;
-        p.win_w = 8 + 2 + 2 * p.margin;
+        p.margin = MDS_MARGIN;
+        p.win_h = MDS_WIN_H;
+        p.win_w = MDS_WIN_W;
         p.win_bytes = (p.win_h * p.win_w * 128 + 1023) / 1024 * 1024;
         p.tiles_w = (d->Wo + 7) / 8;
         p.tiles_h = (d->Ho + 15) / 16;
@@ -638,7 +650,7 @@ extern "C" int dvsr_mdcn_tc_fprop(const dvsr_conv_desc* d, const float* wp, void
         cuuint32_t box[4] = {32, (cuuint32_t)p.win_w, (cuuint32_t)p.win_h, 1};
         cuuint32_t estr[4] = {1, 1, 1, 1};
         CUresult r = encode(&xmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)g.ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         DVSR_REQUIRE(r == CUDA_SUCCESS, "mdcn_tc_fprop: cuTensorMapEncodeTiled(input window) failed with %d", (int)r);
         const size_t smem_s = 1024 + (size_t)MDS_WINBUFS * p.win_bytes + (size_t)MDS_ASTAGES * MDS_STAGE_BYTES + 512;
         if (smem_s <= 232448) {

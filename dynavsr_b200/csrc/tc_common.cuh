@@ -126,6 +126,16 @@ __device__ __forceinline__ void split_bf16x2_packed(float2 x, uint32_t& hi, uint
     const __nv_bfloat162 l = __float22bfloat162_rn(r);
     lo = *reinterpret_cast<const uint32_t*>(&l);
 }
+// explicit shared-window accesses (a pointer obtained by integer arithmetic on the dynamic shared-memory base is generic to
+// the compiler: it emits LD.E / ST.E with a generic-address check instead of LDS / STS)
+__device__ __forceinline__ float4 lds128(uint32_t saddr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -206,6 +216,92 @@ __device__ __forceinline__ void epilogue_chunk(float (&v)[32], int c0, int Co, c
 #pragma unroll
         for (int j = 0; j < 32; j += 4)
             if (j < nvalid) { const float4 t = ldg4(res + j); v[j] += t.x; v[j + 1] += t.y; v[j + 2] += t.z; v[j + 3] += t.w; }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ coalesced epilogue stores
+// tcgen05.ld.32x32b leaves one accumulator ROW (pixel) per thread: storing it directly makes every warp-level store touch 32
+// different 128-byte lines (one 32-byte sector each).  The round-2 ncu capture of conv_tc2 showed what that costs: 59 L1
+// data-stage wavefronts per STG.256 request, 24 % of the (saturated) L1 / shared-memory data pipe of the kernel.  A 4 x 4
+// transpose of 8-float pieces inside each lane quad (2 butterfly steps, 32 SHFL + 96 SEL per thread) turns "32 channels of my
+// pixel" into "my 8 channels of the quad's 4 consecutive pixels", so that in each store instruction a quad writes one full
+// 128-byte line (8 lines per warp instruction instead of 32 sectors).
+//   in : v[8 * c + e] = channel (c0 + 8 * c + e) of pixel row `lane`            (c = 0..3, e = 0..7)
+//   out: v[8 * j + e] = channel (c0 + 8 * (lane & 3) + e) of pixel row (lane & ~3) + j
+__device__ __forceinline__ void quad_transpose32(float (&v)[32], int lane) {
+    const bool b1 = (lane & 2) != 0, b0 = (lane & 1) != 0;
+#pragma unroll
+    for (int s = 0; s < 2; ++s)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            float x = b1 ? v[8 * s + e] : v[8 * (s + 2) + e];
+            x = __shfl_xor_sync(0xffffffffu, x, 2);
+            if (b1) v[8 * s + e] = x; else v[8 * (s + 2) + e] = x;
+        }
+#pragma unroll
+    for (int s = 0; s < 4; s += 2)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            float x = b0 ? v[8 * s + e] : v[8 * (s + 1) + e];
+            x = __shfl_xor_sync(0xffffffffu, x, 1);
+            if (b0) v[8 * s + e] = x; else v[8 * (s + 1) + e] = x;
+        }
+}
+// Epilogue in the transposed domain: v[8 * j + e] = channel (cch + e) of pixel (pixb + j), j < nok (the quad's 4 consecutive
+// pixels, the first nok of them inside the image):  y = act(v + addend + bias) + res, stored as 32 contiguous bytes per pixel
+// (one full line per quad).  bias8 -> 8 bias values of channels cch.. (shared or global, 16-byte aligned) or null; addend / res /
+// y are tensor bases (16-byte aligned rows; vec8: y rows 32-byte aligned).  Channels >= Co are neither read nor written
+// (Co is a multiple of 4).
+__device__ __forceinline__ void epilogue_store_t(float (&v)[32], const float* bias8, int cch, int Co, long long pixb, int nok,
+                                                 const float* addend, int addend_pix_stride, const float* res, int res_pix_stride,
+                                                 float* y, int y_pix_stride, bool vec8, int act, float slope, int sig_split,
+                                                 bool dry = false) {
+    // dry: run every instruction of the body with the loads and stores predicated off (instruction-cache warm-up pass of a
+    // persistent kernel's epilogue warps while they wait for their first accumulator)
+    const int nch = Co - cch;
+    if (nch <= 0) return;
+    const bool full = nch >= 8;
+    float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+    if (bias8) { b0 = *reinterpret_cast<const float4*>(bias8); b1 = *reinterpret_cast<const float4*>(bias8 + 4); }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        if (j < nok || dry) {
+            float* w = &v[8 * j];
+            const long long px = pixb + j;
+            if (addend && !dry) {
+                const float* a = addend + px * addend_pix_stride + cch;
+                const float4 t0 = ldg4(a);
+                w[0] += t0.x; w[1] += t0.y; w[2] += t0.z; w[3] += t0.w;
+                if (full) { const float4 t1 = ldg4(a + 4); w[4] += t1.x; w[5] += t1.y; w[6] += t1.z; w[7] += t1.w; }
+            }
+            w[0] += b0.x; w[1] += b0.y; w[2] += b0.z; w[3] += b0.w; w[4] += b1.x; w[5] += b1.y; w[6] += b1.z; w[7] += b1.w;
+            if (act == DVSR_ACT_LRELU) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) w[e] = w[e] > 0.f ? w[e] : w[e] * slope;
+            } else if (act == DVSR_ACT_RELU) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) w[e] = fmaxf(w[e], 0.f);
+            } else if (act == DVSR_ACT_SIGMOID_SPLIT && cch + 8 > sig_split) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e)
+                    if (cch + e >= sig_split) w[e] = __fdividef(1.f, 1.f + __expf(-w[e]));
+            }
+            if (res && !dry) {
+                const float* a = res + px * res_pix_stride + cch;
+                const float4 t0 = ldg4(a);
+                w[0] += t0.x; w[1] += t0.y; w[2] += t0.z; w[3] += t0.w;
+                if (full) { const float4 t1 = ldg4(a + 4); w[4] += t1.x; w[5] += t1.y; w[6] += t1.z; w[7] += t1.w; }
+            }
+            float* yo = y + px * y_pix_stride + cch;
+            if (dry) {
+                // nothing leaves the thread
+            } else if (vec8 && full) {
+                st_global_v8(yo, w[0], w[1], w[2], w[3], w[4], w[5], w[6], w[7]);
+            } else {
+                *reinterpret_cast<float4*>(yo) = make_float4(w[0], w[1], w[2], w[3]);
+                if (full) *reinterpret_cast<float4*>(yo + 4) = make_float4(w[4], w[5], w[6], w[7]);
+            }
+        }
     }
 }
 

@@ -208,7 +208,9 @@ def test_outer_adam_sensitivity_is_confined_to_near_zero_gradients():
     finally:
         ops.set_conv_backend(False)
     dS0, dS1 = out[('SGD', 0)][0], out[('SGD', 1)][0]
-    assert rel(dS1, dS0) < 5e-4                                     # (2 ranks vs 1 process measured 4.4e-5, profiles/r1_meta_exchange_n2.txt)
+    # (2 ranks vs 1 process measured 4.4e-5, profiles/r1_meta_exchange_n2.txt; swapped task order on one GPU 3e-4 - 5.4e-4 from run
+    # to run: the weight-gradient partial sums are accumulated with atomics, so the order differs between runs as well)
+    assert rel(dS1, dS0) < 1.5e-3
     dA0, dA1, g = out[('Adam', 0)][0], out[('Adam', 1)][0], out[('Adam', 0)][1]
     live = g != 0                                                   # (alignment padding of the flat buffer has no gradient)
     bad = ((dA0 - dA1).abs() > 0.01 * lr) & live

@@ -14,31 +14,25 @@ ops.set_conv_backend(True, PREC)
 x = torch.randn(N, H, W, Ci, device='cuda')
 w = torch.randn(Co, Ci, k, k, device='cuda') * 0.05
 b = torch.zeros(Co, device='cuda')
+from bench import graph_time  # noqa: E402  (CUDA-graph replay of 20 launches, CUDA events: the kernel's time, not the Python launch path's)
 with torch.no_grad():
-    for _ in range(5):
+    for _ in range(3):
         y = ops.conv(x, w, b, pad=k // 2, act=ops.ACT_LRELU)
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(20):
-        y = ops.conv(x, w, b, pad=k // 2, act=ops.ACT_LRELU)
-    e1.record()
-    torch.cuda.synchronize()
-print(PREC, 'avg us', e0.elapsed_time(e1) / 20 * 1e3)
+print(PREC, 'graph-timed avg us %.2f' % (graph_time(lambda: ops.conv(x, w, b, pad=k // 2, act=ops.ACT_LRELU)) * 1e6))
 
 if '--trace' in sys.argv:
     import ctypes
     from dynavsr_b200 import _lib
-    tr = torch.zeros(8 * 64, dtype=torch.int64, device='cuda')
+    tr = torch.zeros(12 * 64, dtype=torch.int64, device='cuda')
     _lib.lib().dvsr_conv_tc2_set_trace(ctypes.c_void_p(tr.data_ptr()))
     with torch.no_grad():
         ops.conv(x, w, b, pad=k // 2, act=ops.ACT_LRELU)
     torch.cuda.synchronize()
     _lib.lib().dvsr_conv_tc2_set_trace(None)
-    t = tr.view(8, 64).cpu()
+    t = tr.view(12, 64).cpu()
     t0 = int(t[0, 0])
-    names = ['prod:slot free', 'round:tile landed', 'round:done', 'mma:ready seen', 'mma:issued', 'epi:acc full', 'epi:done', 'epi:tmem read']
-    for ev in range(8):
+    names = ['prod:slot free', 'round:tile landed', 'round:done', 'mma:ready seen', 'mma:issued', 'epi:acc full', 'epi:done', 'epi:tmem read', 'epi:math']
+    for ev in range(9):
         print('%-18s' % names[ev], ' '.join('%6d' % (int(v) - t0) for v in t[ev, :(30 if ev < 5 else 15)]))
 if '--both' in sys.argv:
     for prec in ('tf32', 'bf16x3'):

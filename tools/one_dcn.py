@@ -19,7 +19,14 @@ w = (torch.randn(64, 64, 3, 3, generator=g) * 0.05).cuda()
 b = torch.zeros(64).cuda()
 
 
+from bench import graph_time  # noqa: E402  (CUDA-graph replay of 20 launches, CUDA events)
+
+
 def timed(fn, reps=20):
+    return graph_time(fn, reps) * 1e6
+
+
+def eager(fn, reps=20):
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
@@ -38,4 +45,4 @@ if '--bwd' in sys.argv:
     xr, omr, wr = x.clone().requires_grad_(True), om.clone().requires_grad_(True), w.clone().requires_grad_(True)
     y = ops.mdcn(xr, omr, wr, b, 8, 1, 1, 1)
     gy = torch.randn_like(y)
-    print('bwd avg us', timed(lambda: torch.autograd.grad(y, [xr, omr, wr], gy, retain_graph=True)))
+    print('bwd avg us (eager launches)', eager(lambda: torch.autograd.grad(y, [xr, omr, wr], gy, retain_graph=True)))
