@@ -75,7 +75,7 @@ def parse():
     ap.add_argument('--tasks-per-rank', type=int, default=1)
     ap.add_argument('--nf', type=int, default=128)
     ap.add_argument('--back-rbs', type=int, default=40)
-    ap.add_argument('--exchange', default='peer', choices=['peer', 'nccl'])
+    ap.add_argument('--exchange', default='peer', choices=['peer', 'peer-all', 'nccl'])
     ap.add_argument('--meta-precision', default='bf16x3', choices=['bf16', 'bf16x3'],
                     help='meta workload: operand precision of the <= 64-channel conv layers (the nf = 128 layers of EDVR-L run TF32 on the streaming kernel)')
     return ap.parse_args()

@@ -122,6 +122,7 @@ SIGNATURES = {
     'dvsr_update_sgd': [_P, _P, _LL, _LL, _F, _F, _F, _P],
     'dvsr_update_adam': [_P, _P, _P, _P, _LL, _LL, _F, _F, _F, _F, _F, _F, _F, _F, _P],
     'dvsr_update_peers': [_P, _P, _I, _LL, _F, _P, _P, _LL, _LL, _F, _F, _F, _F, _F, _F, _F, _F, _I, _P],
+    'dvsr_update_peers_sliced': [_P, _P, _I, _I, _LL, _F, _P, _P, _LL, _LL, _F, _F, _F, _F, _F, _F, _F, _F, _I, _P],
     'dvsr_abs_sum': [_P, _P, _LL, _I, _I, _I, _P],
     'dvsr_sm_count': [],
     'dvsr_last_error': [],

@@ -80,13 +80,13 @@ class MetaLearner(object):
         if exchange != 'none' and torch.distributed.is_available() and torch.distributed.is_initialized() \
                 and torch.distributed.get_world_size() > 1:
             self.exchange = 'nccl'
-            if exchange == 'peer' and torch.distributed.get_backend() == 'nccl':
+            if exchange in ('peer', 'peer-all') and torch.distributed.get_backend() == 'nccl':
                 try:        # flat meta-gradient in symmetric memory: peers read it directly (fused exchange + update)
                     import torch.distributed._symmetric_memory as symm
                     g = symm.empty(self.theta.numel(), dtype=torch.float32, device=self.theta.device)
                     hdl = symm.rendezvous(g, torch.distributed.group.WORLD)
                     g.zero_()
-                    self.meta_grad, self._peer, self.exchange = g, hdl, 'peer'
+                    self.meta_grad, self._peer, self.exchange = g, hdl, exchange
                 except Exception as e:      # no peer access / no symmetric-memory support in this build
                     import warnings
                     warnings.warn('MetaLearner: symmetric memory unavailable (%s); using NCCL all-reduce' % (e,))
@@ -220,11 +220,23 @@ class MetaLearner(object):
                 t = self.outer_steps
                 adam = self.outer_optimizer == 'Adam'
                 h.barrier(channel=0)               # every rank's meta-gradient is complete
-                call('dvsr_update_peers', _p(self.theta), ctypes.c_void_p(int(h.buffer_ptrs_dev)), world,
-                     int(getattr(h, 'offset', 0)) // 4, 1.0 / world, _p(self.m), _p(self.v), n, n, float(lr), float(lr), float(b1),
-                     float(b2), 1e-8, float(1 - b1 ** t) if adam else 1.0, float(1 - b2 ** t) if adam else 1.0, 0.0,
-                     1 if adam else 0, _stream())
-                h.barrier(channel=1)               # nobody overwrites its gradient while a peer still reads it
+                if self.exchange == 'peer':
+                    # reduce-scatter form (update.cu): this rank reduces + updates its slice and writes the new weights of the slice
+                    # into every rank's exchange buffer; after the barrier the buffer IS the new theta (moments are sharded by slice)
+                    call('dvsr_update_peers_sliced', _p(self.theta), ctypes.c_void_p(int(h.buffer_ptrs_dev)), world,
+                         torch.distributed.get_rank(), int(getattr(h, 'offset', 0)) // 4, 1.0 / world, _p(self.m), _p(self.v), n, n,
+                         float(lr), float(lr), float(b1), float(b2), 1e-8, float(1 - b1 ** t) if adam else 1.0,
+                         float(1 - b2 ** t) if adam else 1.0, 0.0, 1 if adam else 0, _stream())
+                    h.barrier(channel=1)           # every slice of every buffer has been written
+                    self.theta.copy_(self.meta_grad)
+                else:
+                    # 'peer-all': every rank reads all ranks' full gradients and updates its whole copy (fewest barriers' worth of
+                    # logic, fine for 2 ranks; traffic grows with the rank count)
+                    call('dvsr_update_peers', _p(self.theta), ctypes.c_void_p(int(h.buffer_ptrs_dev)), world,
+                         int(getattr(h, 'offset', 0)) // 4, 1.0 / world, _p(self.m), _p(self.v), n, n, float(lr), float(lr), float(b1),
+                         float(b2), 1e-8, float(1 - b1 ** t) if adam else 1.0, float(1 - b2 ** t) if adam else 1.0, 0.0,
+                         1 if adam else 0, _stream())
+                    h.barrier(channel=1)           # nobody overwrites its gradient while a peer still reads it
             elif self.exchange == 'nccl':
                 # ---- fallback: ONE all-reduce (mean) of the flat meta-gradient, then the fused update launch
                 ddist.allreduce_flat_gradient(self.meta_grad, average=True)
@@ -261,9 +273,13 @@ class MetaLearner(object):
         world = torch.distributed.get_world_size() if (torch.distributed.is_available() and torch.distributed.is_initialized()) else 1
         med = ms[len(ms) // 2]
         nbytes = self.theta.numel() * 4
+        # NVLink bytes per rank: 'peer' (sliced) reads (world-1)/world of the buffer and writes the same amount; 'peer-all' reads
+        # (world-1) whole buffers; NCCL's ring / tree moves 2 (world-1)/world of it
+        peer_read = (world - 1) * nbytes // world if self.exchange in ('peer', 'nccl') else (world - 1) * nbytes
+        peer_write = (world - 1) * nbytes // world if self.exchange in ('peer', 'nccl') else 0
         return {'path': self.exchange, 'median_us': med * 1e3, 'min_us': ms[0] * 1e3, 'flat_gradient_bytes': nbytes,
-                'peer_bytes_read_per_rank': (world - 1) * nbytes,
-                'nvlink_GBps_per_rank': ((world - 1) * nbytes / (med * 1e-3) / 1e9) if world > 1 else None,
+                'peer_bytes_read_per_rank': peer_read, 'peer_bytes_written_per_rank': peer_write,
+                'nvlink_GBps_per_rank': (max(peer_read, peer_write) / (med * 1e-3) / 1e9) if world > 1 else None,
                 'local_hbm_GBps': ((3 if self.outer_optimizer == 'SGD' else 7) * nbytes / (med * 1e-3) / 1e9)}
 
     def dtype_string(self):

@@ -325,6 +325,14 @@ int dvsr_update_adam(float* p, const float* g, float* m, float* v, long long n, 
 int dvsr_update_peers(float* p, const float* const* grads_dev, int n_peers, long long grad_offset, float scale, float* m, float* v,
                       long long n, long long split, float lr0, float lr1, float b1, float b2, float eps, float bc1, float bc2,
                       float wd, int adam, void* stream);
+/* The same exchange in reduce-scatter form (scales with the rank count): rank `rank` reduces slice `rank` of the flat buffer
+ * ((n / 4 + n_peers - 1) / n_peers float4 elements) over all ranks' buffers bufs_dev[r] + buf_offset, updates that slice of the
+ * meta-weights from p (read only) with its own slice of the moments, and writes the UPDATED WEIGHTS of the slice into the same
+ * slice of every rank's buffer.  After the caller's closing barrier each buffer holds the complete new weights (copy them over p).
+ * Optimiser state is sharded: m / v are only valid for the caller's slice. */
+int dvsr_update_peers_sliced(const float* p, float* const* bufs_dev, int n_peers, int rank, long long buf_offset, float scale, float* m,
+                             float* v, long long n, long long split, float lr0, float lr1, float b1, float b2, float eps, float bc1,
+                             float bc2, float wd, int adam, void* stream);
 /* sum |x| over channels [c0, c1) of an NHWC tensor -> out[0] (+=); the `offset_mean > 100` check of
  * deform_conv.py:285-287 without a host sync per call. */
 int dvsr_abs_sum(const float* x, float* out, long long npix, int pix_stride, int c0, int c1, void* stream);

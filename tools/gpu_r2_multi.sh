@@ -6,9 +6,9 @@ N=${1:-2}
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=index,name --format=csv,noheader | head -8
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
-timeout 600 $TR --master-port 29511 bench.py --gpus $N --steps 36 --warmup 6 --no-cpu-baseline --no-parity > gpurun_out/r2_bench_n$N.json 2> gpurun_out/r2_bench_n$N.err
+[ -z "$SKIP_ADAPT" ] && timeout 600 $TR --master-port 29511 bench.py --gpus $N --steps 36 --warmup 6 --no-cpu-baseline --no-parity > gpurun_out/r2_bench_n$N.json 2> gpurun_out/r2_bench_n$N.err
 tail -1 gpurun_out/r2_bench_n$N.json | cut -c1-300; tail -2 gpurun_out/r2_bench_n$N.err
-for ex in peer nccl; do
+for ex in peer peer-all nccl; do
   timeout 600 $TR --master-port 29512 bench.py --gpus $N --workload meta --steps 10 --warmup 3 --exchange $ex > gpurun_out/r2_meta_n${N}_$ex.json 2> gpurun_out/r2_meta_n${N}_$ex.err
   tail -1 gpurun_out/r2_meta_n${N}_$ex.json | python -c "
 import sys, json

@@ -34,7 +34,7 @@ for outer in ('SGD', 'Adam'):
     ref = MetaLearner(*nets(), outer_optimizer=outer, exchange='none', **kw)
     for _ in range(2):
         ref.outer_step(tasks)
-    for exch in ('peer', 'nccl'):
+    for exch in ('peer', 'peer-all', 'nccl'):
         ml = MetaLearner(*nets(), outer_optimizer=outer, exchange=exch, **kw)
         for _ in range(2):
             ml.outer_step([tasks[rank]])          # sharded: one task per rank, one exchange per outer step
@@ -57,6 +57,17 @@ from dynavsr_b200 import dist as dd  # noqa: E402
 
 
 def t_peer():
+    # the sliced (reduce-scatter) fused kernel: reduce + Adam on this rank's slice, new weights written to every rank's buffer
+    h = ml_p._peer
+    h.barrier(channel=0)
+    call('dvsr_update_peers_sliced', ctypes.c_void_p(ml_p.theta.data_ptr()), ctypes.c_void_p(int(h.buffer_ptrs_dev)), world, rank, 0, 1.0 / world,
+         ctypes.c_void_p(ml_p.m.data_ptr()), ctypes.c_void_p(ml_p.v.data_ptr()), ml_p.theta.numel(), ml_p.theta.numel(), 1e-5, 1e-5, 0.9, 0.99,
+         1e-8, 0.1, 0.01, 0.0, 1, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    h.barrier(channel=1)
+    ml_p.theta.copy_(ml_p.meta_grad)
+
+
+def t_peer_all():
     h = ml_p._peer
     h.barrier(channel=0)
     call('dvsr_update_peers', ctypes.c_void_p(ml_p.theta.data_ptr()), ctypes.c_void_p(int(h.buffer_ptrs_dev)), world, 0, 1.0 / world,
@@ -72,7 +83,8 @@ def t_nccl():
          ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
 
 
-for name, fn in (('peer-memory fused exchange+Adam', t_peer), ('NCCL all-reduce + Adam launch', t_nccl)):
+for name, fn in (('peer-memory fused exchange+Adam (sliced)', t_peer), ('peer-memory fused exchange+Adam (read-all)', t_peer_all),
+                 ('NCCL all-reduce + Adam launch', t_nccl)):
     if name.startswith('peer') and ml_p._peer is None:
         continue
     for _ in range(5):
@@ -87,5 +99,5 @@ for name, fn in (('peer-memory fused exchange+Adam', t_peer), ('NCCL all-reduce 
     tt = torch.tensor([a.elapsed_time(b) / 50 * 1e3], device='cuda')
     dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     if rank == 0:
-        print('%-34s %7.1f us per outer exchange (%.1f MB flat gradient, max over ranks)' % (name, float(tt), ml_p.theta.numel() * 4 / 1e6), flush=True)
+        print('%-44s %7.1f us per outer exchange (%.1f MB flat gradient, max over ranks)' % (name, float(tt), ml_p.theta.numel() * 4 / 1e6), flush=True)
 dist.destroy_process_group()
