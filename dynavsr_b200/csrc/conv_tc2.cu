@@ -100,6 +100,7 @@ conv_tc2_kernel(const __grid_constant__ T2Maps maps, const T2Params p) {
     float* bias_s = (float*)(bars + 32);      // [64] bias of this CTA's output-channel group (zeros when absent)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t acc_cols = 2 * T2_NG;      // TMEM columns per accumulator buffer: [x_hi.w_hi + x_lo.w_hi | x_hi.w_lo]
     const int KK = p.KH * p.KW;
     const int ngrp = blockIdx.y;
     const int tiles_w = (p.Wo + T2_TW - 1) / T2_TW, tiles_h = (p.Ho + T2_TH - 1) / T2_TH;
@@ -121,7 +122,7 @@ conv_tc2_kernel(const __grid_constant__ T2Maps maps, const T2Params p) {
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(2 * acc_cols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (threadIdx.x >= 192 && threadIdx.x < 256) {
@@ -207,11 +208,14 @@ conv_tc2_kernel(const __grid_constant__ T2Maps maps, const T2Params p) {
                         // first weight block of this chunk; BF16x3 blocks hold a PAIR of chunks (64 K-channels per row)
                         const int blk = p.seg_blk0[s] + (p.bf16x3 ? (c >> 1) : c) * KK;
                         uint64_t bd = bd_const + (uint64_t)((smem_u32(smem_b + blk * p.wblk_bytes) + (p.bf16x3 ? (c & 1) * 64 : 0)) >> 4);
-                        const uint32_t dcol = tmem_base + acc * (2 * T2_NG);
+                        const uint32_t dcol = tmem_base + acc * acc_cols;
                         int wy = p.tap_sign < 0 ? p.KH - 1 : 0, wx0 = p.tap_sign < 0 ? p.KW - 1 : 0, wx = wx0, kw = 0;
                         for (int tap = 0; tap < ((p.ablate & 4) ? 0 : KK); ++tap) {
                             const uint64_t ad = ad0 + (uint64_t)((wy * p.halo_w + wx) * 8);     // 128 B per pixel = 8 x 16 B
                             const uint32_t first = (cidx > 0 || tap > 0) ? 1u : 0u;
+                            // (Tried in round 2: alternating the k-steps of a tap between accumulator column ranges that the epilogue sums, to
+                            // break a suspected accumulate-latency chain between consecutive MMAs -- no gain, 2-4 % slower from the extra
+                            // TMEM reads; the MMAs are not serialised on the accumulator.)
                             if (!p.bf16x3) {
                                 mma_tf32(dcol, ad, bd, idesc, first);
                                 mma_tf32(dcol, ad + 2, bd + 2, idesc, 1u);
@@ -337,7 +341,7 @@ conv_tc2_kernel(const __grid_constant__ T2Maps maps, const T2Params p) {
             }
             if (tracer && !dry) T2_TRACE(5, local);
             float v[32];
-            const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 2 * T2_NG + h * 32);
+            const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * acc_cols + (uint32_t)(h * 32);
             const bool wide = p.bf16x3 == 1 && p.n_mma == T2_NG;     // columns [64,128) hold the x_hi . w_lo partial sums
             tmem_ld32(tacc, v);
             if (wide) {
@@ -406,7 +410,7 @@ conv_tc2_kernel(const __grid_constant__ T2Maps maps, const T2Params p) {
     __syncthreads();
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * acc_cols) : "memory");
     }
 }
 
