@@ -636,6 +636,74 @@ static int validate_desc(const dvsr_conv_desc* d) {
 }
 
 // every segment has fewer than 16 channels (RGB inputs): use the dense-K kernels
+// ------------------------------------------------------------------------------------------------------------------------
+// Weight gradient of a conv with very few OUTPUT channels (conv_last 64 -> 3, MFDN conv6): gw[co][ci][tap] += sum_o x[o + tap][ci]
+// gy[o][co].  The implicit-GEMM kernel above spends a 64-wide N tile on 3 columns (120 us at 176 x 320, 3.6 % of the SM time of
+// an adapted frame); this is a memory-bound reduction instead: one thread per input channel (coalesced 256-byte pixel rows), 4
+// pixel lanes per CTA, KK x Co accumulators in registers, one block-level reduction and one red.add per (co, ci, tap) and CTA.
+constexpr int WSC_MAX_KK = 9, WSC_MAX_CO = 4, WSC_PIX = 512;
+__global__ void __launch_bounds__(256) conv_wgrad_small_co_kernel(const dvsr_conv_desc d, const float* __restrict__ gy, int gy_pix_stride,
+                                                                  float* __restrict__ gw, const dvsr_wlayout wl) {
+    __shared__ float red[3][WSC_MAX_KK * WSC_MAX_CO][64];
+    const int c = threadIdx.x & 63, lane_p = threadIdx.x >> 6;
+    const dvsr_conv_seg& sg = d.seg[0];
+    const int KK = d.KH * d.KW;
+    const long long M = (long long)d.N * d.Ho * d.Wo;
+    const long long m0 = (long long)blockIdx.x * WSC_PIX, m1 = m0 + WSC_PIX < M ? m0 + WSC_PIX : M;
+    const long long img_stride = sg.img_stride > 0 ? sg.img_stride : (long long)d.H * d.W * sg.pix_stride;
+    for (int cb = 0; cb < sg.C; cb += 64) {
+        const int ci = cb + c;
+        float acc[WSC_MAX_KK][WSC_MAX_CO];
+#pragma unroll
+        for (int t = 0; t < WSC_MAX_KK; ++t)
+#pragma unroll
+            for (int o = 0; o < WSC_MAX_CO; ++o) acc[t][o] = 0.f;
+        if (ci < sg.C) {
+            for (long long m = m0 + lane_p; m < m1; m += 4) {
+                const int n = (int)(m / ((long long)d.Ho * d.Wo));
+                const int r = (int)(m - (long long)n * d.Ho * d.Wo);
+                const int oy = r / d.Wo, ox = r - oy * d.Wo;
+                float g[WSC_MAX_CO];
+#pragma unroll
+                for (int o = 0; o < WSC_MAX_CO; ++o) g[o] = o < d.Co ? __ldg(gy + m * gy_pix_stride + o) : 0.f;
+                const float* img = sg.ptr + (long long)n * img_stride + ci;
+#pragma unroll
+                for (int t = 0; t < WSC_MAX_KK; ++t) {
+                    if (t < KK) {
+                        const int kh = t / d.KW, kw = t - kh * d.KW;
+                        const int iy = oy - d.pad + kh, ix = ox - d.pad + kw;
+                        if (iy >= 0 && iy < d.H && ix >= 0 && ix < d.W) {
+                            const float xv = __ldg(img + ((long long)iy * d.W + ix) * sg.pix_stride);
+#pragma unroll
+                            for (int o = 0; o < WSC_MAX_CO; ++o) acc[t][o] = fmaf(xv, g[o], acc[t][o]);
+                        }
+                    }
+                }
+            }
+        }
+        // reduce the 4 pixel lanes, then one red.add per element
+        if (lane_p > 0) {
+#pragma unroll
+            for (int t = 0; t < WSC_MAX_KK; ++t)
+#pragma unroll
+                for (int o = 0; o < WSC_MAX_CO; ++o) red[lane_p - 1][t * WSC_MAX_CO + o][c] = acc[t][o];
+        }
+        __syncthreads();
+        if (lane_p == 0 && ci < sg.C) {
+#pragma unroll
+            for (int t = 0; t < WSC_MAX_KK; ++t)
+#pragma unroll
+                for (int o = 0; o < WSC_MAX_CO; ++o) {
+                    if (t < KK && o < d.Co) {
+                        const float v = acc[t][o] + red[0][t * WSC_MAX_CO + o][c] + red[1][t * WSC_MAX_CO + o][c] + red[2][t * WSC_MAX_CO + o][c];
+                        atomicAdd(gw + wl.seg_base[0] + (long long)o * wl.co_stride + (long long)ci * wl.ci_stride + t, v);
+                    }
+                }
+        }
+        __syncthreads();
+    }
+}
+
 static bool small_c(const dvsr_conv_desc* d) {
     for (int s = 0; s < d->nseg; ++s)
         if (d->seg[s].C >= 16) return false;
@@ -695,6 +763,12 @@ extern "C" int dvsr_conv_wgrad(const dvsr_conv_desc* d, const float* gy, int gy_
     DVSR_REQUIRE(gy && gw && wl, "conv_wgrad: null pointer");
     DVSR_REQUIRE(!d->transposed, "conv_wgrad: descriptor must describe the forward op");
     const int KK = d->KH * d->KW;
+    if (!d->deform && d->nseg == 1 && d->Co <= WSC_MAX_CO && KK <= WSC_MAX_KK && d->stride == 1 && d->dil == 1 && wl->ci_bits == 0 &&
+        d->seg[0].T <= 1 && d->seg[0].t_fixed < 0 && d->seg[0].C >= 16) {
+        const long long Mpix = (long long)d->N * d->Ho * d->Wo;
+        conv_wgrad_small_co_kernel<<<(unsigned)((Mpix + WSC_PIX - 1) / WSC_PIX), 256, 0, (cudaStream_t)stream>>>(*d, gy, gy_pix_stride, gw, *wl);
+        return check_launch("conv_wgrad (small Co)");
+    }
     const bool dense = !d->deform && !all_vec4(d) && small_c(d);
     int chunks = 0;
     for (int s = 0; s < d->nseg; ++s) chunks += dense ? (KK * d->seg[s].C + BK - 1) / BK : ((d->seg[s].C + BK - 1) / BK) * KK;

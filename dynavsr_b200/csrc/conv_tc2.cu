@@ -373,7 +373,16 @@ conv_tc2_kernel(const __grid_constant__ T2Maps maps, const T2Params p) {
             }
             const int c0 = ngrp * T2_NG + h * 32;          // first global output channel of this thread
             if (c0 >= p.Co) continue;                      // (warp-uniform)
-            if (p.shuffle == 2) {
+            if (p.ablate & 16) {
+                // A/B aid: the round-1 store pattern (each thread stores its own pixel row: 32 scattered sectors per instruction)
+                if (valid) {
+                    epilogue_chunk(v, c0, p.Co, bias_s + h * 32, p.accum_in ? p.accum_in + pix * p.accum_pix_stride + c0 : nullptr,
+                                   p.res ? p.res + pix * p.res_pix_stride + c0 : nullptr, p.act, p.slope, p.sig_split);
+                    float* yo = p.y + pix * p.y_pix_stride + c0;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 8) st_global_v8(yo + j, v[j], v[j + 1], v[j + 2], v[j + 3], v[j + 4], v[j + 5], v[j + 6], v[j + 7]);
+                }
+            } else if (p.shuffle == 2) {
                 // PixelShuffle(2): conv channel 4 * cq + sub -> output pixel (2 oy + sub / 2, 2 ox + sub % 2), channel cq; the 8 cq of
                 // one sub-pixel are 32 contiguous bytes, their neighbours belong to other channel groups -- stored per thread
                 if (valid) {

@@ -453,6 +453,9 @@ mdcn_tcs_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant_
                     const int h0 = (int)hf, w0 = (int)wf;
                     const float lh = h - hf, lw = w - wf, hh = 1.f - lh, hw = 1.f - lw;
                     const int wy = h0 - cur.wy0, wx = w0 - cur.wx0;
+                    // (Tried in round 2: L1 prefetches of the NEXT tap's corners for samples about to leave the window -- slower at every
+                    // offset spread (std 1.5: 400 -> 583 us): the extra address math sits on every item's path and the prefetched lines do
+                    // not survive in the ~30 KB of L1 left beside 198 KB of shared memory.)
                     // vF* = the 4 channels of the half this lane reads first (lower half in even-pixel lanes, upper in odd), vS* = the other
                     float2 vF01, vF23, vS01, vS23;
                     if ((unsigned)wy < (unsigned)(MDS_WIN_H - 1) && (unsigned)wx < (unsigned)(MDS_WIN_W - 1)) {
