@@ -250,7 +250,7 @@ mdcn_tc_kernel(const __grid_constant__ CUtensorMap wmap, const MdParams p) {
 
 // ------------------------------------------------------------------------------------------------------------------------
 // Staged variant (3x3, stride 1, dilation 1 -- every DCN of EDVR): per 16 x 8 output tile and 32-channel chunk ONE TMA box
-// brings the input window (tile + 1-pixel tap ring + `margin` pixels for the learned offsets; 24 x 16 pixels x 128 B = 48 KB)
+// brings the input window (tile + 1-pixel tap ring + `margin` pixels for the learned offsets; 26 x 18 pixels x 128 B = 60 KB)
 // into shared memory, and the 9 taps x 4 corners x 128 pixels x 4 groups bilinear reads of that chunk are served from there
 // (swizzled LDS.128 pairs) instead of L1/L2 -- 48 KB of L2 traffic per chunk-tile instead of ~590 KB.  Corners that a large
 // offset pushes outside the window fall back to the global 256-bit load, so the result is exact for any offset.
@@ -258,10 +258,16 @@ mdcn_tc_kernel(const __grid_constant__ CUtensorMap wmap, const MdParams p) {
 // showed the 2-stage operand ring that resident weights left room for to be latency-bound (MMA completion -> slot-free
 // round trip: 267 us of 417 us).  Each stage therefore carries its own 8 KiB weight block, streamed by TMA from L2 (317 MB per
 // full-resolution call), which buys a 4-stage ring and a double-buffered input window.
-constexpr int MDS_ASTAGES = 4;             // (A operand tile 16 KiB + streamed weight block 8 KiB) per stage
+#ifndef DVSR_MDS_ASTAGES
+#define DVSR_MDS_ASTAGES 3
+#endif
+#ifndef DVSR_MDS_MARGIN
+#define DVSR_MDS_MARGIN 4
+#endif
+constexpr int MDS_ASTAGES = DVSR_MDS_ASTAGES;             // (A operand tile 16 KiB + streamed weight block 8 KiB) per stage
 constexpr int MDS_STAGE_BYTES = MD_A_BYTES + 8192;
-constexpr int MDS_MARGIN = 3;              // window margin for the learned offsets, pixels
-constexpr int MDS_WIN_H = 16 + 2 + 2 * MDS_MARGIN, MDS_WIN_W = 8 + 2 + 2 * MDS_MARGIN;     // 24 x 16 pixels
+constexpr int MDS_MARGIN = DVSR_MDS_MARGIN;              // window margin for the learned offsets, pixels (4: 26 x 18 window = 60 KB x 2 buffers + 4 x 24 KB stages = 216 KB)
+constexpr int MDS_WIN_H = 16 + 2 + 2 * MDS_MARGIN, MDS_WIN_W = 8 + 2 + 2 * MDS_MARGIN;     // 26 x 18 pixels
 constexpr int MDS_WINBUFS = 2;             // input window double-buffered: the TMA of chunk c+1 flies while chunk c is gathered
 
 __device__ __forceinline__ void lds8(uint32_t addr0, uint32_t addr1, float4& a, float4& b) {
@@ -320,7 +326,7 @@ mdcn_tcs_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant_
                 const int tn = tile / tiles_per_img, tr = tile - tn * tiles_per_img;
                 const int oy0 = (tr / p.tiles_w) * 16, ox0 = (tr % p.tiles_w) * 8;
                 mbar_wait_relaxed(&win_empty[wb], ((cc >> 1) & 1) ^ 1);
-                mbar_expect_tx(&win_full[wb], (uint32_t)p.win_bytes);
+                mbar_expect_tx(&win_full[wb], (uint32_t)(MDS_WIN_H * MDS_WIN_W * 128));      // the box, not the padded buffer
                 tma_load_4d(&xmap, &win_full[wb], smem_w + wb * p.win_bytes, c * 32, ox0 - 1 - p.margin, oy0 - 1 - p.margin, tn);
             };
             int stage = 0, phase = 0, cc = 0;
@@ -377,7 +383,7 @@ mdcn_tcs_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant_
         //   * the TMA window is zero-filled outside the image, so a sample whose 2 x 2 corner block lies inside the window needs NO
         //     bounds test at all -- out-of-image corners read zeros, which is exactly the reference rule (kernel.cu:466-496); one
         //     window-containment test per item selects this branch-free path (4 swizzled LDS.128 pairs at immediate offsets);
-        //     anything else (offsets beyond the 3-pixel margin) takes the exact per-corner path with global 256-bit loads;
+        //     anything else (offsets beyond the 4-pixel margin) takes the exact per-corner path with global 256-bit loads;
         //   * (dy, dx, mask) travel in a 3-deep rolling prefetch queue (9 registers instead of 27, latency hidden behind 3 stages);
         //   * blend and hi|lo split in packed fp32x2 math (FFMA2), mask folded into the four bilinear weights;
         //   * explicit shared-memory stores at per-thread constant offsets; one lane per warp polls / arrives on the mbarriers.

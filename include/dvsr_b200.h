@@ -223,7 +223,7 @@ int dvsr_mdcn_bwd_tc(const dvsr_conv_desc* d, const float* gy, int gy_pix_stride
  * memory, resident weights (pack mode 7), persistent CTAs.  8 channels per deformable group, C*KH*KW <= 576, Co <= 64. */
 int dvsr_mdcn_tc_supported(const dvsr_conv_desc* d);
 int dvsr_mdcn_tc_fprop(const dvsr_conv_desc* d, const float* wp, void* stream);
-/* 3x3 / stride-1 / pad-1 launches (every DCN of EDVR) stage a 24 x 16-pixel input window per 16 x 8 output tile and 32-channel
+/* 3x3 / stride-1 / pad-1 launches (every DCN of EDVR) stage a 26 x 18-pixel input window per 16 x 8 output tile and 32-channel
  * chunk in shared memory with one TMA box and gather the 36 corners per pixel from there (global fallback for corners a large
  * offset pushes outside the window) when the launch has at least two tiles per SM (d->policy.mdcn_staged overrides). */
 
