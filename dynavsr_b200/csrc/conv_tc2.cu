@@ -26,8 +26,14 @@
 //     reach the output frame attenuated by how little the adaptation moves it (profiles/r1_precision_study.md).
 // The kernel is bounded by shared-memory bandwidth (both MMA operands come from shared memory: 321 KB per chunk-tile at
 // 128 B/clk, see profiles/r1_conv_tc2_timeline.txt).
+// Round 2 rebuilt the epilogue and the ring of this kernel and measured every variant against this one on the same box
+// (tools/gpu_r2_14.sh): 8 epilogue warps + quad-transposed full-line stores (stores' share of the L1 data pipe
+// 24 % -> 4 %), a dry-run warm-up pass of the epilogue, hi-only resident weights with a 6-deep ring in the bf16 mode, rotated weight
+// loads, k-steps alternating between accumulator column ranges.  None beat it: BF16x3 56.5 us here vs 61-69 us, bf16 45.4 vs 45.4 us
+// (3x3 64->64 @5x176x320, graph-timed), 102.5 vs 91-100 adapted frames/s.  The kernel is paced by the MMA chain's operand fetch and its
+// ~10 us start-up, not by the stores, so this version stays.
 // Warp roles: 0 = TMA producer, 1 = MMA issuer / TMEM owner, 2-5 = operand conversion of the halo tile,
-// 6-13 = epilogue (one 32-channel half of a pixel per thread: bias, ReLU / LeakyReLU / sigmoid-split, residual, PixelShuffle(2), K-split accumulation; scalar path for
+// 6-9 = epilogue (bias, ReLU / LeakyReLU / sigmoid-split, residual, PixelShuffle(2), K-split accumulation; scalar path for
 // narrow / unaligned outputs such as conv_last 64 -> 3).  Output channels are processed in groups of 64 (blockIdx.y); inputs
 // whose weights do not fit are K-split over several launches by the host wrapper (`accum_in`).  Grid policy: cta_budget() CTAs
 // at most and >= min_tiles tiles per CTA (throughput mode of adapt.AdaptationPool).
@@ -38,8 +44,9 @@ namespace dvsr {
 
 constexpr int T2_TH = 16, T2_TW = 8;      // pixel tile (M = 128): 16 rows of 8 pixels
 constexpr int T2_NG = 64;                 // output channels per CTA
-constexpr int T2_MAX_STAGES = 8;          // halo-tile ring: as many stages as fit beside the resident weights (3 for BF16x3 64->64 3x3, 6 in bf16 mode)
-constexpr int T2_THREADS = 448;            // 14 warps: TMA, MMA, 4 x operand split, 8 x epilogue
+constexpr int T2_ASTAGES = 3;
+constexpr int T2_PF = 6;                  // L2 prefetch distance in chunks
+constexpr int T2_THREADS = 320;
 constexpr int T2_MAX_BLOCKS = 18;         // resident weight blocks of 64 x 32 fp32 (8 KiB) -> 144 KiB
 
 struct T2Seg { int C, T, Tsrc, dt, t_fixed; };
@@ -52,9 +59,7 @@ struct T2Params {
     int halo_h, halo_w, a_bytes;          // halo tile geometry / padded bytes per stage
     int nblocks;                          // resident weight blocks of this launch: TF32 -- ((seg, chunk), tap) blocks of 64 rows
                                           // (8 KiB); BF16x3 -- ((seg, 64-channel pair), tap) blocks of 128 rows (16 KiB)
-    int wblk_bytes, wblk_rows;            // resident block in shared memory (the bf16 single-product mode keeps only the hi rows)
-    int wblk_grows;                       // rows per block in the packed global tensor
-    int stages, pf;                       // halo-tile ring depth; L2 prefetch distance in chunks
+    int wblk_bytes, wblk_rows;
     int seg_blk0[DVSR_MAX_SEG];           // first weight block of each segment
     int tiles_total;
     const float* bias;
@@ -69,7 +74,6 @@ struct T2Params {
     int n_mma;                            // MMA N (16..64): output channels of this launch's widest group, rounded up to 16
     int scalar_out;                       // narrow / unaligned outputs (conv_last 64 -> 3): scalar epilogue, Co <= 32
     long long* trace;                     // optional per-event clock64 trace of CTA (0,0): [event][chunk]
-    int ablate;                           // debugging aid (DVSR_T2_ABLATE): 1 no global stores, 2 no operand split, 4 no MMAs, 8 no halo-tile loads after the first ring fill
 };
 struct __align__(64) T2Maps { CUtensorMap x[DVSR_MAX_SEG]; CUtensorMap w; };
 
@@ -89,18 +93,17 @@ conv_tc2_kernel(const __grid_constant__ T2Maps maps, const T2Params p) {
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* smem_b = smem;                                        // [nblocks][wblk_rows x 128 B]
     uint8_t* smem_a = smem + p.nblocks * p.wblk_bytes;             // [T2_ASTAGES][a_bytes]
-    uint64_t* bars = (uint64_t*)(smem_a + p.stages * p.a_bytes);
+    uint64_t* bars = (uint64_t*)(smem_a + T2_ASTAGES * p.a_bytes);
     uint64_t* b_full = bars;                  // [1]
-    uint64_t* a_full = bars + 1;              // [T2_MAX_STAGES]
-    uint64_t* a_ready = bars + 1 + T2_MAX_STAGES;
-    uint64_t* a_empty = bars + 1 + 2 * T2_MAX_STAGES;
-    uint64_t* acc_full = bars + 1 + 3 * T2_MAX_STAGES;    // [2]
-    uint64_t* acc_empty = acc_full + 2;                   // [2]
-    uint32_t* tmem_slot = (uint32_t*)(acc_empty + 2);
-    float* bias_s = (float*)(bars + 32);      // [64] bias of this CTA's output-channel group (zeros when absent)
+    uint64_t* a_full = bars + 1;              // [3]
+    uint64_t* a_ready = bars + 4;             // [3]
+    uint64_t* a_empty = bars + 7;             // [3]
+    uint64_t* acc_full = bars + 10;           // [2]
+    uint64_t* acc_empty = bars + 12;          // [2]
+    uint32_t* tmem_slot = (uint32_t*)(bars + 14);
+    float* bias_s = (float*)(bars + 16);      // [64] bias of this CTA's output-channel group (zeros when absent)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t acc_cols = 2 * T2_NG;      // TMEM columns per accumulator buffer: [x_hi.w_hi + x_lo.w_hi | x_hi.w_lo]
     const int KK = p.KH * p.KW;
     const int ngrp = blockIdx.y;
     const int tiles_w = (p.Wo + T2_TW - 1) / T2_TW, tiles_h = (p.Ho + T2_TH - 1) / T2_TH;
@@ -117,12 +120,12 @@ conv_tc2_kernel(const __grid_constant__ T2Maps maps, const T2Params p) {
     if (warp == 1) {
         if (elect_one()) {
             mbar_init(b_full, 1);
-            for (int i = 0; i < p.stages; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_ready[i], 128); mbar_init(&a_empty[i], 1); }
-            for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 256); }
+            for (int i = 0; i < T2_ASTAGES; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_ready[i], 128); mbar_init(&a_empty[i], 1); }
+            for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(2 * acc_cols) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (threadIdx.x >= 192 && threadIdx.x < 256) {
@@ -138,14 +141,10 @@ conv_tc2_kernel(const __grid_constant__ T2Maps maps, const T2Params p) {
         // ===================== producer =====================
         if (elect_one()) {
             mbar_expect_tx(b_full, (uint32_t)(p.nblocks * p.wblk_bytes));
-            // every CTA of the launch reads the same weight blocks: start at a CTA-dependent block so that the 148 requests of one
-            // moment are spread over different L2 lines / slices instead of queueing on one (the round-2 trace: 72-147 KB took 4.5 us)
-            for (int b0 = 0; b0 < p.nblocks; ++b0) {
-                const int b = (b0 + (int)blockIdx.x) % p.nblocks;
-                tma_load_2d(&maps.w, b_full, smem_b + b * p.wblk_bytes, 0, (ngrp * p.nblocks + b) * p.wblk_grows);
-            }
+            for (int b = 0; b < p.nblocks; ++b)
+                tma_load_2d(&maps.w, b_full, smem_b + b * p.wblk_bytes, 0, (ngrp * p.nblocks + b) * p.wblk_rows);
             int stage = 0, phase = 0, trace_i = 0;
-            // L2 prefetch cursor running p.pf chunks ahead of the producer (beyond the shared-memory ring)
+            // L2 prefetch cursor running T2_PF chunks ahead of the shared-memory ring (the ring is only 3 deep)
             int pf_tile = blockIdx.x, pf_s = 0, pf_c = 0;
             auto prefetch_next = [&]() {
                 if (pf_tile >= p.tiles_total) return;
@@ -156,7 +155,7 @@ conv_tc2_kernel(const __grid_constant__ T2Maps maps, const T2Params p) {
                     tma_prefetch_4d(&maps.x[pf_s], pf_c * 32, (r % tiles_w) * T2_TW + min_dx, (r / tiles_w) * T2_TH + min_d, img);
                 if (++pf_c == (p.seg[pf_s].C + 31) / 32) { pf_c = 0; if (++pf_s == p.nseg) { pf_s = 0; pf_tile += gridDim.x; } }
             };
-            for (int i = 0; i < p.pf; ++i) prefetch_next();
+            for (int i = 0; i < T2_PF; ++i) prefetch_next();
             for (int tile = blockIdx.x; tile < p.tiles_total; tile += gridDim.x) {
                 const int n = tile / (tiles_w * tiles_h);
                 const int r = tile - n * tiles_w * tiles_h;
@@ -165,18 +164,13 @@ conv_tc2_kernel(const __grid_constant__ T2Maps maps, const T2Params p) {
                     const int img = t2_seg_image(p.seg[s], n);
                     const int chunks = (p.seg[s].C + 31) / 32;
                     for (int c = 0; c < chunks; ++c) {
-                        if (!(p.ablate & 8)) prefetch_next();
+                        prefetch_next();
                         mbar_wait_relaxed(&a_empty[stage], phase ^ 1, 64);
-                        T2_TRACE(0, trace_i);
-                        if ((p.ablate & 8) && trace_i >= p.stages) {
-                            mbar_arrive(&a_full[stage]);
-                        } else {
-                            mbar_expect_tx(&a_full[stage], (uint32_t)(p.halo_h * p.halo_w * 128));
-                            tma_load_4d(&maps.x[s], &a_full[stage], smem_a + stage * p.a_bytes, c * 32, ox0 + min_dx, oy0 + min_d,
-                                        img < 0 ? 0x3fffffff : img);
-                        }
-                        ++trace_i;
-                        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                        T2_TRACE(0, trace_i); ++trace_i;
+                        mbar_expect_tx(&a_full[stage], (uint32_t)(p.halo_h * p.halo_w * 128));
+                        tma_load_4d(&maps.x[s], &a_full[stage], smem_a + stage * p.a_bytes, c * 32, ox0 + min_dx, oy0 + min_d,
+                                    img < 0 ? 0x3fffffff : img);
+                        if (++stage == T2_ASTAGES) { stage = 0; phase ^= 1; }
                     }
                 }
             }
@@ -208,14 +202,11 @@ conv_tc2_kernel(const __grid_constant__ T2Maps maps, const T2Params p) {
                         // first weight block of this chunk; BF16x3 blocks hold a PAIR of chunks (64 K-channels per row)
                         const int blk = p.seg_blk0[s] + (p.bf16x3 ? (c >> 1) : c) * KK;
                         uint64_t bd = bd_const + (uint64_t)((smem_u32(smem_b + blk * p.wblk_bytes) + (p.bf16x3 ? (c & 1) * 64 : 0)) >> 4);
-                        const uint32_t dcol = tmem_base + acc * acc_cols;
+                        const uint32_t dcol = tmem_base + acc * (2 * T2_NG);
                         int wy = p.tap_sign < 0 ? p.KH - 1 : 0, wx0 = p.tap_sign < 0 ? p.KW - 1 : 0, wx = wx0, kw = 0;
-                        for (int tap = 0; tap < ((p.ablate & 4) ? 0 : KK); ++tap) {
+                        for (int tap = 0; tap < KK; ++tap) {
                             const uint64_t ad = ad0 + (uint64_t)((wy * p.halo_w + wx) * 8);     // 128 B per pixel = 8 x 16 B
                             const uint32_t first = (cidx > 0 || tap > 0) ? 1u : 0u;
-                            // (Tried in round 2: alternating the k-steps of a tap between accumulator column ranges that the epilogue sums, to
-                            // break a suspected accumulate-latency chain between consecutive MMAs -- no gain, 2-4 % slower from the extra
-                            // TMEM reads; the MMAs are not serialised on the accumulator.)
                             if (!p.bf16x3) {
                                 mma_tf32(dcol, ad, bd, idesc, first);
                                 mma_tf32(dcol, ad + 2, bd + 2, idesc, 1u);
@@ -249,7 +240,7 @@ conv_tc2_kernel(const __grid_constant__ T2Maps maps, const T2Params p) {
                     }
                     ++trace_i;
                     __syncwarp();
-                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                    if (++stage == T2_ASTAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
@@ -262,46 +253,33 @@ conv_tc2_kernel(const __grid_constant__ T2Maps maps, const T2Params p) {
             for (int c = 0; c < chunks_total; ++c) {
                 mbar_wait_relaxed(&a_full[stage], phase, 32);
                 if (t == 0) T2_TRACE(1, trace_i);
-                const uint32_t a_s = smem_u32(smem_a + stage * p.a_bytes);
-                if (p.ablate & 2) {
-                } else if (!p.bf16x3) {
+                float4* a4 = reinterpret_cast<float4*>(smem_a + stage * p.a_bytes);
+                if (!p.bf16x3) {
                     for (int i = t; i < n16; i += 128) {
-                        float4 v = lds128(a_s + i * 16);
-                        sts128(a_s + i * 16, __float_as_uint(round_tf32(v.x)), __float_as_uint(round_tf32(v.y)),
-                               __float_as_uint(round_tf32(v.z)), __float_as_uint(round_tf32(v.w)));
+                        float4 v = a4[i];
+                        v.x = round_tf32(v.x); v.y = round_tf32(v.y); v.z = round_tf32(v.z); v.w = round_tf32(v.w);
+                        a4[i] = v;
                     }
                 } else {
                     // BF16x3: rewrite every 128-byte pixel row (32 fp32 channels) in place as [32 x bf16 hi | 32 x bf16 lo].
                     // Rows keep the 128B swizzle: logical 16-byte chunk c of row r lives at chunk c ^ ((addr >> 7) & 7).
                     const int nrows = p.halo_h * p.halo_w;
                     for (int r = t; r < nrows; r += 128) {
-                        const uint32_t row = a_s + r * 128;
-                        const uint32_t ph = (row >> 7) & 7;
+                        uint4* row = reinterpret_cast<uint4*>(a4 + r * 8);
+                        const uint32_t ph = (smem_u32(row) >> 7) & 7;
                         float f[32];
 #pragma unroll
                         for (int c = 0; c < 8; ++c) {
-                            const float4 v = lds128(row + ((c ^ ph) << 4));
+                            const float4 v = *reinterpret_cast<const float4*>(row + (c ^ ph));
                             f[4 * c] = v.x; f[4 * c + 1] = v.y; f[4 * c + 2] = v.z; f[4 * c + 3] = v.w;
-                        }
-                        if (p.bf16x3 == 2) {
-                            // single-product mode: only the hi halves are ever read (chunks 4-7 of the row keep stale fp32 bits)
-                            uint32_t hi[16];
-#pragma unroll
-                            for (int q2 = 0; q2 < 16; ++q2) {
-                                const __nv_bfloat162 h2 = __floats2bfloat162_rn(f[2 * q2], f[2 * q2 + 1]);
-                                hi[q2] = *reinterpret_cast<const uint32_t*>(&h2);
-                            }
-#pragma unroll
-                            for (int c = 0; c < 4; ++c) sts128(row + ((c ^ ph) << 4), hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
-                            continue;
                         }
                         uint32_t hi[16], lo[16];
 #pragma unroll
                         for (int q2 = 0; q2 < 16; ++q2) split_bf16x2(f[2 * q2], f[2 * q2 + 1], hi[q2], lo[q2]);
 #pragma unroll
                         for (int c = 0; c < 4; ++c) {
-                            sts128(row + ((c ^ ph) << 4), hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
-                            sts128(row + (((4 + c) ^ ph) << 4), lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
+                            row[c ^ ph] = make_uint4(hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
+                            row[(4 + c) ^ ph] = make_uint4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
                         }
                     }
                 }
@@ -309,60 +287,37 @@ conv_tc2_kernel(const __grid_constant__ T2Maps maps, const T2Params p) {
                 mbar_arrive(&a_ready[stage]);
                 if (t == 0) T2_TRACE(2, trace_i);
                 ++trace_i;
-                if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                if (++stage == T2_ASTAGES) { stage = 0; phase ^= 1; }
             }
         }
     } else {
-        // ===================== epilogue: 8 warps, one (pixel row, 32-channel half) per thread =====================
-        // A warp may only read the TMEM lanes of its quadrant (warp % 4); the two warps of a quadrant take the two 32-column
-        // halves of the 64 output channels.  (Round-2 trace: with 4 warps x 64 columns the epilogue took 3 000-3 500 cycles per
-        // tile -- it, not the MMAs, paced the single-product mode -- and its cold first pass cost another ~7 000.)
+        // ===================== epilogue =====================
         const int q = warp & 3;
-        const int h = (warp - 6) >> 2;
         const int row = q * 32 + lane;
-        const bool tracer = threadIdx.x == 192;
-        // The first pass through this loop is a DRY RUN (no barrier traffic, no loads, no stores): the epilogue warps have nothing
-        // to do until the first accumulator is complete (>= 4 500 cycles after launch), and the round-2 trace showed the first real
-        // pass to cost 7 000-12 000 cycles more than a steady-state one -- cold instruction fetches of this code, by all CTAs of the
-        // launch at once.  Running the same instructions once with every side effect predicated off moves those misses into the
-        // idle start-up window.
         int local = 0;
-        bool dry = true;
-        for (int tile = blockIdx.x; tile < p.tiles_total; tile += dry ? 0 : gridDim.x, local += dry ? 0 : 1, dry = false) {
+        for (int tile = blockIdx.x; tile < p.tiles_total; tile += gridDim.x, ++local) {
             const int acc = local & 1;
             const int n = tile / (tiles_w * tiles_h);
             const int r = tile - n * tiles_w * tiles_h;
             const int oy = (r / tiles_w) * T2_TH + row / T2_TW, ox = (r % tiles_w) * T2_TW + row % T2_TW;
-            const bool valid = (oy < p.Ho) && (ox < p.Wo) && !dry;
+            const bool valid = (oy < p.Ho) && (ox < p.Wo);
             const long long pix = ((long long)n * p.Ho + oy) * p.Wo + ox;
-            if (!dry) {
-                mbar_wait_relaxed(&acc_full[acc], (local >> 1) & 1, 128);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            }
-            if (tracer && !dry) T2_TRACE(5, local);
-            float v[32];
-            const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * acc_cols + (uint32_t)(h * 32);
+            mbar_wait_relaxed(&acc_full[acc], (local >> 1) & 1, 128);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (threadIdx.x == 192) T2_TRACE(5, local);
+            float v0[32], v1[32];
+            const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 2 * T2_NG);
             const bool wide = p.bf16x3 == 1 && p.n_mma == T2_NG;     // columns [64,128) hold the x_hi . w_lo partial sums
-            tmem_ld32(tacc, v);
-            if (wide) {
-                float t[32];
-                tmem_ld32(tacc + T2_NG, t);
-#pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] += t[j];
-            }
-            // the accumulator is in registers: hand the TMEM buffer back to the MMA warp before the global stores
-            if (!dry) {
+            tmem_ld32(tacc, v0);
+            if (p.scalar_out) {
+                // narrow output (Co <= 32, any alignment): one 32-column read, per-channel loads / stores
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 mbar_arrive(&acc_empty[acc]);
-            }
-            if (tracer && !dry) T2_TRACE(7, local);
-            if (p.scalar_out) {
-                // narrow output (Co <= 32, any alignment): per-channel loads / stores, first column half only
-                if (valid && h == 0) {
+                if (valid) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
                         if (j >= p.Co) break;
-                        float t = v[j] + bias_s[j];
+                        float t = v0[j] + bias_s[j];
                         if (p.accum_in) t += __ldg(p.accum_in + pix * p.accum_pix_stride + j);
                         t = (p.act == DVSR_ACT_SIGMOID_SPLIT) ? (j >= p.sig_split ? sigmoidf_(t) : t) : act_apply(t, p.act, p.slope);
                         if (p.res) t += __ldg(p.res + pix * p.res_pix_stride + j);
@@ -371,55 +326,63 @@ conv_tc2_kernel(const __grid_constant__ T2Maps maps, const T2Params p) {
                 }
                 continue;
             }
-            const int c0 = ngrp * T2_NG + h * 32;          // first global output channel of this thread
-            if (c0 >= p.Co) continue;                      // (warp-uniform)
-            if (p.ablate & 16) {
-                // A/B aid: the round-1 store pattern (each thread stores its own pixel row: 32 scattered sectors per instruction)
-                if (valid) {
+            tmem_ld32(tacc + 32, v1);
+            if (wide) {
+                float t[32];
+                tmem_ld32(tacc + 64, t);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v0[j] += t[j];
+                tmem_ld32(tacc + 96, t);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v1[j] += t[j];
+            }
+            // the accumulator is in registers: hand the TMEM buffer back to the MMA warp before the global stores
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(&acc_empty[acc]);
+            if (threadIdx.x == 192) T2_TRACE(7, local);
+            if (valid) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    float (&v)[32] = h == 0 ? v0 : v1;
+                    const int c0 = ngrp * T2_NG + h * 32;          // first global output channel of this chunk
+                    if (c0 >= p.Co) continue;
                     epilogue_chunk(v, c0, p.Co, bias_s + h * 32, p.accum_in ? p.accum_in + pix * p.accum_pix_stride + c0 : nullptr,
                                    p.res ? p.res + pix * p.res_pix_stride + c0 : nullptr, p.act, p.slope, p.sig_split);
-                    float* yo = p.y + pix * p.y_pix_stride + c0;
+                    if (p.shuffle == 2) {
+                        const int cq = c0 >> 2;
 #pragma unroll
-                    for (int j = 0; j < 32; j += 8) st_global_v8(yo + j, v[j], v[j + 1], v[j + 2], v[j + 3], v[j + 4], v[j + 5], v[j + 6], v[j + 7]);
-                }
-            } else if (p.shuffle == 2) {
-                // PixelShuffle(2): conv channel 4 * cq + sub -> output pixel (2 oy + sub / 2, 2 ox + sub % 2), channel cq; the 8 cq of
-                // one sub-pixel are 32 contiguous bytes, their neighbours belong to other channel groups -- stored per thread
-                if (valid) {
-                    epilogue_chunk(v, c0, p.Co, bias_s + h * 32, p.accum_in ? p.accum_in + pix * p.accum_pix_stride + c0 : nullptr,
-                                   p.res ? p.res + pix * p.res_pix_stride + c0 : nullptr, p.act, p.slope, p.sig_split);
-                    const int cq = c0 >> 2;
-#pragma unroll
-                    for (int sub = 0; sub < 4; ++sub) {
-                        const long long op = ((long long)n * (2 * p.Ho) + 2 * oy + (sub >> 1)) * (2 * p.Wo) + 2 * ox + (sub & 1);
-                        float* yo = p.y + op * p.y_pix_stride + cq;
+                        for (int sub = 0; sub < 4; ++sub) {
+                            const long long op = ((long long)n * (2 * p.Ho) + 2 * oy + (sub >> 1)) * (2 * p.Wo) + 2 * ox + (sub & 1);
+                            float* yo = p.y + op * p.y_pix_stride + cq;
+                            if (p.y_vec8) {
+                                st_global_v8(yo, v[sub], v[4 + sub], v[8 + sub], v[12 + sub], v[16 + sub], v[20 + sub], v[24 + sub], v[28 + sub]);
+                            } else {
+                                *reinterpret_cast<float4*>(yo) = make_float4(v[sub], v[4 + sub], v[8 + sub], v[12 + sub]);
+                                *reinterpret_cast<float4*>(yo + 4) = make_float4(v[16 + sub], v[20 + sub], v[24 + sub], v[28 + sub]);
+                            }
+                        }
+                    } else {
+                        float* yo = p.y + pix * p.y_pix_stride + c0;
+                        const int nvalid = min(32, p.Co - c0);
                         if (p.y_vec8) {
-                            st_global_v8(yo, v[sub], v[4 + sub], v[8 + sub], v[12 + sub], v[16 + sub], v[20 + sub], v[24 + sub], v[28 + sub]);
+#pragma unroll
+                            for (int j = 0; j < 32; j += 8)
+                                if (j < nvalid) st_global_v8(yo + j, v[j], v[j + 1], v[j + 2], v[j + 3], v[j + 4], v[j + 5], v[j + 6], v[j + 7]);
                         } else {
-                            *reinterpret_cast<float4*>(yo) = make_float4(v[sub], v[4 + sub], v[8 + sub], v[12 + sub]);
-                            *reinterpret_cast<float4*>(yo + 4) = make_float4(v[16 + sub], v[20 + sub], v[24 + sub], v[28 + sub]);
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4)
+                                if (j < nvalid) *reinterpret_cast<float4*>(yo + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
                         }
                     }
                 }
-            } else {
-                // quad transpose -> each store instruction writes full 128-byte lines (tc_common.cuh)
-                quad_transpose32(v, lane);
-                if (tracer && !dry) T2_TRACE(8, local);
-                const int rb = row & ~3;                   // first pixel row of this lane's quad: 4 consecutive pixels of one image row
-                const int oyb = (r / tiles_w) * T2_TH + rb / T2_TW, oxb = (r % tiles_w) * T2_TW + rb % T2_TW;
-                const int nok = (oyb < p.Ho && !dry && !(p.ablate & 1)) ? min(4, p.Wo - oxb) : 0;
-                const long long pixb = ((long long)n * p.Ho + oyb) * p.Wo + oxb;
-                const int i4 = lane & 3;
-                epilogue_store_t(v, bias_s + h * 32 + 8 * i4, c0 + 8 * i4, p.Co, pixb, nok, p.accum_in, p.accum_pix_stride,
-                                 p.res, p.res_pix_stride, p.y, p.y_pix_stride, p.y_vec8 != 0, p.act, p.slope, p.sig_split, dry);
             }
-            if (tracer && !dry) T2_TRACE(6, local);
+            if (threadIdx.x == 192) T2_TRACE(6, local);
         }
     }
     __syncthreads();
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * acc_cols) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256) : "memory");
     }
 }
 
@@ -430,7 +393,7 @@ using namespace dvsr;
 static long long* g_t2_trace = nullptr;
 // Grid policy (d->policy.min_tiles): 1 (default) = one tile per CTA until the GPU is full (lowest latency of a single launch);
 // n > 1 = at least n tiles per CTA (fewer, longer-lived CTAs: less SM-time per launch when several streams share the GPU).
-// debugging aid: device buffer of 12 x 64 clock64 stamps written by CTA (0,0) of the next launches (nullptr = off)
+// debugging aid: device buffer of 8 x 64 clock64 stamps written by CTA (0,0) of the next launches (nullptr = off)
 extern "C" int dvsr_conv_tc2_set_trace(long long* dev_buffer) { g_t2_trace = dev_buffer; return 0; }
 
 // kernel-side precision code (T2Params.bf16x3): 0 = TF32, 1 = BF16x3, 2 = plain bf16 on the BF16x3 layouts
@@ -441,9 +404,8 @@ static int t2_prec_code(const dvsr_conv_desc* d) {
 // (16 KiB) block per (64-channel pair, tap)
 static int t2_blocks(const dvsr_conv_desc* d) {
     int n = 0;
-    const int pc = t2_prec_code(d);
     for (int s = 0; s < (d->wshare ? 1 : d->nseg); ++s)
-        n += pc ? (pc == 2 ? 1 : 2) * ((d->seg[s].C + 63) / 64) : (d->seg[s].C + 31) / 32;   // bf16 mode: hi rows only
+        n += t2_prec_code(d) ? 2 * ((d->seg[s].C + 63) / 64) : (d->seg[s].C + 31) / 32;
     return n * d->KH * d->KW;
 }
 
@@ -522,8 +484,7 @@ extern "C" int dvsr_conv_tc2_fprop(const dvsr_conv_desc* d, const float* wp, con
     p.halo_h = T2_TH + d->KH - 1; p.halo_w = T2_TW + d->KW - 1;
     p.a_bytes = (p.halo_h * p.halo_w * 128 + 1023) / 1024 * 1024;
     p.bf16x3 = t2_prec_code(d);
-    p.wblk_grows = p.bf16x3 ? 128 : T2_NG;              // packed tensor: [hi rows | lo rows] per block in both bf16 modes
-    p.wblk_rows = p.bf16x3 == 1 ? 128 : T2_NG;          // resident: the single-product mode loads the 64 hi rows only
+    p.wblk_rows = p.bf16x3 ? 128 : T2_NG;
     p.wblk_bytes = p.wblk_rows * 128;
     {
         int b = 0;
@@ -540,7 +501,6 @@ extern "C" int dvsr_conv_tc2_fprop(const dvsr_conv_desc* d, const float* wp, con
     p.y = d->y; p.y_pix_stride = d->y_pix_stride;
     p.y_vec8 = ((((uintptr_t)d->y) & 31) == 0) && (d->y_pix_stride % 8 == 0) && (d->Co % 8 == 0);
     p.trace = g_t2_trace;
-    { static int abl = -1; if (abl < 0) { const char* e = getenv("DVSR_T2_ABLATE"); abl = e ? atoi(e) : 0; } p.ablate = abl; }
     p.scalar_out = d->Co <= 32 && (d->Co < 16 || (d->Co & 3) || (d->y_pix_stride & 3) || ((uintptr_t)d->y & 15) ||
                                    (d->res && ((((uintptr_t)d->res) & 15) || (d->res_pix_stride & 3))));
     p.n_mma = d->Co >= T2_NG ? T2_NG : (d->Co + 15) / 16 * 16;
@@ -565,7 +525,7 @@ extern "C" int dvsr_conv_tc2_fprop(const dvsr_conv_desc* d, const float* wp, con
     }
     {
         // the packed rows are 128 bytes either way: 32 x tf32, or [32 x bf16 hi | 32 x bf16 lo]
-        cuuint64_t dims[2] = {32, (cuuint64_t)p.nblocks * ngroups * p.wblk_grows};
+        cuuint64_t dims[2] = {32, (cuuint64_t)p.nblocks * ngroups * p.wblk_rows};
         cuuint64_t strides[1] = {128};
         cuuint32_t box[2] = {32, (cuuint32_t)p.wblk_rows};
         cuuint32_t estr[2] = {1, 1};
@@ -574,14 +534,7 @@ extern "C" int dvsr_conv_tc2_fprop(const dvsr_conv_desc* d, const float* wp, con
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         DVSR_REQUIRE(r == CUDA_SUCCESS, "conv_tc2_fprop: cuTensorMapEncodeTiled(weights) failed with %d", (int)r);
     }
-    {
-        const long long room = 232448 - 1024 - 512 - (long long)p.nblocks * p.wblk_bytes;
-        int st = (int)(room / p.a_bytes);
-        DVSR_REQUIRE(st >= 2, "conv_tc2_fprop: the halo-tile ring does not fit beside %d resident weight blocks", p.nblocks);
-        p.stages = st > T2_MAX_STAGES ? T2_MAX_STAGES : st;
-        p.pf = p.stages + 3;
-    }
-    const size_t smem = 1024 + (size_t)p.nblocks * p.wblk_bytes + (size_t)p.stages * p.a_bytes + 512;
+    const size_t smem = 1024 + (size_t)p.nblocks * p.wblk_bytes + (size_t)T2_ASTAGES * p.a_bytes + 512;
     DVSR_REQUIRE(smem <= 232448, "conv_tc2_fprop: %zu B of shared memory needed", smem);
     static size_t smem_set = 0;
     if (smem > smem_set) {
