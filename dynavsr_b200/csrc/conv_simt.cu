@@ -641,7 +641,7 @@ static int validate_desc(const dvsr_conv_desc* d) {
 // gy[o][co].  The implicit-GEMM kernel above spends a 64-wide N tile on 3 columns (120 us at 176 x 320, 3.6 % of the SM time of
 // an adapted frame); this is a memory-bound reduction instead: one thread per input channel (coalesced 256-byte pixel rows), 4
 // pixel lanes per CTA, KK x Co accumulators in registers, one block-level reduction and one red.add per (co, ci, tap) and CTA.
-constexpr int WSC_MAX_KK = 9, WSC_MAX_CO = 4, WSC_PIX = 512;
+constexpr int WSC_MAX_KK = 9, WSC_MAX_CO = 4, WSC_PIX = 96;     // 96 pixels per CTA: ~590 CTAs at 176 x 320 (4 per SM), 24 per pixel lane
 __global__ void __launch_bounds__(256) conv_wgrad_small_co_kernel(const dvsr_conv_desc d, const float* __restrict__ gy, int gy_pix_stride,
                                                                   float* __restrict__ gw, const dvsr_wlayout wl) {
     __shared__ float red[3][WSC_MAX_KK * WSC_MAX_CO][64];
@@ -659,6 +659,7 @@ __global__ void __launch_bounds__(256) conv_wgrad_small_co_kernel(const dvsr_con
 #pragma unroll
             for (int o = 0; o < WSC_MAX_CO; ++o) acc[t][o] = 0.f;
         if (ci < sg.C) {
+#pragma unroll 2
             for (long long m = m0 + lane_p; m < m1; m += 4) {
                 const int n = (int)(m / ((long long)d.Ho * d.Wo));
                 const int r = (int)(m - (long long)n * d.Ho * d.Wo);

@@ -29,7 +29,8 @@
 // Round 2 rebuilt the epilogue and the ring of this kernel and measured every variant against this one on the same box
 // (tools/gpu_r2_14.sh): 8 epilogue warps + quad-transposed full-line stores (stores' share of the L1 data pipe
 // 24 % -> 4 %), a dry-run warm-up pass of the epilogue, hi-only resident weights with a 6-deep ring in the bf16 mode, rotated weight
-// loads, k-steps alternating between accumulator column ranges.  None beat it: BF16x3 56.5 us here vs 61-69 us, bf16 45.4 vs 45.4 us
+// loads, k-steps alternating between accumulator column ranges, two CTAs per SM in the bf16 mode (hi-only weights + a 1-deep ring,
+// <= 96 registers: 62 vs 46 us alone, 100.2 vs 101.3 frames/s in the pool).  None beat it: BF16x3 56.5 us here vs 61-69 us, bf16 45.4 vs 45.4 us
 // (3x3 64->64 @5x176x320, graph-timed), 102.5 vs 91-100 adapted frames/s.  The kernel is paced by the MMA chain's operand fetch and its
 // ~10 us start-up, not by the stores, so this version stays.
 // Warp roles: 0 = TMA producer, 1 = MMA issuer / TMEM owner, 2-5 = operand conversion of the halo tile,

@@ -2,11 +2,7 @@
 # Round-2 evidence for profiles/ (code state at the end of the round): bench.py's own launch list under ncu (graph nodes), ncu --set
 # full of the dominant kernels, SASS mnemonic evidence is produced on the build host (tools/sass_evidence.sh).
 mkdir -p gpurun_out
-# A/B of the conv_tc2 epilogue store pattern (DVSR_T2_ABLATE=16 = the round-1 per-thread scattered stores)
-for abl in 0 16; do for prec in bf16x3 bf16; do
-  echo -n "ablate $abl conv 5 176 320: "; DVSR_T2_ABLATE=$abl timeout 120 python tools/one_conv.py 5 176 320 64 64 3 --precision $prec 2>&1 | tail -1
-done; done
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --graph-profiling node -c 40000 --csv --log-file gpurun_out/r2j_bench_launches.csv \
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --graph-profiling node -c 16000 --csv --log-file gpurun_out/r2j_bench_launches.csv \
     python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-reference-cuda --no-parity --no-roofline > gpurun_out/r2j_bench_under_ncu.log 2>&1
 echo "ncu rc=$?"; wc -l gpurun_out/r2j_bench_launches.csv
 python tools/ncu_summary.py gpurun_out/r2j_bench_launches.csv > gpurun_out/r2j_bench_launches_summary.md 2>/dev/null; head -14 gpurun_out/r2j_bench_launches_summary.md
@@ -16,9 +12,5 @@ cap() {  # name regex skip count script...
 }
 cap tc2_x3 conv_tc2 3 python tools/one_conv.py 5 176 320 64 64 3 --precision bf16x3
 cap tc2_bf16 conv_tc2 3 python tools/one_conv.py 5 176 320 64 64 3 --precision bf16
-cap mdcn_fwd mdcn_tcs 3 python tools/one_dcn.py 5 176 320 --offset-std 1.5
-cap mdcn_bwd mdcn_bwd_tc 1 python tools/one_dcn.py 5 44 80 --bwd
-cap wgrad '^conv_wgrad_tc_kernel$' 0 python tools/one_frame.py 1
-cap tsa '^tsa_temporal_kernel$' 2 python tools/one_frame.py 1
-cap sgd '^sgd_kernel$' 0 python tools/one_frame.py 1
+cap mdcn_fwd mdcn_tcs 3 python tools/one_dcn.py 5 176 320 --offset-std 1.0
 ls -la gpurun_out/r2j_*.ncu-rep | awk '{print $5, $9}'
