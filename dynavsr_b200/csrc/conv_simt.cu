@@ -639,12 +639,12 @@ static int validate_desc(const dvsr_conv_desc* d) {
 // ------------------------------------------------------------------------------------------------------------------------
 // Weight gradient of a conv with very few OUTPUT channels (conv_last 64 -> 3, MFDN conv6): gw[co][ci][tap] += sum_o x[o + tap][ci]
 // gy[o][co].  The implicit-GEMM kernel above spends a 64-wide N tile on 3 columns (120 us at 176 x 320, 3.6 % of the SM time of
-// an adapted frame); this is a memory-bound reduction instead: one thread per input channel (coalesced 256-byte pixel rows), 4
+// an adapted frame; this kernel: 68 us); this is a memory-bound reduction instead: one thread per input channel (coalesced 256-byte pixel rows), 4
 // pixel lanes per CTA, KK x Co accumulators in registers, one block-level reduction and one red.add per (co, ci, tap) and CTA.
-constexpr int WSC_MAX_KK = 9, WSC_MAX_CO = 4, WSC_PIX = 96;     // 96 pixels per CTA: ~590 CTAs at 176 x 320 (4 per SM), 24 per pixel lane
+constexpr int WSC_MAX_KK = 9, WSC_MAX_CO = 4, WSC_PIX = 192;    // 192 pixels per CTA: ~294 CTAs at 176 x 320 (2 per SM), 48 per pixel lane
 __global__ void __launch_bounds__(256) conv_wgrad_small_co_kernel(const dvsr_conv_desc d, const float* __restrict__ gy, int gy_pix_stride,
                                                                   float* __restrict__ gw, const dvsr_wlayout wl) {
-    __shared__ float red[3][WSC_MAX_KK * WSC_MAX_CO][64];
+    __shared__ float red[4][WSC_MAX_KK * WSC_MAX_CO][64];
     const int c = threadIdx.x & 63, lane_p = threadIdx.x >> 6;
     const dvsr_conv_seg& sg = d.seg[0];
     const int KK = d.KH * d.KW;
@@ -659,47 +659,58 @@ __global__ void __launch_bounds__(256) conv_wgrad_small_co_kernel(const dvsr_con
 #pragma unroll
             for (int o = 0; o < WSC_MAX_CO; ++o) acc[t][o] = 0.f;
         if (ci < sg.C) {
+            // pixel coordinates advance incrementally (the 64-bit divisions of a per-pixel decode were most of the instruction stream)
+            long long m = m0 + lane_p;
+            int n = (int)(m / ((long long)d.Ho * d.Wo));
+            int r0 = (int)(m - (long long)n * d.Ho * d.Wo);
+            int oy = r0 / d.Wo, ox = r0 - oy * d.Wo;
 #pragma unroll 2
-            for (long long m = m0 + lane_p; m < m1; m += 4) {
-                const int n = (int)(m / ((long long)d.Ho * d.Wo));
-                const int r = (int)(m - (long long)n * d.Ho * d.Wo);
-                const int oy = r / d.Wo, ox = r - oy * d.Wo;
+            for (; m < m1; m += 4, ox += 4) {
+                while (ox >= d.Wo) { ox -= d.Wo; if (++oy == d.Ho) { oy = 0; ++n; } }
                 float g[WSC_MAX_CO];
 #pragma unroll
                 for (int o = 0; o < WSC_MAX_CO; ++o) g[o] = o < d.Co ? __ldg(gy + m * gy_pix_stride + o) : 0.f;
                 const float* img = sg.ptr + (long long)n * img_stride + ci;
+                // all tap loads first, then the FMAs: with load -> FMA per tap the in-order issue serialises nine L2 round trips per
+                // pixel (measured 125 us for 56 320 pixels)
+                float xv[WSC_MAX_KK];
+                int kh = 0, kw = 0;
 #pragma unroll
                 for (int t = 0; t < WSC_MAX_KK; ++t) {
-                    if (t < KK) {
-                        const int kh = t / d.KW, kw = t - kh * d.KW;
-                        const int iy = oy - d.pad + kh, ix = ox - d.pad + kw;
-                        if (iy >= 0 && iy < d.H && ix >= 0 && ix < d.W) {
-                            const float xv = __ldg(img + ((long long)iy * d.W + ix) * sg.pix_stride);
-#pragma unroll
-                            for (int o = 0; o < WSC_MAX_CO; ++o) acc[t][o] = fmaf(xv, g[o], acc[t][o]);
-                        }
-                    }
+                    const int iy = oy - d.pad + kh, ix = ox - d.pad + kw;
+                    const bool inb = t < KK && iy >= 0 && iy < d.H && ix >= 0 && ix < d.W;
+                    const float* px = img + ((long long)(inb ? iy : 0) * d.W + (inb ? ix : 0)) * sg.pix_stride;
+                    xv[t] = __ldg(px);
+                    if (!inb) xv[t] = 0.f;
+                    if (++kw == d.KW) { kw = 0; ++kh; }
                 }
+#pragma unroll
+                for (int t = 0; t < WSC_MAX_KK; ++t)
+#pragma unroll
+                    for (int o = 0; o < WSC_MAX_CO; ++o) acc[t][o] = fmaf(xv[t], g[o], acc[t][o]);
             }
         }
-        // reduce the 4 pixel lanes, then one red.add per element
-        if (lane_p > 0) {
+        // reduce the 4 pixel lanes in shared memory, then one red.add per element -- issued by all 256 threads in a CTA-dependent
+        // rotated order: every CTA of the launch adds into the same KK x Co x C addresses, and in a fixed order they all hit the same
+        // address at the same time (measured: 590 CTAs x 1 728 same-order atomics = 149 us, slower than the GEMM kernel it replaces)
 #pragma unroll
-            for (int t = 0; t < WSC_MAX_KK; ++t)
+        for (int t = 0; t < WSC_MAX_KK; ++t)
 #pragma unroll
-                for (int o = 0; o < WSC_MAX_CO; ++o) red[lane_p - 1][t * WSC_MAX_CO + o][c] = acc[t][o];
-        }
+            for (int o = 0; o < WSC_MAX_CO; ++o) red[lane_p][t * WSC_MAX_CO + o][c] = acc[t][o];
         __syncthreads();
-        if (lane_p == 0 && ci < sg.C) {
-#pragma unroll
-            for (int t = 0; t < WSC_MAX_KK; ++t)
-#pragma unroll
-                for (int o = 0; o < WSC_MAX_CO; ++o) {
-                    if (t < KK && o < d.Co) {
-                        const float v = acc[t][o] + red[0][t * WSC_MAX_CO + o][c] + red[1][t * WSC_MAX_CO + o][c] + red[2][t * WSC_MAX_CO + o][c];
-                        atomicAdd(gw + wl.seg_base[0] + (long long)o * wl.co_stride + (long long)ci * wl.ci_stride + t, v);
-                    }
-                }
+        const int total = KK * d.Co * 64;
+        const int rot = (int)((blockIdx.x * 997u) % (unsigned)total);
+        for (int e0 = threadIdx.x; e0 < total; e0 += 256) {
+            int e = e0 + rot;
+            if (e >= total) e -= total;
+            const int cc = e & 63, to = e >> 6;              // to = t * Co + o
+            const int t = to / d.Co, o = to - t * d.Co;
+            const int cig = cb + cc;
+            if (cig < sg.C) {
+                const int si = t * WSC_MAX_CO + o;
+                const float v = red[0][si][cc] + red[1][si][cc] + red[2][si][cc] + red[3][si][cc];
+                atomicAdd(gw + wl.seg_base[0] + (long long)o * wl.co_stride + (long long)cig * wl.ci_stride + t, v);
+            }
         }
         __syncthreads();
     }
