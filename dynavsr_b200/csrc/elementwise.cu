@@ -383,6 +383,8 @@ __global__ void act_bwd_kernel(const float* __restrict__ gy, const float* __rest
 #pragma unroll
     for (int q = 0; q < VEC; ++q) bsum[q] = 0.f;
     if (active) {
+        // unrolled so that the loads of several pixel rows are in flight together (in-order issue: one row per L2 round trip otherwise)
+#pragma unroll 4
         for (long long p = p0 + prow; p < p1; p += rows) {
             float g[VEC], yv[VEC];
             if (shuffle == 2) {
