@@ -99,8 +99,18 @@ class FrameWriter(object):
                     if event is not None:
                         event.synchronize()
                     job(image)
+                    continue
             except Exception as e:           # keep draining so producers never block on a dead consumer
-                self._err = e
+                if self._err is None:
+                    self._err = e
+            # the job did not run to completion (an earlier error, or this one): give its resources back -- a pinned-ring slot
+            # that is never released would leave the producer blocked in ring.acquire() instead of seeing the error
+            release = getattr(job, 'release', None)
+            if release is not None:
+                try:
+                    release()
+                except Exception:
+                    pass
 
     def put(self, event, image, job):
         if self._err is not None:
@@ -197,11 +207,19 @@ def evaluate(engine, loader, baseline_netG=None, with_GT=True, save_dir=None, co
             ev = torch.cuda.Event()
             ev.record()
 
+        released = []
+
+        def release():
+            if not released:
+                released.append(True)
+                ring.release(slot)
+
         def wrapped(img):
             try:
                 job(img.numpy())
             finally:
-                ring.release(slot)
+                release()
+        wrapped.release = release                 # FrameWriter calls it for items it has to skip after an error
         writer.put(ev, host, wrapped)
 
     try:

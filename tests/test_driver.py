@@ -223,3 +223,39 @@ def test_evaluate_baseline_column_and_sink_errors(fake_device, tmp_path):
     mixed[2]['idx'], mixed[2]['folder'] = ['7/9'], ['c']
     rows = driver.evaluate(_FakeEngine(), mixed, compute_ssim=False)
     assert list(rows) == ['a/00000000', 'a/00000001', 'c/00000007']
+
+
+def test_frame_writer_releases_slots_of_skipped_items_after_an_error():
+    """after the first failing job the writer skips the remaining items; their pinned-ring slots must still come
+    back, or the producer blocks in ring.acquire() instead of seeing the error at close()."""
+    import torch
+    from dynavsr_b200 import driver
+    ring = driver._PinnedRing((4, 4, 3), 2)
+    writer = driver.FrameWriter(depth=8)
+    ran = []
+
+    def submit(i, fail):
+        slot = ring.acquire()                       # would dead-lock on the third item if slots leaked
+        done = []
+
+        def release():
+            if not done:
+                done.append(1)
+                ring.release(slot)
+
+        def job(img):
+            try:
+                if fail:
+                    raise ValueError('boom %d' % i)
+                ran.append(i)
+            finally:
+                release()
+        job.release = release
+        writer._q.put((None, torch.zeros(1), job))
+
+    for i in range(6):
+        submit(i, fail=(i == 1))
+    with pytest.raises(ValueError, match='boom 1'):
+        writer.close()
+    assert ran == [0]                               # items after the failure were skipped ...
+    assert ring.free.qsize() == 2                   # ... and every slot is back in the ring
