@@ -496,6 +496,46 @@ def test_fused_updates_match_torch_optim(ops):
         r1.load_state_dict(m1.state_dict()); r2.load_state_dict(m2.state_dict())
 
 
+@pytest.mark.parametrize('adam', [True, False], ids=['adam', 'sgd'])
+@pytest.mark.parametrize('world', [1, 2, 3], ids=['1rank', '2ranks', '3ranks'])
+def test_sliced_peer_exchange_kernel_in_one_process(ops, world, adam):
+    """dvsr_update_peers_sliced (update.cu), the reduce-scatter form of the meta step's exchange + outer update, with the
+    `world` exchange buffers living on ONE GPU (what peer pointers of a symmetric-memory allocation look like to the kernel):
+    after every rank's launch each buffer holds the complete new weights = torch.optim step on the rank-ordered mean gradient,
+    bit-identical across the buffers; each rank only touches its slice of the moments."""
+    import ctypes
+    from dynavsr_b200._lib import call
+    n = 4 * 1000 + 64                  # not a multiple of the slice size for 3 ranks
+    g = torch.Generator().manual_seed(world)
+    p0 = torch.randn(n, generator=g).cuda()
+    grads = [torch.randn(n, generator=g).cuda() for _ in range(world)]
+    bufs = [t.clone() for t in grads]
+    table = torch.tensor([b.data_ptr() for b in bufs], dtype=torch.int64, device='cuda')
+    m, v = [torch.zeros(n, device='cuda') for _ in range(world)], [torch.zeros(n, device='cuda') for _ in range(world)]
+    lr, b1, b2, step = 1e-2, 0.9, 0.99, 1
+    P = lambda t: ctypes.c_void_p(t.data_ptr())
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for r in range(world):            # every rank reads its slice of all (still unreduced) buffers, then writes it back everywhere
+        call('dvsr_update_peers_sliced', P(p0), P(table), world, r, 0, 1.0 / world, P(m[r]), P(v[r]), n, n, lr, lr, b1, b2, 1e-8,
+             1 - b1 ** step, 1 - b2 ** step, 0.0, 1 if adam else 0, st)
+    torch.cuda.synchronize()
+    ref = torch.nn.Parameter(p0.clone())
+    opt = (torch.optim.Adam([ref], lr=lr, betas=(b1, b2)) if adam else torch.optim.SGD([ref], lr=lr))
+    mean = grads[0].clone()
+    for t in grads[1:]:
+        mean += t
+    ref.grad = mean / world
+    opt.step()
+    for b in bufs:
+        assert rel(b, ref.detach()) < 1e-6
+        assert torch.equal(b, bufs[0])
+    per = ((n // 4 + world - 1) // world) * 4
+    for r in range(world):
+        if adam:
+            lo, hi = r * per, min(n, (r + 1) * per)
+            assert float(m[r][lo:hi].abs().sum()) > 0 and float(m[r][:lo].abs().sum()) == 0 and float(m[r][hi:].abs().sum()) == 0
+
+
 def test_layout_roundtrip_and_cpu_rejection(ops):
     x = torch.randn(3, 5, 7, 9).cuda()
     y = ops.to_nhwc(x)
