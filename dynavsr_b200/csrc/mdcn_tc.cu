@@ -258,14 +258,27 @@ mdcn_tc_kernel(const __grid_constant__ CUtensorMap wmap, const MdParams p) {
 // showed the 2-stage operand ring that resident weights left room for to be latency-bound (MMA completion -> slot-free
 // round trip: 267 us of 417 us).  Each stage therefore carries its own 8 KiB weight block, streamed by TMA from L2 (317 MB per
 // full-resolution call), which buys a 4-stage ring and a double-buffered input window.
+// Offsets / mask of a (tile, chunk) staged in shared memory by TMA (round 2): per pixel the 4 groups x 9 taps x (dy, dx) of a
+// 32-channel chunk are 288 contiguous bytes of the fused [N,H,W,216] tensor and the masks 144 -- two boxes (72 x 8 x 16 and
+// 36 x 8 x 16 floats, 54 KB) per chunk.  The default path fetches (dy, dx) / mask per thread and tap with 8- and 4-byte global loads:
+// 40.5 M L1 sectors per call for 7.6 M of data at a 29 % hit rate (the ~30 KB of L1 beside this kernel's shared memory hold a
+// fraction of the 16 warps' working set) = 26 % of the L1 data pipe and the kernel's top stall (long scoreboard).
+// Measured on one box (tools/gpu_r2_18.sh, 5x176x320, offsets ~N(0, s^2), s = 1.0 / 1.5 / 3.0): staged offsets with a 2-deep
+// operand ring (all that fits beside them) 333 / 339 / 458 us vs 302 / 322 / 550 us for the per-tap global loads with a 3-deep
+// ring -- the rolling prefetch queue already hides those loads on the fast path, and the ring stage they cost is worth more;
+// only large offsets (the global fallback path then has the L1 to itself) profit.  Compile-time option, OFF by default.
+#ifndef DVSR_MDS_OFFSMEM
+#define DVSR_MDS_OFFSMEM 0
+#endif
 #ifndef DVSR_MDS_ASTAGES
-#define DVSR_MDS_ASTAGES 3
+#define DVSR_MDS_ASTAGES (DVSR_MDS_OFFSMEM ? 2 : 3)      // with staged offsets: 2 x 60 KB windows + 54 KB + 2 x 24 KB = 222 KB
 #endif
 #ifndef DVSR_MDS_MARGIN
 #define DVSR_MDS_MARGIN 4
 #endif
 constexpr int MDS_ASTAGES = DVSR_MDS_ASTAGES;             // (A operand tile 16 KiB + streamed weight block 8 KiB) per stage
 constexpr int MDS_STAGE_BYTES = MD_A_BYTES + 8192;
+constexpr int MDS_OFF_BYTES = 128 * 72 * 4, MDS_MSK_BYTES = 128 * 36 * 4;
 constexpr int MDS_MARGIN = DVSR_MDS_MARGIN;              // window margin for the learned offsets, pixels (4: 26 x 18 window = 60 KB x 2 buffers + 4 x 24 KB stages = 216 KB)
 constexpr int MDS_WIN_H = 16 + 2 + 2 * MDS_MARGIN, MDS_WIN_W = 8 + 2 + 2 * MDS_MARGIN;     // 26 x 18 pixels
 constexpr int MDS_WINBUFS = 2;             // input window double-buffered: the TMA of chunk c+1 flies while chunk c is gathered
@@ -276,11 +289,14 @@ __device__ __forceinline__ void lds8(uint32_t addr0, uint32_t addr1, float4& a, 
 }
 
 __global__ void __launch_bounds__(MD_THREADS, 1)
-mdcn_tcs_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__ CUtensorMap xmap, const MdParams p) {
+mdcn_tcs_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap omap,
+                const __grid_constant__ CUtensorMap mmap, const MdParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* smem_w = smem;                                    // [MDS_WINBUFS] input windows [win_h * win_w][128 B], NOT swizzled
-    uint8_t* smem_a = smem_w + MDS_WINBUFS * p.win_bytes;      // [MDS_ASTAGES][A tile 16 KiB | weight block 8 KiB]
+    uint8_t* smem_off = smem_w + MDS_WINBUFS * p.win_bytes;    // [128 pixels][72]: (dy, dx) of 4 groups x 9 taps   (DVSR_MDS_OFFSMEM)
+    uint8_t* smem_msk = smem_off + (DVSR_MDS_OFFSMEM ? MDS_OFF_BYTES : 0);      // [128 pixels][36]: masks of 4 groups x 9 taps
+    uint8_t* smem_a = smem_msk + (DVSR_MDS_OFFSMEM ? MDS_MSK_BYTES : 0);        // [MDS_ASTAGES][A tile 16 KiB | weight block 8 KiB]
     uint64_t* bars = (uint64_t*)(smem_a + MDS_ASTAGES * MDS_STAGE_BYTES);
     uint64_t* w_full = bars;                       // [4] TMA weight block landed
     uint64_t* a_ready = bars + 4;                  // [4] 16 arrivals (one per gather warp)
@@ -289,20 +305,23 @@ mdcn_tcs_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant_
     uint64_t* acc_empty = bars + 14;               // [2]
     uint64_t* win_full = bars + 16;                // [2] TMA
     uint64_t* win_empty = bars + 18;               // [2] 512 gather arrivals
-    uint32_t* tmem_slot = (uint32_t*)(bars + 20);
-    float* bias_s = (float*)(bars + 22);           // [64]
+    uint64_t* off_full = bars + 20;                // [1] TMA: offsets + masks of the chunk landed
+    uint64_t* off_empty = bars + 21;               // [1] 16 gather-warp arrivals: the chunk's last tap has read its offsets
+    uint32_t* tmem_slot = (uint32_t*)(bars + 22);
+    float* bias_s = (float*)(bars + 24);           // [64]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int KK = 9;
     const int chunks = p.C / 32;
     const int tiles_per_img = p.tiles_w * p.tiles_h;
 
-    if (warp == 0 && elect_one()) { prefetch_tmap(&wmap); prefetch_tmap(&xmap); }
+    if (warp == 0 && elect_one()) { prefetch_tmap(&wmap); prefetch_tmap(&xmap); if (DVSR_MDS_OFFSMEM) { prefetch_tmap(&omap); prefetch_tmap(&mmap); } }
     if (warp == 1) {
         if (elect_one()) {
             for (int i = 0; i < MDS_ASTAGES; ++i) { mbar_init(&w_full[i], 1); mbar_init(&a_ready[i], MD_GATHER / 32); mbar_init(&a_empty[i], 1); }
             for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
             for (int i = 0; i < MDS_WINBUFS; ++i) { mbar_init(&win_full[i], 1); mbar_init(&win_empty[i], MD_GATHER / 32); }
+            mbar_init(off_full, 1); mbar_init(off_empty, MD_GATHER / 32);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncwarp();
@@ -329,8 +348,17 @@ mdcn_tcs_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant_
                 mbar_expect_tx(&win_full[wb], (uint32_t)(MDS_WIN_H * MDS_WIN_W * 128));      // the box, not the padded buffer
                 tma_load_4d(&xmap, &win_full[wb], smem_w + wb * p.win_bytes, c * 32, ox0 - 1 - p.margin, oy0 - 1 - p.margin, tn);
             };
+            auto load_offsets = [&](int tile, int c, int cc) {         // single buffer: waits until chunk cc - 1 has read its last tap
+                if (!DVSR_MDS_OFFSMEM) return;
+                const int tn = tile / tiles_per_img, tr = tile - tn * tiles_per_img;
+                const int oy0 = (tr / p.tiles_w) * 16, ox0 = (tr % p.tiles_w) * 8;
+                mbar_wait_relaxed(off_empty, (cc & 1) ^ 1);
+                mbar_expect_tx(off_full, (uint32_t)(MDS_OFF_BYTES + MDS_MSK_BYTES));
+                tma_load_4d(&omap, off_full, smem_off, c * 72, ox0, oy0, tn);
+                tma_load_4d(&mmap, off_full, smem_msk, c * 36, ox0, oy0, tn);
+            };
             int stage = 0, phase = 0, cc = 0;
-            if ((int)blockIdx.x < p.tiles_total) load_window(blockIdx.x, 0, 0);
+            if ((int)blockIdx.x < p.tiles_total) { load_window(blockIdx.x, 0, 0); load_offsets(blockIdx.x, 0, 0); }
             for (int tile = blockIdx.x; tile < p.tiles_total; tile += gridDim.x) {
                 for (int c = 0; c < chunks; ++c, ++cc) {
                     // window of the NEXT chunk (its buffer was freed when chunk cc - 1 finished)
@@ -342,6 +370,9 @@ mdcn_tcs_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant_
                         tma_load_2d(&wmap, &w_full[stage], smem_a + stage * MDS_STAGE_BYTES + MD_A_BYTES, 0, (c * KK + tap) * 64);
                         if (++stage == MDS_ASTAGES) { stage = 0; phase ^= 1; }
                     }
+                    // offsets / masks of the NEXT chunk: the buffer is free as soon as this chunk's last tap has read its offsets
+                    if (c + 1 < chunks) load_offsets(tile, c + 1, cc + 1);
+                    else if (tile + (int)gridDim.x < p.tiles_total) load_offsets(tile + (int)gridDim.x, 0, cc + 1);
                 }
             }
         }
@@ -417,8 +448,15 @@ mdcn_tcs_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant_
             gq.mlin = ((long long)gq.tn * p.Ho + (gq.ok ? gq.oy : 0)) * p.Wo + (gq.ok ? gq.ox : 0);
             return gq;
         };
+#if DVSR_MDS_OFFSMEM
+        // this thread's (dy, dx) pairs / masks of the chunk in the staged boxes: [pixel][group][tap] -- LDS.64 / LDS.32 at immediate
+        // offsets; conflict-free (a half-warp = 4 pixels x 4 groups reads words 72 p + 18 g + 2 tap (+1): 16 distinct even words mod 32)
+        const uint32_t off_t = smem_u32(smem_off) + (uint32_t)(prow * 288 + gl * 72);
+        const uint32_t msk_t = smem_u32(smem_msk) + (uint32_t)(prow * 144 + gl * 36);
+#endif
         float qdy[3], qdx[3], qmk[3];
         auto load_q = [&](int slot, const Geo& gq, int c, int tap) {
+            if (DVSR_MDS_OFFSMEM) return;
             qdy[slot] = qdx[slot] = qmk[slot] = 0.f;
             if (gq.ok) {
                 const int g = c * 4 + gl;
@@ -443,13 +481,19 @@ mdcn_tcs_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant_
                 const int g = c * 4 + gl;
                 const int wb = cc & 1;
                 const uint32_t win_s = smem_u32(smem_w + wb * p.win_bytes);
-                if (lane == 0) mbar_wait(&win_full[wb], (cc >> 1) & 1);
+                if (lane == 0) { mbar_wait(&win_full[wb], (cc >> 1) & 1); if (DVSR_MDS_OFFSMEM) mbar_wait(off_full, cc & 1); }
                 __syncwarp();
 #pragma unroll
                 for (int tap = 0; tap < 9; ++tap) {
                     const int kh = tap / 3, kw = tap - kh * 3;
                     const int slot = tap % 3;
+#if DVSR_MDS_OFFSMEM
+                    float dy, dx, mk;
+                    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(dy), "=f"(dx) : "r"(off_t + (uint32_t)(tap * 8)));
+                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(mk) : "r"(msk_t + (uint32_t)(tap * 4)));
+#else
                     const float dy = qdy[slot], dx = qdx[slot], mk = qmk[slot];
+#endif
                     // refill the slot with the stage three ahead (same chunk, next chunk, or chunk 0 of this CTA's next tile)
                     if (tap + 3 < 9) load_q(slot, cur, c, tap + 3);
                     else if (c + 1 < chunks) load_q(slot, cur, c + 1, tap + 3 - 9);
@@ -520,6 +564,11 @@ mdcn_tcs_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant_
                     // even pixel: first store = hi chunk (F, S), second = lo chunk (F, S); odd pixel: first = lo chunk (S, F), second = hi chunk (S, F)
                     const uint32_t s1a = par ? loS[0] : hiF[0], s1b = par ? loS[1] : hiF[1], s1c = par ? loF[0] : hiS[0], s1d = par ? loF[1] : hiS[1];
                     const uint32_t s2a = par ? hiS[0] : loF[0], s2b = par ? hiS[1] : loF[1], s2c = par ? hiF[0] : loS[0], s2d = par ? hiF[1] : loS[1];
+                    if (DVSR_MDS_OFFSMEM && tap == 8) {
+                        // every lane has consumed its last (dy, dx, mask) of this chunk: the producer may overwrite the boxes
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(off_empty);
+                    }
                     if (lane == 0) mbar_wait(&a_empty[stage], phase ^ 1);
                     __syncwarp();
                     const uint32_t sa = sa0 + (uint32_t)stage * MDS_STAGE_BYTES;
@@ -661,8 +710,28 @@ extern "C" int dvsr_mdcn_tc_fprop(const dvsr_conv_desc* d, const float* wp, void
         CUresult r = encode(&xmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)g.ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         DVSR_REQUIRE(r == CUDA_SUCCESS, "mdcn_tc_fprop: cuTensorMapEncodeTiled(input window) failed with %d", (int)r);
-        const size_t smem_s = 1024 + (size_t)MDS_WINBUFS * p.win_bytes + (size_t)MDS_ASTAGES * MDS_STAGE_BYTES + 512;
-        if (smem_s <= 232448) {
+        // offsets [N,H,W,216] and masks [N,H,W,72] (views of the fused tensor): boxes of 72 / 36 channels x 8 x 16 pixels per chunk
+        CUtensorMap omap, mmap;
+        memset(&omap, 0, sizeof(omap)); memset(&mmap, 0, sizeof(mmap));
+        bool off_ok = !DVSR_MDS_OFFSMEM;
+        if (DVSR_MDS_OFFSMEM && (d->off_pix_stride & 3) == 0 && (d->mask_pix_stride & 3) == 0 &&
+            (((uintptr_t)d->offset) & 15) == 0 && (((uintptr_t)d->mask) & 15) == 0) {
+            cuuint32_t es4[4] = {1, 1, 1, 1};
+            cuuint64_t odims[4] = {(cuuint64_t)(2 * 9 * d->dg), (cuuint64_t)d->Wo, (cuuint64_t)d->Ho, (cuuint64_t)d->N};
+            cuuint64_t ostr[3] = {(cuuint64_t)d->off_pix_stride * 4, (cuuint64_t)d->Wo * d->off_pix_stride * 4, (cuuint64_t)d->Ho * d->Wo * d->off_pix_stride * 4};
+            cuuint32_t obox[4] = {72, 8, 16, 1};
+            CUresult r1 = encode(&omap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)d->offset, odims, ostr, obox, es4, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                 CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            cuuint64_t mdims[4] = {(cuuint64_t)(9 * d->dg), (cuuint64_t)d->Wo, (cuuint64_t)d->Ho, (cuuint64_t)d->N};
+            cuuint64_t mstr[3] = {(cuuint64_t)d->mask_pix_stride * 4, (cuuint64_t)d->Wo * d->mask_pix_stride * 4, (cuuint64_t)d->Ho * d->Wo * d->mask_pix_stride * 4};
+            cuuint32_t mbox[4] = {36, 8, 16, 1};
+            CUresult r2 = encode(&mmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)d->mask, mdims, mstr, mbox, es4, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                 CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            off_ok = r1 == CUDA_SUCCESS && r2 == CUDA_SUCCESS;
+        }
+        const size_t smem_s = 1024 + (size_t)MDS_WINBUFS * p.win_bytes + (DVSR_MDS_OFFSMEM ? MDS_OFF_BYTES + MDS_MSK_BYTES : 0) +
+                              (size_t)MDS_ASTAGES * MDS_STAGE_BYTES + 512;
+        if (smem_s <= 232448 && off_ok) {
             static size_t smem_set_s = 0;
             if (smem_s > smem_set_s) {
                 if (cudaFuncSetAttribute(mdcn_tcs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s) != cudaSuccess)
@@ -670,7 +739,7 @@ extern "C" int dvsr_mdcn_tc_fprop(const dvsr_conv_desc* d, const float* wp, void
                 smem_set_s = smem_s;
             }
             const int ctas_s = p.tiles_total < cta_budget(d->policy) ? p.tiles_total : cta_budget(d->policy);
-            mdcn_tcs_kernel<<<ctas_s, MD_THREADS, smem_s, (cudaStream_t)stream>>>(wmap, xmap, p);
+            mdcn_tcs_kernel<<<ctas_s, MD_THREADS, smem_s, (cudaStream_t)stream>>>(wmap, xmap, omap, mmap, p);
             return check_launch("mdcn_tc_fprop (staged)");
         }
         const long long M2 = (long long)d->N * d->Ho * d->Wo;
