@@ -70,7 +70,13 @@ class Degradation(object):
     def _device_kernels(self, device):
         if self._dev is None or self._dev[0].device != device:
             ks = [self.kernel] if self.kernel.ndim == 2 else list(self.kernel)
-            shifted = np.stack([self.kernel_shift(k) for k in ks]).astype(np.float32)
+            # per-frame kernels: the padding kernel_shift adds depends on each kernel's own shift, so the shifted kernels can differ
+            # in size (always by an even amount: size + 2 * pad).  Zero-padding the smaller ones symmetrically to the common size
+            # keeps every centre, i.e. gives the result of applying each kernel on its own as the reference does (:100-118).
+            sk = [self.kernel_shift(k) for k in ks]
+            Lmax = max(k.shape[0] for k in sk)
+            sk = [np.pad(k, (Lmax - k.shape[0]) // 2, 'constant') for k in sk]
+            shifted = np.stack(sk).astype(np.float32)
             self._dev = (torch.from_numpy(shifted).to(device), shifted.shape[1])
         return self._dev
 

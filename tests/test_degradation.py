@@ -79,3 +79,28 @@ def test_cuda_degradation_full_size_properties():
     assert ya.shape == (5, 180, 320, 3)
     assert float((d.apply_nhwc(torch.full_like(a, 0.37)) - 0.37).abs().max()) < 1e-5
     assert rel(d.apply_nhwc(2.0 * a - 0.5 * b), 2.0 * ya - 0.5 * yb) < 1e-5
+
+
+def test_per_frame_kernels_of_different_shifted_size_are_padded_to_a_common_one():
+    """kernel_shift pads by an amount that depends on the kernel's own shift, so per-frame kernels can come back with
+    different sizes (the reference applies them one at a time, random_kernel_generator.py:100-118); they are zero-padded
+    symmetrically to the largest one, which leaves every centre -- and therefore every filtered frame -- unchanged."""
+    from scipy import ndimage
+    from dynavsr_b200.degradation import Degradation
+    d = Degradation(21, 4)
+    rng = np.random.RandomState(0)
+    ks = []
+    for _ in range(3):
+        k = np.zeros((21, 21))
+        k[10 + rng.randint(-6, 7), 10 + rng.randint(-6, 7)] = 1.0
+        k = ndimage.gaussian_filter(k, 1.5)
+        ks.append(k / k.sum())
+    own = [d.kernel_shift(k) for k in ks]
+    assert len({k.shape for k in own}) > 1                       # the case the plain np.stack could not handle
+    d.set_kernel_directly(np.stack(ks))
+    dev, L = d._device_kernels(torch.device('cpu'))
+    assert tuple(dev.shape) == (3, L, L) and L == max(k.shape[0] for k in own)
+    for i, k in enumerate(own):
+        m = (L - k.shape[0]) // 2
+        inner = dev[i, m:L - m, m:L - m].numpy()
+        assert np.allclose(inner, k.astype(np.float32)) and abs(float(dev[i].sum()) - float(k.sum())) < 1e-6
