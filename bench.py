@@ -73,6 +73,7 @@ def parse():
     ap.add_argument('--width', type=int, default=LR_W)
     # meta workload (BASELINE config 4)
     ap.add_argument('--tasks-per-rank', type=int, default=1)
+    ap.add_argument('--task-lanes', type=int, default=1, help='meta workload: tasks of an outer step run on this many lanes side by side (meta.MetaPool)')
     ap.add_argument('--nf', type=int, default=128)
     ap.add_argument('--back-rbs', type=int, default=40)
     ap.add_argument('--exchange', default='peer', choices=['peer', 'peer-all', 'nccl'])
@@ -346,7 +347,7 @@ def run_meta(args, rank, world, local):
     import torch
     import torch.distributed as dist
     from dynavsr_b200 import _lib
-    from dynavsr_b200.meta import MetaLearner
+    from dynavsr_b200.meta import MetaLearner, MetaPool
     from dynavsr_b200.models.archs import EDVR_arch, LRimg_estimator
     from dynavsr_b200.synth import seed_parameters
     torch.cuda.set_device(local)
@@ -354,9 +355,11 @@ def run_meta(args, rank, world, local):
         dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', local))
     netG = seed_parameters(EDVR_arch.EDVR(nf=args.nf, nframes=5, groups=8, front_RBs=5, back_RBs=args.back_rbs, scale=4), 1).cuda()
     netE = seed_parameters(LRimg_estimator.DirectKernelEstimatorVideo(64, 3, 4), 2).cuda()
-    ml = MetaLearner(netG, netE, inner_steps=1, lr_alpha=1e-5, inner_optimizer='Adam', criterion='cb', outer_optimizer='Adam',
-                     lr_outer=1e-5, exchange=args.exchange, use_graphs=not args.no_graphs,
-                     precision=None if args.meta_precision == 'bf16x3' else args.meta_precision)
+    mkw = dict(inner_steps=1, lr_alpha=1e-5, inner_optimizer='Adam', criterion='cb', outer_optimizer='Adam',
+               lr_outer=1e-5, exchange=args.exchange, use_graphs=not args.no_graphs,
+               precision=None if args.meta_precision == 'bf16x3' else args.meta_precision)
+    lanes = max(1, min(args.task_lanes, args.tasks_per_rank))
+    ml = MetaPool(netG, netE, lanes=lanes, **mkw) if lanes > 1 else MetaLearner(netG, netE, **mkw)
     g = torch.Generator().manual_seed(10 + rank)
     T = args.tasks_per_rank
     host = [{'LQs': torch.rand(1, 5, 3, 64, 64, generator=g).pin_memory(), 'GT': torch.rand(1, 3, 256, 256, generator=g).pin_memory(),
@@ -411,7 +414,7 @@ def run_meta(args, rank, world, local):
                 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
                 'dtype': ml.dtype_string(), 'data': 'synthetic',
                 'config': {'workload': 'meta-train EDVR(nf=%d, back_RBs=%d) + MFDN: task = LR 5x3x64x64 -> HR 3x256x256, SLR 5x3x16x16, inner Adam K=1, '
-                                       'cb loss, outer Adam' % (args.nf, args.back_rbs), 'tasks_per_rank_per_outer_step': T,
+                                       'cb loss, outer Adam' % (args.nf, args.back_rbs), 'tasks_per_rank_per_outer_step': T, 'task_lanes': lanes,
                            'flat_params': n_params, 'flat_gradient_MB': n_params * 4 / 1e6, 'exchange': ml.exchange,
                            'cuda_graphs': ml.use_graphs, 'parallelism': 'clip-sharded dp%d, ONE fused exchange+update per outer step' % world,
                            'l2': 'EDVR-L weights + packs + activations of a task (~1 GB) exceed the 126 MB L2; tasks alternate between two sets'},

@@ -17,13 +17,17 @@ grad L_q(theta)/B + grad L_e(theta)/(10B)]) for a numerical side-by-side on one 
 
 B200-first structure: theta' (EDVR u MFDN) is one flat buffer, so "deepcopy" = one D2D copy, the inner update = one launch,
 ``meta_grad += grad`` = one axpy over the flat gradient (kernels accumulate weight gradients straight into it).  The
-exchange step and the outer update are ONE kernel (``dvsr_update_peers``): the flat meta-gradient lives in symmetric memory
-(torch.distributed._symmetric_memory), every rank reads all ranks' 15 MB (EDVR-M) / 84 MB (EDVR-L) over NVLink peer pointers,
-sums in rank order, averages and applies Adam to its meta-weights in the same pass -- instead of DDP's bucketed hooks firing
-inside the inner loop, a reduced-gradient round trip through HBM and a separate optimiser launch.  ``exchange='nccl'`` (or a
-process group without peer access, e.g. gloo in CPU tests) falls back to ONE NCCL all-reduce of the flat buffer + the fused
-update launch.
+exchange step and the outer update are ONE kernel over NVLink peer memory: the flat meta-gradient lives in symmetric memory
+(torch.distributed._symmetric_memory); in the default reduce-scatter form (``dvsr_update_peers_sliced``) every rank reduces its
+slice of all ranks' buffers in rank order, applies Adam / SGD to that slice with its slice of the moments and writes the new
+weights into every rank's buffer (``exchange='peer-all'``: every rank reads all ranks' full gradients, ``dvsr_update_peers``) --
+instead of DDP's bucketed hooks firing inside the inner loop, a reduced-gradient round trip through HBM and a separate optimiser
+launch.  ``exchange='nccl'`` (or a process group without peer access, e.g. gloo in CPU tests) falls back to ONE NCCL all-reduce
+of the flat buffer + the fused update launch.  ``MetaPool`` runs the tasks of an outer step on several task lanes (own working
+copy, packs, CUDA graphs and stream each) side by side: a task is ~12 000 launches of small-patch kernels and leaves most of the
+GPU idle on its own.
 """
+import copy
 import ctypes
 
 import torch
@@ -190,23 +194,36 @@ class MetaLearner(object):
     # ------------------------------------------------------------------ one outer step
     def outer_step(self, tasks, lr=None):
         """tasks: this rank's clips for the step.  Returns the summed query loss / B (the reference's ``total_loss_q``)."""
-        fl = self.work
         with ops.scope(self.scope):
-            self.meta_grad.zero_()
-            if self.reference_quirk:
-                fl.restore()
-                ops.repack_all()
-                fl.zero_grad()                     # optimizer.zero_grad() (:270): grads then pile up across tasks
-            if fl.m is not None:
-                fl.m.zero_(); fl.v.zero_()
-            lq, le, inner = [], [], []
-            for t in tasks:
-                if self.inner_optimizer == 'Adam' and fl.m is not None:
-                    fl.m.zero_(); fl.v.zero_()     # a fresh inner optimiser per task (:346-353)
-                a, b, c = self._task(t, len(tasks))
-                lq.append(a); le.append(b); inner.append(c)
-            if self.reference_quirk:
-                self.meta_grad.copy_(fl.grad)
+            lq, le, inner = self._run_tasks(tasks, len(tasks))
+            return self._finish_step(lq, le, inner, len(tasks), lr)
+
+    def _run_tasks(self, tasks, n_tasks):
+        """Zero this learner's meta-gradient and accumulate the meta-gradients of ``tasks`` into it (each scaled for a step of
+        ``n_tasks`` tasks).  Call inside ``ops.scope(self.scope)``."""
+        fl = self.work
+        self.meta_grad.zero_()
+        if self.reference_quirk:
+            fl.restore()
+            ops.repack_all()
+            fl.zero_grad()                     # optimizer.zero_grad() (:270): grads then pile up across tasks
+        if fl.m is not None:
+            fl.m.zero_(); fl.v.zero_()
+        lq, le, inner = [], [], []
+        for t in tasks:
+            if self.inner_optimizer == 'Adam' and fl.m is not None:
+                fl.m.zero_(); fl.v.zero_()     # a fresh inner optimiser per task (:346-353)
+            a, b, c = self._task(t, n_tasks)
+            lq.append(a); le.append(b); inner.append(c)
+        if self.reference_quirk:
+            self.meta_grad.copy_(fl.grad)
+        return lq, le, inner
+
+    def _finish_step(self, lq, le, inner, n_tasks, lr=None):
+        """Exchange of the flat meta-gradient + outer update (one kernel on the peer paths), then the modules and packs are
+        brought to the new meta-weights.  Call inside ``ops.scope(self.scope)``."""
+        fl = self.work
+        if True:
             lr = self.lr_outer if lr is None else lr
             self.outer_steps += 1
             n = self.theta.numel()
@@ -258,7 +275,7 @@ class MetaLearner(object):
             if self.use_graphs:
                 ops.snapshot_packs()               # the captured tasks restore theta's packs from this arena
         self.last = {'loss_q': torch.stack(lq), 'loss_e': torch.stack(le), 'inner': inner}
-        return torch.stack(lq).sum() / len(tasks)
+        return torch.stack(lq).sum() / n_tasks
 
     def exchange_timing(self, reset=True):
         """Device time of the exchange + outer-update section of the recorded outer steps (CUDA events on the launching stream;
@@ -297,3 +314,100 @@ class MetaLearner(object):
         """(EDVR state_dict, MFDN state_dict) of the meta-weights, reference key names (checkpoint contract)."""
         return ({k: v.detach().clone() for k, v in self.netG.state_dict().items()},
                 {k: v.detach().clone() for k, v in self.netE.state_dict().items()})
+
+
+class MetaPool(object):
+    """The tasks of an outer step on L task lanes of ONE GPU.
+
+    A task of the meta step (train_dynavsr.py:322-426: theta' <- theta, K inner steps on the 16x16 SLR patch, the meta-test
+    backward on the 64x64 LR patch) is a dependent chain of ~12 000 small-patch launches that keeps a few dozen SMs busy at a
+    time; the tasks of a step are independent (they all start from theta and only ADD into the meta-gradient).  Each lane is a
+    ``MetaLearner`` of its own -- working copy theta', flat gradient, weight packs, CUDA graphs, stream -- so the lanes' tasks
+    run side by side; their meta-gradients are summed into lane 0's, whose exchange + outer update (one kernel over NVLink peer
+    memory) then runs once, and the new theta is copied back to the other lanes.  Numerically the step equals
+    ``MetaLearner.outer_step`` on the same tasks up to the fp32 order of the cross-lane sum.
+    """
+
+    def __init__(self, netG, netE, lanes=4, **kw):
+        assert lanes >= 1 and not kw.get('reference_quirk'), 'the as-written reference mode is sequential by construction'
+        clones = [(copy.deepcopy(netG), copy.deepcopy(netE)) for _ in range(lanes - 1)]     # BEFORE lane 0 re-homes the parameters
+        lane_kw = dict(kw)
+        lane_kw['exchange'] = 'none'
+        self.master = MetaLearner(netG, netE, **kw)
+        self.lanes = [self.master] + [MetaLearner(g, e, **lane_kw) for g, e in clones]
+        self.streams = [torch.cuda.Stream() for _ in self.lanes]
+        self._warm = set()
+
+    # the attributes callers of MetaLearner read
+    theta = property(lambda self: self.master.theta)
+    meta_grad = property(lambda self: self.master.meta_grad)
+    exchange = property(lambda self: self.master.exchange)
+    use_graphs = property(lambda self: self.master.use_graphs)
+    last = property(lambda self: self.master.last)
+
+    @property
+    def replayed_launches(self):
+        return sum(l.replayed_launches for l in self.lanes)
+
+    @replayed_launches.setter
+    def replayed_launches(self, v):
+        for l in self.lanes:
+            l.replayed_launches = v
+
+    @property
+    def exchange_events(self):
+        return self.master.exchange_events
+
+    @exchange_events.setter
+    def exchange_events(self, v):
+        self.master.exchange_events = v
+
+    def exchange_timing(self, reset=True):
+        return self.master.exchange_timing(reset)
+
+    def dtype_string(self):
+        return self.master.dtype_string()
+
+    def state_dicts(self):
+        return self.master.state_dicts()
+
+    def outer_step(self, tasks, lr=None):
+        m, L = self.master, len(self.lanes)
+        n_tasks = len(tasks)
+        cur = torch.cuda.current_stream()
+        share = [list(range(li, n_tasks, L)) for li in range(L)]
+        out = [None] * L
+        # a lane's first task of a given shape captures its CUDA graph: do that with the GPU to itself (capture is a global mode)
+        key = tuple(tuple(tasks[0][k].shape) for k in ('LQs', 'GT', 'SuperLQs')) + (n_tasks,)
+        serial = key not in self._warm
+        for li, lane in enumerate(self.lanes):
+            if not share[li]:
+                continue
+            s = self.streams[li]
+            s.wait_stream(cur)
+            with torch.cuda.stream(s), ops.scope(lane.scope):
+                out[li] = lane._run_tasks([tasks[i] for i in share[li]], n_tasks)
+            if serial:
+                s.synchronize()
+        self._warm.add(key)
+        for li, s in enumerate(self.streams):
+            if share[li]:
+                cur.wait_stream(s)
+        lq, le, inner = [None] * n_tasks, [None] * n_tasks, [None] * n_tasks
+        for li in range(L):
+            if share[li]:
+                for j, i in enumerate(share[li]):
+                    lq[i], le[i], inner[i] = out[li][0][j], out[li][1][j], out[li][2][j]
+                if li > 0:
+                    m.meta_grad.add_(self.lanes[li].meta_grad)          # cross-lane sum, on the caller's stream
+        with ops.scope(m.scope):
+            loss = m._finish_step(lq, le, inner, n_tasks, lr)
+        for lane in self.lanes[1:]:                                     # the other lanes follow the new meta-weights
+            lane.theta.copy_(m.theta)
+            with ops.scope(lane.scope):
+                ops.invalidate_pack_snapshot(lane.scope)
+                lane.work.restore()
+                ops.repack_all()
+                if lane.use_graphs:
+                    ops.snapshot_packs()
+        return loss

@@ -221,3 +221,31 @@ def test_outer_adam_sensitivity_is_confined_to_near_zero_gradients():
         assert float(g[bad].abs().median()) < 0.05 * rms            # the disagreement lives where the gradient is ~0
     good = live & ~bad
     assert rel(dA1[good], dA0[good]) < 1e-2
+
+
+@pytest.mark.parametrize('graphs', [False, True], ids=['eager', 'graphs'])
+def test_meta_pool_lanes_match_the_sequential_step(graphs):
+    """meta.MetaPool: the tasks of an outer step on two task lanes (own working copy, packs, graphs and stream each) give the
+    step MetaLearner.outer_step gives on the same tasks -- same meta-gradient up to the fp32 order of the cross-lane sum and the
+    weight-gradient atomics, same losses -- over two consecutive steps (the second one starts from the lanes' refreshed theta)."""
+    from dynavsr_b200 import ops
+    from dynavsr_b200.meta import MetaLearner, MetaPool
+    kw = dict(inner_steps=1, lr_alpha=1e-3, inner_optimizer='SGD', criterion='l2', est_loss='l1', outer_optimizer='SGD', lr_outer=1e-2,
+              use_graphs=graphs)
+    ops.set_conv_backend(True)
+    try:
+        _, _, netG, netE, tasks = _setup(71)
+        seq = MetaLearner(netG, netE, **kw)
+        _, _, netG2, netE2, _ = _setup(71)
+        pool = MetaPool(netG2, netE2, lanes=2, **kw)
+        th0 = seq.theta.clone()
+        for step in range(2):
+            l_seq = seq.outer_step(_dev(tasks))
+            l_pool = pool.outer_step(_dev(tasks))
+            assert abs(float(l_seq) - float(l_pool)) < 1e-4 * abs(float(l_seq)) + 1e-7
+            assert rel(pool.meta_grad, seq.meta_grad) < 2e-3, step
+            assert rel(pool.theta - th0, seq.theta - th0) < 2e-3, step
+        for lane in pool.lanes[1:]:
+            assert torch.equal(lane.theta, pool.master.theta)
+    finally:
+        ops.set_conv_backend(False)
