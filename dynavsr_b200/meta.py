@@ -24,7 +24,7 @@ weights into every rank's buffer (``exchange='peer-all'``: every rank reads all 
 instead of DDP's bucketed hooks firing inside the inner loop, a reduced-gradient round trip through HBM and a separate optimiser
 launch.  ``exchange='nccl'`` (or a process group without peer access, e.g. gloo in CPU tests) falls back to ONE NCCL all-reduce
 of the flat buffer + the fused update launch.  ``MetaPool`` runs the tasks of an outer step on several task lanes (own working
-copy, packs, CUDA graphs and stream each) side by side: a task is ~12 000 launches of small-patch kernels and leaves most of the
+copy, packs, CUDA graphs and stream each) side by side: a task is ~1 300 launches of small-patch kernels and leaves most of the
 GPU idle on its own.
 """
 import copy
@@ -320,7 +320,7 @@ class MetaPool(object):
     """The tasks of an outer step on L task lanes of ONE GPU.
 
     A task of the meta step (train_dynavsr.py:322-426: theta' <- theta, K inner steps on the 16x16 SLR patch, the meta-test
-    backward on the 64x64 LR patch) is a dependent chain of ~12 000 small-patch launches that keeps a few dozen SMs busy at a
+    backward on the 64x64 LR patch) is a dependent chain of ~1 300 small-patch launches that keeps a few dozen SMs busy at a
     time; the tasks of a step are independent (they all start from theta and only ADD into the meta-gradient).  Each lane is a
     ``MetaLearner`` of its own -- working copy theta', flat gradient, weight packs, CUDA graphs, stream -- so the lanes' tasks
     run side by side; their meta-gradients are summed into lane 0's, whose exchange + outer update (one kernel over NVLink peer
