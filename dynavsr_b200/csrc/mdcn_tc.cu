@@ -689,11 +689,12 @@ extern "C" int dvsr_mdcn_tc_fprop(const dvsr_conv_desc* d, const float* wp, void
             return check_launch("mdcn_tc_fprop: cudaFuncSetAttribute");
         smem_set = smem;
     }
-    // staged-window variant for the EDVR geometry (3x3, stride 1, pad 1, dilation 1); launches with fewer than ~2 tiles per SM
-    // keep the direct kernel: one window load per CTA would not be amortised
+    // staged-window variant for the EDVR geometry (3x3, stride 1, pad 1, dilation 1) from 32 tiles up.  (Round 1 kept the direct kernel
+    // below two tiles per SM; measured in round 2 at the inner-loop sizes, whole GPU / 37-CTA budget: 5x44x80 35 vs 36 / 84 vs 129 us,
+    // 5x88x160 98 vs 149 / 324 vs 570 us, 5x22x40 (50 tiles) 20 vs 33 / 36 vs 33 us -- tools/gpu_r2_21.sh.)
     const int staged_mode = d->policy.mdcn_staged;
     if (staged_mode != 1 && d->KH == 3 && d->KW == 3 && d->stride == 1 && d->dil == 1 && d->pad == 1 && d->Ho == d->H && d->Wo == d->W &&
-        (staged_mode == 2 || (long long)d->N * ((d->Wo + 7) / 8) * ((d->Ho + 15) / 16) >= 2 * sm_count()) &&
+        (staged_mode == 2 || (long long)d->N * ((d->Wo + 7) / 8) * ((d->Ho + 15) / 16) >= 32) &&
         (((uintptr_t)d->offset & 7) == 0) && ((d->off_pix_stride & 1) == 0)) {
         p.margin = MDS_MARGIN;
         p.win_h = MDS_WIN_H;

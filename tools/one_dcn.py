@@ -39,7 +39,9 @@ def eager(fn, reps=20):
     return e0.elapsed_time(e1) / reps * 1e3
 
 
-with torch.no_grad():
+STAGED = int(sys.argv[sys.argv.index('--staged') + 1]) if '--staged' in sys.argv else 0      # dvsr_policy.mdcn_staged: 0 auto, 1 direct, 2 staged
+BUDGET = int(sys.argv[sys.argv.index('--cta-budget') + 1]) if '--cta-budget' in sys.argv else 0
+with torch.no_grad(), ops.scope(ops.new_scope(ops.LaunchPolicy(cta_budget=BUDGET, mdcn_staged=STAGED))):
     print('fwd avg us', timed(lambda: ops.mdcn(x, om, w, b, 8, 1, 1, 1, ops.ACT_LRELU)))
 if '--bwd' in sys.argv:
     xr, omr, wr = x.clone().requires_grad_(True), om.clone().requires_grad_(True), w.clone().requires_grad_(True)
