@@ -31,8 +31,8 @@ if '--trace' in sys.argv:
     _lib.lib().dvsr_conv_tc2_set_trace(None)
     t = tr.view(12, 64).cpu()
     t0 = int(t[0, 0])
-    names = ['prod:slot free', 'round:tile landed', 'round:done', 'mma:ready seen', 'mma:issued', 'epi:acc full', 'epi:done', 'epi:tmem read', 'epi:math']
-    for ev in range(9):
+    names = ['prod:slot free', 'round:tile landed', 'round:done', 'mma:ready seen', 'mma:issued', 'epi:acc full', 'epi:done', 'epi:tmem read']
+    for ev in range(8):
         print('%-18s' % names[ev], ' '.join('%6d' % (int(v) - t0) for v in t[ev, :(30 if ev < 5 else 15)]))
 if '--both' in sys.argv:
     for prec in ('tf32', 'bf16x3'):
